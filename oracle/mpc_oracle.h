@@ -1,0 +1,84 @@
+/* CPU oracle for the MPC solve path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * PARITY UNPINNED: the reference's solve is CasADi nlpsol('ipopt')
+ * (PKG/MPC_CBF_optimize_kin.py:251-254, called at PKG/main_cbf_kin_c_sim.py:100);
+ * neither CasADi nor IPOPT exists in this image and the reference holds no golden
+ * vectors, so this oracle restates the NLP exactly (see oracle/nlp.py for the
+ * per-line citations) and IPOPT's published algorithm approximately
+ * (oracle/ipm_dense.py is the dense specification; this file solves the same Newton
+ * systems with a scalar stage-wise Riccati recursion so that it is fast enough to be
+ * the CPU baseline).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library.
+ */
+#ifndef MPC_ORACLE_H
+#define MPC_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_NMAX 128 /* max horizon */
+#define ORC_MMAX 4   /* max obstacles */
+
+enum { ORC_MODEL_KIN = 0, ORC_MODEL_DYN = 1 };
+enum { ORC_OBS_NONE = 0, ORC_OBS_ELLIPSE = 1, ORC_OBS_SQRT = 2 };
+enum { ORC_INIT_AS_GIVEN = 0, ORC_INIT_ROLLOUT = 1 };
+enum { ORC_CONVERGED = 0, ORC_ACCEPTABLE = 1, ORC_MAXITER = 2, ORC_INFEASIBLE = 3, ORC_NAN = 4 };
+
+typedef struct {
+  int32_t model;      /* ORC_MODEL_* */
+  int32_t N;          /* horizon steps */
+  int32_t M;          /* obstacles per scenario */
+  int32_t obs_mode;   /* ORC_OBS_* */
+  int32_t du0_cost;   /* i=0 control-rate cost vs Ulast=0 (PKG/MPC_CBF_optimize_kin.py:203-204) */
+  int32_t n_rate;     /* number of rate-limited controls (rows for i=1..N-1) */
+  int32_t rate_ctrl[2];
+  int32_t init_mode;  /* ORC_INIT_* */
+  int32_t max_iter;
+  double T;           /* T_S */
+  double Q[6], R[2], DR[2];
+  double rate_lo[2], rate_hi[2];
+  double u_lo[2], u_hi[2];
+  double x_lo[6], x_hi[6]; /* +-inf for free */
+  double obs_lo;      /* lower bound of the obstacle rows (0 kin, 1 dyn) */
+  double ego_hl, ego_hw, safe_l, safe_w; /* sX = ego_hl + l/2 + safe_l (kin rows) */
+  double dyn_sx, dyn_sy; /* fixed semi-axes of the dyn row (4, 1) */
+  /* vehicle */
+  double Veh_l, Veh_lf, Veh_lr, Veh_m, Veh_Iz, aopt_f, aopt_r, Fymax_f, Fymax_r;
+  /* interior-point options */
+  double tol, mu_init, bound_relax;
+} orc_cfg;
+
+typedef struct {
+  double f;       /* unscaled objective */
+  double err;     /* final scaled KKT error */
+  double mu;
+  double obj_scale;
+  int32_t status, iters, n_reg, n_backtrack;
+} orc_info;
+
+/* one scenario.  obs: (M, N+1, 6) rows [x,y,theta,v,l,w]; z_init: nv or NULL (zeros);
+ * z_out: nv = 2N + nx(N+1) in the reference order [vec(U); vec(X)]; lam_g_out: nullable,
+ * multipliers of [X0-x0 ; defects] (nx(N+1)), unscaled. */
+int orc_solve(const orc_cfg *cfg, const double *x0, const double *xs, const double *obs,
+              const double *z_init, double *z_out, double *lam_eq_out, orc_info *info);
+
+/* batch with OpenMP threads; arrays are row-major [B][...]; z_init/z_out nullable */
+int orc_solve_batch(const orc_cfg *cfg, int B, const double *x0, const double *xs, const double *obs,
+                    const double *z_init, double *u0, double *cost, int32_t *status, int32_t *iters,
+                    double *z_out, int nthreads);
+
+/* one Newton step at a given primal point with unit bound multipliers and zero equality
+ * multipliers (used by the Riccati-vs-dense test): returns dz (nv) */
+int orc_newton_step(const orc_cfg *cfg, const double *x0, const double *xs, const double *obs,
+                    const double *z, double mu, double dw, double obj_scale, double *dz, double *lam_plus);
+
+int orc_nx(const orc_cfg *cfg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
