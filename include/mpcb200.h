@@ -1,0 +1,145 @@
+/* mpcb200 — C ABI of the B200-native batched nonlinear-MPC solve path.
+ *
+ * Drop-in boundary for the one hot path of ZhuorenLi/MPC_motion_planning: the per-control-
+ * step "build the multiple-shooting NLP and solve it" pair
+ *
+ *     solver = mpc_solver.optimize_problem(ego_state, ref_state, obstacle)   PKG/main_cbf_kin_c_sim.py:99
+ *     res    = solver(x0=init_control, p=c_p, lbg=, lbx=, ubg=, ubx=)        PKG/main_cbf_kin_c_sim.py:100
+ *
+ * (PKG = CasaDi_MPC_Optimize_Multishoot; same pair at main_cbf_kin_c_sim_pre.py:99-100,
+ * main_cbf_dyn_c_sim.py:89-90, main_kin_c_sim.py:83-84).  The reference has no FFI layer —
+ * the seam is CasADi's functional interface — so these entry points are what a ctypes
+ * binding placed behind `MPC_optimize.optimize_problem` calls.
+ *
+ * All entry points are plain C: pointers + sizes, no C++/torch types, no exceptions.
+ * Buffers are caller-owned.  `*_batch` takes DEVICE pointers and is asynchronous on the
+ * given stream; `*_batch_host` takes HOST pointers and is synchronous (copies inside).
+ */
+#ifndef MPCB200_H
+#define MPCB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCB_VERSION 100 /* 0.1.0 */
+#define MPCB_NMAX 128    /* maximum horizon N */
+#define MPCB_MMAX 2      /* maximum obstacles per scenario in this build */
+
+/* vehicle model: replaces the CasADi `rhs` of PKG/MPC_CBF_optimize_kin.py:153-156 (KIN) and
+ * PKG/MPC_CBF_optimize_dyn.py:156-170 (DYN) */
+enum { MPCB_MODEL_KIN = 0, MPCB_MODEL_DYN = 1 };
+/* obstacle rows: NONE = MPC_optimize_kin (no CBF); ELLIPSE = h(X_i) >= 0, i=0..N-1
+ * (PKG/MPC_CBF_optimize_kin.py:236-247, _kin_pre.py:236-253); SQRT = sqrt(ellipse-1) >= 1,
+ * i=0..N (PKG/MPC_CBF_optimize_dyn.py:238-243) */
+enum { MPCB_OBS_NONE = 0, MPCB_OBS_ELLIPSE = 1, MPCB_OBS_SQRT = 2 };
+/* how `z_init` (the `x0=` argument of the CasADi call, PKG/main_cbf_kin_c_sim.py:92,100) is used:
+ * AS_GIVEN = controls and states as passed; ROLLOUT = controls as passed, states re-integrated
+ * from the parameter x0 with the Euler step of PKG/MPC_CBF_optimize_kin.py:207 */
+enum { MPCB_INIT_AS_GIVEN = 0, MPCB_INIT_ROLLOUT = 1 };
+
+/* per-scenario outcome, mapped to IPOPT return_status strings by the Python shim */
+enum {
+  MPCB_CONVERGED = 0,  /* Solve_Succeeded */
+  MPCB_ACCEPTABLE = 1, /* Solved_To_Acceptable_Level (reserved; acceptable_tol == tol in the reference) */
+  MPCB_MAXITER = 2,    /* Maximum_Iterations_Exceeded */
+  MPCB_INFEASIBLE = 3, /* line search failed / Restoration_Failed / Infeasible_Problem_Detected */
+  MPCB_NAN = 4         /* Invalid_Number_Detected */
+};
+
+/* return codes of the entry points */
+enum {
+  MPCB_OK = 0,
+  MPCB_E_ARG = -1,      /* bad argument / unsupported configuration */
+  MPCB_E_CUDA = -2,     /* CUDA runtime error (see mpcb_last_cuda_error) */
+  MPCB_E_NOMEM = -3,
+  MPCB_E_NODEVICE = -4  /* no CUDA device: there is no CPU fallback */
+};
+
+/* Problem definition.  Everything the reference hard-codes in `optimize_problem` /
+ * `initialize_constraints` / mpc_parameters.yaml is a field here; the Python host fills it
+ * with the reference's values. */
+typedef struct mpcb_cfg {
+  int32_t model;        /* MPCB_MODEL_* */
+  int32_t N;            /* N_p (PKG/MPC_CBF_optimize_kin.py:32-33) */
+  int32_t M;            /* obstacles per scenario */
+  int32_t obs_mode;     /* MPCB_OBS_* */
+  int32_t du0_cost;     /* include (U_0-Ulast)'DR(U_0-Ulast), Ulast=0 (kin-CBF: yes, :203-204; dyn/no-CBF: no) */
+  int32_t n_rate;       /* number of rate-limited controls, rows for i=1..N-1 (:211-216; dyn :229-231) */
+  int32_t rate_ctrl[2]; /* which control each rate row constrains (0 = df, 1 = ax) */
+  int32_t init_mode;    /* MPCB_INIT_* */
+  int32_t max_iter;     /* ipopt.max_iter (:252) */
+  double T;             /* T_S */
+  double Q[6], R[2], DR[2];           /* weights (:168-184) */
+  double rate_lo[2], rate_hi[2];      /* df_dot_min*T_S .. (:119-121); dyn also jerk*T_S */
+  double u_lo[2], u_hi[2];            /* lbx/ubx of the controls (:90-95) */
+  double x_lo[6], x_hi[6];            /* lbx/ubx of the states, +-inf when free (:97-105) */
+  double obs_lo;                      /* lower bound of the obstacle rows (0 kin, 1 dyn) */
+  double ego_hl, ego_hw, safe_l, safe_w; /* Veh_L/2, Veh_W/2, safe_disl, safe_disw (:220-225) */
+  double dyn_sx, dyn_sy;              /* safe_X, safe_Y of the dyn row (_dyn.py:240-241) */
+  double Veh_l, Veh_lf, Veh_lr, Veh_m, Veh_Iz, aopt_f, aopt_r, Fymax_f, Fymax_r;
+  double tol;           /* ipopt.tol (default 1e-8) */
+  double mu_init;       /* initial barrier parameter (IPOPT default 0.1; this library's default 100) */
+  double bound_relax;   /* ipopt.bound_relax_factor (1e-8) */
+} mpcb_cfg;
+
+typedef struct mpcb_handle mpcb_handle;
+
+int mpcb_version(void);
+const char *mpcb_strerror(int code);
+const char *mpcb_last_cuda_error(void);
+
+/* state dimension implied by cfg->model (4 or 6); nv = 2N + nx(N+1) */
+int mpcb_nx(const mpcb_cfg *cfg);
+int mpcb_nv(const mpcb_cfg *cfg);
+
+/* validates cfg, selects the device-resident kernel variant; no device allocation beyond
+ * a few bytes.  One handle per GPU (current device at creation); not re-entrant. */
+int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out);
+void mpcb_destroy(mpcb_handle *h);
+
+/* device scratch the library needs for a batch of B (0 in this version: the whole
+ * iterate lives in shared memory) */
+int mpcb_workspace_bytes(const mpcb_cfg *cfg, int B, size_t *bytes);
+
+/* Replaces optimize_problem + solver(...) for B independent scenarios.  DEVICE pointers,
+ * row-major, float64:
+ *   x0 [B][nx], xs [B][nx]        = the parameter vector p=[x0;xs] (PKG/main_cbf_kin_c_sim.py:89)
+ *   obs [B][M][N+1][6]            = obs_prediction rows [x,y,theta,v,l,w] (PKG/Obs_prediction.py:3-40);
+ *                                   static obstacles repeat the row; dyn uses columns 0,1 only
+ *   z_init [B][nv] or NULL        = `x0=` warm start [vec(U);vec(X)] (NULL = zeros, :47-50)
+ * outputs:
+ *   u0 [B][2]                     = first control, res['x'][0:2]
+ *   cost [B]                      = res['f']
+ *   status [B], iters [B]         = per-scenario outcome (MPCB_CONVERGED ...) and iteration count
+ *   z_out [B][nv] or NULL         = res['x']
+ *   lam_out [B][nx(N+1)] or NULL  = multipliers of [X_0-x0 ; defects] (head of res['lam_g'])
+ * Asynchronous on `stream` (a cudaStream_t passed as void*). */
+int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, const double *obs,
+                     const double *z_init, double *u0, double *cost, int32_t *status, int32_t *iters,
+                     double *z_out, double *lam_out, void *stream);
+
+/* Same with HOST pointers: allocates/reuses device buffers inside the handle, copies in,
+ * solves, copies out, synchronises.  This is the call a ctypes/cgo/JNI stub binds. */
+int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double *xs, const double *obs,
+                          const double *z_init, double *u0, double *cost, int32_t *status, int32_t *iters,
+                          double *z_out, double *lam_out);
+
+/* Closed-loop helper (row N1 of SURVEY.md section 8f; PKG/main_cbf_kin_c_sim.py:16-26):
+ * plant Euler step x0 <- x0 + T f(x0, U_0) and warm-start shift of z (drop first row, repeat last),
+ * in place on DEVICE buffers x0 [B][nx], z [B][nv]. */
+int mpcb_shift_batch(mpcb_handle *h, int B, double *x0, double *z, void *stream);
+
+/* kernel launch statistics of the last solve on this handle */
+typedef struct mpcb_launch_info {
+  int32_t grid, block, smem_bytes, regs_per_thread, blocks_per_sm, num_sms;
+  int64_t launches; /* kernels launched by this handle so far */
+} mpcb_launch_info;
+int mpcb_get_launch_info(mpcb_handle *h, mpcb_launch_info *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCB200_H */

@@ -1,0 +1,328 @@
+// mpcb200 host side of the C ABI declared in include/mpcb200.h.  No torch types, no
+// exceptions across the boundary.  There is no CPU fallback: without a CUDA device
+// mpcb_create fails with MPCB_E_NODEVICE.
+#include "../../include/mpcb200.h"
+#include "mpcb_kernel.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+using namespace mpcb;
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+bool cuda_ok(cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return true;
+  snprintf(g_cuda_err, sizeof g_cuda_err, "%s: %s", what, cudaGetErrorString(e));
+  return false;
+}
+
+typedef cudaError_t (*launch_fn)(const KParams &, int grid, size_t smem, cudaStream_t);
+typedef const void *kernel_ptr;
+
+template <class Mdl, int NR, int MO, int OBS>
+cudaError_t launch_variant(const KParams &p, int grid, size_t smem, cudaStream_t st) {
+  solve_kernel<Mdl, NR, MO, OBS><<<grid, 32, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+struct Variant {
+  launch_fn launch;
+  kernel_ptr kernel;
+  size_t (*smem_bytes)(int N);
+  int nx, nbx;
+};
+
+template <class Mdl, int NR, int MO, int OBS>
+Variant make_variant() {
+  Variant v;
+  v.launch = &launch_variant<Mdl, NR, MO, OBS>;
+  v.kernel = (const void *)&solve_kernel<Mdl, NR, MO, OBS>;
+  v.smem_bytes = [](int N) { return Layout<Mdl, NR, MO>::bytes(N); };
+  v.nx = Mdl::NX;
+  v.nbx = Mdl::NBX;
+  return v;
+}
+
+bool select_variant(const mpcb_cfg &c, Variant &v) {
+  const int M = c.obs_mode == MPCB_OBS_NONE ? 0 : c.M;
+  if (c.model == MPCB_MODEL_KIN) {
+    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 0) { v = make_variant<KinModel, 0, 0, 0>(); return true; }
+    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 1) { v = make_variant<KinModel, 1, 0, 0>(); return true; }
+    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 1) { v = make_variant<KinModel, 1, 1, 1>(); return true; }
+    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 2) { v = make_variant<KinModel, 1, 2, 1>(); return true; }
+  }
+  return false;
+}
+
+double relax_lo(double b, double f) { return std::isfinite(b) ? b - f * std::fmax(1.0, std::fabs(b)) : b; }
+double relax_hi(double b, double f) { return std::isfinite(b) ? b + f * std::fmax(1.0, std::fabs(b)) : b; }
+
+}  // namespace
+
+struct mpcb_handle {
+  mpcb_cfg cfg;
+  Variant var;
+  KParams kp;  // everything except pointers and B
+  size_t smem;
+  int device;
+  mpcb_launch_info info;
+  // device buffers for the host-pointer entry point
+  cudaStream_t stream;
+  int cap_B;
+  double *d_x0, *d_xs, *d_obs, *d_zin, *d_u0, *d_cost, *d_z, *d_lam;
+  int32_t *d_status, *d_iters;
+};
+
+extern "C" {
+
+int mpcb_version(void) { return MPCB_VERSION; }
+
+const char *mpcb_strerror(int code) {
+  switch (code) {
+    case MPCB_OK: return "ok";
+    case MPCB_E_ARG: return "bad argument or unsupported configuration";
+    case MPCB_E_CUDA: return "CUDA runtime error";
+    case MPCB_E_NOMEM: return "out of memory";
+    case MPCB_E_NODEVICE: return "no CUDA device (this library has no CPU fallback)";
+    default: return "unknown error";
+  }
+}
+
+const char *mpcb_last_cuda_error(void) { return g_cuda_err; }
+
+int mpcb_nx(const mpcb_cfg *cfg) { return cfg && cfg->model == MPCB_MODEL_DYN ? 6 : 4; }
+int mpcb_nv(const mpcb_cfg *cfg) { return cfg ? 2 * cfg->N + mpcb_nx(cfg) * (cfg->N + 1) : 0; }
+
+int mpcb_workspace_bytes(const mpcb_cfg *cfg, int B, size_t *bytes) {
+  if (!cfg || !bytes || B < 0) return MPCB_E_ARG;
+  *bytes = 0;  // the whole iterate lives in shared memory
+  return MPCB_OK;
+}
+
+int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
+  if (!cfg || !out) return MPCB_E_ARG;
+  *out = nullptr;
+  const mpcb_cfg &c = *cfg;
+  if (c.N < 2 || c.N > MPCB_NMAX || c.M < 0 || c.M > MPCB_MMAX || c.max_iter < 0) return MPCB_E_ARG;
+  if (c.n_rate < 0 || c.n_rate > 2) return MPCB_E_ARG;
+  for (int r = 0; r < c.n_rate; r++)
+    if (c.rate_ctrl[r] < 0 || c.rate_ctrl[r] > 1 || !(c.rate_lo[r] < c.rate_hi[r])) return MPCB_E_ARG;
+  if (!(c.T > 0) || !(c.tol > 0) || !(c.mu_init > 0) || !(c.bound_relax >= 0)) return MPCB_E_ARG;
+  if (c.obs_mode != MPCB_OBS_NONE && c.M < 1) return MPCB_E_ARG;
+  Variant var;
+  if (!select_variant(c, var)) return MPCB_E_ARG;
+  // the kernels assume: both controls two-sided; the model's bounded states (kin: y, vx; dyn: + vy)
+  // two-sided; every other state free
+  for (int i = 0; i < 2; i++)
+    if (!std::isfinite(c.u_lo[i]) || !std::isfinite(c.u_hi[i]) || !(c.u_lo[i] < c.u_hi[i])) return MPCB_E_ARG;
+  for (int i = 0; i < var.nx; i++) {
+    bool bounded = (i == 1 || i == 3 || (var.nx == 6 && i == 4));
+    bool fin = std::isfinite(c.x_lo[i]) && std::isfinite(c.x_hi[i]);
+    bool free_ = std::isinf(c.x_lo[i]) && c.x_lo[i] < 0 && std::isinf(c.x_hi[i]) && c.x_hi[i] > 0;
+    if (bounded ? !(fin && c.x_lo[i] < c.x_hi[i]) : !free_) return MPCB_E_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    return MPCB_E_NODEVICE;
+  }
+  mpcb_handle *h = new (std::nothrow) mpcb_handle();
+  if (!h) return MPCB_E_NOMEM;
+  memset(h, 0, sizeof *h);
+  h->cfg = c;
+  h->var = var;
+  if (!cuda_ok(cudaGetDevice(&h->device), "cudaGetDevice")) { delete h; return MPCB_E_CUDA; }
+
+  KParams &k = h->kp;
+  memset(&k, 0, sizeof k);
+  const int M = c.obs_mode == MPCB_OBS_NONE ? 0 : c.M;
+  k.N = c.N; k.obs_mode = c.obs_mode; k.du0_cost = c.du0_cost; k.init_mode = c.init_mode; k.max_iter = c.max_iter;
+  k.rate_ctrl[0] = c.rate_ctrl[0]; k.rate_ctrl[1] = c.rate_ctrl[1];
+  const int n_obs_st = c.obs_mode == MPCB_OBS_ELLIPSE ? c.N : (c.obs_mode == MPCB_OBS_SQRT ? c.N + 1 : 0);
+  k.n_eq = var.nx * (c.N + 1) + c.n_rate * (c.N - 1) + M * n_obs_st;
+  k.n_bm = 4 * c.N + 2 * var.nbx * (c.N + 1) + 2 * c.n_rate * (c.N - 1) + M * n_obs_st;
+  k.T = c.T;
+  for (int i = 0; i < 6; i++) { k.Q[i] = c.Q[i]; k.x_lo[i] = relax_lo(c.x_lo[i], c.bound_relax); k.x_hi[i] = relax_hi(c.x_hi[i], c.bound_relax); }
+  for (int i = 0; i < 2; i++) {
+    k.R[i] = c.R[i]; k.DR[i] = c.DR[i];
+    k.rate_lo[i] = relax_lo(c.rate_lo[i], c.bound_relax); k.rate_hi[i] = relax_hi(c.rate_hi[i], c.bound_relax);
+    k.u_lo[i] = relax_lo(c.u_lo[i], c.bound_relax); k.u_hi[i] = relax_hi(c.u_hi[i], c.bound_relax);
+  }
+  k.obs_lo = relax_lo(c.obs_lo, c.bound_relax);
+  k.ego_hl = c.ego_hl; k.ego_hw = c.ego_hw; k.safe_l = c.safe_l; k.safe_w = c.safe_w; k.dyn_sx = c.dyn_sx; k.dyn_sy = c.dyn_sy;
+  k.Veh_l = c.Veh_l; k.lf = c.Veh_lf; k.lr = c.Veh_lr; k.m = c.Veh_m; k.Iz = c.Veh_Iz;
+  k.aopt_f = c.aopt_f; k.aopt_r = c.aopt_r; k.Fymax_f = c.Fymax_f; k.Fymax_r = c.Fymax_r;
+  k.tol = c.tol; k.mu_init = c.mu_init;
+
+  h->smem = var.smem_bytes(c.N);
+  cudaDeviceProp prop;
+  if (!cuda_ok(cudaGetDeviceProperties(&prop, h->device), "cudaGetDeviceProperties")) { delete h; return MPCB_E_CUDA; }
+  if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return MPCB_E_ARG; }
+  if (!cuda_ok(cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem), "cudaFuncSetAttribute")) {
+    delete h;
+    return MPCB_E_CUDA;
+  }
+  cudaFuncAttributes fa;
+  if (!cuda_ok(cudaFuncGetAttributes(&fa, var.kernel), "cudaFuncGetAttributes")) { delete h; return MPCB_E_CUDA; }
+  int bps = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, var.kernel, 32, h->smem);
+  h->info.block = 32;
+  h->info.smem_bytes = (int32_t)h->smem;
+  h->info.regs_per_thread = fa.numRegs;
+  h->info.blocks_per_sm = bps;
+  h->info.num_sms = prop.multiProcessorCount;
+  if (!cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete h; return MPCB_E_CUDA; }
+  *out = h;
+  return MPCB_OK;
+}
+
+static void free_bufs(mpcb_handle *h) {
+  cudaFree(h->d_x0); cudaFree(h->d_xs); cudaFree(h->d_obs); cudaFree(h->d_zin); cudaFree(h->d_u0);
+  cudaFree(h->d_cost); cudaFree(h->d_z); cudaFree(h->d_lam); cudaFree(h->d_status); cudaFree(h->d_iters);
+  h->d_x0 = h->d_xs = h->d_obs = h->d_zin = h->d_u0 = h->d_cost = h->d_z = h->d_lam = nullptr;
+  h->d_status = h->d_iters = nullptr;
+  h->cap_B = 0;
+}
+
+void mpcb_destroy(mpcb_handle *h) {
+  if (!h) return;
+  free_bufs(h);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, const double *obs,
+                     const double *z_init, double *u0, double *cost, int32_t *status, int32_t *iters,
+                     double *z_out, double *lam_out, void *stream) {
+  if (!h || B < 0 || !x0 || !xs || !u0 || !cost || !status || !iters) return MPCB_E_ARG;
+  if (h->cfg.obs_mode != MPCB_OBS_NONE && !obs) return MPCB_E_ARG;
+  if (B == 0) return MPCB_OK;
+  KParams k = h->kp;
+  k.B = B;
+  k.x0 = x0; k.xs = xs; k.obs = obs; k.z_init = z_init;
+  k.u0 = u0; k.cost = cost; k.status = status; k.iters = iters; k.z_out = z_out; k.lam_out = lam_out;
+  int grid = B;
+  cudaError_t e = h->var.launch(k, grid, h->smem, (cudaStream_t)stream);
+  if (!cuda_ok(e, "solve_kernel launch")) return MPCB_E_CUDA;
+  h->info.grid = grid;
+  h->info.launches++;
+  return MPCB_OK;
+}
+
+int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double *xs, const double *obs,
+                          const double *z_init, double *u0, double *cost, int32_t *status, int32_t *iters,
+                          double *z_out, double *lam_out) {
+  if (!h || B < 0 || !x0 || !xs || !u0 || !cost || !status || !iters) return MPCB_E_ARG;
+  if (B == 0) return MPCB_OK;
+  const int nx = h->var.nx, N = h->cfg.N;
+  const int M = h->cfg.obs_mode == MPCB_OBS_NONE ? 0 : h->cfg.M;
+  const size_t nv = 2 * (size_t)N + (size_t)nx * (N + 1);
+  const size_t so = (size_t)M * (N + 1) * 6;
+  if (M > 0 && !obs) return MPCB_E_ARG;
+  if (B > h->cap_B) {
+    free_bufs(h);
+    size_t b = (size_t)B;
+    bool ok = cuda_ok(cudaMalloc(&h->d_x0, b * nx * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_xs, b * nx * 8), "cudaMalloc") &&
+              cuda_ok(cudaMalloc(&h->d_obs, b * (so ? so : 1) * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_zin, b * nv * 8), "cudaMalloc") &&
+              cuda_ok(cudaMalloc(&h->d_u0, b * 2 * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_cost, b * 8), "cudaMalloc") &&
+              cuda_ok(cudaMalloc(&h->d_z, b * nv * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_lam, b * nx * (N + 1) * 8), "cudaMalloc") &&
+              cuda_ok(cudaMalloc(&h->d_status, b * 4), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_iters, b * 4), "cudaMalloc");
+    if (!ok) { free_bufs(h); return MPCB_E_NOMEM; }
+    h->cap_B = B;
+  }
+  cudaStream_t st = h->stream;
+  size_t b = (size_t)B;
+  bool ok = cuda_ok(cudaMemcpyAsync(h->d_x0, x0, b * nx * 8, cudaMemcpyHostToDevice, st), "H2D x0") &&
+            cuda_ok(cudaMemcpyAsync(h->d_xs, xs, b * nx * 8, cudaMemcpyHostToDevice, st), "H2D xs");
+  if (ok && so) ok = cuda_ok(cudaMemcpyAsync(h->d_obs, obs, b * so * 8, cudaMemcpyHostToDevice, st), "H2D obs");
+  if (ok && z_init) ok = cuda_ok(cudaMemcpyAsync(h->d_zin, z_init, b * nv * 8, cudaMemcpyHostToDevice, st), "H2D z_init");
+  if (!ok) return MPCB_E_CUDA;
+  int rc = mpcb_solve_batch(h, B, h->d_x0, h->d_xs, so ? h->d_obs : nullptr, z_init ? h->d_zin : nullptr, h->d_u0, h->d_cost,
+                            h->d_status, h->d_iters, z_out ? h->d_z : nullptr, lam_out ? h->d_lam : nullptr, (void *)st);
+  if (rc != MPCB_OK) return rc;
+  ok = cuda_ok(cudaMemcpyAsync(u0, h->d_u0, b * 2 * 8, cudaMemcpyDeviceToHost, st), "D2H u0") &&
+       cuda_ok(cudaMemcpyAsync(cost, h->d_cost, b * 8, cudaMemcpyDeviceToHost, st), "D2H cost") &&
+       cuda_ok(cudaMemcpyAsync(status, h->d_status, b * 4, cudaMemcpyDeviceToHost, st), "D2H status") &&
+       cuda_ok(cudaMemcpyAsync(iters, h->d_iters, b * 4, cudaMemcpyDeviceToHost, st), "D2H iters");
+  if (ok && z_out) ok = cuda_ok(cudaMemcpyAsync(z_out, h->d_z, b * nv * 8, cudaMemcpyDeviceToHost, st), "D2H z");
+  if (ok && lam_out) ok = cuda_ok(cudaMemcpyAsync(lam_out, h->d_lam, b * nx * (N + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H lam");
+  if (!ok) return MPCB_E_CUDA;
+  if (!cuda_ok(cudaStreamSynchronize(st), "solve (stream sync)")) return MPCB_E_CUDA;
+  return MPCB_OK;
+}
+
+int mpcb_get_launch_info(mpcb_handle *h, mpcb_launch_info *out) {
+  if (!h || !out) return MPCB_E_ARG;
+  *out = h->info;
+  return MPCB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// closed-loop helper: plant Euler step + warm-start shift (PKG/main_cbf_kin_c_sim.py:16-26)
+// ---------------------------------------------------------------------------------------
+namespace {
+
+template <class Mdl>
+__global__ void shift_kernel(KParams p, int B, double *x0, double *z) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  constexpr int NX = Mdl::NX;
+  const int N = p.N, nv = 2 * N + NX * (N + 1);
+  double *zz = z + (size_t)b * nv;
+  double *xx = x0 + (size_t)b * NX;
+  // plant step with the first control
+  double x[NX], u[2] = {zz[0], zz[1]}, f[NX];
+#pragma unroll
+  for (int i = 0; i < NX; i++) x[i] = xx[i];
+  Mdl::f(x, u, p, f);
+  // shifted copies held in registers before anything is overwritten
+  constexpr int PER = (2 * MPCB_NMAX + 6 * (MPCB_NMAX + 1) + 31) / 32;
+  double v[PER];
+#pragma unroll
+  for (int r = 0; r < PER; r++) {
+    int idx = lane + 32 * r;
+    double val = 0;
+    if (idx < 2 * N) {
+      int src = idx + 2 < 2 * N ? idx + 2 : idx;  // repeat the last control row
+      val = zz[src];
+    } else if (idx < nv) {
+      int j = idx - 2 * N;
+      int src = j + NX < NX * (N + 1) ? j + NX : j;  // repeat the last state row
+      val = zz[2 * N + src];
+    }
+    v[r] = val;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < PER; r++) {
+    int idx = lane + 32 * r;
+    if (idx < nv) zz[idx] = v[r];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NX; i++) xx[i] = x[i] + p.T * f[i];
+  }
+}
+
+}  // namespace
+
+extern "C" int mpcb_shift_batch(mpcb_handle *h, int B, double *x0, double *z, void *stream) {
+  if (!h || B < 0 || !x0 || !z) return MPCB_E_ARG;
+  if (B == 0) return MPCB_OK;
+  KParams k = h->kp;
+  const int wpb = 4;
+  int grid = (B + wpb - 1) / wpb;
+  if (h->cfg.model == MPCB_MODEL_KIN) shift_kernel<KinModel><<<grid, 32 * wpb, 0, (cudaStream_t)stream>>>(k, B, x0, z);
+  else return MPCB_E_ARG;
+  if (!cuda_ok(cudaGetLastError(), "shift_kernel launch")) return MPCB_E_CUDA;
+  h->info.launches++;
+  return MPCB_OK;
+}

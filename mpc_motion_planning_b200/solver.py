@@ -1,0 +1,147 @@
+"""Batched solve entry the reference lacks: B independent scenarios per call.
+
+`BatchSolver.solve` is the batched counterpart of
+
+    solver = mpc_solver.optimize_problem(ego_state, ref_state, obstacle)    PKG/main_cbf_kin_c_sim.py:99
+    res = solver(x0=init_control, p=c_p, lbg=, lbx=, ubg=, ubx=)            PKG/main_cbf_kin_c_sim.py:100
+
+It calls the C ABI of include/mpcb200.h.  torch is used only for device memory and
+streams; numpy inputs take the host-pointer entry (copies inside the library).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .helpers import PACKAGE_PARAMS, load_config
+from .problem import make_cfg
+
+
+def _nx(kind):
+    return 6 if kind == "dyn" else 4
+
+
+class BatchSolver:
+    """One handle on the current CUDA device for one NLP kind / horizon / obstacle count."""
+
+    def __init__(self, kind: str = "kin_cbf_pre", config: dict | None = None, N: int | None = None, M: int = 1,
+                 init: str = "rollout", mu_init: float = 100.0, max_iter: int = 100, tol: float = 1e-8,
+                 weights=None, bounds: dict | None = None):
+        self.lib = _lib.load()
+        self.kind = kind
+        self.config = config if config is not None else load_config(PACKAGE_PARAMS)
+        init_mode = {"rollout": _lib.INIT_ROLLOUT, "as_given": _lib.INIT_AS_GIVEN}[init]
+        self.cfg = make_cfg(kind, self.config, N=N, M=M, weights=weights, init_mode=init_mode, mu_init=mu_init,
+                            max_iter=max_iter, tol=tol, bounds=bounds)
+        self.N, self.M = int(self.cfg.N), int(self.cfg.M)
+        self.nx = _nx(kind)
+        self.nv = 2 * self.N + self.nx * (self.N + 1)
+        self._h = C.c_void_p()
+        _lib.check(self.lib.mpcb_create(C.byref(self.cfg), C.byref(self._h)), "mpcb_create")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.mpcb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ device path
+    def solve(self, x0, xs, obs=None, z_init=None, return_z: bool = False, return_lam: bool = False):
+        """x0,xs (B,nx); obs (B,M,N+1,6) or None; z_init (B,nv) or None.
+
+        torch CUDA tensors -> asynchronous on the current stream, returns torch tensors;
+        numpy arrays -> synchronous host entry, returns numpy arrays.
+        dict keys: u0 (B,2), cost (B,), status (B,) int32, iters (B,) int32 [, z (B,nv)] [, lam (B,nx(N+1))]."""
+        if isinstance(x0, np.ndarray):
+            return self._solve_host(x0, xs, obs, z_init, return_z, return_lam)
+        import torch
+
+        B = x0.shape[0]
+        dev = x0.device
+        if dev.type != "cuda":
+            raise _lib.MpcbError("solve() needs CUDA tensors or numpy arrays; there is no CPU fallback")
+
+        def prep(t, shape):
+            if t is None:
+                return None
+            t = t.to(device=dev, dtype=torch.float64).contiguous()
+            if tuple(t.shape) != shape:
+                raise ValueError(f"expected shape {shape}, got {tuple(t.shape)}")
+            return t
+
+        x0 = prep(x0, (B, self.nx))
+        xs = prep(xs, (B, self.nx))
+        obs = prep(obs, (B, self.M, self.N + 1, 6)) if self.M > 0 else None
+        z_init = prep(z_init, (B, self.nv))
+        u0 = torch.empty((B, 2), dtype=torch.float64, device=dev)
+        cost = torch.empty((B,), dtype=torch.float64, device=dev)
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+        iters = torch.empty((B,), dtype=torch.int32, device=dev)
+        z = torch.empty((B, self.nv), dtype=torch.float64, device=dev) if return_z else None
+        lam = torch.empty((B, self.nx * (self.N + 1)), dtype=torch.float64, device=dev) if return_lam else None
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            rc = self.lib.mpcb_solve_batch(self._h, B, ptr(x0), ptr(xs), ptr(obs), ptr(z_init), ptr(u0), ptr(cost),
+                                           ptr(status), ptr(iters), ptr(z), ptr(lam), stream)
+        _lib.check(rc, "mpcb_solve_batch")
+        out = {"u0": u0, "cost": cost, "status": status, "iters": iters}
+        if return_z:
+            out["z"] = z
+        if return_lam:
+            out["lam"] = lam
+        return out
+
+    # ------------------------------------------------------------------ host path
+    def _solve_host(self, x0, xs, obs, z_init, return_z, return_lam):
+        B = x0.shape[0]
+        f64 = lambda a, shape: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(shape)
+        x0 = f64(x0, (B, self.nx))
+        xs = f64(xs, (B, self.nx))
+        obs = f64(obs, (B, self.M, self.N + 1, 6)) if self.M > 0 else None
+        z_init = f64(z_init, (B, self.nv))
+        u0 = np.empty((B, 2))
+        cost = np.empty(B)
+        status = np.empty(B, dtype=np.int32)
+        iters = np.empty(B, dtype=np.int32)
+        z = np.empty((B, self.nv)) if return_z else None
+        lam = np.empty((B, self.nx * (self.N + 1))) if return_lam else None
+        ptr = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+        rc = self.lib.mpcb_solve_batch_host(self._h, B, ptr(x0), ptr(xs), ptr(obs), ptr(z_init), ptr(u0), ptr(cost),
+                                            ptr(status), ptr(iters), ptr(z), ptr(lam))
+        _lib.check(rc, "mpcb_solve_batch_host")
+        out = {"u0": u0, "cost": cost, "status": status, "iters": iters}
+        if return_z:
+            out["z"] = z
+        if return_lam:
+            out["lam"] = lam
+        return out
+
+    def solve_host_ptrs(self, B, x0, xs, obs, z_init, u0, cost, status, iters):
+        """Raw host-pointer call (pinned torch CPU tensors): used by bench.py's e2e timing."""
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        rc = self.lib.mpcb_solve_batch_host(self._h, B, ptr(x0), ptr(xs), ptr(obs), ptr(z_init), ptr(u0), ptr(cost),
+                                            ptr(status), ptr(iters), None, None)
+        _lib.check(rc, "mpcb_solve_batch_host")
+
+    def shift(self, x0, z):
+        """In-place plant Euler step + warm-start shift on CUDA tensors (PKG/main_cbf_kin_c_sim.py:16-26)."""
+        import torch
+
+        B = x0.shape[0]
+        stream = C.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream)
+        with torch.cuda.device(x0.device):
+            rc = self.lib.mpcb_shift_batch(self._h, B, C.c_void_p(x0.data_ptr()), C.c_void_p(z.data_ptr()), stream)
+        _lib.check(rc, "mpcb_shift_batch")
+
+    def launch_info(self) -> dict:
+        info = _lib.MpcbLaunchInfo()
+        _lib.check(self.lib.mpcb_get_launch_info(self._h, C.byref(info)), "mpcb_get_launch_info")
+        return {k: int(getattr(info, k)) for k, _ in info._fields_}
