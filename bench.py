@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""Benchmark of the MPC solve path (BASELINE.json metric: kin-CBF MPC solves/sec, N=50).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on the host cores
+
+A "step" = one pass of the hot path over one batch of synthetic scenarios: B kin-CBF NLPs
+(static obstacle, N=50, M=1; BASELINE.json configs[1], seeded as SURVEY.md section 8d) are
+solved from the reference's zero control guess.  One rank per GPU, each rank owns its own batch
+(weak scaling), no data-path collective; only the timing reduction is collective.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "kin_cbf_mpc_solves_per_sec_N50"
+UNIT = "solves/s"
+B_PER_GPU = 10000          # configs[1]: batch of 10k random initial states
+N_HORIZON = 50
+# algorithmic work per interior-point iteration of one kin-CBF scenario
+FLOP_PER_ITER = 72.4e3
+BYTES_PER_SOLVE_MIN = 912  # x0, xs, per-step obstacle (x,y)+(l,w) in; u0, cost, status, iters out
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def make_batch(rank: int, B: int):
+    from mpc_motion_planning_b200 import scenarios
+    return scenarios.kin_cbf_static(B, N=N_HORIZON, seed=scenarios.BASE_SEED + 2 + 1000 * rank)
+
+
+def cpu_solve(x0, xs, obs, nthreads):
+    from oracle import c_oracle
+    cfg = c_oracle.make_cfg("kin_cbf", N=N_HORIZON, M=1)
+    t = time.perf_counter()
+    u0, cost, st, it, _ = c_oracle.solve_batch(cfg, x0, xs, obs, nthreads=nthreads)
+    return time.perf_counter() - t, st, it
+
+
+def run_reference(args):
+    """CPU arm.  The reference's own solver (CasADi+IPOPT) is not installable here (no wheel, no
+    network), so this times the oracle port on all host cores, as the tier rules say."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 2000
+    x0, xs, obs = make_batch(0, sample)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_solve(x0[:256], xs[:256], obs[:256], cores)
+    tot = 0.0
+    for _ in range(args.steps):
+        dt, st, it = cpu_solve(x0, xs, obs, cores)
+        tot += dt
+    val = sample * args.steps / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"kin-CBF static obstacle MPC, N={N_HORIZON}, M=1, B={B_PER_GPU}/GPU (BASELINE configs[1])",
+                   "sample_per_step": sample, "start": "zero controls, Euler roll-out states"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"first {sample} scenarios of the workload per step, restated CPU IPM (oracle/mpc_oracle.c), not CasADi+IPOPT"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from mpc_motion_planning_b200 import _lib
+    from mpc_motion_planning_b200.solver import BatchSolver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+    B = args.batch
+
+    x0, xs, obs = make_batch(rank, B)
+    solver = BatchSolver("kin_cbf", N=N_HORIZON, M=1)
+    dx0, dxs, dobs = (torch.from_numpy(a).to(dev) for a in (x0, xs, obs))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        out = solver.solve(dx0, dxs, dobs)
+    barrier()
+    launches0 = solver.launch_info()["launches"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for k in range(K):
+        flush.zero_()  # L2 flush between timed iterations (not timed)
+        ev[k][0].record()
+        out = solver.solve(dx0, dxs, dobs)
+        ev[k][1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else {}
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    t_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(t_ms.item())
+    launches = solver.launch_info()["launches"] - launches0
+    iters = out["iters"].cpu().numpy()
+    status = out["status"].cpu().numpy()
+
+    # ---- end to end through the host-pointer C-ABI call (pinned host buffers, copies inside)
+    hx0, hxs, hobs = (torch.from_numpy(a).pin_memory() for a in (x0, xs, obs))
+    hu0 = torch.empty((B, 2), dtype=torch.float64).pin_memory()
+    hcost = torch.empty((B,), dtype=torch.float64).pin_memory()
+    hst = torch.empty((B,), dtype=torch.int32).pin_memory()
+    hit = torch.empty((B,), dtype=torch.int32).pin_memory()
+    for _ in range(2):
+        solver.solve_host_ptrs(B, hx0, hxs, hobs, None, hu0, hcost, hst, hit)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        solver.solve_host_ptrs(B, hx0, hxs, hobs, None, hu0, hcost, hst, hit)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * K / float(e2e_s.item())
+    h2d = int(hx0.numel() + hxs.numel() + hobs.numel()) * 8
+    d2h = int(hu0.numel() + hcost.numel()) * 8 + int(hst.numel() + hit.numel()) * 4
+    assert np.array_equal(hst.numpy(), status), "host-path and device-path verdicts differ"
+
+    if rank == 0:
+        value = world * B * K / (total_ms * 1e-3)
+        ms_kernel = float(np.mean(step_ms))
+        # roofline of the dominant (only) kernel: FP64 FMA pipe; HBM traffic reported beside it
+        tf = C = None
+        import ctypes as C
+        peak = C.c_double(0.0)
+        _lib.check(_lib.load().mpcb_fp64_peak_tflops(C.byref(peak)), "fp64 peak")
+        flops = float(iters.sum()) * FLOP_PER_ITER
+        ach_tf = flops / (ms_kernel * 1e-3) / 1e12
+        hbm_peak, hbm_src = _peaks()
+        ach_gbs = B * BYTES_PER_SOLVE_MIN / (ms_kernel * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"kin-CBF static obstacle MPC, N={N_HORIZON}, M=1, B={B}/GPU (BASELINE configs[1])",
+                       "start": "zero controls, Euler roll-out states", "mu_init": 100.0, "tol": 1e-8, "max_iter": 100,
+                       "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"scenario-sharded x{world}"},
+            "solver": {"converged_frac": float((status == 0).mean()), "mean_iters": float(iters.mean()),
+                       "p99_iters": float(np.percentile(iters, 99))},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": float(peak.value), "unit": "TFLOP/s",
+                         "frac": ach_tf / float(peak.value) if peak.value > 0 else None, "traffic": None,
+                         "peak_source": "DFMA micro-benchmark measured in this run (mpcb_fp64_peak_tflops)",
+                         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                                 "peak_source": hbm_src + " MEASURED_PEAKS.json hbm_gbs"}},
+            "launch": solver.launch_info(),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            sample = min(B, 4000)
+            dt, st_c, it_c = cpu_solve(x0[:sample], xs[:sample], obs[:sample], cores)
+            line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"first {sample} scenarios of the same batch, restated CPU IPM (oracle/mpc_oracle.c, "
+                                              "scalar Riccati, one scenario per thread), not CasADi+IPOPT"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -139,6 +139,10 @@ typedef struct mpcb_launch_info {
 } mpcb_launch_info;
 int mpcb_get_launch_info(mpcb_handle *h, mpcb_launch_info *out);
 
+/* Measured FP64 FMA-pipe throughput of the current device (TFLOP/s, FMA = 2 flops): the
+ * roofline denominator bench.py reports the solve kernel against. */
+int mpcb_fp64_peak_tflops(double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,7 +49,7 @@ class MpcbLaunchInfo(C.Structure):
 
 EXPORTS = [
     "mpcb_version", "mpcb_strerror", "mpcb_last_cuda_error", "mpcb_nx", "mpcb_nv", "mpcb_create", "mpcb_destroy",
-    "mpcb_workspace_bytes", "mpcb_solve_batch", "mpcb_solve_batch_host", "mpcb_shift_batch", "mpcb_get_launch_info",
+    "mpcb_workspace_bytes", "mpcb_solve_batch", "mpcb_solve_batch_host", "mpcb_shift_batch", "mpcb_get_launch_info", "mpcb_fp64_peak_tflops",
 ]
 
 _lib = None
@@ -85,6 +85,7 @@ def load():
     lib.mpcb_solve_batch_host.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, ip, ip, dp, dp]
     lib.mpcb_shift_batch.argtypes = [vp, C.c_int, dp, dp, vp]
     lib.mpcb_get_launch_info.argtypes = [vp, C.POINTER(MpcbLaunchInfo)]
+    lib.mpcb_fp64_peak_tflops.argtypes = [C.POINTER(C.c_double)]
     _lib = lib
     return lib
 

@@ -1,0 +1,288 @@
+"""Shared implementation of the reference-surface classes (`MPC_optimize` in
+MPC_CBF_optimize_kin / _kin_pre / _dyn / MPC_optimize_kin).
+
+Mirrors PKG/MPC_CBF_optimize_kin.py:10-255: same constructor side effects (reads
+mpc_parameters.yaml, computes N_p, converts degrees), same `initialize_constraints` lists,
+and `optimize_problem(...)` returning a callable with CasADi's call convention
+`solver(x0=, p=, lbx=, ubx=, lbg=, ubg=) -> {'x','f','g','lam_g','lam_x'}` plus `.stats()`.
+The solve itself goes through the CUDA library (no CasADi, no CPU fallback).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .helpers import load_config
+from .problem import make_cfg
+
+PARAMS_FILE = "mpc_parameters.yaml"
+
+
+class _DM:
+    """Minimal stand-in for casadi.DM: `.full()` and array conversion."""
+
+    def __init__(self, a):
+        self._a = np.array(a, dtype=np.float64)
+        if self._a.ndim == 1:
+            self._a = self._a.reshape(-1, 1)
+
+    def full(self):
+        return self._a.copy()
+
+    def __array__(self, dtype=None, copy=None):
+        return self._a if dtype is None else self._a.astype(dtype)
+
+    def __float__(self):
+        return float(self._a.reshape(-1)[0])
+
+    @property
+    def shape(self):
+        return self._a.shape
+
+
+class _ModelFunction:
+    """`mpc_solver.f(x, u)` -> object with `.full()` (PKG/MPC_CBF_optimize_kin.py:159, used by
+    shift_movement at PKG/main_cbf_kin_c_sim.py:17-18)."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    def __call__(self, x, u):
+        x = np.asarray(x, dtype=np.float64).reshape(-1)
+        u = np.asarray(u, dtype=np.float64).reshape(-1)
+        return _DM(self._o._rhs(x, u))
+
+
+class _Solver:
+    """Callable returned by optimize_problem; replaces the CasADi `Function` of `nlpsol`."""
+
+    def __init__(self, owner, obs_array):
+        self._o = owner
+        self._obs = obs_array
+        self._stats = {"success": False, "return_status": "not_run", "iter_count": 0}
+
+    def stats(self):
+        return dict(self._stats)
+
+    def __call__(self, x0=None, p=None, lbx=None, ubx=None, lbg=None, ubg=None, lam_x0=None, lam_g0=None):
+        o = self._o
+        nx, N = o.num_states, o.N_p
+        nv = 2 * N + nx * (N + 1)
+        p = np.asarray(p, dtype=np.float64).reshape(-1)
+        if p.size != 2 * nx:
+            raise ValueError(f"p must have {2 * nx} entries [x0; xs], got {p.size}")
+        z0 = np.zeros(nv) if x0 is None else np.asarray(x0, dtype=np.float64).reshape(-1)
+        if z0.size != nv:
+            raise ValueError(f"x0 must have {nv} entries, got {z0.size}")
+        bs = o._batch_solver(lbx, ubx, lbg, ubg, self._obs)
+        obs = self._obs[None] if self._obs is not None else None
+        out = bs.solve(p[None, :nx].copy(), p[None, nx:].copy(), obs, z0[None], return_z=True, return_lam=True)
+        st = int(out["status"][0])
+        self._stats = {"success": st in (_lib.ST_CONVERGED, _lib.ST_ACCEPTABLE), "return_status": _lib.RETURN_STATUS[st],
+                       "iter_count": int(out["iters"][0])}
+        z = out["z"][0]
+        res = {"x": _DM(z), "f": _DM([out["cost"][0]]), "lam_g_eq": _DM(out["lam"][0])}
+        res["g"] = _DM(o._g_of(z, p, self._obs))
+        return res
+
+
+class MPCOptimizeBase:
+    KIND = None  # set by the concrete modules
+
+    def __init__(self):
+        # PKG/MPC_CBF_optimize_kin.py:11-36
+        self.config = load_config(PARAMS_FILE)
+        mp = self.config["mpc_params"]
+        self.T_horizon = mp["horizon"]
+        self.T_S = mp["T_S"]
+        self.pre_time = mp["pre_time"]
+        self.T_L = mp["T_L"]
+        self.t_ratio = mp["t_ratio"]
+        self.is_variable_time = mp["is_variable_time"]
+        if self.is_variable_time == True:  # noqa: E712  (the YAML value 'Flase' never equals True, :19)
+            t1 = np.arange(0, self.T_horizon * self.t_ratio, self.T_S, dtype=float)
+            t2 = np.arange(t1[-1] + self.T_L, t1[-1] + self.T_L + self.T_horizon * (1 - self.t_ratio), self.T_L)
+            self.N_p = len(t1) + len(t2)
+            self.t_vector = np.concatenate((t1, t2))
+            raise NotImplementedError("two-rate time grid: the reference computes it but always steps with T_S; not supported")
+        self.t_vector = np.arange(0, self.T_horizon + self.T_S, self.T_S, dtype=float)
+        self.N_p = len(self.t_vector) - 1
+        vp, dc, tp = self.config["vehicle_params"], self.config["dynamics_constraints"], self.config["tire_params"]
+        kc = self.config["kinematics_constraints"]
+        self.Veh_l, self.Veh_L = vp["Veh_l"], vp["Veh_L"]
+        self.Veh_W = vp["Veh_W"] if "Veh_W" in vp else vp["Veh_w"]
+        self.Veh_w = self.Veh_W
+        self.Veh_m, self.Veh_lf, self.Veh_lr, self.Veh_Iz = vp["Veh_m"], vp["Veh_lf"], vp["Veh_lr"], vp["Veh_Iz"]
+        self.aopt_f, self.aopt_r, self.Cf_0, self.Cr_0 = tp["aopt_f"], tp["aopt_r"], tp["Cf_0"], tp["Cr_0"]
+        self.Fymax_f = self.Cf_0 * self.aopt_f / 2
+        self.Fymax_r = self.Cr_0 * self.aopt_r / 2
+        self.vy_max, self.vy_min = dc["vy_max"], dc["vy_min"]
+        self.jerk_min, self.jerk_max = dc["jerk_min"], dc["jerk_max"]
+        self.df_dot_min = dc["df_dot_min"] * np.pi / 180
+        self.df_dot_max = dc["df_dot_max"] * np.pi / 180
+        self.vx_max, self.vx_min = kc["vx_max"], kc["vx_min"]
+        self.ax_max, self.ax_min = kc["ax_max"], kc["ax_min"]
+        self.df_max = kc["df_max"] * np.pi / 180
+        self.df_min = kc["df_min"] * np.pi / 180
+        self.Y_max, self.Y_min = kc["Y_max"], kc["Y_min"]
+        self.model_type = self.config["model_type"]
+        self.num_states = 6 if self.KIND == "dyn" else 4
+        self.num_controls = 2
+        self.f = _ModelFunction(self)
+        self._solvers = {}
+        # solver options: IPOPT's as passed by the reference (:252-253) and this library's own
+        self.max_iter = 100
+        self.tol = 1e-8
+        self.mu_init = 100.0
+        self.init = "as_given"  # the CasADi call starts IPOPT at x0= exactly
+
+    # ---- ODE right-hand side (host, float64) ---------------------------------------------
+    def _rhs(self, x, u):
+        if self.KIND == "dyn":  # PKG/MPC_CBF_optimize_dyn.py:156-170
+            _, _, phi, vx, vy, r = x
+            df, ax = u
+            af = df - (vy + self.Veh_lf * r) / vx
+            ar = -(vy - self.Veh_lr * r) / vx
+            Cf = self.Fymax_f * 2 * self.aopt_f / (self.aopt_f**2 + af**2)
+            Cr = self.Fymax_r * 2 * self.aopt_r / (self.aopt_r**2 + ar**2)
+            Fcf, Fcr = -Cf * af, -Cr * ar
+            return np.array([vx * np.cos(phi) - vy * np.sin(phi), vx * np.sin(phi) + vy * np.cos(phi), r, ax + r * vy,
+                             -r * vx + 2 / self.Veh_m * (Fcf * np.cos(df) + Fcr),
+                             2 / self.Veh_Iz * (self.Veh_lf * Fcf - self.Veh_lr * Fcr)])
+        _, _, phi, vx = x  # PKG/MPC_CBF_optimize_kin.py:153-156
+        df, ax = u
+        return np.array([vx * np.cos(phi), vx * np.sin(phi), vx * np.tan(df) / self.Veh_l, ax])
+
+    # ---- bound lists (exact lengths / order of the reference) -----------------------------
+    def _n_obs(self, obstacle):
+        if self.KIND == "kin_cbf":
+            return np.asarray(obstacle).shape[0]
+        if self.KIND == "kin_cbf_pre":
+            return len(obstacle)
+        return 0
+
+    def _initialize_constraints(self, obstacle=None):
+        N, nx = self.N_p, self.num_states
+        lbx, ubx, lbg, ubg = [], [], [], []
+        for _ in range(N):
+            lbx += [self.df_min, self.ax_min]
+            ubx += [self.df_max, self.ax_max]
+        for _ in range(N + 1):
+            lo = [-np.inf, self.Y_min, -np.inf, self.vx_min]
+            hi = [np.inf, self.Y_max, np.inf, self.vx_max]
+            if nx == 6:
+                lo += [self.vy_min, -np.inf]
+                hi += [self.vy_max, np.inf]
+            lbx += lo
+            ubx += hi
+        if self.KIND == "kin_nocbf":  # pyc L85-86: scalar zero bounds
+            return 0.0, 0.0, lbx, ubx
+        if self.KIND == "dyn":
+            # Bounds in the order of the rows of g: [init, d0, d1, (ddf1, dax1), d2, (ddf2, dax2), ...].
+            # The reference's own list (PKG/MPC_CBF_optimize_dyn.py:112-129) interleaves the rate pair one
+            # block too early, which pairs 196 rows with the wrong bounds; the
+            # aligned order is what its comments intend and what the CUDA path solves.
+            lbg += [0.0] * 6
+            ubg += [0.0] * 6
+            for i in range(N):
+                lbg += [0.0] * 6
+                ubg += [0.0] * 6
+                if i > 0:
+                    lbg += [self.df_dot_min * self.T_S, self.jerk_min * self.T_S]
+                    ubg += [self.df_dot_max * self.T_S, self.jerk_max * self.T_S]
+            for _ in range(N + 1):
+                lbg.append(1)
+                ubg.append(np.inf)
+            return lbg, ubg, lbx, ubx
+        for _ in range(N + 1):
+            lbg += [0.0] * 4
+            ubg += [0.0] * 4
+        for i in range(1, N):
+            lbg.append(self.df_dot_min * self.T_S)
+            ubg.append(self.df_dot_max * self.T_S)
+        for _ in range(N):
+            for _ in range(self._n_obs(obstacle)):
+                lbg.append(0.0)
+                ubg.append(np.inf)
+        return lbg, ubg, lbx, ubx
+
+    # ---- solver cache keyed by the bounds actually passed at call time --------------------
+    def _batch_solver(self, lbx, ubx, lbg, ubg, obs_array):
+        from .solver import BatchSolver
+
+        N, nx = self.N_p, self.num_states
+        bounds = {}
+        if lbx is not None and ubx is not None:
+            lbx = np.asarray(lbx, dtype=np.float64).reshape(-1)
+            ubx = np.asarray(ubx, dtype=np.float64).reshape(-1)
+            ul, uh = lbx[: 2 * N].reshape(N, 2), ubx[: 2 * N].reshape(N, 2)
+            xl, xh = lbx[2 * N:].reshape(N + 1, nx), ubx[2 * N:].reshape(N + 1, nx)
+            if not (np.all(ul == ul[0]) and np.all(uh == uh[0]) and np.all(xl == xl[0]) and np.all(xh == xh[0])):
+                raise NotImplementedError("stage-varying lbx/ubx are not supported by the CUDA path")
+            bounds.update(u_lo=ul[0], u_hi=uh[0], x_lo=xl[0], x_hi=xh[0])
+        n_rate = {"kin_nocbf": 0, "kin_cbf": 1, "kin_cbf_pre": 1, "dyn": 2}[self.KIND]
+        if lbg is not None and ubg is not None and n_rate and not np.isscalar(lbg):
+            lg = np.asarray(lbg, dtype=np.float64).reshape(-1)
+            ug = np.asarray(ubg, dtype=np.float64).reshape(-1)
+            if self.KIND == "dyn":
+                r0 = 6 + 6 + 6  # init, d0, d1 then the first rate pair
+                bounds.update(rate_lo=lg[r0: r0 + 2], rate_hi=ug[r0: r0 + 2])
+            else:
+                r0 = nx * (N + 1)
+                bounds.update(rate_lo=lg[r0: r0 + 1], rate_hi=ug[r0: r0 + 1])
+        M = 0 if obs_array is None else obs_array.shape[0]
+        key = (M, self.max_iter, self.tol, self.mu_init, self.init) + tuple(np.concatenate([np.ravel(v) for v in bounds.values()]).tolist() if bounds else ())
+        if key not in self._solvers:
+            self._solvers[key] = BatchSolver(self.KIND, config=self.config, N=N, M=max(M, 1), init=self.init, mu_init=self.mu_init,
+                                             max_iter=self.max_iter, tol=self.tol, bounds=bounds or None)
+        return self._solvers[key]
+
+    # ---- g(z) in the reference's row order (host evaluation for res['g']) -----------------
+    def _g_of(self, z, p, obs):
+        N, nx = self.N_p, self.num_states
+        U = z[: 2 * N].reshape(N, 2)
+        X = z[2 * N:].reshape(N + 1, nx)
+        g = [X[0] - p[:nx]]
+        rate = []
+        for i in range(N):
+            g.append(X[i + 1] - (X[i] + self.T_S * self._rhs(X[i], U[i])))
+            if self.KIND == "dyn" and i > 0:
+                g.append(U[i] - U[i - 1])
+            elif self.KIND in ("kin_cbf", "kin_cbf_pre") and i > 0:
+                rate.append(U[i, 0:1] - U[i - 1, 0:1])
+        g += rate
+        if obs is not None:
+            stages = range(N + 1) if self.KIND == "dyn" else range(N)
+            for i in stages:
+                for j in range(obs.shape[0]):
+                    o = obs[j, i]
+                    if self.KIND == "dyn":
+                        sx, sy = 4.0, 1.0
+                    else:
+                        sx = self.Veh_L / 2 + o[4] / 2 + 1.0
+                        sy = self.Veh_W / 2 + o[5] / 2 + 0.5
+                    e = (X[i, 0] - o[0]) ** 2 / sx**2 + (X[i, 1] - o[1]) ** 2 / sy**2 - 1
+                    g.append(np.array([np.sqrt(e) if self.KIND == "dyn" else e]))
+        return np.concatenate(g)
+
+    # ---- obstacle argument -> (M, N+1, 6) array ---------------------------------------------
+    def _obs_array(self, obstacle):
+        N = self.N_p
+        if self.KIND == "kin_nocbf":
+            return None
+        if self.KIND == "kin_cbf":  # static (M,6) rows, PKG/MPC_CBF_optimize_kin.py:236-243
+            ob = np.asarray(obstacle, dtype=np.float64).reshape(-1, 6)
+            return np.repeat(ob[:, None, :], N + 1, axis=1)
+        if self.KIND == "kin_cbf_pre":  # list of (>=N,6) trajectories, _kin_pre.py:239-247
+            out = np.zeros((len(obstacle), N + 1, 6))
+            for j, tr in enumerate(obstacle):
+                tr = np.asarray(tr, dtype=np.float64)
+                n = min(tr.shape[0], N + 1)
+                out[j, :n] = tr[:n]
+                if n < N + 1:
+                    out[j, n:] = tr[n - 1]
+            return out
+        ob = np.asarray(obstacle, dtype=np.float64).reshape(-1)  # dyn: centre (x,y), _dyn.py:238-239
+        out = np.zeros((1, N + 1, 6))
+        out[0, :, 0], out[0, :, 1] = ob[0], ob[1]
+        return out

@@ -326,3 +326,56 @@ extern "C" int mpcb_shift_batch(mpcb_handle *h, int B, double *x0, double *z, vo
   h->info.launches++;
   return MPCB_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// FP64 FMA-pipe micro-benchmark: the roofline denominator of the solve kernel (SURVEY.md
+// section 8d asks for a measured DFMA peak; MEASURED_PEAKS.json only holds HBM and bf16).
+// ---------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, double a, double b) {
+  double v[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = (double)(threadIdx.x + i) * 1e-3;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = fma(v[i], a, b);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += v[i];
+  if (s == 123.456) out[0] = s;  // never true; keeps the chain alive
+}
+}  // namespace
+
+extern "C" int mpcb_fp64_peak_tflops(double *tflops) {
+  if (!tflops) return MPCB_E_ARG;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return MPCB_E_NODEVICE; }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double *d = nullptr;
+  if (!cuda_ok(cudaMalloc(&d, 8), "cudaMalloc")) return MPCB_E_NOMEM;
+  const int iters = 4096, grid = sms * 8, block = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    dfma_kernel<<<grid, block>>>(d, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    if (!cuda_ok(cudaEventSynchronize(e1), "dfma_kernel")) { cudaFree(d); return MPCB_E_CUDA; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double flops = 2.0 * 32.0 * iters * (double)grid * block;
+    double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return MPCB_OK;
+}

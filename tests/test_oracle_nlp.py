@@ -1,0 +1,102 @@
+"""The numpy restatement of the reference NLPs: sizes, orderings, derivatives."""
+import numpy as np
+import pytest
+
+from oracle.nlp import NLP, Params, default_scenario, predict_obstacles
+
+
+def test_horizon_and_sizes():
+    p = Params()
+    assert p.N_p == 50  # arange(0, 5.1, 0.1) has 51 points (PKG/MPC_CBF_optimize_kin.py:32-33)
+    sizes = {"kin_nocbf": (304, 204), "kin_cbf": (304, 303), "kin_cbf_pre": (304, 303), "dyn": (406, 455)}
+    for kind, (nv, rows) in sizes.items():
+        nlp = default_scenario(kind)
+        assert nlp.nv == nv
+        assert nlp.n_eq + nlp.n_ineq == rows
+        assert len(nlp.g_ref(nlp.rollout_start())) == rows
+
+
+def test_bounds_values():
+    nlp = default_scenario("kin_cbf")
+    N = nlp.N
+    assert np.allclose(nlp.zL[:2], [-0.6108652381980153, -3.0])
+    assert np.allclose(nlp.zU[:2], [0.6108652381980153, 3.0])
+    xb = nlp.zL[2 * N: 2 * N + 4], nlp.zU[2 * N: 2 * N + 4]
+    assert xb[0][0] == -np.inf and xb[0][1] == -1 and xb[0][3] == 0 and xb[1][1] == 5 and xb[1][3] == 40
+    assert np.allclose(nlp.dL[:49], -0.008726646259971648) and np.allclose(nlp.dU[:49], 0.008726646259971648)
+    assert np.all(nlp.dL[49:] == 0) and np.all(np.isinf(nlp.dU[49:]))
+    # obstacle semi-axes: 2.4 + 2.4 + 1.0, 0.9 + 0.9 + 0.5
+    assert np.allclose(nlp.osx, 5.8) and np.allclose(nlp.osy, 2.3)
+
+
+def test_dyn_row_order_and_aligned_bounds():
+    nlp = default_scenario("dyn")
+    perm = nlp.g_perm()
+    assert sorted(perm) == list(range(455))
+    lo, hi = nlp.lbg_ubg_aligned()
+    # [init(6), d0(6), d1(6), ddf1, dax1, d2(6), ...]
+    assert np.all(lo[:18] == 0) and np.all(hi[:18] == 0)
+    assert np.isclose(lo[18], -0.008726646259971648) and np.isclose(lo[19], -0.3) and np.isclose(hi[19], 0.15)
+    assert np.all(lo[-51:] == 1) and np.all(np.isinf(hi[-51:]))
+
+
+def test_objective_matches_definition():
+    nlp = default_scenario("kin_cbf", N=5)
+    rng = np.random.default_rng(1)
+    z = rng.standard_normal(nlp.nv)
+    U, X = nlp.split(z)
+    Q, R, DR = np.diag(nlp.w.Q), np.diag(nlp.w.R), np.diag(nlp.w.DR)
+    f = 0.0
+    for i in range(5):
+        e = X[i] - nlp.xs
+        du = U[i] - (U[i - 1] if i > 0 else 0)
+        f += e @ Q @ e + U[i] @ R @ U[i] + du @ DR @ du
+    assert np.isclose(nlp.objective(z), f, rtol=1e-13)
+    nlp0 = default_scenario("kin_nocbf", N=5)  # no i=0 rate cost
+    f0 = 0.0
+    Q, R, DR = np.diag(nlp0.w.Q), np.diag(nlp0.w.R), np.diag(nlp0.w.DR)
+    for i in range(5):
+        e = X[i] - nlp0.xs
+        f0 += e @ Q @ e + U[i] @ R @ U[i] + (0 if i == 0 else (U[i] - U[i - 1]) @ DR @ (U[i] - U[i - 1]))
+    assert np.isclose(nlp0.objective(z), f0, rtol=1e-13)
+
+
+@pytest.mark.parametrize("kind", ["kin_nocbf", "kin_cbf", "kin_cbf_pre", "dyn"])
+def test_derivatives_against_central_differences(kind):
+    N = 6
+    nlp = default_scenario(kind, N=N)
+    rng = np.random.default_rng(0)
+    z = nlp.rollout_start(rng.uniform(-0.1, 0.1, (N, 2))) + 0.05 * rng.standard_normal(nlp.nv)
+    eps = 1e-6
+
+    def fd(fun):
+        cols = []
+        for i in range(nlp.nv):
+            e = np.zeros(nlp.nv)
+            e[i] = eps
+            cols.append((np.atleast_1d(fun(z + e)) - np.atleast_1d(fun(z - e))) / (2 * eps))
+        return np.array(cols).T
+
+    g = nlp.grad(z)
+    assert np.max(np.abs(fd(nlp.objective)[0] - g)) <= 1e-6 * np.max(np.abs(g))
+    assert np.max(np.abs(fd(nlp.eq) - nlp.jac_eq(z))) <= 1e-7
+    if nlp.n_ineq:
+        assert np.max(np.abs(fd(nlp.ineq) - nlp.jac_ineq(z))) <= 1e-6
+    le, li = rng.standard_normal(nlp.n_eq), rng.standard_normal(nlp.n_ineq)
+
+    def gl(zz):
+        return 0.7 * nlp.grad(zz) + nlp.jac_eq(zz).T @ le + (nlp.jac_ineq(zz).T @ li if nlp.n_ineq else 0)
+
+    H = nlp.hess_lag(z, le, li, 0.7)
+    assert np.max(np.abs(H - fd(gl))) <= 1e-8 * np.max(np.abs(H))
+    assert np.max(np.abs(H - H.T)) == 0
+
+
+def test_predict_obstacles_is_the_reference_recursion():
+    obs = [np.array([[60, 10, np.pi / 4, 10, 3.6, 1.5]])]
+    tr = predict_obstacles(obs, 0.1, 50)[0]
+    x, y = 60.0, 10.0
+    for k in range(51):
+        assert tr[k, 0] == x and tr[k, 1] == y
+        x = x + 10 * np.cos(np.pi / 4) * 0.1
+        y = y + 10 * np.sin(np.pi / 4) * 0.1

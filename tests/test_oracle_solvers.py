@@ -1,0 +1,117 @@
+"""The C oracle (scalar Riccati) against the dense specification and the golden fixtures."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle, ipm_dense
+from oracle.nlp import NLP, default_scenario
+
+
+def _obs_for(nlp):
+    N = nlp.N
+    if nlp.kind == "kin_nocbf":
+        return None
+    ob = np.zeros((nlp.M, N + 1, 6))
+    ob[:, :, 0:2] = nlp.oc
+    ob[:, :, 4], ob[:, :, 5] = 4.8, 1.8
+    return ob
+
+
+@pytest.mark.parametrize("kind", ["kin_nocbf", "kin_cbf", "kin_cbf_pre", "dyn"])
+def test_newton_step_riccati_equals_dense_solve(kind):
+    """One regularised Newton step: stage-wise Riccati vs a dense KKT solve (<= 1e-9)."""
+    N = 12
+    nlp = default_scenario(kind, N=N)
+    rng = np.random.default_rng(3)
+    z = nlp.rollout_start(rng.uniform(-0.005, 0.005, (N, 2)))
+    mu, dw, sigma = 0.5, 1e-2, 1e-3
+    cfg = c_oracle.make_cfg(kind, N=N, init_mode=0)
+    rc, dz, lamp = c_oracle.newton_step(cfg, nlp.x0, nlp.xs, _obs_for(nlp), z, mu, dw, sigma)
+    assert rc == 0
+    # dense replica of the same step: unit bound multipliers, zero constraint multipliers
+    zL, zU = ipm_dense._relax(nlp.zL, nlp.zU, 1e-8)
+    dL, dU = ipm_dense._relax(nlp.dL, nlp.dU, 1e-8) if nlp.n_ineq else (nlp.dL, nlp.dU)
+    zp = ipm_dense._push(z, zL, zU, 1e-2, 1e-2)
+    nv, ne, ni = nlp.nv, nlp.n_eq, nlp.n_ineq
+    s = ipm_dense._push(nlp.ineq(zp), dL, dU, 1e-2, 1e-2) if ni else np.zeros(0)
+    hl, hu = np.isfinite(zL), np.isfinite(zU)
+    sl, su = np.where(hl, zp - zL, 1.0), np.where(hu, zU - zp, 1.0)
+    Sig = np.where(hl, 1 / sl, 0) + np.where(hu, 1 / su, 0)
+    g = sigma * nlp.grad(zp) - np.where(hl, mu / sl, 0) + np.where(hu, mu / su, 0)
+    Jc = nlp.jac_eq(zp)
+    W = nlp.hess_lag(zp, np.zeros(ne), np.zeros(ni), sigma) + np.diag(Sig + dw)
+    rhs_z = -g.copy()
+    if ni:
+        Jd = nlp.jac_ineq(zp)
+        hdl, hdu = np.isfinite(dL), np.isfinite(dU)
+        gl, gu = np.where(hdl, s - dL, 1.0), np.where(hdu, dU - s, 1.0)
+        D = np.where(hdl, 1 / gl, 0) + np.where(hdu, 1 / gu, 0) + dw
+        gs = -np.where(hdl, mu / gl, 0) + np.where(hdu, mu / gu, 0) + 1e-5 * mu * (hdl & ~hdu)
+        W = W + (Jd.T * D) @ Jd
+        rhs_z -= Jd.T @ (D * (nlp.ineq(zp) - s) + gs)
+    K = np.block([[W, Jc.T], [Jc, np.zeros((ne, ne))]])
+    sol = np.linalg.solve(K, np.concatenate([rhs_z, -nlp.eq(zp)]))
+    assert np.max(np.abs(sol[:nv] - dz)) <= 1e-9 * max(1.0, np.max(np.abs(dz)))
+    assert np.max(np.abs(sol[nv:] - lamp)) <= 1e-9 * max(1.0, np.max(np.abs(lamp)))
+
+
+@pytest.mark.parametrize("kind", ["kin_nocbf", "kin_cbf_pre", "dyn"])
+def test_c_oracle_follows_the_dense_specification(kind):
+    """Same iterates: identical iteration / regularisation counts, solutions equal to 1e-10."""
+    N = 16
+    nlp = default_scenario(kind, N=N)
+    cfg = c_oracle.make_cfg(kind, N=N)
+    z, lam, info = c_oracle.solve(cfg, nlp.x0, nlp.xs, _obs_for(nlp))
+    r = ipm_dense.solve(nlp, nlp.rollout_start(), ipm_dense.IpmOptions())
+    assert info.status == r.status == 0
+    assert info.iters == r.iters and info.n_reg == r.n_reg
+    assert np.max(np.abs(z - r.z)) <= 1e-10
+    assert abs(info.f - r.f) <= 1e-12 * abs(r.f)
+    assert np.max(np.abs(lam - r.lam_eq)) <= 1e-8 * max(1.0, np.max(np.abs(lam)))
+
+
+def test_c_oracle_reproduces_golden_fixtures(golden):
+    """Fixtures come from the dense solver + SLSQP cross-check (tests/golden/make_golden.py)."""
+    n_checked = 0
+    for name, c in golden.items():
+        kind = str(c["kind"])
+        obs = c["obs"] if c["obs"].shape[0] else None
+        cfg = c_oracle.make_cfg("kin_cbf_pre" if kind == "kin_cbf" else kind)
+        z, lam, info = c_oracle.solve(cfg, c["x0"], c["xs"], obs)
+        assert info.status == int(c["status"]), name
+        if info.status == 0:
+            assert info.iters == int(c["iters"]), name
+            assert np.max(np.abs(z[:2] - c["z"][:2])) <= 1e-8, name
+            assert abs(info.f - float(c["f"])) <= 1e-10 * abs(float(c["f"])), name
+            n_checked += 1
+    assert n_checked >= 15
+
+
+def test_golden_fixtures_are_local_minima_confirmed_by_slsqp(golden):
+    conv = [c for c in golden.values() if int(c["status"]) == 0]
+    assert sum(int(c["local_min"]) for c in conv) >= 0.9 * len(conv)
+    # anchor values recorded in SURVEY.md section 8c (bound_relax shifts them by ~2e-8 relative)
+    assert abs(float(golden["kin_cbf_default"]["f"]) - 1.0947508480e8) <= 1e-6 * 1.09e8
+    assert np.allclose(golden["kin_cbf_default"]["z"][:2], [0.03564617, 3.0], atol=1e-6)
+    assert abs(float(golden["kin_cbf_pre_default"]["f"]) - 1.0859930886e8) <= 1e-6 * 1.09e8
+    assert np.allclose(golden["kin_cbf_pre_default"]["z"][:2], [0.03581586, 3.0], atol=1e-6)
+
+
+def test_infeasible_start_state_is_reported():
+    """x0 outside the lane bound: the initial-condition rows cannot be met -> not converged."""
+    nlp = default_scenario("kin_cbf")
+    cfg = c_oracle.make_cfg("kin_cbf")
+    x0 = nlp.x0.copy()
+    x0[1] = 6.0  # Y_max = 5
+    z, lam, info = c_oracle.solve(cfg, x0, nlp.xs, _obs_for(nlp))
+    assert info.status != 0
+
+
+def test_batch_threads_equal_serial():
+    from mpc_motion_planning_b200 import scenarios
+
+    x0, xs, obs = scenarios.kin_cbf_moving(24)
+    cfg = c_oracle.make_cfg("kin_cbf_pre")
+    a = c_oracle.solve_batch(cfg, x0, xs, obs, nthreads=1)
+    b = c_oracle.solve_batch(cfg, x0, xs, obs, nthreads=4)
+    for u, v in zip(a[:4], b[:4]):
+        assert np.array_equal(u, v)
