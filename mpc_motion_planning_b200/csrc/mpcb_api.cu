@@ -199,9 +199,10 @@ void mpcb_destroy(mpcb_handle *h) {
 int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, const double *obs,
                      const double *z_init, double *u0, double *cost, int32_t *status, int32_t *iters,
                      double *z_out, double *lam_out, void *stream) {
-  if (!h || B < 0 || !x0 || !xs || !u0 || !cost || !status || !iters) return MPCB_E_ARG;
+  if (!h || B < 0) return MPCB_E_ARG;
+  if (B == 0) return MPCB_OK;  // empty batch: nothing to read or write
+  if (!x0 || !xs || !u0 || !cost || !status || !iters) return MPCB_E_ARG;
   if (h->cfg.obs_mode != MPCB_OBS_NONE && !obs) return MPCB_E_ARG;
-  if (B == 0) return MPCB_OK;
   KParams k = h->kp;
   k.B = B;
   k.x0 = x0; k.xs = xs; k.obs = obs; k.z_init = z_init;
@@ -217,8 +218,9 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
 int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double *xs, const double *obs,
                           const double *z_init, double *u0, double *cost, int32_t *status, int32_t *iters,
                           double *z_out, double *lam_out) {
-  if (!h || B < 0 || !x0 || !xs || !u0 || !cost || !status || !iters) return MPCB_E_ARG;
+  if (!h || B < 0) return MPCB_E_ARG;
   if (B == 0) return MPCB_OK;
+  if (!x0 || !xs || !u0 || !cost || !status || !iters) return MPCB_E_ARG;
   const int nx = h->var.nx, N = h->cfg.N;
   const int M = h->cfg.obs_mode == MPCB_OBS_NONE ? 0 : h->cfg.M;
   const size_t nv = 2 * (size_t)N + (size_t)nx * (N + 1);
