@@ -24,9 +24,9 @@ bool cuda_ok(cudaError_t e, const char *what) {
 typedef cudaError_t (*launch_fn)(const KParams &, int grid, size_t smem, cudaStream_t);
 typedef const void *kernel_ptr;
 
-template <class Mdl, int NR, int MO, int OBS>
-cudaError_t launch_variant(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-  solve_kernel<Mdl, NR, MO, OBS><<<grid, 32, smem, st>>>(p);
+template <int NR, int MO, int OBS>
+cudaError_t launch_kin(const KParams &p, int grid, size_t smem, cudaStream_t st) {
+  kin_solve_kernel<NR, MO, OBS><<<grid, 32, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -37,24 +37,24 @@ struct Variant {
   int nx, nbx;
 };
 
-template <class Mdl, int NR, int MO, int OBS>
-Variant make_variant() {
+template <int NR, int MO, int OBS>
+Variant make_kin_variant() {
   Variant v;
-  v.launch = &launch_variant<Mdl, NR, MO, OBS>;
-  v.kernel = (const void *)&solve_kernel<Mdl, NR, MO, OBS>;
-  v.smem_bytes = [](int N) { return Layout<Mdl, NR, MO>::bytes(N); };
-  v.nx = Mdl::NX;
-  v.nbx = Mdl::NBX;
+  v.launch = &launch_kin<NR, MO, OBS>;
+  v.kernel = (const void *)&kin_solve_kernel<NR, MO, OBS>;
+  v.smem_bytes = [](int N) { return KinLayout<NR, MO>::bytes(N); };
+  v.nx = 4;
+  v.nbx = 2;
   return v;
 }
 
 bool select_variant(const mpcb_cfg &c, Variant &v) {
   const int M = c.obs_mode == MPCB_OBS_NONE ? 0 : c.M;
   if (c.model == MPCB_MODEL_KIN) {
-    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 0) { v = make_variant<KinModel, 0, 0, 0>(); return true; }
-    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 1) { v = make_variant<KinModel, 1, 0, 0>(); return true; }
-    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 1) { v = make_variant<KinModel, 1, 1, 1>(); return true; }
-    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 2) { v = make_variant<KinModel, 1, 2, 1>(); return true; }
+    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 0) { v = make_kin_variant<0, 0, 0>(); return true; }
+    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 1) { v = make_kin_variant<1, 0, 0>(); return true; }
+    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 1) { v = make_kin_variant<1, 1, 1>(); return true; }
+    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 2) { v = make_kin_variant<1, 2, 1>(); return true; }
   }
   return false;
 }
@@ -284,7 +284,11 @@ __global__ void shift_kernel(KParams p, int B, double *x0, double *z) {
   double x[NX], u[2] = {zz[0], zz[1]}, f[NX];
 #pragma unroll
   for (int i = 0; i < NX; i++) x[i] = xx[i];
-  Mdl::f(x, u, p, f);
+  {
+    double s_, c_, t_;
+    d_trig(x[2], u[0], &s_, &c_, &t_);
+    f[0] = x[3] * c_; f[1] = x[3] * s_; f[2] = x[3] * t_ / p.Veh_l; f[3] = u[1];
+  }
   // shifted copies held in registers before anything is overwritten
   constexpr int PER = (2 * MPCB_NMAX + 6 * (MPCB_NMAX + 1) + 31) / 32;
   double v[PER];

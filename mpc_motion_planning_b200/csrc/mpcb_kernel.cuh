@@ -3,16 +3,22 @@
 //
 // What this replaces in the reference (PKG = CasaDi_MPC_Optimize_Multishoot):
 //   * CasADi SX graph + AD of the NLP built in MPC_optimize.optimize_problem
-//     (PKG/MPC_CBF_optimize_kin.py:136-255, _kin_pre.py:136-261, _dyn.py:137-250)
-//       -> Model::f / jac / hess below (analytic derivatives), stage_* functions
+//     (PKG/MPC_CBF_optimize_kin.py:136-255, _kin_pre.py:136-261)
+//       -> kin_point / build_qp below (hand-derived first and second derivatives)
 //   * IPOPT + MUMPS behind ca.nlpsol / solver(...)  (PKG/MPC_CBF_optimize_kin.py:251-254,
 //     PKG/main_cbf_kin_c_sim.py:100)
-//       -> solve_kernel: barrier loop, filter line search, inertia correction;
-//          riccati_backward/forward replace the sparse LDL^T of the KKT matrix.
+//       -> Solver::run: barrier loop, filter line search, inertia correction;
+//          riccati_backward/forward/adjoint replace the sparse LDL^T of the KKT matrix.
 //
-// Data layout: every per-stage quantity of one scenario is a row [S = N+1] of doubles in
-// shared memory (struct-of-arrays, stage index fastest), so the stage-parallel phases
-// (lane = stage) are bank-conflict free and the serial recursions read broadcasts.
+// Data layout: one record of NF doubles per stage in shared memory (stage-major, NF odd):
+// field offsets are compile-time immediates of LDS/STS, the stage-parallel phases (lane =
+// stage) are bank-conflict free and the serial recursions read broadcasts.
+//
+// Code-size discipline: the v1 kernel was 17k SASS instructions and spent most of its time
+// in instruction-cache misses (profiles/r01_v1_*).  Transcendentals are therefore called
+// through __noinline__ wrappers, and the Riccati sweep is written out for the sparsity of
+// the kinematic model (A = I + T df/dx has 5 off-diagonal entries, B has 2) so that the whole
+// serial loop body fits the L0/L1 instruction caches.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -69,6 +75,23 @@ struct KParams {
 };
 
 // ------------------------------------------------------------------------------------
+// out-of-line math (one copy each in the instruction stream)
+// ------------------------------------------------------------------------------------
+extern __shared__ double g_smem[];
+
+__device__ __noinline__ double d_log(double x) { return log(x); }
+__device__ __noinline__ double d_pow(double x, double y) { return pow(x, y); }
+__device__ __noinline__ double3 d_trig3(double phi, double delta) {  // (sin phi, cos phi, tan delta)
+  double s, c;
+  sincos(phi, &s, &c);
+  return make_double3(s, c, tan(delta));
+}
+__device__ __forceinline__ void d_trig(double phi, double delta, double *s, double *c, double *t) {
+  double3 r = d_trig3(phi, delta);
+  *s = r.x; *c = r.y; *t = r.z;
+}
+
+// ------------------------------------------------------------------------------------
 // warp reductions (all lanes end with the same value)
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
@@ -87,83 +110,19 @@ __device__ __forceinline__ double warp_min(double v) {
   return v;
 }
 
-// ------------------------------------------------------------------------------------
-// vehicle models
-// ------------------------------------------------------------------------------------
 // Kinematic bicycle, x=[x,y,phi,vx], u=[df,ax]   (PKG/MPC_CBF_optimize_kin.py:153-156)
 struct KinModel {
   static constexpr int NX = 4;
   static constexpr int NBX = 2;  // bounded state components: y, vx  (PKG/..._kin.py:97-105)
-  static constexpr int NJ = 6;   // stored Jacobian entries
   __device__ static __forceinline__ constexpr int bx(int i) { return i == 0 ? 1 : 3; }
-
-  __device__ static __forceinline__ void f(const double *x, const double *u, const KParams &p, double *f) {
-    double s, c;
-    sincos(x[2], &s, &c);
-    f[0] = x[3] * c;
-    f[1] = x[3] * s;
-    f[2] = x[3] * tan(u[0]) / p.Veh_l;
-    f[3] = u[1];
-  }
-  // f and the nonzero entries of df/d[x;u]
-  __device__ static __forceinline__ void fjac(const double *x, const double *u, const KParams &p, double *f, double *J) {
-    double s, c;
-    sincos(x[2], &s, &c);
-    double t = tan(u[0]);
-    f[0] = x[3] * c;
-    f[1] = x[3] * s;
-    f[2] = x[3] * t / p.Veh_l;
-    f[3] = u[1];
-    J[0] = -x[3] * s;                       // d f0 / d phi
-    J[1] = c;                               // d f0 / d v
-    J[2] = x[3] * c;                        // d f1 / d phi
-    J[3] = s;                               // d f1 / d v
-    J[4] = t / p.Veh_l;                     // d f2 / d v
-    J[5] = x[3] * (1.0 + t * t) / p.Veh_l;  // d f2 / d df
-  }
-  // A = I + T df/dx, B = T df/du (dense, structural zeros written as literals)
-  __device__ static __forceinline__ void expand(const double *J, double T, double A[4][4], double B[4][2]) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-#pragma unroll
-      for (int j = 0; j < 4; j++) A[i][j] = (i == j) ? 1.0 : 0.0;
-      B[i][0] = 0.0;
-      B[i][1] = 0.0;
-    }
-    A[0][2] = T * J[0];
-    A[0][3] = T * J[1];
-    A[1][2] = T * J[2];
-    A[1][3] = T * J[3];
-    A[2][3] = T * J[4];
-    B[2][0] = T * J[5];
-    B[3][1] = T;
-  }
-  // H += -T * sum_i lam_i d2 f_i / d[x;u]^2 (Hxx symmetric full, Hux 2xNX, Huu 2x2)
-  __device__ static __forceinline__ void add_hess(const double *x, const double *u, const KParams &p, const double *lam,
-                                                  double Hxx[4][4], double Hux[2][4], double Huu[2][2]) {
-    double s, c;
-    sincos(x[2], &s, &c);
-    double t = tan(u[0]), v = x[3];
-    double sec2 = 1.0 + t * t;
-    double h22 = lam[0] * (-v * c) + lam[1] * (-v * s);
-    double h23 = lam[0] * (-s) + lam[1] * c;
-    double h3d = lam[2] * sec2 / p.Veh_l;
-    double hdd = lam[2] * 2.0 * v * sec2 * t / p.Veh_l;
-    Hxx[2][2] += -p.T * h22;
-    Hxx[2][3] += -p.T * h23;
-    Hxx[3][2] += -p.T * h23;
-    Hux[0][3] += -p.T * h3d;
-    Huu[0][0] += -p.T * hdd;
-  }
 };
 
 // ------------------------------------------------------------------------------------
-// shared-memory layout of one scenario
+// shared-memory layout of one scenario (rows of S = N+1 doubles)
 // ------------------------------------------------------------------------------------
-template <class Mdl, int NR, int MO>
-struct Layout {
-  static constexpr int NX = Mdl::NX, NBX = Mdl::NBX, NJ = Mdl::NJ;
-  static constexpr int NP = NX * (NX + 1) / 2;
+template <int NR, int MO>
+struct KinLayout {
+  static constexpr int NX = 4, NBX = 2;
   // iterate
   static constexpr int X = 0;
   static constexpr int U = X + NX;
@@ -179,36 +138,35 @@ struct Layout {
   static constexpr int SO = LR + NR;
   static constexpr int VLO = SO + MO;
   static constexpr int LO = VLO + MO;
-  // obstacle data
+  // obstacle trajectory: centre and 1/semi-axis^2 per step
   static constexpr int OCX = LO + MO;
   static constexpr int OCY = OCX + MO;
   static constexpr int ISX = OCY + MO;
   static constexpr int ISY = ISX + MO;
-  // evaluation
-  static constexpr int CDEF = ISY + MO;
-  static constexpr int JAC = CDEF + NX;
-  // condensed QP
-  static constexpr int HXX = JAC + NJ;
-  static constexpr int HUX = HXX + NP;
-  static constexpr int HUU = HUX + 2 * NX;
-  static constexpr int EE = HUU + 3;
-  static constexpr int GX = EE + 2;
-  static constexpr int GU = GX + NX;
-  static constexpr int TK = GU + 2;
-  // Riccati gains
-  static constexpr int KX = TK + 2;
-  static constexpr int KW = KX + 2 * NX;
-  static constexpr int KK = KW + 4;
+  // evaluation at the current iterate
+  static constexpr int CDEF = ISY + MO;  // c_0 = X0 - x0, c_k = defect into stage k
+  static constexpr int LAMP = CDEF;      // alias: new dynamics multipliers (written after the forward sweep)
+  static constexpr int JAC = CDEF + NX;  // a02 a03 a12 a13 a23 b2  (A = I + T df/dx, B = T df/du)
+  // condensed QP that survives the backward sweep (needed again by the adjoint)
+  static constexpr int HXX = JAC + 6;    // h00 h01 h11 h22 h23 h33
+  static constexpr int HUX = HXX + 6;    // d2L/(d delta d v)
+  static constexpr int GX = HUX + 1;
+  // 14-slot region: [HUU(2) EE(2) GU(2) TK(2) -(6)] before the backward sweep of a stage,
+  // the Riccati gains [KX(8) KW(4) KK(2)] after it, the slack steps after the forward sweep
+  static constexpr int R14 = GX + NX;
+  static constexpr int HUU = R14, EE = R14 + 2, GU = R14 + 4, TK = R14 + 6;
+  static constexpr int KX = R14, KW = R14 + 8, KK = R14 + 12;
+  static constexpr int DSR = R14, LRP = DSR + NR, DSO = LRP + NR, LOP = DSO + MO;
+  static_assert(2 * NR + 2 * MO <= 14, "slack steps must fit the gain region");
   // direction
-  static constexpr int DX = KK + 2;
+  static constexpr int DX = R14 + 14;
   static constexpr int DU = DX + NX;
-  static constexpr int LAMP = DU + 2;
-  static constexpr int DSR = LAMP + NX;
-  static constexpr int LRP = DSR + NR;
-  static constexpr int DSO = LRP + NR;
-  static constexpr int LOP = DSO + MO;
-  static constexpr int NFIELDS = LOP + MO;
-  __host__ __device__ static constexpr size_t bytes(int N) { return sizeof(double) * (size_t)NFIELDS * (size_t)(N + 1); }
+  static constexpr int NFIELDS = DU + 2;
+  // stage-major storage: element (field, k) lives at k*NF + field.  NF is odd so that the
+  // stage-parallel phases (lane = stage, stride NF doubles) touch 16 distinct even banks per
+  // half-warp: conflict free; the serial sweeps read broadcasts.
+  static constexpr int NF = NFIELDS | 1;
+  __host__ __device__ static constexpr size_t bytes(int N) { return sizeof(double) * (size_t)NF * (size_t)(N + 1); }
 };
 
 __device__ __forceinline__ double push_in(double v, double lo, double hi) {
@@ -220,20 +178,18 @@ __device__ __forceinline__ double push_in(double v, double lo, double hi) {
   return v;
 }
 __device__ __forceinline__ double push_lo(double v, double lo) { return fmax(v, lo + MPCB_BOUND_PUSH * fmax(1.0, fabs(lo))); }
-__device__ __forceinline__ double clampz(double z, double mu, double gap) {
-  return fmax(fmin(z, MPCB_KAPPA_SIGMA * mu / gap), mu / (MPCB_KAPPA_SIGMA * gap));
-}
-__device__ __forceinline__ int pidx(int i, int j, int n) {  // packed upper-triangular index, i<=j
-  return i * n - i * (i - 1) / 2 + (j - i);
+__device__ __forceinline__ double clampz(double z, double mu, double rgap) {
+  // kappa_sigma safeguard; rgap = 1/gap
+  return fmax(fmin(z, MPCB_KAPPA_SIGMA * mu * rgap), mu * rgap * (1.0 / MPCB_KAPPA_SIGMA));
 }
 
 // ------------------------------------------------------------------------------------
-// the solver: one warp = one scenario
+// the solver: one warp = one scenario (kinematic model family)
 // ------------------------------------------------------------------------------------
-template <class Mdl, int NR, int MO, int OBS_MODE>
-struct Solver {
-  using L = Layout<Mdl, NR, MO>;
-  static constexpr int NX = Mdl::NX, NBX = Mdl::NBX, NJ = Mdl::NJ, NP = L::NP;
+template <int NR, int MO, int OBS_MODE>
+struct KinSolver {
+  using L = KinLayout<NR, MO>;
+  static constexpr int NX = 4, NBX = 2;
 
   const KParams &p;
   double *sm;
@@ -241,38 +197,11 @@ struct Solver {
   double sigma;
   double x0[NX], xs[NX];
 
-  __device__ Solver(const KParams &p_, double *sm_, int lane_) : p(p_), sm(sm_), S(p_.N + 1), N(p_.N), lane(lane_) {}
+  __device__ KinSolver(const KParams &p_, double *sm_, int lane_) : p(p_), sm(sm_), S(p_.N + 1), N(p_.N), lane(lane_) {}
 
-  __device__ __forceinline__ double &at(int field, int k) { return sm[field * S + k]; }
+  __device__ __forceinline__ double &at(int field, int k) { return g_smem[k * L::NF + field]; }
   __device__ __forceinline__ bool has_rate(int k) const { return NR > 0 && k >= 1 && k <= N - 1; }
-  __device__ __forceinline__ bool has_obs(int k) const {
-    if (OBS_MODE == 1) return k <= N - 1;
-    if (OBS_MODE == 2) return k <= N;
-    return false;
-  }
-
-  // obstacle row value (+ gradient, Hessian) at (px,py) for stage k, obstacle j
-  __device__ __forceinline__ double obs_val(int k, int j, double px, double py) {
-    double dx = px - at(L::OCX + j, k), dy = py - at(L::OCY + j, k);
-    double e = dx * dx * at(L::ISX + j, k) + dy * dy * at(L::ISY + j, k) - 1.0;
-    if (OBS_MODE == 1) return e;              // PKG/MPC_CBF_optimize_kin.py:244,247
-    return e > 0.0 ? sqrt(e) : nan("");       // PKG/MPC_CBF_optimize_dyn.py:243
-  }
-  __device__ __forceinline__ void obs_grad(int k, int j, double px, double py, double &d, double &gx, double &gy, double &hxx,
-                                           double &hxy, double &hyy) {
-    double dx = px - at(L::OCX + j, k), dy = py - at(L::OCY + j, k);
-    double a = at(L::ISX + j, k), b = at(L::ISY + j, k);
-    double e = dx * dx * a + dy * dy * b - 1.0;
-    if (OBS_MODE == 1) {
-      d = e; gx = 2 * dx * a; gy = 2 * dy * b; hxx = 2 * a; hxy = 0.0; hyy = 2 * b;
-    } else {
-      double q = sqrt(e);
-      double ex = 2 * dx * a, ey = 2 * dy * b;
-      d = q; gx = ex / (2 * q); gy = ey / (2 * q);
-      double q3 = 4 * q * q * q;
-      hxx = a / q - ex * ex / q3; hxy = -ex * ey / q3; hyy = b / q - ey * ey / q3;
-    }
-  }
+  __device__ __forceinline__ bool has_obs(int k) const { return OBS_MODE == 1 && k <= N - 1; }
 
   // gradient of the unscaled objective wrt u_k[i]  (PKG/MPC_CBF_optimize_kin.py:199-205)
   __device__ __forceinline__ double grad_u(int k, int i, double uk, double ukm1, double ukp1) const {
@@ -283,44 +212,57 @@ struct Solver {
     return v;
   }
 
-  // ---------------------------------------------------------------- primal evaluation
-  // constraint residual 1-norm, objective, barrier pieces at z + alpha*dz (TRIAL) or at z
-  // (storing the defects).  Returns lane-uniform sums.
-  template <bool TRIAL>
-  __device__ void eval_primal(double alpha, double &theta, double &fobj, double &bar, double &lin) {
+  // ---------------------------------------------------------------- point evaluation
+  // constraint residual 1-norm, objective and barrier pieces at z + alpha*dz.  With store=true
+  // (alpha = 0) the defects and the dynamics Jacobian of the iterate are kept for the QP.
+  __device__ __forceinline__ void eval_point(double alpha, bool store, double &theta, double &fobj, double &bar, double &lin) {
     double th = 0, fo = 0, br = 0, ln = 0;
+    #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
       double xk[NX], uk[2] = {0, 0};
 #pragma unroll
-      for (int i = 0; i < NX; i++) xk[i] = at(L::X + i, k) + (TRIAL ? alpha * at(L::DX + i, k) : 0.0);
+      for (int i = 0; i < NX; i++) xk[i] = at(L::X + i, k) + alpha * at(L::DX + i, k);
       if (k == 0) {
 #pragma unroll
         for (int i = 0; i < NX; i++) {
           double c0 = xk[i] - x0[i];
           th += fabs(c0);
-          if (!TRIAL) at(L::CDEF + i, 0) = c0;
+          if (store) at(L::CDEF + i, 0) = c0;
         }
       }
       if (k < N) {
 #pragma unroll
-        for (int i = 0; i < 2; i++) uk[i] = at(L::U + i, k) + (TRIAL ? alpha * at(L::DU + i, k) : 0.0);
+        for (int i = 0; i < 2; i++) uk[i] = at(L::U + i, k) + alpha * at(L::DU + i, k);
+        double s, c, t;
+        d_trig(xk[2], uk[0], &s, &c, &t);
         double f[NX];
-        Mdl::f(xk, uk, p, f);
+        f[0] = xk[3] * c;                 // PKG/MPC_CBF_optimize_kin.py:153-156
+        f[1] = xk[3] * s;
+        f[2] = xk[3] * t / p.Veh_l;
+        f[3] = uk[1];
+        if (store) {
+          at(L::JAC + 0, k) = p.T * (-xk[3] * s);                       // a02 = T d f0/d phi
+          at(L::JAC + 1, k) = p.T * c;                                  // a03 = T d f0/d v
+          at(L::JAC + 2, k) = p.T * (xk[3] * c);                        // a12
+          at(L::JAC + 3, k) = p.T * s;                                  // a13
+          at(L::JAC + 4, k) = p.T * (t / p.Veh_l);                      // a23
+          at(L::JAC + 5, k) = p.T * (xk[3] * (1.0 + t * t) / p.Veh_l);  // b2  = T d f2/d delta
+        }
 #pragma unroll
         for (int i = 0; i < NX; i++) {
-          double xn = at(L::X + i, k + 1) + (TRIAL ? alpha * at(L::DX + i, k + 1) : 0.0);
+          double xn = at(L::X + i, k + 1) + alpha * at(L::DX + i, k + 1);
           double d = xn - (xk[i] + p.T * f[i]);
           th += fabs(d);
-          if (!TRIAL) at(L::CDEF + i, k + 1) = d;
+          if (store) at(L::CDEF + i, k + 1) = d;
           double e = xk[i] - xs[i];
           fo += p.Q[i] * e * e;
         }
 #pragma unroll
         for (int i = 0; i < 2; i++) {
-          br += log(uk[i] - p.u_lo[i]) + log(p.u_hi[i] - uk[i]);
+          br += d_log(uk[i] - p.u_lo[i]) + d_log(p.u_hi[i] - uk[i]);
           fo += p.R[i] * uk[i] * uk[i];
           if (k > 0) {
-            double um = at(L::U + i, k - 1) + (TRIAL ? alpha * at(L::DU + i, k - 1) : 0.0);
+            double um = at(L::U + i, k - 1) + alpha * at(L::DU + i, k - 1);
             double e = uk[i] - um;
             fo += p.DR[i] * e * e;
           } else if (p.du0_cost) {
@@ -330,27 +272,29 @@ struct Solver {
       }
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
-        int i = Mdl::bx(b);
-        br += log(xk[i] - p.x_lo[i]) + log(p.x_hi[i] - xk[i]);
+        int i = KinModel::bx(b);
+        br += d_log(xk[i] - p.x_lo[i]) + d_log(p.x_hi[i] - xk[i]);
       }
       if (has_rate(k)) {
 #pragma unroll
         for (int r = 0; r < NR; r++) {
           int ci = p.rate_ctrl[r];
-          double um = at(L::U + ci, k - 1) + (TRIAL ? alpha * at(L::DU + ci, k - 1) : 0.0);
+          double um = at(L::U + ci, k - 1) + alpha * at(L::DU + ci, k - 1);
           double ukc = ci == 0 ? uk[0] : uk[1];
-          double s = at(L::SR + r, k) + (TRIAL ? alpha * at(L::DSR + r, k) : 0.0);
+          // the slack step lives in the gain region, which holds gains while alpha == 0
+          double s = at(L::SR + r, k) + (alpha != 0.0 ? alpha * at(L::DSR + r, k) : 0.0);
           th += fabs(ukc - um - s);
-          br += log(s - p.rate_lo[r]) + log(p.rate_hi[r] - s);
+          br += d_log(s - p.rate_lo[r]) + d_log(p.rate_hi[r] - s);
         }
       }
       if (has_obs(k)) {
 #pragma unroll
         for (int j = 0; j < MO; j++) {
-          double d = obs_val(k, j, xk[0], xk[1]);
-          double s = at(L::SO + j, k) + (TRIAL ? alpha * at(L::DSO + j, k) : 0.0);
+          double dx = xk[0] - at(L::OCX + j, k), dy = xk[1] - at(L::OCY + j, k);
+          double d = dx * dx * at(L::ISX + j, k) + dy * dy * at(L::ISY + j, k) - 1.0;  // PKG/..._kin.py:244,247
+          double s = at(L::SO + j, k) + (alpha != 0.0 ? alpha * at(L::DSO + j, k) : 0.0);
           th += fabs(d - s);
-          br += log(s - p.obs_lo);
+          br += d_log(s - p.obs_lo);
           ln += s - p.obs_lo;
         }
       }
@@ -359,54 +303,44 @@ struct Solver {
     fobj = warp_sum(fo);
     bar = warp_sum(br);
     lin = warp_sum(ln);
+    __syncwarp();
   }
 
-  // ---------------------------------------------------------------- Jacobians + KKT error pieces
+  // ---------------------------------------------------------------- KKT error pieces
   struct Kkt { double dual, prim, cmin, cmax, sum_lam, sum_z; };
 
-  __device__ void eval_lin_kkt(Kkt &o) {
-    // pass 1: Jacobians of the dynamics (stored compactly)
-    for (int k = lane; k < N; k += 32) {
-      double xk[NX], uk[2], f[NX], J[NJ];
-#pragma unroll
-      for (int i = 0; i < NX; i++) xk[i] = at(L::X + i, k);
-      uk[0] = at(L::U + 0, k);
-      uk[1] = at(L::U + 1, k);
-      Mdl::fjac(xk, uk, p, f, J);
-#pragma unroll
-      for (int i = 0; i < NJ; i++) at(L::JAC + i, k) = J[i];
-    }
-    __syncwarp();
+  __device__ __forceinline__ void kkt_pieces(Kkt &o) {
     double dual = 0, prim = 0, cmin = INFINITY, cmax = -INFINITY, sl = 0, sz = 0;
 #define MPCB_COMPL(gap, mult) do { double p_ = (gap) * (mult); cmin = fmin(cmin, p_); cmax = fmax(cmax, p_); sz += (mult); } while (0)
+    #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
-      double xk[NX], lam[NX], lam1[NX], A[NX][NX], B[NX][2];
-#pragma unroll
-      for (int i = 0; i < NX; i++) { xk[i] = at(L::X + i, k); lam[i] = at(L::LAM + i, k); lam1[i] = 0; }
-      if (k < N) {
-        double J[NJ];
-#pragma unroll
-        for (int i = 0; i < NJ; i++) J[i] = at(L::JAC + i, k);
-        Mdl::expand(J, p.T, A, B);
-#pragma unroll
-        for (int i = 0; i < NX; i++) lam1[i] = at(L::LAM + i, k + 1);
-      }
-      double rx[NX];
+      double xk[NX], lam[NX], l1[NX] = {0, 0, 0, 0};
 #pragma unroll
       for (int i = 0; i < NX; i++) {
-        double r = lam[i];
-        if (k < N) {
-          r += sigma * 2 * p.Q[i] * (xk[i] - xs[i]);
-#pragma unroll
-          for (int a = 0; a < NX; a++) r -= A[a][i] * lam1[a];
-        }
-        rx[i] = r;
+        xk[i] = at(L::X + i, k);
+        lam[i] = at(L::LAM + i, k);
         prim = fmax(prim, fabs(at(L::CDEF + i, k)));
         sl += fabs(lam[i]);
       }
+      double rx[NX] = {lam[0], lam[1], lam[2], lam[3]};
+      double a02 = 0, a03 = 0, a12 = 0, a13 = 0, a23 = 0, b2 = 0;
+      if (k < N) {
+        a02 = at(L::JAC + 0, k); a03 = at(L::JAC + 1, k); a12 = at(L::JAC + 2, k);
+        a13 = at(L::JAC + 3, k); a23 = at(L::JAC + 4, k); b2 = at(L::JAC + 5, k);
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+          l1[i] = at(L::LAM + i, k + 1);
+          rx[i] += sigma * 2 * p.Q[i] * (xk[i] - xs[i]);
+        }
+        // - A' lam_{k+1}
+        rx[0] -= l1[0];
+        rx[1] -= l1[1];
+        rx[2] -= l1[2] + a02 * l1[0] + a12 * l1[1];
+        rx[3] -= l1[3] + a03 * l1[0] + a13 * l1[1] + a23 * l1[2];
+      }
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
-        int i = Mdl::bx(b);
+        int i = KinModel::bx(b);
         double zl = at(L::ZLX + b, k), zu = at(L::ZUX + b, k);
         rx[i] += -zl + zu;
         MPCB_COMPL(xk[i] - p.x_lo[i], zl);
@@ -415,11 +349,12 @@ struct Solver {
       if (has_obs(k)) {
 #pragma unroll
         for (int j = 0; j < MO; j++) {
-          double d, gx, gy, hxx, hxy, hyy;
-          obs_grad(k, j, xk[0], xk[1], d, gx, gy, hxx, hxy, hyy);
+          double dx = xk[0] - at(L::OCX + j, k), dy = xk[1] - at(L::OCY + j, k);
+          double a = at(L::ISX + j, k), b = at(L::ISY + j, k);
+          double d = dx * dx * a + dy * dy * b - 1.0;
           double lo = at(L::LO + j, k), vl = at(L::VLO + j, k), s = at(L::SO + j, k);
-          rx[0] += lo * gx;
-          rx[1] += lo * gy;
+          rx[0] += lo * (2 * dx * a);
+          rx[1] += lo * (2 * dy * b);
           dual = fmax(dual, fabs(-lo - vl));
           prim = fmax(prim, fabs(d - s));
           MPCB_COMPL(s - p.obs_lo, vl);
@@ -436,8 +371,7 @@ struct Solver {
           double up = k + 1 <= N - 1 ? at(L::U + i, k + 1) : 0.0;
           double zl = at(L::ZLU + i, k), zu = at(L::ZUU + i, k);
           double r = sigma * grad_u(k, i, uk, um, up) - zl + zu;
-#pragma unroll
-          for (int a = 0; a < NX; a++) r -= B[a][i] * lam1[a];
+          r -= (i == 0) ? b2 * l1[2] : p.T * l1[3];  // - B' lam_{k+1}
 #pragma unroll
           for (int rr = 0; rr < NR; rr++)
             if (p.rate_ctrl[rr] == i) {
@@ -481,86 +415,86 @@ struct Solver {
   // ---------------------------------------------------------------- condensed QP (stage parallel)
   // Effective stage Hessian/gradient with the slack rows eliminated and the primal
   // regularisation dw applied.
-  __device__ void build_qp(double mu, double dw) {
+  __device__ __forceinline__ void build_qp(double mu, double dw) {
+    #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
-      double xk[NX], uk[2] = {0, 0};
-      double Hxx[NX][NX], Hux[2][NX], Huu[2][2], gx[NX];
+      double xk[NX];
 #pragma unroll
-      for (int i = 0; i < NX; i++) {
-        xk[i] = at(L::X + i, k);
-#pragma unroll
-        for (int j = 0; j < NX; j++) Hxx[i][j] = 0;
-        Hux[0][i] = 0;
-        Hux[1][i] = 0;
-      }
-      Huu[0][0] = Huu[0][1] = Huu[1][0] = Huu[1][1] = 0;
+      for (int i = 0; i < NX; i++) xk[i] = at(L::X + i, k);
+      double h[NX] = {dw, dw, dw, dw};  // diagonal of Hxx
+      double h01 = 0, h23 = 0, hdv = 0, hdd_f = 0;
+      double gx[NX] = {0, 0, 0, 0};
       if (k < N) {
-        uk[0] = at(L::U + 0, k);
-        uk[1] = at(L::U + 1, k);
-        double lam1[NX];
+        // - T sum_i lam_i d2 f_i, written with the stored Jacobian entries
+        double l0 = at(L::LAM + 0, k + 1), l1 = at(L::LAM + 1, k + 1), l2 = at(L::LAM + 2, k + 1);
+        double a02 = at(L::JAC + 0, k), a03 = at(L::JAC + 1, k), a12 = at(L::JAC + 2, k), a13 = at(L::JAC + 3, k);
+        double a23 = at(L::JAC + 4, k), b2 = at(L::JAC + 5, k);
+        double t = a23 * (p.Veh_l / p.T);               // tan(delta)
+        double jd = (p.T / p.Veh_l) * (1.0 + t * t);    // T sec^2(delta) / L
+        h[2] += l0 * a12 - l1 * a02;                    // -T (-l0 v cos - l1 v sin)
+        h23 = l0 * a13 - l1 * a03;                      // -T (-l0 sin + l1 cos)
+        hdv = -l2 * jd;
+        hdd_f = -2.0 * l2 * b2 * t;
 #pragma unroll
-        for (int i = 0; i < NX; i++) lam1[i] = at(L::LAM + i, k + 1);
-        Mdl::add_hess(xk, uk, p, lam1, Hxx, Hux, Huu);
-      }
-#pragma unroll
-      for (int i = 0; i < NX; i++) {
-        double g = 0;
-        if (k < N) {
-          Hxx[i][i] += sigma * 2 * p.Q[i];
-          g += sigma * 2 * p.Q[i] * (xk[i] - xs[i]);
+        for (int i = 0; i < NX; i++) {
+          h[i] += sigma * 2 * p.Q[i];
+          gx[i] = sigma * 2 * p.Q[i] * (xk[i] - xs[i]);
         }
-        Hxx[i][i] += dw;
-        gx[i] = g;
       }
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
-        int i = Mdl::bx(b);
-        double gl = xk[i] - p.x_lo[i], gh = p.x_hi[i] - xk[i];
-        Hxx[i][i] += at(L::ZLX + b, k) / gl + at(L::ZUX + b, k) / gh;
-        gx[i] += -mu / gl + mu / gh;
+        int i = KinModel::bx(b);
+        double rl = 1.0 / (xk[i] - p.x_lo[i]), rh = 1.0 / (p.x_hi[i] - xk[i]);
+        h[i] += at(L::ZLX + b, k) * rl + at(L::ZUX + b, k) * rh;
+        gx[i] += mu * (rh - rl);
       }
       if (has_obs(k)) {
 #pragma unroll
         for (int j = 0; j < MO; j++) {
-          double d, ox, oy, hxx, hxy, hyy;
-          obs_grad(k, j, xk[0], xk[1], d, ox, oy, hxx, hxy, hyy);
-          double s = at(L::SO + j, k), gap = s - p.obs_lo;
-          double D = at(L::VLO + j, k) / gap + dw;
-          double gs = -mu / gap + MPCB_KAPPA_D * mu;
+          double dx = xk[0] - at(L::OCX + j, k), dy = xk[1] - at(L::OCY + j, k);
+          double a = at(L::ISX + j, k), b = at(L::ISY + j, k);
+          double d = dx * dx * a + dy * dy * b - 1.0;
+          double ox = 2 * dx * a, oy = 2 * dy * b;
+          double s = at(L::SO + j, k), rg = 1.0 / (s - p.obs_lo);
+          double D = at(L::VLO + j, k) * rg + dw;
+          double gs = -mu * rg + MPCB_KAPPA_D * mu;
           double lo = at(L::LO + j, k);
           double t = D * (d - s) + gs;
-          Hxx[0][0] += lo * hxx + D * ox * ox;
-          Hxx[0][1] += lo * hxy + D * ox * oy;
-          Hxx[1][0] += lo * hxy + D * ox * oy;
-          Hxx[1][1] += lo * hyy + D * oy * oy;
+          h[0] += lo * (2 * a) + D * ox * ox;
+          h01 += D * ox * oy;
+          h[1] += lo * (2 * b) + D * oy * oy;
           gx[0] += ox * t;
           gx[1] += oy * t;
         }
       }
+      at(L::HXX + 0, k) = h[0];
+      at(L::HXX + 1, k) = h01;
+      at(L::HXX + 2, k) = h[1];
+      at(L::HXX + 3, k) = h[2];
+      at(L::HXX + 4, k) = h23;
+      at(L::HXX + 5, k) = h[3];
+      at(L::HUX, k) = hdv;
 #pragma unroll
-      for (int i = 0; i < NX; i++) {
-        at(L::GX + i, k) = gx[i];
-#pragma unroll
-        for (int j = i; j < NX; j++) at(L::HXX + pidx(i, j, NX), k) = Hxx[i][j];
-      }
+      for (int i = 0; i < NX; i++) at(L::GX + i, k) = gx[i];
       if (k < N) {
         double E[2] = {0, 0}, t[2] = {0, 0};
 #pragma unroll
         for (int i = 0; i < 2; i++) {
-          double g = sigma * 2 * p.R[i] * uk[i];
-          double hd = sigma * 2 * p.R[i] + dw;
+          double uk = at(L::U + i, k);
+          double g = sigma * 2 * p.R[i] * uk;
+          double hd = sigma * 2 * p.R[i] + dw + (i == 0 ? hdd_f : 0.0);
           if (k == 0 && p.du0_cost) {
             hd += sigma * 2 * p.DR[i];
-            g += sigma * 2 * p.DR[i] * uk[i];
+            g += sigma * 2 * p.DR[i] * uk;
           }
-          double gl = uk[i] - p.u_lo[i], gh = p.u_hi[i] - uk[i];
-          hd += at(L::ZLU + i, k) / gl + at(L::ZUU + i, k) / gh;
-          g += -mu / gl + mu / gh;
-          Huu[i][i] += hd;
+          double rl = 1.0 / (uk - p.u_lo[i]), rh = 1.0 / (p.u_hi[i] - uk);
+          hd += at(L::ZLU + i, k) * rl + at(L::ZUU + i, k) * rh;
+          g += mu * (rh - rl);
+          at(L::HUU + i, k) = hd;
           at(L::GU + i, k) = g;
           if (k >= 1) {
             E[i] = sigma * 2 * p.DR[i];
-            t[i] = sigma * 2 * p.DR[i] * (uk[i] - at(L::U + i, k - 1));
+            t[i] = sigma * 2 * p.DR[i] * (uk - at(L::U + i, k - 1));
           }
         }
         if (has_rate(k)) {
@@ -568,310 +502,215 @@ struct Solver {
           for (int r = 0; r < NR; r++) {
             int ci = p.rate_ctrl[r];
             double s = at(L::SR + r, k);
-            double gl = s - p.rate_lo[r], gh = p.rate_hi[r] - s;
-            double D = at(L::VLR + r, k) / gl + at(L::VUR + r, k) / gh + dw;
-            double gs = -mu / gl + mu / gh;
+            double rl = 1.0 / (s - p.rate_lo[r]), rh = 1.0 / (p.rate_hi[r] - s);
+            double D = at(L::VLR + r, k) * rl + at(L::VUR + r, k) * rh + dw;
+            double gs = mu * (rh - rl);
             double res = at(L::U + ci, k) - at(L::U + ci, k - 1) - s;
             double tt = D * res + gs;
             if (ci == 0) { E[0] += D; t[0] += tt; } else { E[1] += D; t[1] += tt; }
           }
         }
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-          at(L::EE + i, k) = E[i];
-          at(L::TK + i, k) = t[i];
-#pragma unroll
-          for (int j = 0; j < NX; j++) at(L::HUX + i * NX + j, k) = Hux[i][j];
-        }
-        at(L::HUU + 0, k) = Huu[0][0];
-        at(L::HUU + 1, k) = Huu[0][1];
-        at(L::HUU + 2, k) = Huu[1][1];
+        at(L::EE + 0, k) = E[0];
+        at(L::EE + 1, k) = E[1];
+        at(L::TK + 0, k) = t[0];
+        at(L::TK + 1, k) = t[1];
       }
     }
     __syncwarp();
   }
 
   // ---------------------------------------------------------------- Riccati (serial over stages)
-  // Every lane runs the same recursion on broadcast reads; lane 0 stores the gains.
+  // Value function V_k(x, w) = 1/2 [x;w]' [P W; W' Q] [x;w] + [px;pw]' [x;w] on the state
+  // augmented with the previous control w = u_{k-1}.  Every lane runs the same recursion on
+  // broadcast reads; lane 0 stores the gains over the consumed QP slots of the stage.
   // Returns false when some F_uu is not positive definite (wrong inertia).
-  __device__ bool riccati_backward() {
-    double Pxx[NX][NX], Pxw[NX][2], Pww[2][2], px[NX], pw[2];
-#pragma unroll
-    for (int i = 0; i < NX; i++) {
-#pragma unroll
-      for (int j = 0; j < NX; j++) Pxx[i][j] = at(L::HXX + (i <= j ? pidx(i, j, NX) : pidx(j, i, NX)), N);
-      px[i] = at(L::GX + i, N);
-      Pxw[i][0] = Pxw[i][1] = 0;
-    }
-    Pww[0][0] = Pww[0][1] = Pww[1][0] = Pww[1][1] = 0;
-    pw[0] = pw[1] = 0;
+  __device__ __forceinline__ bool riccati_backward() {
+    const double T = p.T;
+    double p00 = at(L::HXX + 0, N), p01 = at(L::HXX + 1, N), p11 = at(L::HXX + 2, N), p22 = at(L::HXX + 3, N);
+    double p23 = at(L::HXX + 4, N), p33 = at(L::HXX + 5, N), p02 = 0, p03 = 0, p12 = 0, p13 = 0;
+    double px0 = at(L::GX + 0, N), px1 = at(L::GX + 1, N), px2 = at(L::GX + 2, N), px3 = at(L::GX + 3, N);
+    double w0d = 0, w0a = 0, w1d = 0, w1a = 0, w2d = 0, w2a = 0, w3d = 0, w3a = 0;  // Pxw
+    double qdd = 0, qda = 0, qaa = 0, pwd = 0, pwa = 0;                             // Pww, pw
     bool ok = true;
+    #pragma unroll 1
     for (int k = N - 1; k >= 0; k--) {
-      double A[NX][NX], B[NX][2];
-      {
-        double J[NJ];
-#pragma unroll
-        for (int i = 0; i < NJ; i++) J[i] = at(L::JAC + i, k);
-        Mdl::expand(J, p.T, A, B);
-      }
-      double E[2] = {at(L::EE + 0, k), at(L::EE + 1, k)};
-      double t[2] = {at(L::TK + 0, k), at(L::TK + 1, k)};
-      double b[NX], Pb[NX];
-#pragma unroll
-      for (int i = 0; i < NX; i++) b[i] = -at(L::CDEF + i, k + 1);
-#pragma unroll
-      for (int i = 0; i < NX; i++) {
-        double s = px[i];
-#pragma unroll
-        for (int j = 0; j < NX; j++) s += Pxx[i][j] * b[j];
-        Pb[i] = s;
-      }
-      double PA[NX][NX], PB[NX][2];
-#pragma unroll
-      for (int i = 0; i < NX; i++) {
-#pragma unroll
-        for (int j = 0; j < NX; j++) {
-          double s = 0;
-#pragma unroll
-          for (int a = 0; a < NX; a++) s += Pxx[i][a] * A[a][j];
-          PA[i][j] = s;
-        }
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-          double s = 0;
-#pragma unroll
-          for (int a = 0; a < NX; a++) s += Pxx[i][a] * B[a][j];
-          PB[i][j] = s;
-        }
-      }
-      double Fxx[NX][NX], Fux[2][NX], Fuu[2][2], fx[NX], fu[2];
-#pragma unroll
-      for (int i = 0; i < NX; i++)
-#pragma unroll
-        for (int j = 0; j < NX; j++) {
-          double s = at(L::HXX + (i <= j ? pidx(i, j, NX) : pidx(j, i, NX)), k);
-#pragma unroll
-          for (int a = 0; a < NX; a++) s += A[a][i] * PA[a][j];
-          Fxx[i][j] = s;
-        }
-#pragma unroll
-      for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int j = 0; j < NX; j++) {
-          double s = at(L::HUX + i * NX + j, k);
-#pragma unroll
-          for (int a = 0; a < NX; a++) s += B[a][i] * PA[a][j] + Pxw[a][i] * A[a][j];
-          Fux[i][j] = s;
-        }
-#pragma unroll
-      for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-          double s = at(L::HUU + (i + j), k) + Pww[i][j];  // packed [00,01,11]
-          if (i == j) s += E[i];
-#pragma unroll
-          for (int a = 0; a < NX; a++) s += B[a][i] * PB[a][j] + B[a][i] * Pxw[a][j] + Pxw[a][i] * B[a][j];
-          Fuu[i][j] = s;
-        }
-#pragma unroll
-      for (int i = 0; i < NX; i++) {
-        double s = at(L::GX + i, k);
-#pragma unroll
-        for (int a = 0; a < NX; a++) s += A[a][i] * Pb[a];
-        fx[i] = s;
-      }
-#pragma unroll
-      for (int i = 0; i < 2; i++) {
-        double s = at(L::GU + i, k) + t[i] + pw[i];
-#pragma unroll
-        for (int a = 0; a < NX; a++) s += B[a][i] * Pb[a] + Pxw[a][i] * b[a];
-        fu[i] = s;
-      }
-      double det = Fuu[0][0] * Fuu[1][1] - Fuu[0][1] * Fuu[1][0];
-      if (!(Fuu[0][0] > 0.0) || !(det > 0.0) || !isfinite(det)) { ok = false; break; }
-      double id = 1.0 / det;
-      double Fi[2][2] = {{Fuu[1][1] * id, -Fuu[0][1] * id}, {-Fuu[1][0] * id, Fuu[0][0] * id}};
-      double Kx[2][NX], Kw[2][2], kk[2];
-#pragma unroll
-      for (int i = 0; i < 2; i++) {
-#pragma unroll
-        for (int j = 0; j < NX; j++) Kx[i][j] = -(Fi[i][0] * Fux[0][j] + Fi[i][1] * Fux[1][j]);
-#pragma unroll
-        for (int j = 0; j < 2; j++) Kw[i][j] = Fi[i][j] * E[j];
-        kk[i] = -(Fi[i][0] * fu[0] + Fi[i][1] * fu[1]);
-      }
+      const double a02 = at(L::JAC + 0, k), a03 = at(L::JAC + 1, k), a12 = at(L::JAC + 2, k), a13 = at(L::JAC + 3, k);
+      const double a23 = at(L::JAC + 4, k), b2 = at(L::JAC + 5, k);
+      const double Ed = at(L::EE + 0, k), Ea = at(L::EE + 1, k), td = at(L::TK + 0, k), ta = at(L::TK + 1, k);
+      const double b0 = -at(L::CDEF + 0, k + 1), b1 = -at(L::CDEF + 1, k + 1), b2_ = -at(L::CDEF + 2, k + 1), b3 = -at(L::CDEF + 3, k + 1);
+      // M = P A (columns 0,1 are those of P)
+      const double m02 = p02 + a02 * p00 + a12 * p01;
+      const double m12 = p12 + a02 * p01 + a12 * p11;
+      const double m22 = p22 + a02 * p02 + a12 * p12;
+      const double m32 = p23 + a02 * p03 + a12 * p13;
+      const double m03 = p03 + a03 * p00 + a13 * p01 + a23 * p02;
+      const double m13 = p13 + a03 * p01 + a13 * p11 + a23 * p12;
+      const double m23 = p23 + a03 * p02 + a13 * p12 + a23 * p22;
+      const double m33 = p33 + a03 * p03 + a13 * p13 + a23 * p23;
+      // Fxx = Hxx + A' M (upper triangle)
+      const double f00 = at(L::HXX + 0, k) + p00, f01 = at(L::HXX + 1, k) + p01, f11 = at(L::HXX + 2, k) + p11;
+      const double f02 = m02, f03 = m03, f12 = m12, f13 = m13;
+      const double f22 = at(L::HXX + 3, k) + m22 + a02 * m02 + a12 * m12;
+      const double f23 = at(L::HXX + 4, k) + m23 + a02 * m03 + a12 * m13;
+      const double f33 = at(L::HXX + 5, k) + m33 + a03 * m03 + a13 * m13 + a23 * m23;
+      // Fux = Hux + B' M + Pwx A
+      const double ud0 = b2 * p02 + w0d, ud1 = b2 * p12 + w1d;
+      const double ud2 = b2 * m22 + w2d + a02 * w0d + a12 * w1d;
+      const double ud3 = at(L::HUX, k) + b2 * m23 + w3d + a03 * w0d + a13 * w1d + a23 * w2d;
+      const double ua0 = T * p03 + w0a, ua1 = T * p13 + w1a;
+      const double ua2 = T * m32 + w2a + a02 * w0a + a12 * w1a;
+      const double ua3 = T * m33 + w3a + a03 * w0a + a13 * w1a + a23 * w2a;
+      // Fuu = Huu + E + Pww + B'PB + B'Pxw + (B'Pxw)'
+      const double Fdd = at(L::HUU + 0, k) + Ed + qdd + b2 * (b2 * p22 + 2.0 * w2d);
+      const double Fda = qda + b2 * (T * p23) + b2 * w2a + T * w3d;
+      const double Faa = at(L::HUU + 1, k) + Ea + qaa + T * (T * p33 + 2.0 * w3a);
+      // vectors
+      const double Pb0 = px0 + p00 * b0 + p01 * b1 + p02 * b2_ + p03 * b3;
+      const double Pb1 = px1 + p01 * b0 + p11 * b1 + p12 * b2_ + p13 * b3;
+      const double Pb2 = px2 + p02 * b0 + p12 * b1 + p22 * b2_ + p23 * b3;
+      const double Pb3 = px3 + p03 * b0 + p13 * b1 + p23 * b2_ + p33 * b3;
+      const double fx0 = at(L::GX + 0, k) + Pb0, fx1 = at(L::GX + 1, k) + Pb1;
+      const double fx2 = at(L::GX + 2, k) + Pb2 + a02 * Pb0 + a12 * Pb1;
+      const double fx3 = at(L::GX + 3, k) + Pb3 + a03 * Pb0 + a13 * Pb1 + a23 * Pb2;
+      const double fud = at(L::GU + 0, k) + td + pwd + b2 * Pb2 + w0d * b0 + w1d * b1 + w2d * b2_ + w3d * b3;
+      const double fua = at(L::GU + 1, k) + ta + pwa + T * Pb3 + w0a * b0 + w1a * b1 + w2a * b2_ + w3a * b3;
+      const double det = Fdd * Faa - Fda * Fda;
+      if (!(Fdd > 0.0) || !(det > 0.0) || !isfinite(det)) { ok = false; break; }
+      const double id = 1.0 / det;
+      const double idd = Faa * id, ida = -Fda * id, iaa = Fdd * id;  // Fuu^{-1}
+      // gains: u = Kx x + Kw w + kk
+      const double kd0 = -(idd * ud0 + ida * ua0), kd1 = -(idd * ud1 + ida * ua1), kd2 = -(idd * ud2 + ida * ua2), kd3 = -(idd * ud3 + ida * ua3);
+      const double ka0 = -(ida * ud0 + iaa * ua0), ka1 = -(ida * ud1 + iaa * ua1), ka2 = -(ida * ud2 + iaa * ua2), ka3 = -(ida * ud3 + iaa * ua3);
+      const double wdd = idd * Ed, wda = ida * Ea, wad = ida * Ed, waa = iaa * Ea;  // Kw = Fuu^{-1} diag(E)
+      const double kkd = -(idd * fud + ida * fua), kka = -(ida * fud + iaa * fua);
       if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-#pragma unroll
-          for (int j = 0; j < NX; j++) at(L::KX + i * NX + j, k) = Kx[i][j];
-          at(L::KW + i * 2 + 0, k) = Kw[i][0];
-          at(L::KW + i * 2 + 1, k) = Kw[i][1];
-          at(L::KK + i, k) = kk[i];
-        }
+        at(L::KX + 0, k) = kd0; at(L::KX + 1, k) = kd1; at(L::KX + 2, k) = kd2; at(L::KX + 3, k) = kd3;
+        at(L::KX + 4, k) = ka0; at(L::KX + 5, k) = ka1; at(L::KX + 6, k) = ka2; at(L::KX + 7, k) = ka3;
+        at(L::KW + 0, k) = wdd; at(L::KW + 1, k) = wda; at(L::KW + 2, k) = wad; at(L::KW + 3, k) = waa;
+        at(L::KK + 0, k) = kkd; at(L::KK + 1, k) = kka;
       }
-#pragma unroll
-      for (int i = 0; i < NX; i++) {
-#pragma unroll
-        for (int j = 0; j < NX; j++) Pxx[i][j] = Fxx[i][j] + Fux[0][i] * Kx[0][j] + Fux[1][i] * Kx[1][j];
-#pragma unroll
-        for (int j = 0; j < 2; j++) Pxw[i][j] = Fux[0][i] * Kw[0][j] + Fux[1][i] * Kw[1][j];
-        px[i] = fx[i] + Fux[0][i] * kk[0] + Fux[1][i] * kk[1];
-      }
-#pragma unroll
-      for (int i = 0; i < NX; i++)
-#pragma unroll
-        for (int j = i + 1; j < NX; j++) {
-          double m = 0.5 * (Pxx[i][j] + Pxx[j][i]);
-          Pxx[i][j] = m;
-          Pxx[j][i] = m;
-        }
-#pragma unroll
-      for (int i = 0; i < 2; i++) {
-#pragma unroll
-        for (int j = 0; j < 2; j++) Pww[i][j] = (i == j ? E[i] : 0.0) - E[i] * Kw[i][j];
-        pw[i] = -t[i] - E[i] * kk[i];
-      }
-      double m = 0.5 * (Pww[0][1] + Pww[1][0]);
-      Pww[0][1] = m;
-      Pww[1][0] = m;
+      // value function of stage k
+      p00 = f00 + ud0 * kd0 + ua0 * ka0;
+      p01 = f01 + ud0 * kd1 + ua0 * ka1;
+      p02 = f02 + ud0 * kd2 + ua0 * ka2;
+      p03 = f03 + ud0 * kd3 + ua0 * ka3;
+      p11 = f11 + ud1 * kd1 + ua1 * ka1;
+      p12 = f12 + ud1 * kd2 + ua1 * ka2;
+      p13 = f13 + ud1 * kd3 + ua1 * ka3;
+      p22 = f22 + ud2 * kd2 + ua2 * ka2;
+      p23 = f23 + ud2 * kd3 + ua2 * ka3;
+      p33 = f33 + ud3 * kd3 + ua3 * ka3;
+      w0d = ud0 * wdd + ua0 * wad; w0a = ud0 * wda + ua0 * waa;
+      w1d = ud1 * wdd + ua1 * wad; w1a = ud1 * wda + ua1 * waa;
+      w2d = ud2 * wdd + ua2 * wad; w2a = ud2 * wda + ua2 * waa;
+      w3d = ud3 * wdd + ua3 * wad; w3a = ud3 * wda + ua3 * waa;
+      px0 = fx0 + ud0 * kkd + ua0 * kka;
+      px1 = fx1 + ud1 * kkd + ua1 * kka;
+      px2 = fx2 + ud2 * kkd + ua2 * kka;
+      px3 = fx3 + ud3 * kkd + ua3 * kka;
+      qdd = Ed - Ed * wdd;
+      qda = -0.5 * (Ed * wda + Ea * wad);
+      qaa = Ea - Ea * waa;
+      pwd = -td - Ed * kkd;
+      pwa = -ta - Ea * kka;
     }
     __syncwarp();
     return ok;
   }
 
-  __device__ void riccati_forward() {
-    double dx[NX], dum[2] = {0, 0};
-#pragma unroll
-    for (int i = 0; i < NX; i++) dx[i] = -at(L::CDEF + i, 0);
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < NX; i++) at(L::DX + i, 0) = dx[i];
-    }
+  __device__ __forceinline__ void riccati_forward() {
+    const double T = p.T;
+    double d0 = -at(L::CDEF + 0, 0), d1 = -at(L::CDEF + 1, 0), d2 = -at(L::CDEF + 2, 0), d3 = -at(L::CDEF + 3, 0);
+    double vd = 0, va = 0;  // previous control step
+    if (lane == 0) { at(L::DX + 0, 0) = d0; at(L::DX + 1, 0) = d1; at(L::DX + 2, 0) = d2; at(L::DX + 3, 0) = d3; }
+    #pragma unroll 1
     for (int k = 0; k < N; k++) {
-      double A[NX][NX], B[NX][2], du[2];
-      {
-        double J[NJ];
-#pragma unroll
-        for (int i = 0; i < NJ; i++) J[i] = at(L::JAC + i, k);
-        Mdl::expand(J, p.T, A, B);
-      }
-#pragma unroll
-      for (int i = 0; i < 2; i++) {
-        double s = at(L::KK + i, k);
-#pragma unroll
-        for (int j = 0; j < NX; j++) s += at(L::KX + i * NX + j, k) * dx[j];
-        if (k > 0) s += at(L::KW + i * 2 + 0, k) * dum[0] + at(L::KW + i * 2 + 1, k) * dum[1];
-        du[i] = s;
-      }
-      double dn[NX];
-#pragma unroll
-      for (int i = 0; i < NX; i++) {
-        double s = -at(L::CDEF + i, k + 1);
-#pragma unroll
-        for (int j = 0; j < NX; j++) s += A[i][j] * dx[j];
-        s += B[i][0] * du[0] + B[i][1] * du[1];
-        dn[i] = s;
-      }
+      const double ud = at(L::KK + 0, k) + at(L::KX + 0, k) * d0 + at(L::KX + 1, k) * d1 + at(L::KX + 2, k) * d2 + at(L::KX + 3, k) * d3 +
+                        at(L::KW + 0, k) * vd + at(L::KW + 1, k) * va;
+      const double ua = at(L::KK + 1, k) + at(L::KX + 4, k) * d0 + at(L::KX + 5, k) * d1 + at(L::KX + 6, k) * d2 + at(L::KX + 7, k) * d3 +
+                        at(L::KW + 2, k) * vd + at(L::KW + 3, k) * va;
+      const double n0 = d0 + at(L::JAC + 0, k) * d2 + at(L::JAC + 1, k) * d3 - at(L::CDEF + 0, k + 1);
+      const double n1 = d1 + at(L::JAC + 2, k) * d2 + at(L::JAC + 3, k) * d3 - at(L::CDEF + 1, k + 1);
+      const double n2 = d2 + at(L::JAC + 4, k) * d3 + at(L::JAC + 5, k) * ud - at(L::CDEF + 2, k + 1);
+      const double n3 = d3 + T * ua - at(L::CDEF + 3, k + 1);
       if (lane == 0) {
-        at(L::DU + 0, k) = du[0];
-        at(L::DU + 1, k) = du[1];
-#pragma unroll
-        for (int i = 0; i < NX; i++) at(L::DX + i, k + 1) = dn[i];
+        at(L::DU + 0, k) = ud; at(L::DU + 1, k) = ua;
+        at(L::DX + 0, k + 1) = n0; at(L::DX + 1, k + 1) = n1; at(L::DX + 2, k + 1) = n2; at(L::DX + 3, k + 1) = n3;
       }
-#pragma unroll
-      for (int i = 0; i < NX; i++) dx[i] = dn[i];
-      dum[0] = du[0];
-      dum[1] = du[1];
+      d0 = n0; d1 = n1; d2 = n2; d3 = n3; vd = ud; va = ua;
     }
+    if (lane == 0) { at(L::DU + 0, N) = 0.0; at(L::DU + 1, N) = 0.0; }
     __syncwarp();
   }
 
-  // new dynamics multipliers: parallel r_k = Hxx_eff dx + Hux' du + gx_eff, then the serial
-  // adjoint recursion lam+_k = A_k' lam+_{k+1} - r_k
-  __device__ void adjoint() {
+  // new dynamics multipliers: parallel r_k = Hxx_eff dx + Hux' du + gx_eff (written over the
+  // consumed defects), then the serial adjoint recursion lam+_k = A_k' lam+_{k+1} - r_k
+  __device__ __forceinline__ void adjoint() {
+    #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
-      double dx[NX], du[2] = {0, 0};
-#pragma unroll
-      for (int i = 0; i < NX; i++) dx[i] = at(L::DX + i, k);
-      if (k < N) { du[0] = at(L::DU + 0, k); du[1] = at(L::DU + 1, k); }
-#pragma unroll
-      for (int i = 0; i < NX; i++) {
-        double s = at(L::GX + i, k);
-#pragma unroll
-        for (int j = 0; j < NX; j++) s += at(L::HXX + (i <= j ? pidx(i, j, NX) : pidx(j, i, NX)), k) * dx[j];
-        if (k < N) s += at(L::HUX + 0 * NX + i, k) * du[0] + at(L::HUX + 1 * NX + i, k) * du[1];
-        at(L::LAMP + i, k) = s;
-      }
+      double d0 = at(L::DX + 0, k), d1 = at(L::DX + 1, k), d2 = at(L::DX + 2, k), d3 = at(L::DX + 3, k);
+      double ud = k < N ? at(L::DU + 0, k) : 0.0;
+      double h00 = at(L::HXX + 0, k), h01 = at(L::HXX + 1, k), h11 = at(L::HXX + 2, k), h22 = at(L::HXX + 3, k);
+      double h23 = at(L::HXX + 4, k), h33 = at(L::HXX + 5, k), hdv = at(L::HUX, k);
+      double r0 = at(L::GX + 0, k) + h00 * d0 + h01 * d1;
+      double r1 = at(L::GX + 1, k) + h01 * d0 + h11 * d1;
+      double r2 = at(L::GX + 2, k) + h22 * d2 + h23 * d3;
+      double r3 = at(L::GX + 3, k) + h23 * d2 + h33 * d3 + hdv * ud;
+      at(L::LAMP + 0, k) = r0; at(L::LAMP + 1, k) = r1; at(L::LAMP + 2, k) = r2; at(L::LAMP + 3, k) = r3;
     }
     __syncwarp();
-    double lp[NX];
-#pragma unroll
-    for (int i = 0; i < NX; i++) lp[i] = -at(L::LAMP + i, N);
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < NX; i++) at(L::LAMP + i, N) = lp[i];
-    }
+    double l0 = -at(L::LAMP + 0, N), l1 = -at(L::LAMP + 1, N), l2 = -at(L::LAMP + 2, N), l3 = -at(L::LAMP + 3, N);
+    if (lane == 0) { at(L::LAMP + 0, N) = l0; at(L::LAMP + 1, N) = l1; at(L::LAMP + 2, N) = l2; at(L::LAMP + 3, N) = l3; }
+    #pragma unroll 1
     for (int k = N - 1; k >= 0; k--) {
-      double A[NX][NX], B[NX][2], ln[NX];
-      {
-        double J[NJ];
-#pragma unroll
-        for (int i = 0; i < NJ; i++) J[i] = at(L::JAC + i, k);
-        Mdl::expand(J, p.T, A, B);
-      }
-#pragma unroll
-      for (int i = 0; i < NX; i++) {
-        double s = -at(L::LAMP + i, k);
-#pragma unroll
-        for (int a = 0; a < NX; a++) s += A[a][i] * lp[a];
-        ln[i] = s;
-      }
+      const double n0 = l0 - at(L::LAMP + 0, k);
+      const double n1 = l1 - at(L::LAMP + 1, k);
+      const double n2 = l2 + at(L::JAC + 0, k) * l0 + at(L::JAC + 2, k) * l1 - at(L::LAMP + 2, k);
+      const double n3 = l3 + at(L::JAC + 1, k) * l0 + at(L::JAC + 3, k) * l1 + at(L::JAC + 4, k) * l2 - at(L::LAMP + 3, k);
       __syncwarp();
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NX; i++) at(L::LAMP + i, k) = ln[i];
-      }
-#pragma unroll
-      for (int i = 0; i < NX; i++) lp[i] = ln[i];
+      if (lane == 0) { at(L::LAMP + 0, k) = n0; at(L::LAMP + 1, k) = n1; at(L::LAMP + 2, k) = n2; at(L::LAMP + 3, k) = n3; }
+      l0 = n0; l1 = n1; l2 = n2; l3 = n3;
     }
     __syncwarp();
   }
 
-  // slack steps, new row multipliers, step sizes (fraction to boundary), barrier slope
-  __device__ void slack_and_steps(double mu, double dw, double tau, double &a_pr, double &a_du, double &gd_out) {
-    double ap = 1.0, ad = 1.0, gd = 0.0;
-#define MPCB_LOWER(gap, dv, z) do { double dz_ = -(z) + (mu - (z) * (dv)) / (gap); \
-    if ((dv) < 0) ap = fmin(ap, -tau * (gap) / (dv)); if (dz_ < 0) ad = fmin(ad, -tau * (z) / dz_); } while (0)
-#define MPCB_UPPER(gap, dv, z) do { double dz_ = -(z) + (mu + (z) * (dv)) / (gap); \
-    if ((dv) > 0) ap = fmin(ap, tau * (gap) / (dv)); if (dz_ < 0) ad = fmin(ad, -tau * (z) / dz_); } while (0)
+  // slack steps, new row multipliers, step sizes (fraction to boundary), barrier slope.
+  // The largest step a with v + a dv >= (1-tau) v-bound for every bounded quantity is
+  // a = min(1, tau / max_i(-dv_i / gap_i)).
+  __device__ __forceinline__ void slack_and_steps(double mu, double dw, double tau, double &a_pr, double &a_du, double &gd_out) {
+    double rp = 0.0, rd = 0.0, gd = 0.0;  // largest primal / dual shrink ratios
+#define MPCB_LOWER(rgap, dv, z) do { double dz_ = -(z) + (mu - (z) * (dv)) * (rgap); \
+    rp = fmax(rp, -(dv) * (rgap)); rd = fmax(rd, -dz_ / (z)); } while (0)
+#define MPCB_UPPER(rgap, dv, z) do { double dz_ = -(z) + (mu + (z) * (dv)) * (rgap); \
+    rp = fmax(rp, (dv) * (rgap)); rd = fmax(rd, -dz_ / (z)); } while (0)
+    #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
       double xk[NX], dx[NX];
 #pragma unroll
       for (int i = 0; i < NX; i++) {
         xk[i] = at(L::X + i, k);
         dx[i] = at(L::DX + i, k);
-        double g = (k < N) ? sigma * 2 * p.Q[i] * (xk[i] - xs[i]) : 0.0;
-        gd += g * dx[i];
+        if (k < N) gd += sigma * 2 * p.Q[i] * (xk[i] - xs[i]) * dx[i];
       }
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
-        int i = Mdl::bx(b);
-        double gl = xk[i] - p.x_lo[i], gh = p.x_hi[i] - xk[i];
-        gd += (-mu / gl + mu / gh) * dx[i];
-        MPCB_LOWER(gl, dx[i], at(L::ZLX + b, k));
-        MPCB_UPPER(gh, dx[i], at(L::ZUX + b, k));
+        int i = KinModel::bx(b);
+        double rl = 1.0 / (xk[i] - p.x_lo[i]), rh = 1.0 / (p.x_hi[i] - xk[i]);
+        gd += mu * (rh - rl) * dx[i];
+        MPCB_LOWER(rl, dx[i], at(L::ZLX + b, k));
+        MPCB_UPPER(rh, dx[i], at(L::ZUX + b, k));
       }
+      double dsr[NR > 0 ? NR : 1], lrp[NR > 0 ? NR : 1], dso[MO > 0 ? MO : 1], lop[MO > 0 ? MO : 1];
       if (k < N) {
 #pragma unroll
         for (int i = 0; i < 2; i++) {
           double uk = at(L::U + i, k), du = at(L::DU + i, k);
           double um = k > 0 ? at(L::U + i, k - 1) : 0.0;
           double up = k + 1 <= N - 1 ? at(L::U + i, k + 1) : 0.0;
-          double gl = uk - p.u_lo[i], gh = p.u_hi[i] - uk;
-          gd += (sigma * grad_u(k, i, uk, um, up) - mu / gl + mu / gh) * du;
-          MPCB_LOWER(gl, du, at(L::ZLU + i, k));
-          MPCB_UPPER(gh, du, at(L::ZUU + i, k));
+          double rl = 1.0 / (uk - p.u_lo[i]), rh = 1.0 / (p.u_hi[i] - uk);
+          gd += (sigma * grad_u(k, i, uk, um, up) + mu * (rh - rl)) * du;
+          MPCB_LOWER(rl, du, at(L::ZLU + i, k));
+          MPCB_UPPER(rh, du, at(L::ZUU + i, k));
         }
       }
       if (has_rate(k)) {
@@ -879,43 +718,58 @@ struct Solver {
         for (int r = 0; r < NR; r++) {
           int ci = p.rate_ctrl[r];
           double s = at(L::SR + r, k);
-          double gl = s - p.rate_lo[r], gh = p.rate_hi[r] - s;
+          double rl = 1.0 / (s - p.rate_lo[r]), rh = 1.0 / (p.rate_hi[r] - s);
           double vl = at(L::VLR + r, k), vu = at(L::VUR + r, k);
-          double D = vl / gl + vu / gh + dw;
-          double gs = -mu / gl + mu / gh;
+          double D = vl * rl + vu * rh + dw;
+          double gs = mu * (rh - rl);
           double res = at(L::U + ci, k) - at(L::U + ci, k - 1) - s;
           double ds = at(L::DU + ci, k) - at(L::DU + ci, k - 1) + res;
-          at(L::DSR + r, k) = ds;
-          at(L::LRP + r, k) = D * ds + gs;
+          dsr[r] = ds;
+          lrp[r] = D * ds + gs;
           gd += gs * ds;
-          MPCB_LOWER(gl, ds, vl);
-          MPCB_UPPER(gh, ds, vu);
+          MPCB_LOWER(rl, ds, vl);
+          MPCB_UPPER(rh, ds, vu);
         }
       }
       if (has_obs(k)) {
 #pragma unroll
         for (int j = 0; j < MO; j++) {
-          double d, ox, oy, hxx, hxy, hyy;
-          obs_grad(k, j, xk[0], xk[1], d, ox, oy, hxx, hxy, hyy);
-          double s = at(L::SO + j, k), gap = s - p.obs_lo, vl = at(L::VLO + j, k);
-          double D = vl / gap + dw;
-          double gs = -mu / gap + MPCB_KAPPA_D * mu;
-          double ds = ox * dx[0] + oy * dx[1] + (d - s);
-          at(L::DSO + j, k) = ds;
-          at(L::LOP + j, k) = D * ds + gs;
+          double ex = xk[0] - at(L::OCX + j, k), ey = xk[1] - at(L::OCY + j, k);
+          double a = at(L::ISX + j, k), b = at(L::ISY + j, k);
+          double d = ex * ex * a + ey * ey * b - 1.0;
+          double s = at(L::SO + j, k), rg = 1.0 / (s - p.obs_lo), vl = at(L::VLO + j, k);
+          double D = vl * rg + dw;
+          double gs = -mu * rg + MPCB_KAPPA_D * mu;
+          double ds = (2 * ex * a) * dx[0] + (2 * ey * b) * dx[1] + (d - s);
+          dso[j] = ds;
+          lop[j] = D * ds + gs;
           gd += gs * ds;
-          MPCB_LOWER(gap, ds, vl);
+          MPCB_LOWER(rg, ds, vl);
         }
       }
+      // the gains of this stage are dead (forward sweep done): reuse their slots
+      if (has_rate(k)) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) { at(L::DSR + r, k) = dsr[r]; at(L::LRP + r, k) = lrp[r]; }
+      }
+      if (has_obs(k)) {
+#pragma unroll
+        for (int j = 0; j < MO; j++) { at(L::DSO + j, k) = dso[j]; at(L::LOP + j, k) = lop[j]; }
+      }
     }
-    a_pr = warp_min(ap);
-    a_du = warp_min(ad);
+#undef MPCB_LOWER
+#undef MPCB_UPPER
+    rp = warp_max(rp);
+    rd = warp_max(rd);
+    a_pr = rp > tau ? tau / rp : 1.0;
+    a_du = rd > tau ? tau / rd : 1.0;
     gd_out = warp_sum(gd);
     __syncwarp();
   }
 
   // accept the step: primal a, duals a_du (IPOPT: equality multipliers move with a)
-  __device__ void accept_step(double a, double ad, double mu) {
+  __device__ __forceinline__ void accept_step(double a, double ad, double mu) {
+    #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
 #pragma unroll
       for (int i = 0; i < NX; i++) {
@@ -924,14 +778,14 @@ struct Solver {
       }
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
-        int i = Mdl::bx(b);
+        int i = KinModel::bx(b);
         double x = at(L::X + i, k), dx = at(L::DX + i, k);
-        double gl = x - p.x_lo[i], gh = p.x_hi[i] - x;
+        double rl = 1.0 / (x - p.x_lo[i]), rh = 1.0 / (p.x_hi[i] - x);
         double zl = at(L::ZLX + b, k), zu = at(L::ZUX + b, k);
-        double dzl = -zl + (mu - zl * dx) / gl, dzu = -zu + (mu + zu * dx) / gh;
+        double dzl = -zl + (mu - zl * dx) * rl, dzu = -zu + (mu + zu * dx) * rh;
         double xn = x + a * dx;
-        at(L::ZLX + b, k) = clampz(zl + ad * dzl, mu, xn - p.x_lo[i]);
-        at(L::ZUX + b, k) = clampz(zu + ad * dzu, mu, p.x_hi[i] - xn);
+        at(L::ZLX + b, k) = clampz(zl + ad * dzl, mu, 1.0 / (xn - p.x_lo[i]));
+        at(L::ZUX + b, k) = clampz(zu + ad * dzu, mu, 1.0 / (p.x_hi[i] - xn));
       }
 #pragma unroll
       for (int i = 0; i < NX; i++) at(L::X + i, k) += a * at(L::DX + i, k);
@@ -939,25 +793,26 @@ struct Solver {
 #pragma unroll
         for (int i = 0; i < 2; i++) {
           double u = at(L::U + i, k), du = at(L::DU + i, k);
-          double gl = u - p.u_lo[i], gh = p.u_hi[i] - u;
+          double rl = 1.0 / (u - p.u_lo[i]), rh = 1.0 / (p.u_hi[i] - u);
           double zl = at(L::ZLU + i, k), zu = at(L::ZUU + i, k);
-          double dzl = -zl + (mu - zl * du) / gl, dzu = -zu + (mu + zu * du) / gh;
+          double dzl = -zl + (mu - zl * du) * rl, dzu = -zu + (mu + zu * du) * rh;
           double un = u + a * du;
-          at(L::ZLU + i, k) = clampz(zl + ad * dzl, mu, un - p.u_lo[i]);
-          at(L::ZUU + i, k) = clampz(zu + ad * dzu, mu, p.u_hi[i] - un);
+          at(L::U + i, k) = un;
+          at(L::ZLU + i, k) = clampz(zl + ad * dzl, mu, 1.0 / (un - p.u_lo[i]));
+          at(L::ZUU + i, k) = clampz(zu + ad * dzu, mu, 1.0 / (p.u_hi[i] - un));
         }
       }
       if (has_rate(k)) {
 #pragma unroll
         for (int r = 0; r < NR; r++) {
           double s = at(L::SR + r, k), ds = at(L::DSR + r, k);
-          double gl = s - p.rate_lo[r], gh = p.rate_hi[r] - s;
+          double rl = 1.0 / (s - p.rate_lo[r]), rh = 1.0 / (p.rate_hi[r] - s);
           double vl = at(L::VLR + r, k), vu = at(L::VUR + r, k);
-          double dvl = -vl + (mu - vl * ds) / gl, dvu = -vu + (mu + vu * ds) / gh;
+          double dvl = -vl + (mu - vl * ds) * rl, dvu = -vu + (mu + vu * ds) * rh;
           double sn = s + a * ds;
           at(L::SR + r, k) = sn;
-          at(L::VLR + r, k) = clampz(vl + ad * dvl, mu, sn - p.rate_lo[r]);
-          at(L::VUR + r, k) = clampz(vu + ad * dvu, mu, p.rate_hi[r] - sn);
+          at(L::VLR + r, k) = clampz(vl + ad * dvl, mu, 1.0 / (sn - p.rate_lo[r]));
+          at(L::VUR + r, k) = clampz(vu + ad * dvu, mu, 1.0 / (p.rate_hi[r] - sn));
           double l = at(L::LR + r, k);
           at(L::LR + r, k) = l + a * (at(L::LRP + r, k) - l);
         }
@@ -966,88 +821,80 @@ struct Solver {
 #pragma unroll
         for (int j = 0; j < MO; j++) {
           double s = at(L::SO + j, k), ds = at(L::DSO + j, k);
-          double gap = s - p.obs_lo, vl = at(L::VLO + j, k);
-          double dvl = -vl + (mu - vl * ds) / gap;
+          double rg = 1.0 / (s - p.obs_lo), vl = at(L::VLO + j, k);
+          double dvl = -vl + (mu - vl * ds) * rg;
           double sn = s + a * ds;
           at(L::SO + j, k) = sn;
-          at(L::VLO + j, k) = clampz(vl + ad * dvl, mu, sn - p.obs_lo);
+          at(L::VLO + j, k) = clampz(vl + ad * dvl, mu, 1.0 / (sn - p.obs_lo));
           double l = at(L::LO + j, k);
           at(L::LO + j, k) = l + a * (at(L::LOP + j, k) - l);
         }
       }
     }
     __syncwarp();
-    // the controls are read by neighbouring stages (rate rows), update them last
-    for (int k = lane; k < N; k += 32) {
-      at(L::U + 0, k) += a * at(L::DU + 0, k);
-      at(L::U + 1, k) += a * at(L::DU + 1, k);
-    }
-    __syncwarp();
   }
 
   // ---------------------------------------------------------------- start point
-  __device__ bool init_iterate(int b) {
+  __device__ __forceinline__ bool init_iterate(int b) {
     const int nv = 2 * N + NX * (N + 1);
     const double *zi = p.z_init ? p.z_init + (size_t)b * nv : nullptr;
     const double *ob = p.obs ? p.obs + (size_t)b * MO * (N + 1) * 6 : nullptr;
     // obstacle trajectory staged in shared memory (centre and 1/semi-axis^2 per step)
+    #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
 #pragma unroll
       for (int j = 0; j < MO; j++) {
         const double *o = ob + ((size_t)j * (N + 1) + k) * 6;
-        double sx, sy;
-        if (OBS_MODE == 1) {  // PKG/MPC_CBF_optimize_kin_pre.py:246-249
-          sx = p.ego_hl + o[4] / 2 + p.safe_l;
-          sy = p.ego_hw + o[5] / 2 + p.safe_w;
-        } else {
-          sx = p.dyn_sx;
-          sy = p.dyn_sy;
-        }
+        double sx = p.ego_hl + o[4] / 2 + p.safe_l;  // PKG/MPC_CBF_optimize_kin_pre.py:246-249
+        double sy = p.ego_hw + o[5] / 2 + p.safe_w;
         at(L::OCX + j, k) = o[0];
         at(L::OCY + j, k) = o[1];
         at(L::ISX + j, k) = 1.0 / (sx * sx);
         at(L::ISY + j, k) = 1.0 / (sy * sy);
       }
-      if (k < N) {
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-          at(L::U + i, k) = push_in(zi ? zi[2 * k + i] : 0.0, p.u_lo[i], p.u_hi[i]);
-          at(L::ZLU + i, k) = 1.0;
-          at(L::ZUU + i, k) = 1.0;
-        }
-      }
-      if (p.init_mode == 0) {
-#pragma unroll
-        for (int i = 0; i < NX; i++) at(L::X + i, k) = zi ? zi[2 * N + NX * k + i] : 0.0;
+      for (int i = 0; i < 2; i++) {
+        at(L::U + i, k) = k < N ? push_in(zi ? zi[2 * k + i] : 0.0, p.u_lo[i], p.u_hi[i]) : 0.0;
+        at(L::ZLU + i, k) = 1.0;
+        at(L::ZUU + i, k) = 1.0;
+        at(L::DU + i, k) = 0.0;
       }
 #pragma unroll
-      for (int i = 0; i < NX; i++) at(L::LAM + i, k) = 0.0;
+      for (int i = 0; i < NX; i++) {
+        if (p.init_mode == 0) at(L::X + i, k) = zi ? zi[2 * N + NX * k + i] : 0.0;
+        at(L::LAM + i, k) = 0.0;
+        at(L::DX + i, k) = 0.0;
+      }
     }
     __syncwarp();
     if (p.init_mode == 1) {  // Euler roll-out of the guessed controls (PKG/MPC_CBF_optimize_kin.py:207)
       double x[NX];
 #pragma unroll
       for (int i = 0; i < NX; i++) x[i] = x0[i];
+      #pragma unroll 1
       for (int k = 0; k <= N; k++) {
         if (lane == 0) {
 #pragma unroll
           for (int i = 0; i < NX; i++) at(L::X + i, k) = x[i];
         }
         if (k < N) {
-          double u[2] = {at(L::U + 0, k), at(L::U + 1, k)}, f[NX];
-          Mdl::f(x, u, p, f);
-#pragma unroll
-          for (int i = 0; i < NX; i++) x[i] = x[i] + p.T * f[i];
+          double u0_ = at(L::U + 0, k), u1_ = at(L::U + 1, k), s, c, t;
+          d_trig(x[2], u0_, &s, &c, &t);
+          double f0 = x[3] * c, f1 = x[3] * s, f2 = x[3] * t / p.Veh_l;
+          x[0] = x[0] + p.T * f0;
+          x[1] = x[1] + p.T * f1;
+          x[2] = x[2] + p.T * f2;
+          x[3] = x[3] + p.T * u1_;
         }
       }
       __syncwarp();
     }
-    bool fin = true;
     double gmax = 0;
+    #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
 #pragma unroll
       for (int b2 = 0; b2 < NBX; b2++) {
-        int i = Mdl::bx(b2);
+        int i = KinModel::bx(b2);
         at(L::X + i, k) = push_in(at(L::X + i, k), p.x_lo[i], p.x_hi[i]);
         at(L::ZLX + b2, k) = 1.0;
         at(L::ZUX + b2, k) = 1.0;
@@ -1065,8 +912,8 @@ struct Solver {
       if (has_obs(k)) {
 #pragma unroll
         for (int j = 0; j < MO; j++) {
-          double d = obs_val(k, j, at(L::X + 0, k), at(L::X + 1, k));
-          if (!isfinite(d)) fin = false;
+          double dx = at(L::X + 0, k) - at(L::OCX + j, k), dy = at(L::X + 1, k) - at(L::OCY + j, k);
+          double d = dx * dx * at(L::ISX + j, k) + dy * dy * at(L::ISY + j, k) - 1.0;
           at(L::SO + j, k) = push_lo(d, p.obs_lo);
           at(L::VLO + j, k) = 1.0;
           at(L::LO + j, k) = 0.0;
@@ -1088,7 +935,7 @@ struct Solver {
     sigma = gmax > MPCB_OBJ_SCALE_MAX_GRAD ? MPCB_OBJ_SCALE_MAX_GRAD / gmax : 1.0;
     if (sigma < 1e-8) sigma = 1e-8;
     __syncwarp();
-    return __all_sync(0xffffffffu, fin);
+    return true;
   }
 
   // ---------------------------------------------------------------- main loop
@@ -1109,86 +956,39 @@ struct Solver {
 #pragma unroll
     for (int s = 0; s < MPCB_FILTER_SLOTS; s++) { ft[s] = INFINITY; fp[s] = INFINITY; }
 
-    bool okinit = init_iterate(b);
-    if (okinit) eval_primal<false>(0.0, theta, fobj, bar, lin);
-    if (!okinit || !isfinite(theta) || !isfinite(bar)) {
-      status = 4;
-    } else {
-      __syncwarp();
-      const double theta_min = 1e-4 * fmax(1.0, theta), theta_max = 1e4 * fmax(1.0, theta);
-      for (;;) {
-        Kkt kk;
-        eval_lin_kkt(kk);
-        double co0;
-        double err0 = kkt_error(kk, 0.0, co0);
-        if (err0 <= tol && kk.dual <= MPCB_DUAL_INF_TOL && kk.prim <= MPCB_CONSTR_VIOL_TOL && co0 <= MPCB_COMPL_INF_TOL) { status = 0; break; }
-        if (it >= p.max_iter) { status = 2; break; }
-        {
-          double co;
-          while (kkt_error(kk, mu, co) <= MPCB_KAPPA_EPS * mu && mu > tol / 10) {
-            mu = fmax(tol / 10, fmin(MPCB_KAPPA_MU * mu, pow(mu, MPCB_THETA_MU)));
-            tau = fmax(MPCB_TAU_MIN, 1 - mu);
-            nfilt = 0;
+    init_iterate(b);
+    // State machine with ONE call site per phase (every phase is inlined exactly once, which
+    // keeps the kernel small enough for the instruction caches):
+    //   eval_point is run either on the iterate (alpha = 0, storing defects + Jacobians) or on
+    //   a line-search trial point; the branch below decides what the evaluation was for.
+    double theta_min = 0, theta_max = 0;
+    double a = 0.0, a_min = 0, a_dual = 1.0, gd = 0, pgd = 0, pth = 0;
+    bool trial = false, first = true;
+    for (;;) {
+      double th_e, f_e, bar_e, lin_e;
+      eval_point(a, !trial, th_e, f_e, bar_e, lin_e);
+      if (trial) {
+        // ---------------- filter line search: test the trial point z + a dz
+        double ph_t = sigma * f_e - mu * bar_e + MPCB_KAPPA_D * mu * lin_e;
+        bool fin = isfinite(th_e) && isfinite(ph_t);
+        bool blocked = th_e >= theta_max;
 #pragma unroll
-            for (int s = 0; s < MPCB_FILTER_SLOTS; s++) { ft[s] = INFINITY; fp[s] = INFINITY; }
-          }
-        }
-        phi = sigma * fobj - mu * bar + MPCB_KAPPA_D * mu * lin;
-        double dw = 0.0;
-        build_qp(mu, 0.0);
-        bool ok = riccati_backward();
-        if (!ok) {
-          dw = dw_last == 0.0 ? MPCB_DW_FIRST : fmax(MPCB_DW_MIN, MPCB_KW_MINUS * dw_last);
-          for (;;) {
-            build_qp(mu, dw);
-            ok = riccati_backward();
-            if (ok) break;
-            dw *= dw_last == 0.0 ? MPCB_KW_PLUS_FIRST : MPCB_KW_PLUS;
-            if (dw > MPCB_DW_MAX) break;
-          }
-          if (!ok) { status = 3; break; }
-          dw_last = dw;
-        }
-        riccati_forward();
-        adjoint();
-        double a_max, a_dual, gd;
-        slack_and_steps(mu, dw, tau, a_max, a_dual, gd);
-        double a_min;
-        if (gd < 0 && theta <= theta_min) {
-          a_min = MPCB_GAMMA_THETA;
-          if (theta > 0) {
-            a_min = fmin(a_min, MPCB_GAMMA_PHI * theta / (-gd));
-            a_min = fmin(a_min, pow(theta, MPCB_S_THETA) / pow(-gd, MPCB_S_PHI));
-          }
-        } else if (gd < 0) {
-          a_min = fmin(MPCB_GAMMA_THETA, MPCB_GAMMA_PHI * theta / (-gd));
-        } else {
-          a_min = MPCB_GAMMA_THETA;
-        }
-        a_min = fmax(MPCB_GAMMA_ALPHA * a_min, 1e-14);
-        double a = a_max;
+        for (int s = 0; s < MPCB_FILTER_SLOTS; s++) blocked = blocked || (th_e >= ft[s] && ph_t >= fp[s]);
+        blocked = __any_sync(0xffffffffu, blocked);
         bool accepted = false, armijo = false;
-        double th_t = 0, f_t = 0, bar_t = 0, lin_t = 0;
-        while (a >= a_min) {
-          eval_primal<true>(a, th_t, f_t, bar_t, lin_t);
-          double ph_t = sigma * f_t - mu * bar_t + MPCB_KAPPA_D * mu * lin_t;
-          bool fin = isfinite(th_t) && isfinite(ph_t);
-          bool blocked = th_t >= theta_max;
-#pragma unroll
-          for (int s = 0; s < MPCB_FILTER_SLOTS; s++) blocked = blocked || (th_t >= ft[s] && ph_t >= fp[s]);
-          blocked = __any_sync(0xffffffffu, blocked);
-          if (fin && !blocked) {
-            bool sw = gd < 0 && a * pow(-gd, MPCB_S_PHI) > pow(theta, MPCB_S_THETA);
-            if (theta <= theta_min && sw) {
-              if (ph_t <= phi + MPCB_ETA_PHI * a * gd + 10 * MPCB_DBL_EPS * fabs(phi)) { accepted = true; armijo = true; }
-            } else if (th_t <= (1 - MPCB_GAMMA_THETA) * theta || ph_t <= phi - MPCB_GAMMA_PHI * theta + 10 * MPCB_DBL_EPS * fabs(phi)) {
-              accepted = true;
-            }
+        if (fin && !blocked) {
+          bool sw = gd < 0 && a * pgd > pth;
+          if (theta <= theta_min && sw) {
+            if (ph_t <= phi + MPCB_ETA_PHI * a * gd + 10 * MPCB_DBL_EPS * fabs(phi)) { accepted = true; armijo = true; }
+          } else if (th_e <= (1 - MPCB_GAMMA_THETA) * theta || ph_t <= phi - MPCB_GAMMA_PHI * theta + 10 * MPCB_DBL_EPS * fabs(phi)) {
+            accepted = true;
           }
-          if (accepted) break;
-          a *= 0.5;
         }
-        if (!accepted) { status = 3; break; }
+        if (!accepted) {
+          a *= 0.5;
+          if (a < a_min) { status = 3; break; }
+          continue;  // next trial
+        }
         if (!armijo) {
           int slot = nfilt % (32 * MPCB_FILTER_SLOTS);
           if ((slot & 31) == lane) {
@@ -1199,10 +999,74 @@ struct Solver {
           nfilt++;
         }
         accept_step(a, a_dual, mu);
-        eval_primal<false>(0.0, theta, fobj, bar, lin);
-        __syncwarp();
         it++;
+        trial = false;
+        a = 0.0;
+        continue;  // evaluate the new iterate (stores defects and Jacobians)
       }
+      // ---------------- a fresh iterate has been evaluated
+      theta = th_e; fobj = f_e; bar = bar_e; lin = lin_e;
+      if (first) {
+        first = false;
+        if (!isfinite(theta) || !isfinite(bar)) { status = 4; break; }
+        theta_min = 1e-4 * fmax(1.0, theta);
+        theta_max = 1e4 * fmax(1.0, theta);
+      }
+      Kkt kk;
+      kkt_pieces(kk);
+      double co0;
+      double err0 = kkt_error(kk, 0.0, co0);
+      if (err0 <= tol && kk.dual <= MPCB_DUAL_INF_TOL && kk.prim <= MPCB_CONSTR_VIOL_TOL && co0 <= MPCB_COMPL_INF_TOL) { status = 0; break; }
+      if (it >= p.max_iter) { status = 2; break; }
+      {
+        double co;
+        while (kkt_error(kk, mu, co) <= MPCB_KAPPA_EPS * mu && mu > tol / 10) {
+          mu = fmax(tol / 10, fmin(MPCB_KAPPA_MU * mu, d_pow(mu, MPCB_THETA_MU)));
+          tau = fmax(MPCB_TAU_MIN, 1 - mu);
+          nfilt = 0;
+#pragma unroll
+          for (int s = 0; s < MPCB_FILTER_SLOTS; s++) { ft[s] = INFINITY; fp[s] = INFINITY; }
+        }
+      }
+      phi = sigma * fobj - mu * bar + MPCB_KAPPA_D * mu * lin;
+      // ---------------- Newton system with inertia correction (IPOPT's delta_w schedule)
+      double dw = 0.0;
+      bool ok, tried0 = false;
+      for (;;) {
+        build_qp(mu, dw);
+        ok = riccati_backward();
+        if (ok) break;
+        if (!tried0) {
+          tried0 = true;
+          dw = dw_last == 0.0 ? MPCB_DW_FIRST : fmax(MPCB_DW_MIN, MPCB_KW_MINUS * dw_last);
+        } else {
+          dw *= dw_last == 0.0 ? MPCB_KW_PLUS_FIRST : MPCB_KW_PLUS;
+          if (dw > MPCB_DW_MAX) break;
+        }
+      }
+      if (!ok) { status = 3; break; }
+      if (dw > 0.0) dw_last = dw;
+      riccati_forward();
+      adjoint();
+      double a_max;
+      slack_and_steps(mu, dw, tau, a_max, a_dual, gd);
+      pgd = 0.0; pth = 0.0;
+      if (gd < 0) { pgd = d_pow(-gd, MPCB_S_PHI); pth = d_pow(theta, MPCB_S_THETA); }
+      if (gd < 0 && theta <= theta_min) {
+        a_min = MPCB_GAMMA_THETA;
+        if (theta > 0) {
+          a_min = fmin(a_min, MPCB_GAMMA_PHI * theta / (-gd));
+          a_min = fmin(a_min, pth / pgd);
+        }
+      } else if (gd < 0) {
+        a_min = fmin(MPCB_GAMMA_THETA, MPCB_GAMMA_PHI * theta / (-gd));
+      } else {
+        a_min = MPCB_GAMMA_THETA;
+      }
+      a_min = fmax(MPCB_GAMMA_ALPHA * a_min, 1e-14);
+      a = a_max;
+      trial = true;
+      if (a < a_min) { status = 3; break; }
     }
     // ---- results
     const int nv = 2 * N + NX * (N + 1);
@@ -1225,12 +1089,11 @@ struct Solver {
   }
 };
 
-template <class Mdl, int NR, int MO, int OBS_MODE>
-__global__ void __launch_bounds__(32) solve_kernel(const __grid_constant__ KParams p) {
-  extern __shared__ double smem[];
+template <int NR, int MO, int OBS_MODE>
+__global__ void __launch_bounds__(32) kin_solve_kernel(const __grid_constant__ KParams p) {
   const int lane = threadIdx.x;
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-    Solver<Mdl, NR, MO, OBS_MODE> s(p, smem, lane);
+    KinSolver<NR, MO, OBS_MODE> s(p, g_smem, lane);
     s.run(b);
     __syncwarp();
   }
