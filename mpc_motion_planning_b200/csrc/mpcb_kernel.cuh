@@ -79,6 +79,17 @@ struct KParams {
 // ------------------------------------------------------------------------------------
 extern __shared__ double g_smem[];
 
+// Reciprocal from the MUFU seed (about 20 bits) and two Newton steps: ~1 ulp, 5 instructions,
+// no slow-path call (IEEE division costs a 77-instruction subroutine per use, see
+// profiles/r01_v3_*).  Arguments here are bound gaps and pivots: positive normal numbers.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+
 __device__ __noinline__ double d_log(double x) { return log(x); }
 __device__ __noinline__ double d_pow(double x, double y) { return pow(x, y); }
 __device__ __noinline__ double3 d_trig3(double phi, double delta) {  // (sin phi, cos phi, tan delta)
@@ -220,6 +231,7 @@ struct KinSolver {
     #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
       double xk[NX], uk[2] = {0, 0};
+      double gp = 1.0;  // product of the bound gaps of this stage: sum of logs = log of the product
 #pragma unroll
       for (int i = 0; i < NX; i++) xk[i] = at(L::X + i, k) + alpha * at(L::DX + i, k);
       if (k == 0) {
@@ -259,7 +271,7 @@ struct KinSolver {
         }
 #pragma unroll
         for (int i = 0; i < 2; i++) {
-          br += d_log(uk[i] - p.u_lo[i]) + d_log(p.u_hi[i] - uk[i]);
+          gp *= (uk[i] - p.u_lo[i]) * (p.u_hi[i] - uk[i]);
           fo += p.R[i] * uk[i] * uk[i];
           if (k > 0) {
             double um = at(L::U + i, k - 1) + alpha * at(L::DU + i, k - 1);
@@ -273,7 +285,7 @@ struct KinSolver {
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
         int i = KinModel::bx(b);
-        br += d_log(xk[i] - p.x_lo[i]) + d_log(p.x_hi[i] - xk[i]);
+        gp *= (xk[i] - p.x_lo[i]) * (p.x_hi[i] - xk[i]);
       }
       if (has_rate(k)) {
 #pragma unroll
@@ -284,7 +296,7 @@ struct KinSolver {
           // the slack step lives in the gain region, which holds gains while alpha == 0
           double s = at(L::SR + r, k) + (alpha != 0.0 ? alpha * at(L::DSR + r, k) : 0.0);
           th += fabs(ukc - um - s);
-          br += d_log(s - p.rate_lo[r]) + d_log(p.rate_hi[r] - s);
+          gp *= (s - p.rate_lo[r]) * (p.rate_hi[r] - s);
         }
       }
       if (has_obs(k)) {
@@ -294,10 +306,11 @@ struct KinSolver {
           double d = dx * dx * at(L::ISX + j, k) + dy * dy * at(L::ISY + j, k) - 1.0;  // PKG/..._kin.py:244,247
           double s = at(L::SO + j, k) + (alpha != 0.0 ? alpha * at(L::DSO + j, k) : 0.0);
           th += fabs(d - s);
-          br += d_log(s - p.obs_lo);
+          gp *= s - p.obs_lo;
           ln += s - p.obs_lo;
         }
       }
+      br += d_log(gp);
     }
     theta = warp_sum(th);
     fobj = warp_sum(fo);
@@ -444,7 +457,7 @@ struct KinSolver {
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
         int i = KinModel::bx(b);
-        double rl = 1.0 / (xk[i] - p.x_lo[i]), rh = 1.0 / (p.x_hi[i] - xk[i]);
+        double rl = fast_rcp(xk[i] - p.x_lo[i]), rh = fast_rcp(p.x_hi[i] - xk[i]);
         h[i] += at(L::ZLX + b, k) * rl + at(L::ZUX + b, k) * rh;
         gx[i] += mu * (rh - rl);
       }
@@ -455,7 +468,7 @@ struct KinSolver {
           double a = at(L::ISX + j, k), b = at(L::ISY + j, k);
           double d = dx * dx * a + dy * dy * b - 1.0;
           double ox = 2 * dx * a, oy = 2 * dy * b;
-          double s = at(L::SO + j, k), rg = 1.0 / (s - p.obs_lo);
+          double s = at(L::SO + j, k), rg = fast_rcp(s - p.obs_lo);
           double D = at(L::VLO + j, k) * rg + dw;
           double gs = -mu * rg + MPCB_KAPPA_D * mu;
           double lo = at(L::LO + j, k);
@@ -487,7 +500,7 @@ struct KinSolver {
             hd += sigma * 2 * p.DR[i];
             g += sigma * 2 * p.DR[i] * uk;
           }
-          double rl = 1.0 / (uk - p.u_lo[i]), rh = 1.0 / (p.u_hi[i] - uk);
+          double rl = fast_rcp(uk - p.u_lo[i]), rh = fast_rcp(p.u_hi[i] - uk);
           hd += at(L::ZLU + i, k) * rl + at(L::ZUU + i, k) * rh;
           g += mu * (rh - rl);
           at(L::HUU + i, k) = hd;
@@ -502,7 +515,7 @@ struct KinSolver {
           for (int r = 0; r < NR; r++) {
             int ci = p.rate_ctrl[r];
             double s = at(L::SR + r, k);
-            double rl = 1.0 / (s - p.rate_lo[r]), rh = 1.0 / (p.rate_hi[r] - s);
+            double rl = fast_rcp(s - p.rate_lo[r]), rh = fast_rcp(p.rate_hi[r] - s);
             double D = at(L::VLR + r, k) * rl + at(L::VUR + r, k) * rh + dw;
             double gs = mu * (rh - rl);
             double res = at(L::U + ci, k) - at(L::U + ci, k - 1) - s;
@@ -576,7 +589,7 @@ struct KinSolver {
       const double fua = at(L::GU + 1, k) + ta + pwa + T * Pb3 + w0a * b0 + w1a * b1 + w2a * b2_ + w3a * b3;
       const double det = Fdd * Faa - Fda * Fda;
       if (!(Fdd > 0.0) || !(det > 0.0) || !isfinite(det)) { ok = false; break; }
-      const double id = 1.0 / det;
+      const double id = fast_rcp(det);
       const double idd = Faa * id, ida = -Fda * id, iaa = Fdd * id;  // Fuu^{-1}
       // gains: u = Kx x + Kw w + kk
       const double kd0 = -(idd * ud0 + ida * ua0), kd1 = -(idd * ud1 + ida * ua1), kd2 = -(idd * ud2 + ida * ua2), kd3 = -(idd * ud3 + ida * ua3);
@@ -680,9 +693,9 @@ struct KinSolver {
   __device__ __forceinline__ void slack_and_steps(double mu, double dw, double tau, double &a_pr, double &a_du, double &gd_out) {
     double rp = 0.0, rd = 0.0, gd = 0.0;  // largest primal / dual shrink ratios
 #define MPCB_LOWER(rgap, dv, z) do { double dz_ = -(z) + (mu - (z) * (dv)) * (rgap); \
-    rp = fmax(rp, -(dv) * (rgap)); rd = fmax(rd, -dz_ / (z)); } while (0)
+    rp = fmax(rp, -(dv) * (rgap)); rd = fmax(rd, -dz_ * fast_rcp(z)); } while (0)
 #define MPCB_UPPER(rgap, dv, z) do { double dz_ = -(z) + (mu + (z) * (dv)) * (rgap); \
-    rp = fmax(rp, (dv) * (rgap)); rd = fmax(rd, -dz_ / (z)); } while (0)
+    rp = fmax(rp, (dv) * (rgap)); rd = fmax(rd, -dz_ * fast_rcp(z)); } while (0)
     #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
       double xk[NX], dx[NX];
@@ -695,7 +708,7 @@ struct KinSolver {
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
         int i = KinModel::bx(b);
-        double rl = 1.0 / (xk[i] - p.x_lo[i]), rh = 1.0 / (p.x_hi[i] - xk[i]);
+        double rl = fast_rcp(xk[i] - p.x_lo[i]), rh = fast_rcp(p.x_hi[i] - xk[i]);
         gd += mu * (rh - rl) * dx[i];
         MPCB_LOWER(rl, dx[i], at(L::ZLX + b, k));
         MPCB_UPPER(rh, dx[i], at(L::ZUX + b, k));
@@ -707,7 +720,7 @@ struct KinSolver {
           double uk = at(L::U + i, k), du = at(L::DU + i, k);
           double um = k > 0 ? at(L::U + i, k - 1) : 0.0;
           double up = k + 1 <= N - 1 ? at(L::U + i, k + 1) : 0.0;
-          double rl = 1.0 / (uk - p.u_lo[i]), rh = 1.0 / (p.u_hi[i] - uk);
+          double rl = fast_rcp(uk - p.u_lo[i]), rh = fast_rcp(p.u_hi[i] - uk);
           gd += (sigma * grad_u(k, i, uk, um, up) + mu * (rh - rl)) * du;
           MPCB_LOWER(rl, du, at(L::ZLU + i, k));
           MPCB_UPPER(rh, du, at(L::ZUU + i, k));
@@ -718,7 +731,7 @@ struct KinSolver {
         for (int r = 0; r < NR; r++) {
           int ci = p.rate_ctrl[r];
           double s = at(L::SR + r, k);
-          double rl = 1.0 / (s - p.rate_lo[r]), rh = 1.0 / (p.rate_hi[r] - s);
+          double rl = fast_rcp(s - p.rate_lo[r]), rh = fast_rcp(p.rate_hi[r] - s);
           double vl = at(L::VLR + r, k), vu = at(L::VUR + r, k);
           double D = vl * rl + vu * rh + dw;
           double gs = mu * (rh - rl);
@@ -737,7 +750,7 @@ struct KinSolver {
           double ex = xk[0] - at(L::OCX + j, k), ey = xk[1] - at(L::OCY + j, k);
           double a = at(L::ISX + j, k), b = at(L::ISY + j, k);
           double d = ex * ex * a + ey * ey * b - 1.0;
-          double s = at(L::SO + j, k), rg = 1.0 / (s - p.obs_lo), vl = at(L::VLO + j, k);
+          double s = at(L::SO + j, k), rg = fast_rcp(s - p.obs_lo), vl = at(L::VLO + j, k);
           double D = vl * rg + dw;
           double gs = -mu * rg + MPCB_KAPPA_D * mu;
           double ds = (2 * ex * a) * dx[0] + (2 * ey * b) * dx[1] + (d - s);
@@ -780,12 +793,12 @@ struct KinSolver {
       for (int b = 0; b < NBX; b++) {
         int i = KinModel::bx(b);
         double x = at(L::X + i, k), dx = at(L::DX + i, k);
-        double rl = 1.0 / (x - p.x_lo[i]), rh = 1.0 / (p.x_hi[i] - x);
+        double rl = fast_rcp(x - p.x_lo[i]), rh = fast_rcp(p.x_hi[i] - x);
         double zl = at(L::ZLX + b, k), zu = at(L::ZUX + b, k);
         double dzl = -zl + (mu - zl * dx) * rl, dzu = -zu + (mu + zu * dx) * rh;
         double xn = x + a * dx;
-        at(L::ZLX + b, k) = clampz(zl + ad * dzl, mu, 1.0 / (xn - p.x_lo[i]));
-        at(L::ZUX + b, k) = clampz(zu + ad * dzu, mu, 1.0 / (p.x_hi[i] - xn));
+        at(L::ZLX + b, k) = clampz(zl + ad * dzl, mu, fast_rcp(xn - p.x_lo[i]));
+        at(L::ZUX + b, k) = clampz(zu + ad * dzu, mu, fast_rcp(p.x_hi[i] - xn));
       }
 #pragma unroll
       for (int i = 0; i < NX; i++) at(L::X + i, k) += a * at(L::DX + i, k);
@@ -793,26 +806,26 @@ struct KinSolver {
 #pragma unroll
         for (int i = 0; i < 2; i++) {
           double u = at(L::U + i, k), du = at(L::DU + i, k);
-          double rl = 1.0 / (u - p.u_lo[i]), rh = 1.0 / (p.u_hi[i] - u);
+          double rl = fast_rcp(u - p.u_lo[i]), rh = fast_rcp(p.u_hi[i] - u);
           double zl = at(L::ZLU + i, k), zu = at(L::ZUU + i, k);
           double dzl = -zl + (mu - zl * du) * rl, dzu = -zu + (mu + zu * du) * rh;
           double un = u + a * du;
           at(L::U + i, k) = un;
-          at(L::ZLU + i, k) = clampz(zl + ad * dzl, mu, 1.0 / (un - p.u_lo[i]));
-          at(L::ZUU + i, k) = clampz(zu + ad * dzu, mu, 1.0 / (p.u_hi[i] - un));
+          at(L::ZLU + i, k) = clampz(zl + ad * dzl, mu, fast_rcp(un - p.u_lo[i]));
+          at(L::ZUU + i, k) = clampz(zu + ad * dzu, mu, fast_rcp(p.u_hi[i] - un));
         }
       }
       if (has_rate(k)) {
 #pragma unroll
         for (int r = 0; r < NR; r++) {
           double s = at(L::SR + r, k), ds = at(L::DSR + r, k);
-          double rl = 1.0 / (s - p.rate_lo[r]), rh = 1.0 / (p.rate_hi[r] - s);
+          double rl = fast_rcp(s - p.rate_lo[r]), rh = fast_rcp(p.rate_hi[r] - s);
           double vl = at(L::VLR + r, k), vu = at(L::VUR + r, k);
           double dvl = -vl + (mu - vl * ds) * rl, dvu = -vu + (mu + vu * ds) * rh;
           double sn = s + a * ds;
           at(L::SR + r, k) = sn;
-          at(L::VLR + r, k) = clampz(vl + ad * dvl, mu, 1.0 / (sn - p.rate_lo[r]));
-          at(L::VUR + r, k) = clampz(vu + ad * dvu, mu, 1.0 / (p.rate_hi[r] - sn));
+          at(L::VLR + r, k) = clampz(vl + ad * dvl, mu, fast_rcp(sn - p.rate_lo[r]));
+          at(L::VUR + r, k) = clampz(vu + ad * dvu, mu, fast_rcp(p.rate_hi[r] - sn));
           double l = at(L::LR + r, k);
           at(L::LR + r, k) = l + a * (at(L::LRP + r, k) - l);
         }
@@ -821,11 +834,11 @@ struct KinSolver {
 #pragma unroll
         for (int j = 0; j < MO; j++) {
           double s = at(L::SO + j, k), ds = at(L::DSO + j, k);
-          double rg = 1.0 / (s - p.obs_lo), vl = at(L::VLO + j, k);
+          double rg = fast_rcp(s - p.obs_lo), vl = at(L::VLO + j, k);
           double dvl = -vl + (mu - vl * ds) * rg;
           double sn = s + a * ds;
           at(L::SO + j, k) = sn;
-          at(L::VLO + j, k) = clampz(vl + ad * dvl, mu, 1.0 / (sn - p.obs_lo));
+          at(L::VLO + j, k) = clampz(vl + ad * dvl, mu, fast_rcp(sn - p.obs_lo));
           double l = at(L::LO + j, k);
           at(L::LO + j, k) = l + a * (at(L::LOP + j, k) - l);
         }
@@ -849,8 +862,8 @@ struct KinSolver {
         double sy = p.ego_hw + o[5] / 2 + p.safe_w;
         at(L::OCX + j, k) = o[0];
         at(L::OCY + j, k) = o[1];
-        at(L::ISX + j, k) = 1.0 / (sx * sx);
-        at(L::ISY + j, k) = 1.0 / (sy * sy);
+        at(L::ISX + j, k) = fast_rcp(sx * sx);
+        at(L::ISY + j, k) = fast_rcp(sy * sy);
       }
 #pragma unroll
       for (int i = 0; i < 2; i++) {
