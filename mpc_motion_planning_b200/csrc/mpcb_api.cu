@@ -3,6 +3,7 @@
 // mpcb_create fails with MPCB_E_NODEVICE.
 #include "../../include/mpcb200.h"
 #include "mpcb_kernel.cuh"
+#include "mpcb_dyn_kernel.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -48,8 +49,28 @@ Variant make_kin_variant() {
   return v;
 }
 
+cudaError_t launch_dyn(const KParams &p, int grid, size_t smem, cudaStream_t st) {
+  dyn_solve_kernel<<<grid, 32, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+Variant make_dyn_variant() {
+  Variant v;
+  v.launch = &launch_dyn;
+  v.kernel = (const void *)&dyn_solve_kernel;
+  v.smem_bytes = [](int N) { return DynLayout::bytes(N); };
+  v.nx = 6;
+  v.nbx = 3;
+  return v;
+}
+
 bool select_variant(const mpcb_cfg &c, Variant &v) {
   const int M = c.obs_mode == MPCB_OBS_NONE ? 0 : c.M;
+  if (c.model == MPCB_MODEL_DYN) {
+    // the reference's dyn NLP: both rate rows (df, ax in that order), one obstacle, sqrt rows
+    if (c.obs_mode == MPCB_OBS_SQRT && c.n_rate == 2 && M == 1 && c.rate_ctrl[0] == 0 && c.rate_ctrl[1] == 1) { v = make_dyn_variant(); return true; }
+    return false;
+  }
   if (c.model == MPCB_MODEL_KIN) {
     if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 0) { v = make_kin_variant<0, 0, 0>(); return true; }
     if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 1) { v = make_kin_variant<1, 0, 0>(); return true; }
@@ -271,12 +292,11 @@ int mpcb_get_launch_info(mpcb_handle *h, mpcb_launch_info *out) {
 // ---------------------------------------------------------------------------------------
 namespace {
 
-template <class Mdl>
+template <int NX>
 __global__ void shift_kernel(KParams p, int B, double *x0, double *z) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
-  constexpr int NX = Mdl::NX;
   const int N = p.N, nv = 2 * N + NX * (N + 1);
   double *zz = z + (size_t)b * nv;
   double *xx = x0 + (size_t)b * NX;
@@ -284,10 +304,12 @@ __global__ void shift_kernel(KParams p, int B, double *x0, double *z) {
   double x[NX], u[2] = {zz[0], zz[1]}, f[NX];
 #pragma unroll
   for (int i = 0; i < NX; i++) x[i] = xx[i];
-  {
+  if constexpr (NX == 4) {
     double s_, c_, t_;
     d_trig(x[2], u[0], &s_, &c_, &t_);
     f[0] = x[3] * c_; f[1] = x[3] * s_; f[2] = x[3] * t_ / p.Veh_l; f[3] = u[1];
+  } else {
+    dyn_f(x, u, p, f);
   }
   // shifted copies held in registers before anything is overwritten
   constexpr int PER = (2 * MPCB_NMAX + 6 * (MPCB_NMAX + 1) + 31) / 32;
@@ -326,8 +348,8 @@ extern "C" int mpcb_shift_batch(mpcb_handle *h, int B, double *x0, double *z, vo
   KParams k = h->kp;
   const int wpb = 4;
   int grid = (B + wpb - 1) / wpb;
-  if (h->cfg.model == MPCB_MODEL_KIN) shift_kernel<KinModel><<<grid, 32 * wpb, 0, (cudaStream_t)stream>>>(k, B, x0, z);
-  else return MPCB_E_ARG;
+  if (h->cfg.model == MPCB_MODEL_KIN) shift_kernel<4><<<grid, 32 * wpb, 0, (cudaStream_t)stream>>>(k, B, x0, z);
+  else shift_kernel<6><<<grid, 32 * wpb, 0, (cudaStream_t)stream>>>(k, B, x0, z);
   if (!cuda_ok(cudaGetLastError(), "shift_kernel launch")) return MPCB_E_CUDA;
   h->info.launches++;
   return MPCB_OK;

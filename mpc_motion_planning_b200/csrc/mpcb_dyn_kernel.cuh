@@ -1,0 +1,875 @@
+// mpcb200 device code for the dynamic bicycle NLP (PKG/MPC_CBF_optimize_dyn.py:137-250):
+// x = [x, y, phi, vx, vy, r], u = [df, ax], saturating tire forces, both control-rate rows,
+// obstacle row sqrt(ellipse - 1) >= 1 at stages 0..N.  Same interior-point algorithm and
+// warp-per-scenario organisation as the kinematic kernel (mpcb_kernel.cuh); the Riccati sweep
+// is the generic dense one (nx = 6) and the model derivatives come from dyn_model.cuh.
+#pragma once
+#include "mpcb_kernel.cuh"
+#include "dyn_model.cuh"
+
+namespace mpcb {
+
+struct DynLayout {
+  static constexpr int NX = 6, NBX = 3, NR = 2, MO = 1, NJ = DYN_NJ;
+  static constexpr int X = 0;
+  static constexpr int U = X + NX;
+  static constexpr int LAM = U + 2;
+  static constexpr int ZLX = LAM + NX;
+  static constexpr int ZUX = ZLX + NBX;
+  static constexpr int ZLU = ZUX + NBX;
+  static constexpr int ZUU = ZLU + 2;
+  static constexpr int SR = ZUU + 2;
+  static constexpr int VLR = SR + NR;
+  static constexpr int VUR = VLR + NR;
+  static constexpr int LR = VUR + NR;
+  static constexpr int SO = LR + NR;
+  static constexpr int VLO = SO + MO;
+  static constexpr int LO = VLO + MO;
+  static constexpr int OCX = LO + MO;
+  static constexpr int OCY = OCX + MO;
+  static constexpr int CDEF = OCY + MO;
+  static constexpr int LAMP = CDEF;  // alias, see KinLayout
+  static constexpr int JAC = CDEF + NX;
+  static constexpr int HXX = JAC + NJ;     // packed upper triangle 6x6 (21)
+  static constexpr int HUX = HXX + 21;     // d2L/(d delta d x_j), 6 entries (the ax row is zero)
+  static constexpr int GX = HUX + NX;
+  static constexpr int R18 = GX + NX;      // [HUU(2) EE(2) GU(2) TK(2) ...] -> gains [KX(12) KW(4) KK(2)] -> slack steps
+  static constexpr int HUU = R18, EE = R18 + 2, GU = R18 + 4, TK = R18 + 6;
+  static constexpr int KX = R18, KW = R18 + 12, KK = R18 + 16;
+  static constexpr int DSR = R18, LRP = DSR + NR, DSO = LRP + NR, LOP = DSO + MO;
+  static constexpr int DX = R18 + 18;
+  static constexpr int DU = DX + NX;
+  static constexpr int NFIELDS = DU + 2;
+  static constexpr int NF = NFIELDS | 1;
+  __host__ __device__ static constexpr size_t bytes(int N) { return sizeof(double) * (size_t)NF * (size_t)(N + 1); }
+};
+
+__device__ __forceinline__ int pidx6(int i, int j) { return i * 6 - i * (i - 1) / 2 + (j - i); }  // i <= j
+__device__ __forceinline__ int sidx6(int i, int j) { return i <= j ? pidx6(i, j) : pidx6(j, i); }
+
+struct DynSolver {
+  using L = DynLayout;
+  static constexpr int NX = 6, NBX = 3, NR = 2, MO = 1, NJ = DYN_NJ;
+  __device__ static __forceinline__ constexpr int bx(int i) { return i == 0 ? 1 : (i == 1 ? 3 : 4); }  // y, vx, vy
+
+  const KParams &p;
+  int N, lane;
+  double sigma;
+  double x0[NX], xs[NX];
+
+  __device__ DynSolver(const KParams &p_, int lane_) : p(p_), N(p_.N), lane(lane_) {}
+
+  __device__ __forceinline__ double &at(int field, int k) { return g_smem[k * L::NF + field]; }
+  __device__ __forceinline__ bool has_rate(int k) const { return k >= 1 && k <= N - 1; }
+
+  __device__ __forceinline__ double grad_u(int k, int i, double uk, double ukm1, double ukp1) const {
+    double v = 2 * p.R[i] * uk;                    // PKG/MPC_CBF_optimize_dyn.py:218-225
+    if (k > 0) v += 2 * p.DR[i] * (uk - ukm1);
+    else if (p.du0_cost) v += 2 * p.DR[i] * uk;
+    if (k + 1 <= N - 1) v -= 2 * p.DR[i] * (ukp1 - uk);
+    return v;
+  }
+
+  // obstacle row d = sqrt(e), e = (x-ox)^2/sX^2 + (y-oy)^2/sY^2 - 1   (PKG/..._dyn.py:238-243)
+  __device__ __forceinline__ void obs_row(int k, double px, double py, double &d, double &gx, double &gy, double &hxx, double &hxy,
+                                          double &hyy) {
+    double dx = px - at(L::OCX, k), dy = py - at(L::OCY, k);
+    double a = 1.0 / (p.dyn_sx * p.dyn_sx), b = 1.0 / (p.dyn_sy * p.dyn_sy);
+    double e = dx * dx * a + dy * dy * b - 1.0;
+    double q = e > 0.0 ? sqrt(e) : nan("");
+    double ex = 2 * dx * a, ey = 2 * dy * b;
+    d = q;
+    gx = ex / (2 * q);
+    gy = ey / (2 * q);
+    double q3 = 4 * q * q * q;
+    hxx = a / q - ex * ex / q3;
+    hxy = -ex * ey / q3;
+    hyy = b / q - ey * ey / q3;
+  }
+
+  __device__ __forceinline__ void eval_point(double alpha, bool store, double &theta, double &fobj, double &bar, double &lin) {
+    double th = 0, fo = 0, br = 0, ln = 0;
+#pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
+      double xk[NX], uk[2] = {0, 0};
+      double gp = 1.0;
+#pragma unroll
+      for (int i = 0; i < NX; i++) xk[i] = at(L::X + i, k) + alpha * at(L::DX + i, k);
+      if (k == 0) {
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+          double c0 = xk[i] - x0[i];
+          th += fabs(c0);
+          if (store) at(L::CDEF + i, 0) = c0;
+        }
+      }
+      if (k < N) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) uk[i] = at(L::U + i, k) + alpha * at(L::DU + i, k);
+        double f[NX];
+        if (store) {
+          double J[NJ];
+          dyn_fjac(xk, uk, p, f, J);
+#pragma unroll
+          for (int i = 0; i < NJ; i++) at(L::JAC + i, k) = J[i];
+        } else {
+          dyn_f(xk, uk, p, f);
+        }
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+          double xn = at(L::X + i, k + 1) + alpha * at(L::DX + i, k + 1);
+          double d = xn - (xk[i] + p.T * f[i]);
+          th += fabs(d);
+          if (store) at(L::CDEF + i, k + 1) = d;
+          double e = xk[i] - xs[i];
+          fo += p.Q[i] * e * e;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          gp *= (uk[i] - p.u_lo[i]) * (p.u_hi[i] - uk[i]);
+          fo += p.R[i] * uk[i] * uk[i];
+          if (k > 0) {
+            double um = at(L::U + i, k - 1) + alpha * at(L::DU + i, k - 1);
+            double e = uk[i] - um;
+            fo += p.DR[i] * e * e;
+          } else if (p.du0_cost) {
+            fo += p.DR[i] * uk[i] * uk[i];
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < NBX; b++) {
+        int i = bx(b);
+        gp *= (xk[i] - p.x_lo[i]) * (p.x_hi[i] - xk[i]);
+      }
+      if (has_rate(k)) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          double um = at(L::U + r, k - 1) + alpha * at(L::DU + r, k - 1);
+          double s = at(L::SR + r, k) + (alpha != 0.0 ? alpha * at(L::DSR + r, k) : 0.0);
+          th += fabs(uk[r] - um - s);
+          gp *= (s - p.rate_lo[r]) * (p.rate_hi[r] - s);
+        }
+      }
+      {
+        double dx = xk[0] - at(L::OCX, k), dy = xk[1] - at(L::OCY, k);
+        double e = dx * dx / (p.dyn_sx * p.dyn_sx) + dy * dy / (p.dyn_sy * p.dyn_sy) - 1.0;
+        double d = e > 0.0 ? sqrt(e) : nan("");
+        double s = at(L::SO, k) + (alpha != 0.0 ? alpha * at(L::DSO, k) : 0.0);
+        th += fabs(d - s);
+        gp *= s - p.obs_lo;
+        ln += s - p.obs_lo;
+      }
+      br += d_log(gp);
+    }
+    theta = warp_sum(th);
+    fobj = warp_sum(fo);
+    bar = warp_sum(br);
+    lin = warp_sum(ln);
+    __syncwarp();
+  }
+
+  struct Kkt { double dual, prim, cmin, cmax, sum_lam, sum_z; };
+
+  __device__ __forceinline__ void kkt_pieces(Kkt &o) {
+    double dual = 0, prim = 0, cmin = INFINITY, cmax = -INFINITY, sl = 0, sz = 0;
+#define MPCB_COMPL(gap, mult) do { double p_ = (gap) * (mult); cmin = fmin(cmin, p_); cmax = fmax(cmax, p_); sz += (mult); } while (0)
+#pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
+      double xk[NX], rx[NX], l1[NX], A[NX][NX], B[NX][2];
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        xk[i] = at(L::X + i, k);
+        rx[i] = at(L::LAM + i, k);
+        l1[i] = 0;
+        prim = fmax(prim, fabs(at(L::CDEF + i, k)));
+        sl += fabs(rx[i]);
+      }
+      if (k < N) {
+        double J[NJ];
+#pragma unroll
+        for (int i = 0; i < NJ; i++) J[i] = at(L::JAC + i, k);
+        dyn_expand(J, p.T, A, B);
+#pragma unroll
+        for (int i = 0; i < NX; i++) l1[i] = at(L::LAM + i, k + 1);
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+          double r = sigma * 2 * p.Q[i] * (xk[i] - xs[i]);
+#pragma unroll
+          for (int a = 0; a < NX; a++) r -= A[a][i] * l1[a];
+          rx[i] += r;
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < NBX; b++) {
+        int i = bx(b);
+        double zl = at(L::ZLX + b, k), zu = at(L::ZUX + b, k);
+        rx[i] += -zl + zu;
+        MPCB_COMPL(xk[i] - p.x_lo[i], zl);
+        MPCB_COMPL(p.x_hi[i] - xk[i], zu);
+      }
+      {
+        double d, gx, gy, hxx, hxy, hyy;
+        obs_row(k, xk[0], xk[1], d, gx, gy, hxx, hxy, hyy);
+        double lo = at(L::LO, k), vl = at(L::VLO, k), s = at(L::SO, k);
+        rx[0] += lo * gx;
+        rx[1] += lo * gy;
+        dual = fmax(dual, fabs(-lo - vl));
+        prim = fmax(prim, fabs(d - s));
+        MPCB_COMPL(s - p.obs_lo, vl);
+        sl += fabs(lo);
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) dual = fmax(dual, fabs(rx[i]));
+      if (k < N) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          double uk = at(L::U + i, k);
+          double um = k > 0 ? at(L::U + i, k - 1) : 0.0;
+          double up = k + 1 <= N - 1 ? at(L::U + i, k + 1) : 0.0;
+          double zl = at(L::ZLU + i, k), zu = at(L::ZUU + i, k);
+          double r = sigma * grad_u(k, i, uk, um, up) - zl + zu;
+#pragma unroll
+          for (int a = 0; a < NX; a++) r -= B[a][i] * l1[a];
+          if (has_rate(k)) r += at(L::LR + i, k);
+          if (has_rate(k + 1)) r -= at(L::LR + i, k + 1);
+          dual = fmax(dual, fabs(r));
+          MPCB_COMPL(uk - p.u_lo[i], zl);
+          MPCB_COMPL(p.u_hi[i] - uk, zu);
+        }
+      }
+      if (has_rate(k)) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          double s = at(L::SR + r, k), vl = at(L::VLR + r, k), vu = at(L::VUR + r, k), lr = at(L::LR + r, k);
+          dual = fmax(dual, fabs(-lr - vl + vu));
+          prim = fmax(prim, fabs(at(L::U + r, k) - at(L::U + r, k - 1) - s));
+          MPCB_COMPL(s - p.rate_lo[r], vl);
+          MPCB_COMPL(p.rate_hi[r] - s, vu);
+          sl += fabs(lr);
+        }
+      }
+    }
+#undef MPCB_COMPL
+    o.dual = warp_max(dual);
+    o.prim = warp_max(prim);
+    o.cmin = warp_min(cmin);
+    o.cmax = warp_max(cmax);
+    o.sum_lam = warp_sum(sl);
+    o.sum_z = warp_sum(sz);
+  }
+
+  __device__ __forceinline__ double kkt_error(const Kkt &o, double mu, double &co) const {
+    co = p.n_bm > 0 ? fmax(fabs(o.cmax - mu), fabs(o.cmin - mu)) : 0.0;
+    double s_d = fmax(MPCB_S_MAX, (o.sum_lam + o.sum_z) / fmax(1.0, (double)(p.n_eq + p.n_bm))) / MPCB_S_MAX;
+    double s_c = fmax(MPCB_S_MAX, o.sum_z / fmax(1.0, (double)p.n_bm)) / MPCB_S_MAX;
+    return fmax(fmax(o.dual / s_d, o.prim), co / s_c);
+  }
+
+  __device__ __forceinline__ void build_qp(double mu, double dw) {
+#pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
+      double xk[NX], uk[2] = {0, 0}, gx[NX];
+      double Hxx[NX][NX];
+      double hud[NX];  // d2L / (d delta d x_j)
+      double hdd_f = 0;
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        xk[i] = at(L::X + i, k);
+        hud[i] = 0;
+        gx[i] = 0;
+#pragma unroll
+        for (int j = 0; j < NX; j++) Hxx[i][j] = 0;
+        Hxx[i][i] = dw;
+      }
+      if (k < N) {
+        uk[0] = at(L::U + 0, k);
+        uk[1] = at(L::U + 1, k);
+        double l1[NX], H[DYN_NH];
+#pragma unroll
+        for (int i = 0; i < NX; i++) l1[i] = at(L::LAM + i, k + 1);
+        dyn_hess(xk, uk, p, l1, H);
+        // packed upper triangle over (phi, vx, vy, r, df) = state indices 2..5 and the steering input
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < 5; a++)
+#pragma unroll
+          for (int b = a; b < 5; b++) {
+            double v = -p.T * H[q++];
+            if (b < 4) { Hxx[2 + a][2 + b] += v; if (a != b) Hxx[2 + b][2 + a] += v; }
+            else if (a < 4) hud[2 + a] += v;
+            else hdd_f = v;
+          }
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+          Hxx[i][i] += sigma * 2 * p.Q[i];
+          gx[i] = sigma * 2 * p.Q[i] * (xk[i] - xs[i]);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < NBX; b++) {
+        int i = bx(b);
+        double rl = 1.0 / (xk[i] - p.x_lo[i]), rh = 1.0 / (p.x_hi[i] - xk[i]);
+        Hxx[i][i] += at(L::ZLX + b, k) * rl + at(L::ZUX + b, k) * rh;
+        gx[i] += mu * (rh - rl);
+      }
+      {
+        double d, ox, oy, hxx, hxy, hyy;
+        obs_row(k, xk[0], xk[1], d, ox, oy, hxx, hxy, hyy);
+        double s = at(L::SO, k), rg = 1.0 / (s - p.obs_lo);
+        double D = at(L::VLO, k) * rg + dw;
+        double gs = -mu * rg + MPCB_KAPPA_D * mu;
+        double lo = at(L::LO, k);
+        double t = D * (d - s) + gs;
+        Hxx[0][0] += lo * hxx + D * ox * ox;
+        Hxx[0][1] += lo * hxy + D * ox * oy;
+        Hxx[1][0] += lo * hxy + D * ox * oy;
+        Hxx[1][1] += lo * hyy + D * oy * oy;
+        gx[0] += ox * t;
+        gx[1] += oy * t;
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        at(L::GX + i, k) = gx[i];
+        at(L::HUX + i, k) = hud[i];
+#pragma unroll
+        for (int j = i; j < NX; j++) at(L::HXX + pidx6(i, j), k) = Hxx[i][j];
+      }
+      if (k < N) {
+        double E[2] = {0, 0}, t[2] = {0, 0};
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          double g = sigma * 2 * p.R[i] * uk[i];
+          double hd = sigma * 2 * p.R[i] + dw + (i == 0 ? hdd_f : 0.0);
+          if (k == 0 && p.du0_cost) {
+            hd += sigma * 2 * p.DR[i];
+            g += sigma * 2 * p.DR[i] * uk[i];
+          }
+          double rl = 1.0 / (uk[i] - p.u_lo[i]), rh = 1.0 / (p.u_hi[i] - uk[i]);
+          hd += at(L::ZLU + i, k) * rl + at(L::ZUU + i, k) * rh;
+          g += mu * (rh - rl);
+          at(L::HUU + i, k) = hd;
+          at(L::GU + i, k) = g;
+          if (k >= 1) {
+            E[i] = sigma * 2 * p.DR[i];
+            t[i] = sigma * 2 * p.DR[i] * (uk[i] - at(L::U + i, k - 1));
+          }
+        }
+        if (has_rate(k)) {
+#pragma unroll
+          for (int r = 0; r < NR; r++) {
+            double s = at(L::SR + r, k);
+            double rl = 1.0 / (s - p.rate_lo[r]), rh = 1.0 / (p.rate_hi[r] - s);
+            double D = at(L::VLR + r, k) * rl + at(L::VUR + r, k) * rh + dw;
+            double gs = mu * (rh - rl);
+            double res = uk[r] - at(L::U + r, k - 1) - s;
+            E[r] += D;
+            t[r] += D * res + gs;
+          }
+        }
+        at(L::EE + 0, k) = E[0];
+        at(L::EE + 1, k) = E[1];
+        at(L::TK + 0, k) = t[0];
+        at(L::TK + 1, k) = t[1];
+      }
+    }
+    __syncwarp();
+  }
+
+  // dense Riccati on the state augmented with the previous control (see KinSolver)
+  __device__ __forceinline__ bool riccati_backward() {
+    double Pxx[NX][NX], Pxw[NX][2], Pww[2][2], px[NX], pw[2];
+#pragma unroll
+    for (int i = 0; i < NX; i++) {
+#pragma unroll
+      for (int j = 0; j < NX; j++) Pxx[i][j] = at(L::HXX + sidx6(i, j), N);
+      px[i] = at(L::GX + i, N);
+      Pxw[i][0] = Pxw[i][1] = 0;
+    }
+    Pww[0][0] = Pww[0][1] = Pww[1][0] = Pww[1][1] = 0;
+    pw[0] = pw[1] = 0;
+    bool ok = true;
+#pragma unroll 1
+    for (int k = N - 1; k >= 0; k--) {
+      double A[NX][NX], B[NX][2];
+      {
+        double J[NJ];
+#pragma unroll
+        for (int i = 0; i < NJ; i++) J[i] = at(L::JAC + i, k);
+        dyn_expand(J, p.T, A, B);
+      }
+      double E[2] = {at(L::EE + 0, k), at(L::EE + 1, k)};
+      double t[2] = {at(L::TK + 0, k), at(L::TK + 1, k)};
+      double b[NX], Pb[NX];
+#pragma unroll
+      for (int i = 0; i < NX; i++) b[i] = -at(L::CDEF + i, k + 1);
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        double s = px[i];
+#pragma unroll
+        for (int j = 0; j < NX; j++) s += Pxx[i][j] * b[j];
+        Pb[i] = s;
+      }
+      double PA[NX][NX], PB[NX][2];
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+#pragma unroll
+        for (int j = 0; j < NX; j++) {
+          double s = 0;
+#pragma unroll
+          for (int a = 0; a < NX; a++) s += Pxx[i][a] * A[a][j];
+          PA[i][j] = s;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          double s = 0;
+#pragma unroll
+          for (int a = 0; a < NX; a++) s += Pxx[i][a] * B[a][j];
+          PB[i][j] = s;
+        }
+      }
+      double Fxx[NX][NX], Fux[2][NX], Fuu[2][2], fx[NX], fu[2];
+#pragma unroll
+      for (int i = 0; i < NX; i++)
+#pragma unroll
+        for (int j = 0; j < NX; j++) {
+          double s = at(L::HXX + sidx6(i, j), k);
+#pragma unroll
+          for (int a = 0; a < NX; a++) s += A[a][i] * PA[a][j];
+          Fxx[i][j] = s;
+        }
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < NX; j++) {
+          double s = i == 0 ? at(L::HUX + j, k) : 0.0;
+#pragma unroll
+          for (int a = 0; a < NX; a++) s += B[a][i] * PA[a][j] + Pxw[a][i] * A[a][j];
+          Fux[i][j] = s;
+        }
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          double s = Pww[i][j];
+          if (i == j) s += at(L::HUU + i, k) + E[i];
+#pragma unroll
+          for (int a = 0; a < NX; a++) s += B[a][i] * PB[a][j] + B[a][i] * Pxw[a][j] + Pxw[a][i] * B[a][j];
+          Fuu[i][j] = s;
+        }
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        double s = at(L::GX + i, k);
+#pragma unroll
+        for (int a = 0; a < NX; a++) s += A[a][i] * Pb[a];
+        fx[i] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        double s = at(L::GU + i, k) + t[i] + pw[i];
+#pragma unroll
+        for (int a = 0; a < NX; a++) s += B[a][i] * Pb[a] + Pxw[a][i] * b[a];
+        fu[i] = s;
+      }
+      double det = Fuu[0][0] * Fuu[1][1] - Fuu[0][1] * Fuu[1][0];
+      if (!(Fuu[0][0] > 0.0) || !(det > 0.0) || !isfinite(det)) { ok = false; break; }
+      double id = 1.0 / det;
+      double Fi[2][2] = {{Fuu[1][1] * id, -Fuu[0][1] * id}, {-Fuu[1][0] * id, Fuu[0][0] * id}};
+      double Kx[2][NX], Kw[2][2], kk[2];
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+#pragma unroll
+        for (int j = 0; j < NX; j++) Kx[i][j] = -(Fi[i][0] * Fux[0][j] + Fi[i][1] * Fux[1][j]);
+#pragma unroll
+        for (int j = 0; j < 2; j++) Kw[i][j] = Fi[i][j] * E[j];
+        kk[i] = -(Fi[i][0] * fu[0] + Fi[i][1] * fu[1]);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+#pragma unroll
+          for (int j = 0; j < NX; j++) at(L::KX + i * NX + j, k) = Kx[i][j];
+          at(L::KW + i * 2 + 0, k) = Kw[i][0];
+          at(L::KW + i * 2 + 1, k) = Kw[i][1];
+          at(L::KK + i, k) = kk[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+#pragma unroll
+        for (int j = 0; j < NX; j++) Pxx[i][j] = Fxx[i][j] + Fux[0][i] * Kx[0][j] + Fux[1][i] * Kx[1][j];
+#pragma unroll
+        for (int j = 0; j < 2; j++) Pxw[i][j] = Fux[0][i] * Kw[0][j] + Fux[1][i] * Kw[1][j];
+        px[i] = fx[i] + Fux[0][i] * kk[0] + Fux[1][i] * kk[1];
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++)
+#pragma unroll
+        for (int j = i + 1; j < NX; j++) {
+          double mm = 0.5 * (Pxx[i][j] + Pxx[j][i]);
+          Pxx[i][j] = mm;
+          Pxx[j][i] = mm;
+        }
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) Pww[i][j] = (i == j ? E[i] : 0.0) - E[i] * Kw[i][j];
+        pw[i] = -t[i] - E[i] * kk[i];
+      }
+      double mm = 0.5 * (Pww[0][1] + Pww[1][0]);
+      Pww[0][1] = mm;
+      Pww[1][0] = mm;
+    }
+    __syncwarp();
+    return ok;
+  }
+
+  __device__ __forceinline__ void riccati_forward() {
+    double dx[NX], dum[2] = {0, 0};
+#pragma unroll
+    for (int i = 0; i < NX; i++) dx[i] = -at(L::CDEF + i, 0);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NX; i++) at(L::DX + i, 0) = dx[i];
+    }
+#pragma unroll 1
+    for (int k = 0; k < N; k++) {
+      double A[NX][NX], B[NX][2], du[2];
+      {
+        double J[NJ];
+#pragma unroll
+        for (int i = 0; i < NJ; i++) J[i] = at(L::JAC + i, k);
+        dyn_expand(J, p.T, A, B);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        double s = at(L::KK + i, k);
+#pragma unroll
+        for (int j = 0; j < NX; j++) s += at(L::KX + i * NX + j, k) * dx[j];
+        s += at(L::KW + i * 2 + 0, k) * dum[0] + at(L::KW + i * 2 + 1, k) * dum[1];
+        du[i] = s;
+      }
+      double dn[NX];
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        double s = -at(L::CDEF + i, k + 1);
+#pragma unroll
+        for (int j = 0; j < NX; j++) s += A[i][j] * dx[j];
+        s += B[i][0] * du[0] + B[i][1] * du[1];
+        dn[i] = s;
+      }
+      if (lane == 0) {
+        at(L::DU + 0, k) = du[0];
+        at(L::DU + 1, k) = du[1];
+#pragma unroll
+        for (int i = 0; i < NX; i++) at(L::DX + i, k + 1) = dn[i];
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) dx[i] = dn[i];
+      dum[0] = du[0];
+      dum[1] = du[1];
+    }
+    if (lane == 0) { at(L::DU + 0, N) = 0.0; at(L::DU + 1, N) = 0.0; }
+    __syncwarp();
+  }
+
+  __device__ __forceinline__ void adjoint() {
+#pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
+      double dx[NX], ud = k < N ? at(L::DU + 0, k) : 0.0, r[NX];
+#pragma unroll
+      for (int i = 0; i < NX; i++) dx[i] = at(L::DX + i, k);
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        double s = at(L::GX + i, k) + at(L::HUX + i, k) * ud;
+#pragma unroll
+        for (int j = 0; j < NX; j++) s += at(L::HXX + sidx6(i, j), k) * dx[j];
+        r[i] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) at(L::LAMP + i, k) = r[i];
+    }
+    __syncwarp();
+    double lp[NX];
+#pragma unroll
+    for (int i = 0; i < NX; i++) lp[i] = -at(L::LAMP + i, N);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NX; i++) at(L::LAMP + i, N) = lp[i];
+    }
+#pragma unroll 1
+    for (int k = N - 1; k >= 0; k--) {
+      double A[NX][NX], B[NX][2], ln[NX];
+      {
+        double J[NJ];
+#pragma unroll
+        for (int i = 0; i < NJ; i++) J[i] = at(L::JAC + i, k);
+        dyn_expand(J, p.T, A, B);
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        double s = -at(L::LAMP + i, k);
+#pragma unroll
+        for (int a = 0; a < NX; a++) s += A[a][i] * lp[a];
+        ln[i] = s;
+      }
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NX; i++) at(L::LAMP + i, k) = ln[i];
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) lp[i] = ln[i];
+    }
+    __syncwarp();
+  }
+
+  __device__ __forceinline__ void slack_and_steps(double mu, double dw, double tau, double &a_pr, double &a_du, double &gd_out) {
+    double rp = 0.0, rd = 0.0, gd = 0.0;
+#define MPCB_LOWER(rgap, dv, z) do { double dz_ = -(z) + (mu - (z) * (dv)) * (rgap); \
+    rp = fmax(rp, -(dv) * (rgap)); rd = fmax(rd, -dz_ / (z)); } while (0)
+#define MPCB_UPPER(rgap, dv, z) do { double dz_ = -(z) + (mu + (z) * (dv)) * (rgap); \
+    rp = fmax(rp, (dv) * (rgap)); rd = fmax(rd, -dz_ / (z)); } while (0)
+#pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
+      double xk[NX], dx[NX];
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        xk[i] = at(L::X + i, k);
+        dx[i] = at(L::DX + i, k);
+        if (k < N) gd += sigma * 2 * p.Q[i] * (xk[i] - xs[i]) * dx[i];
+      }
+#pragma unroll
+      for (int b = 0; b < NBX; b++) {
+        int i = bx(b);
+        double rl = 1.0 / (xk[i] - p.x_lo[i]), rh = 1.0 / (p.x_hi[i] - xk[i]);
+        gd += mu * (rh - rl) * dx[i];
+        MPCB_LOWER(rl, dx[i], at(L::ZLX + b, k));
+        MPCB_UPPER(rh, dx[i], at(L::ZUX + b, k));
+      }
+      double dsr[NR] = {0, 0}, lrp[NR] = {0, 0};
+      if (k < N) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          double uk = at(L::U + i, k), du = at(L::DU + i, k);
+          double um = k > 0 ? at(L::U + i, k - 1) : 0.0;
+          double up = k + 1 <= N - 1 ? at(L::U + i, k + 1) : 0.0;
+          double rl = 1.0 / (uk - p.u_lo[i]), rh = 1.0 / (p.u_hi[i] - uk);
+          gd += (sigma * grad_u(k, i, uk, um, up) + mu * (rh - rl)) * du;
+          MPCB_LOWER(rl, du, at(L::ZLU + i, k));
+          MPCB_UPPER(rh, du, at(L::ZUU + i, k));
+        }
+      }
+      if (has_rate(k)) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          double s = at(L::SR + r, k);
+          double rl = 1.0 / (s - p.rate_lo[r]), rh = 1.0 / (p.rate_hi[r] - s);
+          double vl = at(L::VLR + r, k), vu = at(L::VUR + r, k);
+          double D = vl * rl + vu * rh + dw;
+          double gs = mu * (rh - rl);
+          double res = at(L::U + r, k) - at(L::U + r, k - 1) - s;
+          double ds = at(L::DU + r, k) - at(L::DU + r, k - 1) + res;
+          dsr[r] = ds;
+          lrp[r] = D * ds + gs;
+          gd += gs * ds;
+          MPCB_LOWER(rl, ds, vl);
+          MPCB_UPPER(rh, ds, vu);
+        }
+      }
+      double dso, lop;
+      {
+        double d, ox, oy, hxx, hxy, hyy;
+        obs_row(k, xk[0], xk[1], d, ox, oy, hxx, hxy, hyy);
+        double s = at(L::SO, k), rg = 1.0 / (s - p.obs_lo), vl = at(L::VLO, k);
+        double D = vl * rg + dw;
+        double gs = -mu * rg + MPCB_KAPPA_D * mu;
+        double ds = ox * dx[0] + oy * dx[1] + (d - s);
+        dso = ds;
+        lop = D * ds + gs;
+        gd += gs * ds;
+        MPCB_LOWER(rg, ds, vl);
+      }
+      if (has_rate(k)) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) { at(L::DSR + r, k) = dsr[r]; at(L::LRP + r, k) = lrp[r]; }
+      }
+      at(L::DSO, k) = dso;
+      at(L::LOP, k) = lop;
+    }
+#undef MPCB_LOWER
+#undef MPCB_UPPER
+    rp = warp_max(rp);
+    rd = warp_max(rd);
+    a_pr = rp > tau ? tau / rp : 1.0;
+    a_du = rd > tau ? tau / rd : 1.0;
+    gd_out = warp_sum(gd);
+    __syncwarp();
+  }
+
+  __device__ __forceinline__ void accept_step(double a, double ad, double mu) {
+#pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        double l = at(L::LAM + i, k);
+        at(L::LAM + i, k) = l + a * (at(L::LAMP + i, k) - l);
+      }
+#pragma unroll
+      for (int b = 0; b < NBX; b++) {
+        int i = bx(b);
+        double x = at(L::X + i, k), dx = at(L::DX + i, k);
+        double rl = 1.0 / (x - p.x_lo[i]), rh = 1.0 / (p.x_hi[i] - x);
+        double zl = at(L::ZLX + b, k), zu = at(L::ZUX + b, k);
+        double dzl = -zl + (mu - zl * dx) * rl, dzu = -zu + (mu + zu * dx) * rh;
+        double xn = x + a * dx;
+        at(L::ZLX + b, k) = clampz(zl + ad * dzl, mu, 1.0 / (xn - p.x_lo[i]));
+        at(L::ZUX + b, k) = clampz(zu + ad * dzu, mu, 1.0 / (p.x_hi[i] - xn));
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) at(L::X + i, k) += a * at(L::DX + i, k);
+      if (k < N) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          double u = at(L::U + i, k), du = at(L::DU + i, k);
+          double rl = 1.0 / (u - p.u_lo[i]), rh = 1.0 / (p.u_hi[i] - u);
+          double zl = at(L::ZLU + i, k), zu = at(L::ZUU + i, k);
+          double dzl = -zl + (mu - zl * du) * rl, dzu = -zu + (mu + zu * du) * rh;
+          double un = u + a * du;
+          at(L::U + i, k) = un;
+          at(L::ZLU + i, k) = clampz(zl + ad * dzl, mu, 1.0 / (un - p.u_lo[i]));
+          at(L::ZUU + i, k) = clampz(zu + ad * dzu, mu, 1.0 / (p.u_hi[i] - un));
+        }
+      }
+      if (has_rate(k)) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          double s = at(L::SR + r, k), ds = at(L::DSR + r, k);
+          double rl = 1.0 / (s - p.rate_lo[r]), rh = 1.0 / (p.rate_hi[r] - s);
+          double vl = at(L::VLR + r, k), vu = at(L::VUR + r, k);
+          double dvl = -vl + (mu - vl * ds) * rl, dvu = -vu + (mu + vu * ds) * rh;
+          double sn = s + a * ds;
+          at(L::SR + r, k) = sn;
+          at(L::VLR + r, k) = clampz(vl + ad * dvl, mu, 1.0 / (sn - p.rate_lo[r]));
+          at(L::VUR + r, k) = clampz(vu + ad * dvu, mu, 1.0 / (p.rate_hi[r] - sn));
+          double l = at(L::LR + r, k);
+          at(L::LR + r, k) = l + a * (at(L::LRP + r, k) - l);
+        }
+      }
+      {
+        double s = at(L::SO, k), ds = at(L::DSO, k);
+        double rg = 1.0 / (s - p.obs_lo), vl = at(L::VLO, k);
+        double dvl = -vl + (mu - vl * ds) * rg;
+        double sn = s + a * ds;
+        at(L::SO, k) = sn;
+        at(L::VLO, k) = clampz(vl + ad * dvl, mu, 1.0 / (sn - p.obs_lo));
+        double l = at(L::LO, k);
+        at(L::LO, k) = l + a * (at(L::LOP, k) - l);
+      }
+    }
+    __syncwarp();
+  }
+
+  __device__ __forceinline__ bool init_iterate(int b) {
+    const int nv = 2 * N + NX * (N + 1);
+    const double *zi = p.z_init ? p.z_init + (size_t)b * nv : nullptr;
+    const double *ob = p.obs + (size_t)b * MO * (N + 1) * 6;
+#pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
+      at(L::OCX, k) = ob[(size_t)k * 6 + 0];
+      at(L::OCY, k) = ob[(size_t)k * 6 + 1];
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        at(L::U + i, k) = k < N ? push_in(zi ? zi[2 * k + i] : 0.0, p.u_lo[i], p.u_hi[i]) : 0.0;
+        at(L::ZLU + i, k) = 1.0;
+        at(L::ZUU + i, k) = 1.0;
+        at(L::DU + i, k) = 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        if (p.init_mode == 0) at(L::X + i, k) = zi ? zi[2 * N + NX * k + i] : 0.0;
+        at(L::LAM + i, k) = 0.0;
+        at(L::DX + i, k) = 0.0;
+      }
+    }
+    __syncwarp();
+    if (p.init_mode == 1) {
+      double x[NX];
+#pragma unroll
+      for (int i = 0; i < NX; i++) x[i] = x0[i];
+#pragma unroll 1
+      for (int k = 0; k <= N; k++) {
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < NX; i++) at(L::X + i, k) = x[i];
+        }
+        if (k < N) {
+          double u[2] = {at(L::U + 0, k), at(L::U + 1, k)}, f[NX];
+          dyn_f(x, u, p, f);
+#pragma unroll
+          for (int i = 0; i < NX; i++) x[i] = x[i] + p.T * f[i];
+        }
+      }
+      __syncwarp();
+    }
+    bool fin = true;
+    double gmax = 0;
+#pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
+#pragma unroll
+      for (int b2 = 0; b2 < NBX; b2++) {
+        int i = bx(b2);
+        at(L::X + i, k) = push_in(at(L::X + i, k), p.x_lo[i], p.x_hi[i]);
+        at(L::ZLX + b2, k) = 1.0;
+        at(L::ZUX + b2, k) = 1.0;
+      }
+      if (has_rate(k)) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          at(L::SR + r, k) = push_in(at(L::U + r, k) - at(L::U + r, k - 1), p.rate_lo[r], p.rate_hi[r]);
+          at(L::VLR + r, k) = 1.0;
+          at(L::VUR + r, k) = 1.0;
+          at(L::LR + r, k) = 0.0;
+        }
+      }
+      {
+        double dx = at(L::X + 0, k) - at(L::OCX, k), dy = at(L::X + 1, k) - at(L::OCY, k);
+        double e = dx * dx / (p.dyn_sx * p.dyn_sx) + dy * dy / (p.dyn_sy * p.dyn_sy) - 1.0;
+        double d = e > 0.0 ? sqrt(e) : nan("");
+        if (!isfinite(d)) fin = false;
+        at(L::SO, k) = push_lo(d, p.obs_lo);
+        at(L::VLO, k) = 1.0;
+        at(L::LO, k) = 0.0;
+      }
+      if (k < N) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          double uk = at(L::U + i, k);
+          double um = k > 0 ? at(L::U + i, k - 1) : 0.0;
+          double up = k + 1 <= N - 1 ? at(L::U + i, k + 1) : 0.0;
+          gmax = fmax(gmax, fabs(grad_u(k, i, uk, um, up)));
+        }
+#pragma unroll
+        for (int i = 0; i < NX; i++) gmax = fmax(gmax, fabs(2 * p.Q[i] * (at(L::X + i, k) - xs[i])));
+      }
+    }
+    gmax = warp_max(gmax);
+    sigma = gmax > MPCB_OBJ_SCALE_MAX_GRAD ? MPCB_OBJ_SCALE_MAX_GRAD / gmax : 1.0;
+    if (sigma < 1e-8) sigma = 1e-8;
+    __syncwarp();
+    return __all_sync(0xffffffffu, fin);
+  }
+
+#include "mpcb_run_loop.inc"
+};
+
+__global__ void __launch_bounds__(32) dyn_solve_kernel(const __grid_constant__ KParams p) {
+  const int lane = threadIdx.x;
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    DynSolver s(p, lane);
+    s.run(b);
+    __syncwarp();
+  }
+}
+
+}  // namespace mpcb

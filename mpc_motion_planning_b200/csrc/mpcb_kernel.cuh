@@ -951,155 +951,7 @@ struct KinSolver {
     return true;
   }
 
-  // ---------------------------------------------------------------- main loop
-  __device__ void run(int b) {
-#pragma unroll
-    for (int i = 0; i < NX; i++) {
-      x0[i] = p.x0[(size_t)b * NX + i];
-      xs[i] = p.xs[(size_t)b * NX + i];
-    }
-    double mu = p.mu_init, tau = fmax(MPCB_TAU_MIN, 1 - mu);
-    const double tol = p.tol;
-    int status = 2, it = 0;
-    double dw_last = 0.0;
-    double theta = 0, fobj = 0, bar = 0, lin = 0, phi = 0;
-    // filter entries distributed over the lanes' registers
-    double ft[MPCB_FILTER_SLOTS], fp[MPCB_FILTER_SLOTS];
-    int nfilt = 0;
-#pragma unroll
-    for (int s = 0; s < MPCB_FILTER_SLOTS; s++) { ft[s] = INFINITY; fp[s] = INFINITY; }
-
-    init_iterate(b);
-    // State machine with ONE call site per phase (every phase is inlined exactly once, which
-    // keeps the kernel small enough for the instruction caches):
-    //   eval_point is run either on the iterate (alpha = 0, storing defects + Jacobians) or on
-    //   a line-search trial point; the branch below decides what the evaluation was for.
-    double theta_min = 0, theta_max = 0;
-    double a = 0.0, a_min = 0, a_dual = 1.0, gd = 0, pgd = 0, pth = 0;
-    bool trial = false, first = true;
-    for (;;) {
-      double th_e, f_e, bar_e, lin_e;
-      eval_point(a, !trial, th_e, f_e, bar_e, lin_e);
-      if (trial) {
-        // ---------------- filter line search: test the trial point z + a dz
-        double ph_t = sigma * f_e - mu * bar_e + MPCB_KAPPA_D * mu * lin_e;
-        bool fin = isfinite(th_e) && isfinite(ph_t);
-        bool blocked = th_e >= theta_max;
-#pragma unroll
-        for (int s = 0; s < MPCB_FILTER_SLOTS; s++) blocked = blocked || (th_e >= ft[s] && ph_t >= fp[s]);
-        blocked = __any_sync(0xffffffffu, blocked);
-        bool accepted = false, armijo = false;
-        if (fin && !blocked) {
-          bool sw = gd < 0 && a * pgd > pth;
-          if (theta <= theta_min && sw) {
-            if (ph_t <= phi + MPCB_ETA_PHI * a * gd + 10 * MPCB_DBL_EPS * fabs(phi)) { accepted = true; armijo = true; }
-          } else if (th_e <= (1 - MPCB_GAMMA_THETA) * theta || ph_t <= phi - MPCB_GAMMA_PHI * theta + 10 * MPCB_DBL_EPS * fabs(phi)) {
-            accepted = true;
-          }
-        }
-        if (!accepted) {
-          a *= 0.5;
-          if (a < a_min) { status = 3; break; }
-          continue;  // next trial
-        }
-        if (!armijo) {
-          int slot = nfilt % (32 * MPCB_FILTER_SLOTS);
-          if ((slot & 31) == lane) {
-#pragma unroll
-            for (int s = 0; s < MPCB_FILTER_SLOTS; s++)
-              if (s == (slot >> 5)) { ft[s] = (1 - MPCB_GAMMA_THETA) * theta; fp[s] = phi - MPCB_GAMMA_PHI * theta; }
-          }
-          nfilt++;
-        }
-        accept_step(a, a_dual, mu);
-        it++;
-        trial = false;
-        a = 0.0;
-        continue;  // evaluate the new iterate (stores defects and Jacobians)
-      }
-      // ---------------- a fresh iterate has been evaluated
-      theta = th_e; fobj = f_e; bar = bar_e; lin = lin_e;
-      if (first) {
-        first = false;
-        if (!isfinite(theta) || !isfinite(bar)) { status = 4; break; }
-        theta_min = 1e-4 * fmax(1.0, theta);
-        theta_max = 1e4 * fmax(1.0, theta);
-      }
-      Kkt kk;
-      kkt_pieces(kk);
-      double co0;
-      double err0 = kkt_error(kk, 0.0, co0);
-      if (err0 <= tol && kk.dual <= MPCB_DUAL_INF_TOL && kk.prim <= MPCB_CONSTR_VIOL_TOL && co0 <= MPCB_COMPL_INF_TOL) { status = 0; break; }
-      if (it >= p.max_iter) { status = 2; break; }
-      {
-        double co;
-        while (kkt_error(kk, mu, co) <= MPCB_KAPPA_EPS * mu && mu > tol / 10) {
-          mu = fmax(tol / 10, fmin(MPCB_KAPPA_MU * mu, d_pow(mu, MPCB_THETA_MU)));
-          tau = fmax(MPCB_TAU_MIN, 1 - mu);
-          nfilt = 0;
-#pragma unroll
-          for (int s = 0; s < MPCB_FILTER_SLOTS; s++) { ft[s] = INFINITY; fp[s] = INFINITY; }
-        }
-      }
-      phi = sigma * fobj - mu * bar + MPCB_KAPPA_D * mu * lin;
-      // ---------------- Newton system with inertia correction (IPOPT's delta_w schedule)
-      double dw = 0.0;
-      bool ok, tried0 = false;
-      for (;;) {
-        build_qp(mu, dw);
-        ok = riccati_backward();
-        if (ok) break;
-        if (!tried0) {
-          tried0 = true;
-          dw = dw_last == 0.0 ? MPCB_DW_FIRST : fmax(MPCB_DW_MIN, MPCB_KW_MINUS * dw_last);
-        } else {
-          dw *= dw_last == 0.0 ? MPCB_KW_PLUS_FIRST : MPCB_KW_PLUS;
-          if (dw > MPCB_DW_MAX) break;
-        }
-      }
-      if (!ok) { status = 3; break; }
-      if (dw > 0.0) dw_last = dw;
-      riccati_forward();
-      adjoint();
-      double a_max;
-      slack_and_steps(mu, dw, tau, a_max, a_dual, gd);
-      pgd = 0.0; pth = 0.0;
-      if (gd < 0) { pgd = d_pow(-gd, MPCB_S_PHI); pth = d_pow(theta, MPCB_S_THETA); }
-      if (gd < 0 && theta <= theta_min) {
-        a_min = MPCB_GAMMA_THETA;
-        if (theta > 0) {
-          a_min = fmin(a_min, MPCB_GAMMA_PHI * theta / (-gd));
-          a_min = fmin(a_min, pth / pgd);
-        }
-      } else if (gd < 0) {
-        a_min = fmin(MPCB_GAMMA_THETA, MPCB_GAMMA_PHI * theta / (-gd));
-      } else {
-        a_min = MPCB_GAMMA_THETA;
-      }
-      a_min = fmax(MPCB_GAMMA_ALPHA * a_min, 1e-14);
-      a = a_max;
-      trial = true;
-      if (a < a_min) { status = 3; break; }
-    }
-    // ---- results
-    const int nv = 2 * N + NX * (N + 1);
-    if (lane == 0) {
-      p.u0[2 * (size_t)b + 0] = at(L::U + 0, 0);
-      p.u0[2 * (size_t)b + 1] = at(L::U + 1, 0);
-      p.cost[b] = status == 4 ? nan("") : fobj;
-      p.status[b] = status;
-      p.iters[b] = it;
-    }
-    if (p.z_out) {
-      double *z = p.z_out + (size_t)b * nv;
-      for (int idx = lane; idx < 2 * N; idx += 32) z[idx] = at(L::U + (idx & 1), idx >> 1);
-      for (int idx = lane; idx < NX * (N + 1); idx += 32) z[2 * N + idx] = at(L::X + (idx % NX), idx / NX);
-    }
-    if (p.lam_out) {
-      double *l = p.lam_out + (size_t)b * NX * (N + 1);
-      for (int idx = lane; idx < NX * (N + 1); idx += 32) l[idx] = at(L::LAM + (idx % NX), idx / NX) / sigma;
-    }
-  }
+#include "mpcb_run_loop.inc"
 };
 
 template <int NR, int MO, int OBS_MODE>

@@ -34,6 +34,7 @@ def compare(kind, gen, B, **kw):
 if __name__ == '__main__':
     print(torch.cuda.get_device_name(0))
     compare('kin_nocbf', scenarios.kin_nocbf, 64)
+    compare('dyn', scenarios.dyn_static, 256)
     compare('kin_cbf', scenarios.kin_cbf_static, 256)
     s, (x0, xs, obs) = compare('kin_cbf_pre', scenarios.kin_cbf_moving, 512)
     # rough timing

@@ -47,7 +47,7 @@ def _check(gpu, ref_u0, ref_cost, ref_st, min_conv, min_same_verdict=0.97):
 
 
 @pytest.mark.parametrize("kind,gen,B", [("kin_nocbf", "kin_nocbf", 128), ("kin_cbf", "kin_cbf_static", 512),
-                                         ("kin_cbf_pre", "kin_cbf_moving", 512)])
+                                         ("kin_cbf_pre", "kin_cbf_moving", 512), ("dyn", "dyn_static", 256)])
 def test_batch_parity_with_oracle(dev, kind, gen, B):
     from mpc_motion_planning_b200 import scenarios
     from mpc_motion_planning_b200.solver import BatchSolver
@@ -58,7 +58,7 @@ def test_batch_parity_with_oracle(dev, kind, gen, B):
     g = _gpu(s, dev, x0, xs, obs)
     cfg = c_oracle.make_cfg(kind)
     u0, cost, st, it, _ = c_oracle.solve_batch(cfg, x0, xs, obs if obs.shape[1] else None, nthreads=os.cpu_count())
-    both, same = _check(g, u0, cost, st, 0.75 if kind != "kin_nocbf" else 1.0)
+    both, same = _check(g, u0, cost, st, 0.75 if kind not in ("kin_nocbf",) else 1.0)
     # same algorithm, same arithmetic up to libm ulps: iteration counts agree on almost every scenario
     assert (g["iters"][both] == it[both]).mean() >= 0.9
     assert s.launch_info()["launches"] >= 1
@@ -71,8 +71,6 @@ def test_golden_fixtures(dev, golden):
     n = 0
     for name, c in golden.items():
         kind = str(c["kind"])
-        if kind == "dyn":
-            continue  # see test_dyn_* (own kernel variant)
         if int(c["status"]) != 0:
             continue
         k = "kin_cbf_pre" if kind == "kin_cbf" else kind
@@ -84,7 +82,37 @@ def test_golden_fixtures(dev, golden):
         assert abs(g["cost"][0] - float(c["f"])) <= COST_RTOL * abs(float(c["f"])), name
         assert np.abs(g["z"][0] - c["z"]).max() <= 1e-5, name
         n += 1
-    assert n >= 12
+    assert n >= 16
+
+
+def test_dyn_default_scenario_and_shift(dev):
+    """PKG/main_cbf_dyn_c_sim.py:44-51 first step; plant step + shift for the 6-state model."""
+    import torch
+
+    from mpc_motion_planning_b200.solver import BatchSolver
+    from oracle import c_oracle
+
+    x0 = np.array([[0, 0, 0, 10, 0, 0.0]])
+    xs = np.array([[600, 3.5, 0, 15, 0, 0.0]])
+    obs = np.zeros((1, 1, 51, 6))
+    obs[0, 0, :, 0], obs[0, 0, :, 1] = 100, -3.5
+    s = BatchSolver("dyn")
+    g = _gpu(s, dev, x0, xs, obs, return_z=True, return_lam=True)
+    z, lam, info = c_oracle.solve(c_oracle.make_cfg("dyn"), x0[0], xs[0], obs[0])
+    assert g["status"][0] == 0 == info.status
+    assert abs(g["cost"][0] - info.f) <= COST_RTOL * info.f and np.abs(g["u0"][0] - z[:2]).max() <= U0_ATOL
+    assert np.abs(g["z"][0] - z).max() <= 1e-5
+    assert np.abs(g["lam"][0] - lam).max() <= 1e-5 * max(1.0, np.abs(lam).max())
+    tx0, tz = torch.from_numpy(x0.copy()).to(dev), torch.from_numpy(g["z"].copy()).to(dev)
+    s.shift(tx0, tz)
+    torch.cuda.synchronize()
+    from mpc_motion_planning_b200 import MPC_CBF_optimize_dyn
+
+    f = MPC_CBF_optimize_dyn.MPC_optimize().f(x0[0], g["z"][0, :2]).full().ravel()
+    assert np.allclose(tx0.cpu().numpy()[0], x0[0] + 0.1 * f, rtol=1e-13, atol=1e-13)
+    U, X = g["z"][0, :100].reshape(50, 2), g["z"][0, 100:].reshape(51, 6)
+    zs = np.concatenate([np.concatenate([U[1:], U[-1:]]).ravel(), np.concatenate([X[1:], X[-1:]]).ravel()])
+    assert np.array_equal(tz.cpu().numpy()[0], zs)
 
 
 def test_reference_default_scenarios_known_answers(dev):
