@@ -230,7 +230,6 @@ def main():
         value = world * B * K / (total_ms * 1e-3)
         ms_kernel = float(np.mean(step_ms))
         # roofline of the dominant (only) kernel: FP64 FMA pipe; HBM traffic reported beside it
-        tf = C = None
         import ctypes as C
         peak = C.c_double(0.0)
         _lib.check(_lib.load().mpcb_fp64_peak_tflops(C.byref(peak)), "fp64 peak")
@@ -245,7 +244,7 @@ def main():
             "config": {"workload": f"kin-CBF static obstacle MPC, N={N_HORIZON}, M=1, B={B}/GPU (BASELINE configs[1])",
                        "start": "zero controls, Euler roll-out states", "mu_init": 100.0, "tol": 1e-8, "max_iter": 100,
                        "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"scenario-sharded x{world}"},
-            "solver": {"converged_frac": float((status == 0).mean()), "mean_iters": float(iters.mean()),
+            "solver": {"converged_frac": float((status <= 1).mean()), "acceptable_frac": float((status == 1).mean()), "mean_iters": float(iters.mean()),
                        "p99_iters": float(np.percentile(iters, 99))},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

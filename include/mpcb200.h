@@ -132,6 +132,12 @@ int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double 
  * in place on DEVICE buffers x0 [B][nx], z [B][nv]. */
 int mpcb_shift_batch(mpcb_handle *h, int B, double *x0, double *z, void *stream);
 
+/* Diagnostics (the reference only has IPOPT's print_level log, PKG/MPC_CBF_optimize_kin.py:252):
+ * when set, every later solve writes one row per interior-point iteration and scenario into the
+ * DEVICE buffer trace[B][rows][8] = (mu, theta, kkt_error, dual_inf, primal_inf, compl_inf,
+ * accepted step size of the previous iteration, last inertia regularisation).  rows = 0 disables. */
+int mpcb_set_trace_buffer(mpcb_handle *h, double *trace, int rows);
+
 /* kernel launch statistics of the last solve on this handle */
 typedef struct mpcb_launch_info {
   int32_t grid, block, smem_bytes, regs_per_thread, blocks_per_sm, num_sms;

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libmpcb200.so")
+SO_PATH = os.environ.get("MPCB200_LIB") or os.path.join(HERE, "libmpcb200.so")  # env override: A/B builds
 
 MODEL_KIN, MODEL_DYN = 0, 1
 OBS_NONE, OBS_ELLIPSE, OBS_SQRT = 0, 1, 2
@@ -49,7 +49,7 @@ class MpcbLaunchInfo(C.Structure):
 
 EXPORTS = [
     "mpcb_version", "mpcb_strerror", "mpcb_last_cuda_error", "mpcb_nx", "mpcb_nv", "mpcb_create", "mpcb_destroy",
-    "mpcb_workspace_bytes", "mpcb_solve_batch", "mpcb_solve_batch_host", "mpcb_shift_batch", "mpcb_get_launch_info", "mpcb_fp64_peak_tflops",
+    "mpcb_workspace_bytes", "mpcb_solve_batch", "mpcb_solve_batch_host", "mpcb_shift_batch", "mpcb_get_launch_info", "mpcb_fp64_peak_tflops", "mpcb_set_trace_buffer",
 ]
 
 _lib = None
@@ -86,6 +86,7 @@ def load():
     lib.mpcb_shift_batch.argtypes = [vp, C.c_int, dp, dp, vp]
     lib.mpcb_get_launch_info.argtypes = [vp, C.POINTER(MpcbLaunchInfo)]
     lib.mpcb_fp64_peak_tflops.argtypes = [C.POINTER(C.c_double)]
+    lib.mpcb_set_trace_buffer.argtypes = [vp, dp, C.c_int]
     _lib = lib
     return lib
 

@@ -279,6 +279,13 @@ int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double 
   return MPCB_OK;
 }
 
+int mpcb_set_trace_buffer(mpcb_handle *h, double *trace, int rows) {
+  if (!h || rows < 0) return MPCB_E_ARG;
+  h->kp.trace = rows > 0 ? trace : nullptr;
+  h->kp.trace_rows = rows;
+  return MPCB_OK;
+}
+
 int mpcb_get_launch_info(mpcb_handle *h, mpcb_launch_info *out) {
   if (!h || !out) return MPCB_E_ARG;
   *out = h->info;

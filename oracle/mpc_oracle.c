@@ -28,6 +28,7 @@ static const double GAMMA_THETA = 1e-5, GAMMA_PHI = 1e-8, DELTA_SW = 1.0, S_THET
 static const double ETA_PHI = 1e-8, GAMMA_ALPHA = 0.05;
 static const double DW_FIRST = 1e-4, DW_MIN = 1e-20, DW_MAX = 1e40, KW_MINUS = 1.0 / 3.0, KW_PLUS = 8.0,
                     KW_PLUS_FIRST = 100.0;
+static const double ACCEPTABLE_TOL = 1e-6; /* line-search-failure exit only, see ipm_dense.py */
 static const double DUAL_INF_TOL = 1.0, CONSTR_VIOL_TOL = 1e-4, COMPL_INF_TOL = 1e-4;
 #define FILTER_CAP 128
 
@@ -887,7 +888,7 @@ static int solve_ws(ws_t *w, const double *z_init, double *z_out, double *lam_eq
       a *= 0.5;
       n_bt++;
     }
-    if (!accepted) { status = ORC_INFEASIBLE; break; }
+    if (!accepted) { status = err0 <= ACCEPTABLE_TOL ? ORC_ACCEPTABLE : ORC_INFEASIBLE; break; }
     if (!armijo) filter_add(w, (1 - GAMMA_THETA) * theta, phi - GAMMA_PHI * theta);
     accept_step(w, a, a_dual, mu);
     eval_primal(w, &w->it, mu, &theta, &phi, &fobj, 1);

@@ -32,11 +32,11 @@ def _gpu(solver, dev, x0, xs, obs, z_init=None, **kw):
 
 def _check(gpu, ref_u0, ref_cost, ref_st, min_conv, min_same_verdict=0.97):
     st = gpu["status"]
-    both = (st == 0) & (ref_st == 0)
+    both = (st <= 1) & (ref_st <= 1)  # 0 converged, 1 acceptable level: both count as success (IPOPT convention)
     assert both.mean() >= min_conv, both.mean()
     # verdict: converged vs not.  Scenarios that sit on the line-search failure boundary are chaotic
     # (an ulp changes the path); they are counted, reported and bounded, not hidden.
-    same = (st == 0) == (ref_st == 0)
+    same = (st <= 1) == (ref_st <= 1)
     assert same.mean() >= min_same_verdict, same.mean()
     du = np.abs(gpu["u0"] - ref_u0).max(axis=1)
     dc = np.abs(gpu["cost"] - ref_cost) / np.abs(ref_cost)
@@ -142,7 +142,7 @@ def test_size_independent_properties_at_full_batch(dev):
     x0, xs, obs = scenarios.kin_cbf_static(B)
     s = BatchSolver("kin_cbf")
     g = _gpu(s, dev, x0, xs, obs, return_z=True)
-    conv = g["status"] == 0
+    conv = g["status"] <= 1
     assert conv.mean() >= 0.75
     z = g["z"][conv]
     U = z[:, : 2 * N].reshape(-1, N, 2)
@@ -170,7 +170,7 @@ def test_size_independent_properties_at_full_batch(dev):
     assert np.abs(cost - g["cost"][conv]).max() <= 1e-9 * cost.max()
     # idempotence: restarting from the solution stays there
     g2 = _gpu(s, dev, x0[conv][:512], xs[conv][:512], obs[conv][:512], z_init=z[:512])
-    ok = g2["status"] == 0
+    ok = g2["status"] <= 1
     assert ok.mean() >= 0.99
     assert (np.abs(g2["cost"] - g["cost"][conv][:512]) <= COST_RTOL * np.abs(g2["cost"]))[ok].mean() >= 0.99
 
@@ -265,11 +265,11 @@ def test_as_given_start_and_warm_start_shift(dev):
     assert np.allclose(tx0.cpu().numpy(), x1, rtol=1e-14, atol=1e-14)
     assert np.array_equal(tz.cpu().numpy(), zs)
     # warm-started second step agrees with the oracle and needs fewer iterations than the cold one
-    conv = g["status"] == 0
+    conv = g["status"] <= 1
     g2 = _gpu(s, dev, x1[conv], xs[conv], obs[conv], z_init=zs[conv])
     u2, c2, st2, it2, _ = c_oracle.solve_batch(cfg, x1[conv], xs[conv], obs[conv], z_init=zs[conv], nthreads=os.cpu_count())
     _check(g2, u2, c2, st2, 0.9, 0.95)
-    assert g2["iters"][g2["status"] == 0].mean() < g["iters"][conv].mean()
+    assert g2["iters"][g2["status"] <= 1].mean() < g["iters"][conv].mean()
 
 
 def test_reference_surface_call_protocol(dev, tmp_path, monkeypatch):
