@@ -32,6 +32,9 @@ N_HORIZON = 50
 # algorithmic work per interior-point iteration of one kin-CBF scenario
 FLOP_PER_ITER = 72.4e3
 BYTES_PER_SOLVE_MIN = 912  # x0, xs, per-step obstacle (x,y)+(l,w) in; u0, cost, status, iters out
+# dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of kin_solve_kernel<1,1,1>
+# at B = 2960 (profiles/r01_final_solve_kernel_kin_cbf_B2960.txt): 7,654,656 B -> per scenario
+DRAM_BYTES_PER_SOLVE_NCU = 7654656 / 2960
 
 
 def _peaks():
@@ -250,7 +253,9 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": float(peak.value), "unit": "TFLOP/s",
-                         "frac": ach_tf / float(peak.value) if peak.value > 0 else None, "traffic": None,
+                         "frac": ach_tf / float(peak.value) if peak.value > 0 else None,
+                         "traffic": int(B * DRAM_BYTES_PER_SOLVE_NCU),
+                         "traffic_source": "ncu --set full capture at B=2960 scaled to this batch (profiles/r01_final_*)",
                          "peak_source": "DFMA micro-benchmark measured in this run (mpcb_fp64_peak_tflops)",
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "peak_source": hbm_src + " MEASURED_PEAKS.json hbm_gbs"}},
