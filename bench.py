@@ -229,6 +229,27 @@ def main():
     d2h = int(hu0.numel() + hcost.numel()) * 8 + int(hst.numel() + hit.numel()) * 4
     assert np.array_equal(hst.numpy(), status), "host-path and device-path verdicts differ"
 
+    # ---- single-solve latency: BASELINE configs[0] (main_kin_c_sim.py: no-CBF kin MPC, closed loop, B = 1)
+    latency = None
+    if rank == 0:
+        from mpc_motion_planning_b200.closed_loop import run_closed_loop  # noqa: F401
+        s1 = BatchSolver("kin_nocbf", N=N_HORIZON)
+        lx = torch.tensor([[0.0, 0.0, 0.0, 20.0]], dtype=torch.float64, device=dev)   # PKG/main_kin_c_sim.py:42
+        lxs = torch.tensor([[500.0, 3.5, 0.0, 30.0]], dtype=torch.float64, device=dev)  # :46
+        lz = torch.zeros((1, s1.nv), dtype=torch.float64, device=dev)
+        lat = []
+        for i in range(100):  # sim_time / T_S = 100 MPC steps (:55,70)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            o1 = s1.solve(lx, lxs, None, lz, return_z=True)
+            torch.cuda.synchronize()
+            lat.append((time.perf_counter() - t1) * 1e3)
+            lz = o1["z"]
+            s1.shift(lx, lz)
+        lat = np.array(lat[1:])
+        latency = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
+                   "workload": "kin no-CBF closed loop (main_kin_c_sim.py), B=1, 99 warm-started solves, host wall clock incl. launch+sync"}
+
     if rank == 0:
         value = world * B * K / (total_ms * 1e-3)
         ms_kernel = float(np.mean(step_ms))
@@ -260,6 +281,7 @@ def main():
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "peak_source": hbm_src + " MEASURED_PEAKS.json hbm_gbs"}},
             "launch": solver.launch_info(),
+            "latency": latency,
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1

@@ -1,0 +1,62 @@
+"""Batched closed-loop simulation on the device — the `while` loops of the reference mains
+(PKG/main_cbf_kin_c_sim.py:87-123, main_cbf_kin_c_sim_pre.py:86-126, main_kin_c_sim.py:70-97,
+main_cbf_dyn_c_sim.py:75-108) for B vehicles at once: solve, apply the first control with the
+plant Euler step, shift the warm start, advance the obstacle one step.  Nothing leaves the GPU
+between steps except what the caller asks to record.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def predict_obstacles(obs_state: torch.Tensor, dt: float, N: int) -> torch.Tensor:
+    """obs_state (B,M,6) rows [x,y,theta,v,l,w] -> (B,M,N+1,6), the constant-velocity roll-out of
+    PKG/Obs_prediction.py:3-40 accumulated step by step (same operation order)."""
+    B, M, _ = obs_state.shape
+    out = obs_state[:, :, None, :].repeat(1, 1, N + 1, 1)
+    dx = obs_state[..., 3] * torch.cos(obs_state[..., 2]) * dt
+    dy = obs_state[..., 3] * torch.sin(obs_state[..., 2]) * dt
+    x = obs_state[..., 0].clone()
+    y = obs_state[..., 1].clone()
+    for k in range(N + 1):
+        out[:, :, k, 0] = x
+        out[:, :, k, 1] = y
+        x = x + dx
+        y = y + dy
+    return out.contiguous()
+
+
+def run_closed_loop(solver, x0: torch.Tensor, xs: torch.Tensor, obs_state: torch.Tensor | None, steps: int,
+                    moving: bool = True, disturbance_step: int | None = None):
+    """Returns dict(x (steps+1,B,nx), u (steps,B,2), status (steps,B), iters (steps,B)).
+
+    obs_state: (B,M,6) obstacle states (kin kinds; `moving=False` keeps them fixed as in
+    main_cbf_kin_c_sim.py), (B,1,6) with only columns 0,1 used for dyn, or None for the no-CBF NLP.
+    disturbance_step: zero the applied control at that step (PKG/main_cbf_dyn_c_sim.py:98-100)."""
+    dev = x0.device
+    B = x0.shape[0]
+    N, nv = solver.N, solver.nv
+    dt = float(solver.cfg.T)
+    x = x0.clone().to(torch.float64).contiguous()
+    z = torch.zeros((B, nv), dtype=torch.float64, device=dev)  # zero first guess (PKG/main_cbf_kin_c_sim.py:47-50)
+    xs = xs.to(torch.float64).contiguous()
+    obs = None if obs_state is None else obs_state.clone().to(torch.float64)
+    xh = [x.clone()]
+    uh, sth, ith = [], [], []
+    for step in range(steps):
+        traj = None
+        if obs is not None:
+            traj = predict_obstacles(obs, dt, N) if moving else obs[:, :, None, :].repeat(1, 1, N + 1, 1).contiguous()
+        out = solver.solve(x, xs, traj, z, return_z=True)
+        z = out["z"]
+        if disturbance_step is not None and step == disturbance_step:
+            z[:, 0:2] = 0.0
+        uh.append(z[:, 0:2].clone())
+        sth.append(out["status"])
+        ith.append(out["iters"])
+        solver.shift(x, z)  # plant Euler step with U_0 and warm-start shift, in place
+        if obs is not None and moving:
+            obs[..., 0] = obs[..., 0] + obs[..., 3] * torch.cos(obs[..., 2]) * dt  # main_cbf_kin_c_sim_pre.py:106
+            obs[..., 1] = obs[..., 1] + obs[..., 3] * torch.sin(obs[..., 2]) * dt
+        xh.append(x.clone())
+    return {"x": torch.stack(xh), "u": torch.stack(uh), "status": torch.stack(sth), "iters": torch.stack(ith)}

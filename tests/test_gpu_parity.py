@@ -318,3 +318,50 @@ def test_reference_surface_call_protocol(dev, tmp_path, monkeypatch):
         u0 = np.concatenate((u0[1:], u0[-1:]))
         next_states = np.concatenate((x_m[1:], x_m[-1:]), axis=0)
     assert abs(costs[0] - 1.0947508480e8) <= 1e-6 * 1.1e8
+
+
+def test_batched_closed_loop_matches_oracle_loop(dev):
+    """PKG/main_cbf_kin_c_sim_pre.py:86-126 for a batch: 15 MPC steps with a moving obstacle,
+    warm starts and obstacle advance on the device, against the same loop around the CPU oracle."""
+    import torch
+
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.closed_loop import predict_obstacles, run_closed_loop
+    from mpc_motion_planning_b200.Obs_prediction import obs_prediction_batch
+    from mpc_motion_planning_b200.solver import BatchSolver
+    from oracle import c_oracle
+
+    B, steps, N = 24, 15, 50
+    x0, xs, obs = scenarios.kin_cbf_moving(B, seed=5)
+    x0[0] = [0, 3, 0, 15]
+    ob0 = obs[:, :, 0, :].copy()
+    ob0[0, 0] = [50, 3.5, 0, 10, 4.8, 1.8]  # the reference's own scenario (main_cbf_kin_c_sim_pre.py:45-56)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    assert np.array_equal(predict_obstacles(t(ob0), 0.1, N).cpu().numpy(), obs_prediction_batch(ob0, 0.1, N))
+    s = BatchSolver("kin_cbf_pre")
+    out = run_closed_loop(s, t(x0), t(xs), t(ob0), steps)
+    torch.cuda.synchronize()
+    xg, ug, stg = out["x"].cpu().numpy(), out["u"].cpu().numpy(), out["status"].cpu().numpy()
+    # oracle loop
+    cfg = c_oracle.make_cfg("kin_cbf_pre")
+    x, ob, z = x0.copy(), ob0.copy(), np.zeros((B, 304))
+    alive = np.ones(B, bool)
+    n_cmp = 0
+    for k in range(steps):
+        traj = obs_prediction_batch(ob, 0.1, N)
+        u0, cost, st, it, zz = c_oracle.solve_batch(cfg, x, xs, traj, z_init=z, want_z=True, nthreads=os.cpu_count())
+        alive &= (st <= 1) & (stg[k] <= 1)  # a failed solve makes the two loops diverge legitimately
+        assert np.abs(ug[k][alive] - u0[alive]).max() <= U0_ATOL
+        assert np.abs(xg[k][alive] - x[alive]).max() <= 1e-5
+        n_cmp += alive.sum()
+        U, X = zz[:, :100].reshape(B, 50, 2), zz[:, 100:].reshape(B, 51, 4)
+        x = x + 0.1 * np.stack([x[:, 3] * np.cos(x[:, 2]), x[:, 3] * np.sin(x[:, 2]), x[:, 3] * np.tan(U[:, 0, 0]) / 2.6, U[:, 0, 1]], axis=1)
+        z = np.concatenate([np.concatenate([U[:, 1:], U[:, -1:]], axis=1).reshape(B, -1),
+                            np.concatenate([X[:, 1:], X[:, -1:]], axis=1).reshape(B, -1)], axis=1)
+        ob = ob.copy()
+        ob[..., 0] = ob[..., 0] + ob[..., 3] * np.cos(ob[..., 2]) * 0.1
+        ob[..., 1] = ob[..., 1] + ob[..., 3] * np.sin(ob[..., 2]) * 0.1
+    assert alive[0] and alive.mean() >= 0.6 and n_cmp >= 0.6 * B * steps
+    # warm starts: later steps need far fewer iterations than the cold first one
+    itg = out["iters"].cpu().numpy()
+    assert itg[5:, alive].mean() < 0.7 * itg[0, alive].mean()
