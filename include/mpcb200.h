@@ -100,8 +100,8 @@ int mpcb_nv(const mpcb_cfg *cfg);
 int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out);
 void mpcb_destroy(mpcb_handle *h);
 
-/* device scratch the library needs for a batch of B (0 in this version: the whole
- * iterate lives in shared memory) */
+/* upper bound of the device scratch mpcb_create allocates for this configuration (independent of
+ * B: a slab per RESIDENT warp of the persistent kernel; 0 for the dyn kernel) */
 int mpcb_workspace_bytes(const mpcb_cfg *cfg, int B, size_t *bytes);
 
 /* Replaces optimize_problem + solver(...) for B independent scenarios.  DEVICE pointers,

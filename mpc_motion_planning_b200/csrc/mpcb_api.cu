@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 
 using namespace mpcb;
@@ -36,6 +37,7 @@ struct Variant {
   kernel_ptr kernel;
   size_t (*smem_bytes)(int N);
   int nx, nbx;
+  size_t slab_doubles;  // per resident block; 0 = one block per scenario, no slab
 };
 
 template <int NR, int MO, int OBS>
@@ -46,6 +48,7 @@ Variant make_kin_variant() {
   v.smem_bytes = [](int N) { return KinLayout<NR, MO>::bytes(N); };
   v.nx = 4;
   v.nbx = 2;
+  v.slab_doubles = KinLayout<NR, MO>::slab_doubles();
   return v;
 }
 
@@ -61,6 +64,7 @@ Variant make_dyn_variant() {
   v.smem_bytes = [](int N) { return DynLayout::bytes(N); };
   v.nx = 6;
   v.nbx = 3;
+  v.slab_doubles = 0;
   return v;
 }
 
@@ -92,6 +96,9 @@ struct mpcb_handle {
   size_t smem;
   int device;
   mpcb_launch_info info;
+  int persistent_grid;  // resident blocks of the persistent kernel (0: grid = B)
+  double *d_slab;
+  int *d_counter;
   // device buffers for the host-pointer entry point
   cudaStream_t stream;
   int cap_B;
@@ -121,7 +128,16 @@ int mpcb_nv(const mpcb_cfg *cfg) { return cfg ? 2 * cfg->N + mpcb_nx(cfg) * (cfg
 
 int mpcb_workspace_bytes(const mpcb_cfg *cfg, int B, size_t *bytes) {
   if (!cfg || !bytes || B < 0) return MPCB_E_ARG;
-  *bytes = 0;  // the whole iterate lives in shared memory
+  // Independent of B: the kinematic kernels are persistent and keep the primal-dual iterate of each
+  // RESIDENT warp in a global-memory slab (allocated by mpcb_create, sized by the occupancy of the
+  // device: at most 32 warps x #SMs).  The dyn kernel keeps everything in shared memory.
+  Variant v;
+  if (!select_variant(*cfg, v)) return MPCB_E_ARG;
+  int ndev = 0, dev = 0, sms = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); *bytes = 0; return MPCB_OK; }
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  *bytes = v.slab_doubles * sizeof(double) * (size_t)sms * 32;
   return MPCB_OK;
 }
 
@@ -181,6 +197,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   k.tol = c.tol; k.mu_init = c.mu_init;
 
   h->smem = var.smem_bytes(c.N);
+  if (const char *pad = getenv("MPCB_SMEM_PAD")) h->smem += (size_t)atoi(pad);  // tuning knob: lowers occupancy
   cudaDeviceProp prop;
   if (!cuda_ok(cudaGetDeviceProperties(&prop, h->device), "cudaGetDeviceProperties")) { delete h; return MPCB_E_CUDA; }
   if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return MPCB_E_ARG; }
@@ -197,6 +214,17 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   h->info.regs_per_thread = fa.numRegs;
   h->info.blocks_per_sm = bps;
   h->info.num_sms = prop.multiProcessorCount;
+  if (var.slab_doubles) {
+    if (bps < 1) { delete h; return MPCB_E_ARG; }
+    h->persistent_grid = bps * prop.multiProcessorCount;
+    size_t bytes = (size_t)h->persistent_grid * var.slab_doubles * sizeof(double);
+    if (!cuda_ok(cudaMalloc(&h->d_slab, bytes), "cudaMalloc slab") || !cuda_ok(cudaMalloc(&h->d_counter, sizeof(int)), "cudaMalloc counter")) {
+      cudaFree(h->d_slab);
+      delete h;
+      return MPCB_E_NOMEM;
+    }
+    cudaMemset(h->d_slab, 0, bytes);
+  }
   if (!cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete h; return MPCB_E_CUDA; }
   *out = h;
   return MPCB_OK;
@@ -213,6 +241,8 @@ static void free_bufs(mpcb_handle *h) {
 void mpcb_destroy(mpcb_handle *h) {
   if (!h) return;
   free_bufs(h);
+  cudaFree(h->d_slab);
+  cudaFree(h->d_counter);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -229,6 +259,12 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
   k.x0 = x0; k.xs = xs; k.obs = obs; k.z_init = z_init;
   k.u0 = u0; k.cost = cost; k.status = status; k.iters = iters; k.z_out = z_out; k.lam_out = lam_out;
   int grid = B;
+  if (h->persistent_grid) {
+    grid = B < h->persistent_grid ? B : h->persistent_grid;
+    k.slab = h->d_slab;
+    k.counter = h->d_counter;
+    if (!cuda_ok(cudaMemsetAsync(h->d_counter, 0, sizeof(int), (cudaStream_t)stream), "queue reset")) return MPCB_E_CUDA;
+  }
   cudaError_t e = h->var.launch(k, grid, h->smem, (cudaStream_t)stream);
   if (!cuda_ok(e, "solve_kernel launch")) return MPCB_E_CUDA;
   h->info.grid = grid;

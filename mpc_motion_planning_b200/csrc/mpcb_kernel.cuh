@@ -76,6 +76,8 @@ struct KParams {
   const double *x0, *xs, *obs, *z_init;
   double *u0, *cost, *z_out, *lam_out;
   int32_t *status, *iters;
+  double *slab;    // per-resident-block scratch in global memory (kinematic kernels)
+  int *counter;    // work queue head (persistent kernels)
   double *trace;   // optional [B][trace_rows][8] per-iteration log (mu, theta, err, dual, prim, compl, alpha, dw)
   int trace_rows;
 };
@@ -140,8 +142,33 @@ struct KinModel {
 template <int NR, int MO>
 struct KinLayout {
   static constexpr int NX = 4, NBX = 2;
-  // iterate
-  static constexpr int X = 0;
+  // ---- shared memory: the working set of the serial sweeps (one record of NF doubles per stage)
+  static constexpr int CDEF = 0;         // c_0 = X0 - x0, c_k = defect into stage k
+  static constexpr int LAMP = CDEF;      // alias: new dynamics multipliers (written after the forward sweep)
+  static constexpr int JAC = CDEF + NX;  // a02 a03 a12 a13 a23 b2  (A = I + T df/dx, B = T df/du)
+  static constexpr int HXX = JAC + 6;    // h00 h01 h11 h22 h23 h33
+  static constexpr int HUX = HXX + 6;    // d2L/(d delta d v)
+  static constexpr int GX = HUX + 1;
+  // 14-slot region: [HUU(2) EE(2) GU(2) TK(2) -(6)] before the backward sweep of a stage,
+  // the Riccati gains [KX(8) KW(4) KK(2)] after it, the slack steps after the forward sweep
+  static constexpr int R14 = GX + NX;
+  static constexpr int HUU = R14, EE = R14 + 2, GU = R14 + 4, TK = R14 + 6;
+  static constexpr int KX = R14, KW = R14 + 8, KK = R14 + 12;
+  static constexpr int DSR = R14, LRP = DSR + NR, DSO = LRP + NR, LOP = DSO + MO;
+  static_assert(2 * NR + 2 * MO <= 14, "slack steps must fit the gain region");
+  static constexpr int DX = R14 + 14;
+  static constexpr int DU = DX + NX;
+  static constexpr int NSH = DU + 2;
+  // stage-major storage: element (field, k) lives at k*NF + field.  NF is odd so that the
+  // stage-parallel phases (lane = stage, stride NF doubles) touch 16 distinct even banks per
+  // half-warp: conflict free; the serial sweeps read broadcasts.
+  static constexpr int NF = NSH | 1;
+  // ---- global memory (L2-resident slab of the resident block): everything only the
+  // stage-parallel phases touch - the primal-dual iterate and the staged obstacle trajectory.
+  // Rows of SG doubles per field, stage index fastest: lane = stage accesses are coalesced.
+  static constexpr int G0 = 64;
+  static_assert(NF <= G0, "field id spaces overlap");
+  static constexpr int X = G0;
   static constexpr int U = X + NX;
   static constexpr int LAM = U + 2;
   static constexpr int ZLX = LAM + NX;
@@ -155,35 +182,14 @@ struct KinLayout {
   static constexpr int SO = LR + NR;
   static constexpr int VLO = SO + MO;
   static constexpr int LO = VLO + MO;
-  // obstacle trajectory: centre and 1/semi-axis^2 per step
-  static constexpr int OCX = LO + MO;
+  static constexpr int OCX = LO + MO;   // obstacle trajectory: centre and 1/semi-axis^2 per step
   static constexpr int OCY = OCX + MO;
   static constexpr int ISX = OCY + MO;
   static constexpr int ISY = ISX + MO;
-  // evaluation at the current iterate
-  static constexpr int CDEF = ISY + MO;  // c_0 = X0 - x0, c_k = defect into stage k
-  static constexpr int LAMP = CDEF;      // alias: new dynamics multipliers (written after the forward sweep)
-  static constexpr int JAC = CDEF + NX;  // a02 a03 a12 a13 a23 b2  (A = I + T df/dx, B = T df/du)
-  // condensed QP that survives the backward sweep (needed again by the adjoint)
-  static constexpr int HXX = JAC + 6;    // h00 h01 h11 h22 h23 h33
-  static constexpr int HUX = HXX + 6;    // d2L/(d delta d v)
-  static constexpr int GX = HUX + 1;
-  // 14-slot region: [HUU(2) EE(2) GU(2) TK(2) -(6)] before the backward sweep of a stage,
-  // the Riccati gains [KX(8) KW(4) KK(2)] after it, the slack steps after the forward sweep
-  static constexpr int R14 = GX + NX;
-  static constexpr int HUU = R14, EE = R14 + 2, GU = R14 + 4, TK = R14 + 6;
-  static constexpr int KX = R14, KW = R14 + 8, KK = R14 + 12;
-  static constexpr int DSR = R14, LRP = DSR + NR, DSO = LRP + NR, LOP = DSO + MO;
-  static_assert(2 * NR + 2 * MO <= 14, "slack steps must fit the gain region");
-  // direction
-  static constexpr int DX = R14 + 14;
-  static constexpr int DU = DX + NX;
-  static constexpr int NFIELDS = DU + 2;
-  // stage-major storage: element (field, k) lives at k*NF + field.  NF is odd so that the
-  // stage-parallel phases (lane = stage, stride NF doubles) touch 16 distinct even banks per
-  // half-warp: conflict free; the serial sweeps read broadcasts.
-  static constexpr int NF = NFIELDS | 1;
+  static constexpr int NG = ISY + MO - G0;
+  static constexpr int SG = 132;        // row stride (>= MPCB_NMAX + 1)
   __host__ __device__ static constexpr size_t bytes(int N) { return sizeof(double) * (size_t)NF * (size_t)(N + 1); }
+  __host__ __device__ static constexpr size_t slab_doubles() { return (size_t)NG * SG; }
 };
 
 __device__ __forceinline__ double push_in(double v, double lo, double hi) {
@@ -209,14 +215,17 @@ struct KinSolver {
   static constexpr int NX = 4, NBX = 2;
 
   const KParams &p;
-  double *sm;
-  int S, N, lane;
+  double *gs;  // this block's slab in global memory
+  int N, lane;
   double sigma;
   double x0[NX], xs[NX];
 
-  __device__ KinSolver(const KParams &p_, double *sm_, int lane_) : p(p_), sm(sm_), S(p_.N + 1), N(p_.N), lane(lane_) {}
+  __device__ KinSolver(const KParams &p_, double *gs_, int lane_) : p(p_), gs(gs_), N(p_.N), lane(lane_) {}
 
-  __device__ __forceinline__ double &at(int field, int k) { return g_smem[k * L::NF + field]; }
+  // field ids are compile-time constants at (almost) every use, so the space test folds away
+  __device__ __forceinline__ double &at(int field, int k) {
+    return field >= L::G0 ? gs[(field - L::G0) * L::SG + k] : g_smem[k * L::NF + field];
+  }
   __device__ __forceinline__ bool has_rate(int k) const { return NR > 0 && k >= 1 && k <= N - 1; }
   __device__ __forceinline__ bool has_obs(int k) const { return OBS_MODE == 1 && k <= N - 1; }
 
@@ -973,11 +982,21 @@ struct KinSolver {
 #include "mpcb_run_loop.inc"
 };
 
+// Persistent kernel: every resident warp pulls scenarios from a global queue until it is empty
+// (iteration counts differ by 5x between scenarios: dynamic assignment keeps the SMs busy).
+#ifndef MPCB_KIN_MIN_BLOCKS
+#define MPCB_KIN_MIN_BLOCKS 10
+#endif
 template <int NR, int MO, int OBS_MODE>
-__global__ void __launch_bounds__(32) kin_solve_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(32, MPCB_KIN_MIN_BLOCKS) kin_solve_kernel(const __grid_constant__ KParams p) {
   const int lane = threadIdx.x;
-  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-    KinSolver<NR, MO, OBS_MODE> s(p, g_smem, lane);
+  double *gs = p.slab + (size_t)blockIdx.x * KinLayout<NR, MO>::slab_doubles();
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(p.counter, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= p.B) break;
+    KinSolver<NR, MO, OBS_MODE> s(p, gs, lane);
     s.run(b);
     __syncwarp();
   }
