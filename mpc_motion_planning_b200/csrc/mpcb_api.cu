@@ -28,7 +28,7 @@ typedef const void *kernel_ptr;
 
 template <int NR, int MO, int OBS>
 cudaError_t launch_kin(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-  kin_solve_kernel<NR, MO, OBS><<<grid, 32, smem, st>>>(p);
+  kin_solve_kernel<NR, MO, OBS><<<grid, 32 * MPCB_KIN_WARPS, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -37,7 +37,8 @@ struct Variant {
   kernel_ptr kernel;
   size_t (*smem_bytes)(int N);
   int nx, nbx;
-  size_t slab_doubles;  // per resident block; 0 = one block per scenario, no slab
+  size_t slab_doubles;  // per resident warp; 0 = one block per scenario, no slab
+  int warps;            // warps (= scenarios in flight) per block
 };
 
 template <int NR, int MO, int OBS>
@@ -49,6 +50,7 @@ Variant make_kin_variant() {
   v.nx = 4;
   v.nbx = 2;
   v.slab_doubles = KinLayout<NR, MO>::slab_doubles();
+  v.warps = MPCB_KIN_WARPS;
   return v;
 }
 
@@ -65,6 +67,7 @@ Variant make_dyn_variant() {
   v.nx = 6;
   v.nbx = 3;
   v.slab_doubles = 0;
+  v.warps = 1;
   return v;
 }
 
@@ -196,7 +199,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   k.aopt_f = c.aopt_f; k.aopt_r = c.aopt_r; k.Fymax_f = c.Fymax_f; k.Fymax_r = c.Fymax_r;
   k.tol = c.tol; k.mu_init = c.mu_init;
 
-  h->smem = var.smem_bytes(c.N);
+  h->smem = var.smem_bytes(c.N) * var.warps;
   if (const char *pad = getenv("MPCB_SMEM_PAD")) h->smem += (size_t)atoi(pad);  // tuning knob: lowers occupancy
   cudaDeviceProp prop;
   if (!cuda_ok(cudaGetDeviceProperties(&prop, h->device), "cudaGetDeviceProperties")) { delete h; return MPCB_E_CUDA; }
@@ -208,8 +211,8 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   cudaFuncAttributes fa;
   if (!cuda_ok(cudaFuncGetAttributes(&fa, var.kernel), "cudaFuncGetAttributes")) { delete h; return MPCB_E_CUDA; }
   int bps = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, var.kernel, 32, h->smem);
-  h->info.block = 32;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, var.kernel, 32 * var.warps, h->smem);
+  h->info.block = 32 * var.warps;
   h->info.smem_bytes = (int32_t)h->smem;
   h->info.regs_per_thread = fa.numRegs;
   h->info.blocks_per_sm = bps;
@@ -217,7 +220,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   if (var.slab_doubles) {
     if (bps < 1) { delete h; return MPCB_E_ARG; }
     h->persistent_grid = bps * prop.multiProcessorCount;
-    size_t bytes = (size_t)h->persistent_grid * var.slab_doubles * sizeof(double);
+    size_t bytes = (size_t)h->persistent_grid * var.warps * var.slab_doubles * sizeof(double);
     if (!cuda_ok(cudaMalloc(&h->d_slab, bytes), "cudaMalloc slab") || !cuda_ok(cudaMalloc(&h->d_counter, sizeof(int)), "cudaMalloc counter")) {
       cudaFree(h->d_slab);
       delete h;
@@ -260,7 +263,8 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
   k.u0 = u0; k.cost = cost; k.status = status; k.iters = iters; k.z_out = z_out; k.lam_out = lam_out;
   int grid = B;
   if (h->persistent_grid) {
-    grid = B < h->persistent_grid ? B : h->persistent_grid;
+    const int need = (B + h->var.warps - 1) / h->var.warps;
+    grid = need < h->persistent_grid ? need : h->persistent_grid;
     k.slab = h->d_slab;
     k.counter = h->d_counter;
     if (!cuda_ok(cudaMemsetAsync(h->d_counter, 0, sizeof(int), (cudaStream_t)stream), "queue reset")) return MPCB_E_CUDA;

@@ -37,6 +37,7 @@ struct DynLayout {
   static constexpr int HUU = R18, EE = R18 + 2, GU = R18 + 4, TK = R18 + 6;
   static constexpr int KX = R18, KW = R18 + 12, KK = R18 + 16;
   static constexpr int DSR = R18, LRP = DSR + NR, DSO = LRP + NR, LOP = DSO + MO;
+  static constexpr int CDEFT = R18 + 8;  // defects of the trial point (6 slots), see KinLayout
   static constexpr int DX = R18 + 18;
   static constexpr int DU = DX + NX;
   static constexpr int NFIELDS = DU + 2;
@@ -87,7 +88,8 @@ struct DynSolver {
     hyy = b / q - ey * ey / q3;
   }
 
-  __device__ __forceinline__ void eval_point(double alpha, bool store, double &theta, double &fobj, double &bar, double &lin) {
+  __device__ __forceinline__ void eval_point(double alpha, bool fresh, double &theta, double &fobj, double &bar, double &lin) {
+    const int cdst = fresh ? L::CDEF : L::CDEFT;
     double th = 0, fo = 0, br = 0, ln = 0;
 #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
@@ -100,27 +102,25 @@ struct DynSolver {
         for (int i = 0; i < NX; i++) {
           double c0 = xk[i] - x0[i];
           th += fabs(c0);
-          if (store) at(L::CDEF + i, 0) = c0;
+          at(cdst + i, 0) = c0;
         }
       }
       if (k < N) {
 #pragma unroll
         for (int i = 0; i < 2; i++) uk[i] = at(L::U + i, k) + alpha * at(L::DU + i, k);
         double f[NX];
-        if (store) {
+        {
           double J[NJ];
           dyn_fjac(xk, uk, p, f, J);
 #pragma unroll
           for (int i = 0; i < NJ; i++) at(L::JAC + i, k) = J[i];
-        } else {
-          dyn_f(xk, uk, p, f);
         }
 #pragma unroll
         for (int i = 0; i < NX; i++) {
           double xn = at(L::X + i, k + 1) + alpha * at(L::DX + i, k + 1);
           double d = xn - (xk[i] + p.T * f[i]);
           th += fabs(d);
-          if (store) at(L::CDEF + i, k + 1) = d;
+          at(cdst + i, k + 1) = d;
           double e = xk[i] - xs[i];
           fo += p.Q[i] * e * e;
         }
@@ -714,6 +714,7 @@ struct DynSolver {
       for (int i = 0; i < NX; i++) {
         double l = at(L::LAM + i, k);
         at(L::LAM + i, k) = l + a * (at(L::LAMP + i, k) - l);
+        at(L::CDEF + i, k) = at(L::CDEFT + i, k);
       }
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
@@ -860,7 +861,9 @@ struct DynSolver {
     return __all_sync(0xffffffffu, fin);
   }
 
+#define MPCB_ITER_SYNC() ((void)0)
 #include "mpcb_run_loop.inc"
+#undef MPCB_ITER_SYNC
 };
 
 __global__ void __launch_bounds__(32) dyn_solve_kernel(const __grid_constant__ KParams p) {

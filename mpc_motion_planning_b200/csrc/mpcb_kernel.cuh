@@ -155,7 +155,8 @@ struct KinLayout {
   static constexpr int HUU = R14, EE = R14 + 2, GU = R14 + 4, TK = R14 + 6;
   static constexpr int KX = R14, KW = R14 + 8, KK = R14 + 12;
   static constexpr int DSR = R14, LRP = DSR + NR, DSO = LRP + NR, LOP = DSO + MO;
-  static_assert(2 * NR + 2 * MO <= 14, "slack steps must fit the gain region");
+  static constexpr int CDEFT = R14 + 8;  // defects of the line-search trial point (moved to CDEF on acceptance)
+  static_assert(2 * NR + 2 * MO <= 8, "slack steps and trial defects must fit the gain region");
   static constexpr int DX = R14 + 14;
   static constexpr int DU = DX + NX;
   static constexpr int NSH = DU + 2;
@@ -215,16 +216,17 @@ struct KinSolver {
   static constexpr int NX = 4, NBX = 2;
 
   const KParams &p;
-  double *gs;  // this block's slab in global memory
+  double *gs;  // this warp's slab in global memory
+  int woff;    // this warp's offset into the block's shared memory (in doubles)
   int N, lane;
   double sigma;
   double x0[NX], xs[NX];
 
-  __device__ KinSolver(const KParams &p_, double *gs_, int lane_) : p(p_), gs(gs_), N(p_.N), lane(lane_) {}
+  __device__ KinSolver(const KParams &p_, double *gs_, int woff_, int lane_) : p(p_), gs(gs_), woff(woff_), N(p_.N), lane(lane_) {}
 
   // field ids are compile-time constants at (almost) every use, so the space test folds away
   __device__ __forceinline__ double &at(int field, int k) {
-    return field >= L::G0 ? gs[(field - L::G0) * L::SG + k] : g_smem[k * L::NF + field];
+    return field >= L::G0 ? gs[(field - L::G0) * L::SG + k] : g_smem[woff + k * L::NF + field];
   }
   __device__ __forceinline__ bool has_rate(int k) const { return NR > 0 && k >= 1 && k <= N - 1; }
   __device__ __forceinline__ bool has_obs(int k) const { return OBS_MODE == 1 && k <= N - 1; }
@@ -239,9 +241,12 @@ struct KinSolver {
   }
 
   // ---------------------------------------------------------------- point evaluation
-  // constraint residual 1-norm, objective and barrier pieces at z + alpha*dz.  With store=true
-  // (alpha = 0) the defects and the dynamics Jacobian of the iterate are kept for the QP.
-  __device__ __forceinline__ void eval_point(double alpha, bool store, double &theta, double &fobj, double &bar, double &lin) {
+  // constraint residual 1-norm, objective and barrier pieces at z + alpha*dz.  The dynamics
+  // Jacobian of the point is always kept (the old one is dead once the step is known) and its
+  // defects go to CDEF (first iterate) or CDEFT (trial point; accept_step moves them), so an
+  // accepted trial point needs no second evaluation.
+  __device__ __forceinline__ void eval_point(double alpha, bool fresh, double &theta, double &fobj, double &bar, double &lin) {
+    const int cdst = fresh ? L::CDEF : L::CDEFT;
     double th = 0, fo = 0, br = 0, ln = 0;
     #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
@@ -254,7 +259,7 @@ struct KinSolver {
         for (int i = 0; i < NX; i++) {
           double c0 = xk[i] - x0[i];
           th += fabs(c0);
-          if (store) at(L::CDEF + i, 0) = c0;
+          at(cdst + i, 0) = c0;
         }
       }
       if (k < N) {
@@ -267,7 +272,7 @@ struct KinSolver {
         f[1] = xk[3] * s;
         f[2] = xk[3] * t / p.Veh_l;
         f[3] = uk[1];
-        if (store) {
+        {
           at(L::JAC + 0, k) = p.T * (-xk[3] * s);                       // a02 = T d f0/d phi
           at(L::JAC + 1, k) = p.T * c;                                  // a03 = T d f0/d v
           at(L::JAC + 2, k) = p.T * (xk[3] * c);                        // a12
@@ -280,7 +285,7 @@ struct KinSolver {
           double xn = at(L::X + i, k + 1) + alpha * at(L::DX + i, k + 1);
           double d = xn - (xk[i] + p.T * f[i]);
           th += fabs(d);
-          if (store) at(L::CDEF + i, k + 1) = d;
+          at(cdst + i, k + 1) = d;
           double e = xk[i] - xs[i];
           fo += p.Q[i] * e * e;
         }
@@ -816,6 +821,7 @@ struct KinSolver {
       for (int i = 0; i < NX; i++) {
         double l = at(L::LAM + i, k);
         at(L::LAM + i, k) = l + a * (at(L::LAMP + i, k) - l);
+        at(L::CDEF + i, k) = at(L::CDEFT + i, k);  // LAMP aliases CDEF: consumed just above
       }
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
@@ -979,26 +985,41 @@ struct KinSolver {
     return true;
   }
 
+// All warps of a block start every interior-point iteration together (see kin_solve_kernel).
+#define MPCB_ITER_SYNC() __syncthreads_and(0)
 #include "mpcb_run_loop.inc"
+#undef MPCB_ITER_SYNC
 };
 
 // Persistent kernel: every resident warp pulls scenarios from a global queue until it is empty
 // (iteration counts differ by 5x between scenarios: dynamic assignment keeps the SMs busy).
+// W warps per block, one scenario per warp.  The warps of a block are kept in step at iteration
+// granularity by one block barrier per interior-point iteration: the stage-parallel phases are
+// ~4k instructions of straight-line code that stream through the instruction cache once per
+// iteration, and unsynchronised warps thrash it (profiles/r01_*: `no_instruction` was the top
+// stall and throughput did not scale with resident warps).  Warps in step fetch each line once.
+// A warp whose queue is empty keeps answering the barrier until every warp of the block is done.
+#ifndef MPCB_KIN_WARPS
+#define MPCB_KIN_WARPS 4
+#endif
 #ifndef MPCB_KIN_MIN_BLOCKS
-#define MPCB_KIN_MIN_BLOCKS 10
+#define MPCB_KIN_MIN_BLOCKS 3
 #endif
 template <int NR, int MO, int OBS_MODE>
-__global__ void __launch_bounds__(32, MPCB_KIN_MIN_BLOCKS) kin_solve_kernel(const __grid_constant__ KParams p) {
-  const int lane = threadIdx.x;
-  double *gs = p.slab + (size_t)blockIdx.x * KinLayout<NR, MO>::slab_doubles();
+__global__ void __launch_bounds__(32 * MPCB_KIN_WARPS, MPCB_KIN_MIN_BLOCKS) kin_solve_kernel(const __grid_constant__ KParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *gs = p.slab + ((size_t)blockIdx.x * MPCB_KIN_WARPS + warp) * KinLayout<NR, MO>::slab_doubles();
+  const int woff = warp * KinLayout<NR, MO>::NF * (p.N + 1);
   for (;;) {
     int b = 0;
     if (lane == 0) b = atomicAdd(p.counter, 1);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= p.B) break;
-    KinSolver<NR, MO, OBS_MODE> s(p, gs, lane);
+    KinSolver<NR, MO, OBS_MODE> s(p, gs, woff, lane);
     s.run(b);
     __syncwarp();
+  }
+  while (!__syncthreads_and(1)) {
   }
 }
 
