@@ -26,9 +26,9 @@ bool cuda_ok(cudaError_t e, const char *what) {
 typedef cudaError_t (*launch_fn)(const KParams &, int grid, size_t smem, cudaStream_t);
 typedef const void *kernel_ptr;
 
-template <int NR, int MO, int OBS>
+template <int NR, int MO, int OBS, int W>
 cudaError_t launch_kin(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-  kin_solve_kernel<NR, MO, OBS><<<grid, 32 * MPCB_KIN_WARPS, smem, st>>>(p);
+  kin_solve_kernel<NR, MO, OBS, W><<<grid, 32 * W, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -41,17 +41,32 @@ struct Variant {
   int warps;            // warps (= scenarios in flight) per block
 };
 
-template <int NR, int MO, int OBS>
-Variant make_kin_variant() {
+template <int NR, int MO, int OBS, int W>
+Variant make_kin_variant_w() {
   Variant v;
-  v.launch = &launch_kin<NR, MO, OBS>;
-  v.kernel = (const void *)&kin_solve_kernel<NR, MO, OBS>;
+  v.launch = &launch_kin<NR, MO, OBS, W>;
+  v.kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, W>;
   v.smem_bytes = [](int N) { return KinLayout<NR, MO>::bytes(N); };
   v.nx = 4;
   v.nbx = 2;
   v.slab_doubles = KinLayout<NR, MO>::slab_doubles();
-  v.warps = MPCB_KIN_WARPS;
+  v.warps = W;
   return v;
+}
+
+// warps per block: the candidate that keeps the most warps resident for this horizon (ties: larger W)
+template <int NR, int MO, int OBS>
+Variant make_kin_variant(int N) {
+  Variant cand[3] = {make_kin_variant_w<NR, MO, OBS, 4>(), make_kin_variant_w<NR, MO, OBS, 2>(), make_kin_variant_w<NR, MO, OBS, 1>()};
+  int best = 0, best_warps = -1;
+  for (int i = 0; i < 3; i++) {
+    size_t smem = cand[i].smem_bytes(N) * cand[i].warps;
+    int bps = 0;
+    if (cudaFuncSetAttribute(cand[i].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, cand[i].kernel, 32 * cand[i].warps, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (bps * cand[i].warps > best_warps) { best_warps = bps * cand[i].warps; best = i; }
+  }
+  return cand[best];
 }
 
 cudaError_t launch_dyn(const KParams &p, int grid, size_t smem, cudaStream_t st) {
@@ -79,10 +94,10 @@ bool select_variant(const mpcb_cfg &c, Variant &v) {
     return false;
   }
   if (c.model == MPCB_MODEL_KIN) {
-    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 0) { v = make_kin_variant<0, 0, 0>(); return true; }
-    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 1) { v = make_kin_variant<1, 0, 0>(); return true; }
-    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 1) { v = make_kin_variant<1, 1, 1>(); return true; }
-    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 2) { v = make_kin_variant<1, 2, 1>(); return true; }
+    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 0) { v = make_kin_variant<0, 0, 0>(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 1) { v = make_kin_variant<1, 0, 0>(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 1) { v = make_kin_variant<1, 1, 1>(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 2) { v = make_kin_variant<1, 2, 1>(c.N); return true; }
   }
   return false;
 }

@@ -999,16 +999,12 @@ struct KinSolver {
 // iteration, and unsynchronised warps thrash it (profiles/r01_*: `no_instruction` was the top
 // stall and throughput did not scale with resident warps).  Warps in step fetch each line once.
 // A warp whose queue is empty keeps answering the barrier until every warp of the block is done.
-#ifndef MPCB_KIN_WARPS
-#define MPCB_KIN_WARPS 4
-#endif
-#ifndef MPCB_KIN_MIN_BLOCKS
-#define MPCB_KIN_MIN_BLOCKS 3
-#endif
-template <int NR, int MO, int OBS_MODE>
-__global__ void __launch_bounds__(32 * MPCB_KIN_WARPS, MPCB_KIN_MIN_BLOCKS) kin_solve_kernel(const __grid_constant__ KParams p) {
+// W = 4 (one warp per SM sub-partition) measured best at N = 50; long horizons need more shared
+// memory per scenario, the host picks the W in {4, 2, 1} that keeps most warps resident.
+template <int NR, int MO, int OBS_MODE, int W>
+__global__ void __launch_bounds__(32 * W, 12 / W) kin_solve_kernel(const __grid_constant__ KParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *gs = p.slab + ((size_t)blockIdx.x * MPCB_KIN_WARPS + warp) * KinLayout<NR, MO>::slab_doubles();
+  double *gs = p.slab + ((size_t)blockIdx.x * W + warp) * KinLayout<NR, MO>::slab_doubles();
   const int woff = warp * KinLayout<NR, MO>::NF * (p.N + 1);
   for (;;) {
     int b = 0;
