@@ -484,6 +484,7 @@ struct DynSolver {
         for (int j = 0; j < 2; j++) Kw[i][j] = Fi[i][j] * E[j];
         kk[i] = -(Fi[i][0] * fu[0] + Fi[i][1] * fu[1]);
       }
+      __syncwarp();  // every lane has consumed the QP slots of this stage before lane 0 reuses them
       if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < 2; i++) {

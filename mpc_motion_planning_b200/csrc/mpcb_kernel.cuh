@@ -620,6 +620,7 @@ struct KinSolver {
       const double ka0 = -(ida * ud0 + iaa * ua0), ka1 = -(ida * ud1 + iaa * ua1), ka2 = -(ida * ud2 + iaa * ua2), ka3 = -(ida * ud3 + iaa * ua3);
       const double wdd = idd * Ed, wda = ida * Ea, wad = ida * Ed, waa = iaa * Ea;  // Kw = Fuu^{-1} diag(E)
       const double kkd = -(idd * fud + ida * fua), kka = -(ida * fud + iaa * fua);
+      __syncwarp();  // every lane has consumed the QP slots of this stage before lane 0 reuses them
       if (lane == 0) {
         at(L::KX + 0, k) = kd0; at(L::KX + 1, k) = kd1; at(L::KX + 2, k) = kd2; at(L::KX + 3, k) = kd3;
         at(L::KX + 4, k) = ka0; at(L::KX + 5, k) = ka1; at(L::KX + 6, k) = ka2; at(L::KX + 7, k) = ka3;

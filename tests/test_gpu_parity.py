@@ -365,3 +365,16 @@ def test_batched_closed_loop_matches_oracle_loop(dev):
     # warm starts: later steps need far fewer iterations than the cold first one
     itg = out["iters"].cpu().numpy()
     assert itg[5:, alive].mean() < 0.7 * itg[0, alive].mean()
+
+
+def test_reference_mains_run_closed_loop(dev):
+    """mains/ = the reference's closed-loop mains on the drop-in modules (plots stripped)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name, steps in (("main_cbf_kin_c_sim_pre", 80), ("main_cbf_dyn_c_sim", 100)):
+        out = subprocess.run([sys.executable, f"{name}.py"], cwd=os.path.join(root, "mains"), capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        last = out.stdout.strip().splitlines()[-1]
+        assert f"{steps} MPC steps, {steps} solved" in last, last

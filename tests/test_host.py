@@ -186,3 +186,19 @@ def test_shard_ranges_cover_the_batch():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(G - 1))
     p = balanced_permutation(100, 0)
     assert sorted(p) == list(range(100)) and np.array_equal(p, balanced_permutation(100, 0))
+
+
+def test_install_reference_names_registers_flat_modules():
+    import sys
+
+    import mpc_motion_planning_b200 as pkg
+
+    pkg.install_reference_names()
+    import MPC_CBF_optimize_kin_pre  # noqa: F401  (the reference's flat module names)
+    from Obs_prediction import obs_prediction  # noqa: F401
+
+    for name in pkg.REFERENCE_MODULES:
+        assert sys.modules[name].__name__ == f"mpc_motion_planning_b200.{name}"
+    assert hasattr(sys.modules["MPC_optimize_kin"], "MPC_optimize")
+    for name in pkg.REFERENCE_MODULES:
+        sys.modules.pop(name, None)
