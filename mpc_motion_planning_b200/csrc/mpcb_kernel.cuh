@@ -1002,8 +1002,11 @@ struct KinSolver {
 // A warp whose queue is empty keeps answering the barrier until every warp of the block is done.
 // W = 4 (one warp per SM sub-partition) measured best at N = 50; long horizons need more shared
 // memory per scenario, the host picks the W in {4, 2, 1} that keeps most warps resident.
+#ifndef MPCB_KIN_RESIDENT_WARPS
+#define MPCB_KIN_RESIDENT_WARPS 12  // register budget: 65536 / (12 * 32) = 170 registers per thread
+#endif
 template <int NR, int MO, int OBS_MODE, int W>
-__global__ void __launch_bounds__(32 * W, 12 / W) kin_solve_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(32 * W, MPCB_KIN_RESIDENT_WARPS / W) kin_solve_kernel(const __grid_constant__ KParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *gs = p.slab + ((size_t)blockIdx.x * W + warp) * KinLayout<NR, MO>::slab_doubles();
   const int woff = warp * KinLayout<NR, MO>::NF * (p.N + 1);
