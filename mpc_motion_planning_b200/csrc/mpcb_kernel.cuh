@@ -218,11 +218,13 @@ struct KinSolver {
   const KParams &p;
   double *gs;  // this warp's slab in global memory
   int woff;    // this warp's offset into the block's shared memory (in doubles)
+  int &tick;   // this warp's running iteration count (across scenarios) for the block barrier
   int N, lane;
   double sigma;
   double x0[NX], xs[NX];
 
-  __device__ KinSolver(const KParams &p_, double *gs_, int woff_, int lane_) : p(p_), gs(gs_), woff(woff_), N(p_.N), lane(lane_) {}
+  __device__ KinSolver(const KParams &p_, double *gs_, int woff_, int &tick_, int lane_)
+      : p(p_), gs(gs_), woff(woff_), tick(tick_), N(p_.N), lane(lane_) {}
 
   // field ids are compile-time constants at (almost) every use, so the space test folds away
   __device__ __forceinline__ double &at(int field, int k) {
@@ -987,7 +989,10 @@ struct KinSolver {
   }
 
 // All warps of a block start every interior-point iteration together (see kin_solve_kernel).
-#define MPCB_ITER_SYNC() __syncthreads_and(0)
+#ifndef MPCB_SYNC_EVERY
+#define MPCB_SYNC_EVERY 1  // barrier every k-th iteration (power of two)
+#endif
+#define MPCB_ITER_SYNC() do { if (((++tick) & (MPCB_SYNC_EVERY - 1)) == 0) __syncthreads_and(0); } while (0)
 #include "mpcb_run_loop.inc"
 #undef MPCB_ITER_SYNC
 };
@@ -1010,12 +1015,13 @@ __global__ void __launch_bounds__(32 * W, MPCB_KIN_RESIDENT_WARPS / W) kin_solve
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *gs = p.slab + ((size_t)blockIdx.x * W + warp) * KinLayout<NR, MO>::slab_doubles();
   const int woff = warp * KinLayout<NR, MO>::NF * (p.N + 1);
+  int tick = 0;
   for (;;) {
     int b = 0;
     if (lane == 0) b = atomicAdd(p.counter, 1);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= p.B) break;
-    KinSolver<NR, MO, OBS_MODE> s(p, gs, woff, lane);
+    KinSolver<NR, MO, OBS_MODE> s(p, gs, woff, tick, lane);
     s.run(b);
     __syncwarp();
   }
