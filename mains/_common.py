@@ -35,6 +35,7 @@ def rollout_guess(mpc, x0, u0):
 
 
 def summary(name, xh, uh, caltimeh, stats):
+    np.set_printoptions(linewidth=200)
     xh = np.array(xh).reshape(len(xh), -1)
     uh = np.array(uh)
     ok = sum(1 for s in stats if s["success"])

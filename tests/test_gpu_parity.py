@@ -376,5 +376,5 @@ def test_reference_mains_run_closed_loop(dev):
     for name, steps in (("main_cbf_kin_c_sim_pre", 80), ("main_cbf_dyn_c_sim", 100)):
         out = subprocess.run([sys.executable, f"{name}.py"], cwd=os.path.join(root, "mains"), capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stderr[-2000:]
-        last = out.stdout.strip().splitlines()[-1]
-        assert f"{steps} MPC steps, {steps} solved" in last, last
+        text = " ".join(out.stdout.split())  # the 6-state summary wraps over two lines
+        assert f"{name}: {steps} MPC steps, {steps} solved" in text, text[-400:]
