@@ -39,6 +39,11 @@ enum { MPCB_OBS_NONE = 0, MPCB_OBS_ELLIPSE = 1, MPCB_OBS_SQRT = 2 };
  * AS_GIVEN = controls and states as passed; ROLLOUT = controls as passed, states re-integrated
  * from the parameter x0 with the Euler step of PKG/MPC_CBF_optimize_kin.py:207 */
 enum { MPCB_INIT_AS_GIVEN = 0, MPCB_INIT_ROLLOUT = 1 };
+/* layout of the `obs` argument: TRAJECTORY = [B][M][N+1][6], the output of obs_prediction
+ * (PKG/Obs_prediction.py:3-40); INITIAL = [B][M][6], the obstacle states themselves - the library
+ * then runs the same constant-velocity recursion (x += v cos(theta) dt, step by step, :27-28) on the
+ * device while staging the trajectory, so nothing per-step crosses PCIe or HBM */
+enum { MPCB_OBS_TRAJECTORY = 0, MPCB_OBS_INITIAL = 1 };
 
 /* per-scenario outcome, mapped to IPOPT return_status strings by the Python shim */
 enum {
@@ -83,6 +88,8 @@ typedef struct mpcb_cfg {
   double tol;           /* ipopt.tol (default 1e-8) */
   double mu_init;       /* initial barrier parameter (IPOPT default 0.1; this library's default 100) */
   double bound_relax;   /* ipopt.bound_relax_factor (1e-8) */
+  int32_t obs_input;    /* MPCB_OBS_TRAJECTORY (default) or MPCB_OBS_INITIAL */
+  int32_t reserved;
 } mpcb_cfg;
 
 typedef struct mpcb_handle mpcb_handle;
@@ -108,7 +115,8 @@ int mpcb_workspace_bytes(const mpcb_cfg *cfg, int B, size_t *bytes);
  * row-major, float64:
  *   x0 [B][nx], xs [B][nx]        = the parameter vector p=[x0;xs] (PKG/main_cbf_kin_c_sim.py:89)
  *   obs [B][M][N+1][6]            = obs_prediction rows [x,y,theta,v,l,w] (PKG/Obs_prediction.py:3-40);
- *                                   static obstacles repeat the row; dyn uses columns 0,1 only
+ *                                   static obstacles repeat the row; dyn uses columns 0,1 only.
+ *                                   With cfg.obs_input = MPCB_OBS_INITIAL: [B][M][6] (see above)
  *   z_init [B][nv] or NULL        = `x0=` warm start [vec(U);vec(X)] (NULL = zeros, :47-50)
  * outputs:
  *   u0 [B][2]                     = first control, res['x'][0:2]

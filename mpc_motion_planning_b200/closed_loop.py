@@ -45,7 +45,9 @@ def run_closed_loop(solver, x0: torch.Tensor, xs: torch.Tensor, obs_state: torch
     uh, sth, ith = [], [], []
     for step in range(steps):
         traj = None
-        if obs is not None:
+        if obs is not None and solver.obs_initial:
+            traj = obs if moving else torch.cat([obs[..., :3], torch.zeros_like(obs[..., 3:4]), obs[..., 4:]], dim=-1)  # prediction in-kernel
+        elif obs is not None:
             traj = predict_obstacles(obs, dt, N) if moving else obs[:, :, None, :].repeat(1, 1, N + 1, 1).contiguous()
         out = solver.solve(x, xs, traj, z, return_z=True)
         z = out["z"]

@@ -169,6 +169,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
     if (c.rate_ctrl[r] < 0 || c.rate_ctrl[r] > 1 || !(c.rate_lo[r] < c.rate_hi[r])) return MPCB_E_ARG;
   if (!(c.T > 0) || !(c.tol > 0) || !(c.mu_init > 0) || !(c.bound_relax >= 0)) return MPCB_E_ARG;
   if (c.obs_mode != MPCB_OBS_NONE && c.M < 1) return MPCB_E_ARG;
+  if (c.obs_input != MPCB_OBS_TRAJECTORY && c.obs_input != MPCB_OBS_INITIAL) return MPCB_E_ARG;
   Variant var;
   if (!select_variant(c, var)) return MPCB_E_ARG;
   // the kernels assume: both controls two-sided; the model's bounded states (kin: y, vx; dyn: + vy)
@@ -196,6 +197,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   KParams &k = h->kp;
   memset(&k, 0, sizeof k);
   const int M = c.obs_mode == MPCB_OBS_NONE ? 0 : c.M;
+  k.obs_input = c.obs_input;
   k.N = c.N; k.obs_mode = c.obs_mode; k.du0_cost = c.du0_cost; k.init_mode = c.init_mode; k.max_iter = c.max_iter;
   k.rate_ctrl[0] = c.rate_ctrl[0]; k.rate_ctrl[1] = c.rate_ctrl[1];
   const int n_obs_st = c.obs_mode == MPCB_OBS_ELLIPSE ? c.N : (c.obs_mode == MPCB_OBS_SQRT ? c.N + 1 : 0);
@@ -300,7 +302,7 @@ int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double 
   const int nx = h->var.nx, N = h->cfg.N;
   const int M = h->cfg.obs_mode == MPCB_OBS_NONE ? 0 : h->cfg.M;
   const size_t nv = 2 * (size_t)N + (size_t)nx * (N + 1);
-  const size_t so = (size_t)M * (N + 1) * 6;
+  const size_t so = (size_t)M * (h->cfg.obs_input == MPCB_OBS_INITIAL ? 1 : (N + 1)) * 6;
   if (M > 0 && !obs) return MPCB_E_ARG;
   if (B > h->cap_B) {
     free_bufs(h);

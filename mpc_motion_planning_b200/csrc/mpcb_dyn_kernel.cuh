@@ -775,11 +775,11 @@ struct DynSolver {
   __device__ __forceinline__ bool init_iterate(int b) {
     const int nv = 2 * N + NX * (N + 1);
     const double *zi = p.z_init ? p.z_init + (size_t)b * nv : nullptr;
-    const double *ob = p.obs + (size_t)b * MO * (N + 1) * 6;
+    const double *ob = p.obs + (size_t)b * MO * (p.obs_input ? 1 : (N + 1)) * 6;
 #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
-      at(L::OCX, k) = ob[(size_t)k * 6 + 0];
-      at(L::OCY, k) = ob[(size_t)k * 6 + 1];
+      at(L::OCX, k) = ob[p.obs_input ? 0 : (size_t)k * 6 + 0];  // static centre (PKG/MPC_CBF_optimize_dyn.py:238-239)
+      at(L::OCY, k) = ob[p.obs_input ? 1 : (size_t)k * 6 + 1];
 #pragma unroll
       for (int i = 0; i < 2; i++) {
         at(L::U + i, k) = k < N ? push_in(zi ? zi[2 * k + i] : 0.0, p.u_lo[i], p.u_hi[i]) : 0.0;

@@ -61,7 +61,7 @@ namespace mpcb {
 #define MPCB_FILTER_SLOTS 4 /* 4 x 32 lanes = 128 filter entries */
 
 struct KParams {
-  int B, N, obs_mode, du0_cost, init_mode, max_iter;
+  int B, N, obs_mode, du0_cost, init_mode, max_iter, obs_input;
   int rate_ctrl[2];
   int n_eq, n_bm;  // counts used by the IPOPT error scaling
   double T;
@@ -888,19 +888,40 @@ struct KinSolver {
   __device__ __forceinline__ bool init_iterate(int b) {
     const int nv = 2 * N + NX * (N + 1);
     const double *zi = p.z_init ? p.z_init + (size_t)b * nv : nullptr;
-    const double *ob = p.obs ? p.obs + (size_t)b * MO * (N + 1) * 6 : nullptr;
-    // obstacle trajectory staged in shared memory (centre and 1/semi-axis^2 per step)
-    #pragma unroll 1
-    for (int k = lane; k <= N; k += 32) {
+    // obstacle trajectory staged per step (centre and 1/semi-axis^2)
+    const double *ob = p.obs ? p.obs + (size_t)b * MO * (p.obs_input ? 1 : (N + 1)) * 6 : nullptr;
+    if (MO > 0 && p.obs_input) {
+      // obstacle states given: the constant-velocity recursion of PKG/Obs_prediction.py:27-28,
+      // accumulated step by step in the reference's operation order (device cos/sin may differ from
+      // libm in the last ulp, nothing else does)
 #pragma unroll
       for (int j = 0; j < MO; j++) {
-        const double *o = ob + ((size_t)j * (N + 1) + k) * 6;
-        double sx = p.ego_hl + o[4] / 2 + p.safe_l;  // PKG/MPC_CBF_optimize_kin_pre.py:246-249
-        double sy = p.ego_hw + o[5] / 2 + p.safe_w;
-        at(L::OCX + j, k) = o[0];
-        at(L::OCY + j, k) = o[1];
-        at(L::ISX + j, k) = fast_rcp(sx * sx);
-        at(L::ISY + j, k) = fast_rcp(sy * sy);
+        const double *o = ob + (size_t)j * 6;
+        double x = o[0], y = o[1];
+        const double dx = o[3] * cos(o[2]) * p.T, dy = o[3] * sin(o[2]) * p.T;
+        const double sx = p.ego_hl + o[4] / 2 + p.safe_l, sy = p.ego_hw + o[5] / 2 + p.safe_w;
+        const double isx = 1.0 / (sx * sx), isy = 1.0 / (sy * sy);
+#pragma unroll 1
+        for (int k = 0; k <= N; k++) {
+          if ((k & 31) == lane) { at(L::OCX + j, k) = x; at(L::OCY + j, k) = y; at(L::ISX + j, k) = isx; at(L::ISY + j, k) = isy; }
+          x = x + dx;
+          y = y + dy;
+        }
+      }
+    }
+    #pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
+      if (!p.obs_input) {
+#pragma unroll
+        for (int j = 0; j < MO; j++) {
+          const double *o = ob + ((size_t)j * (N + 1) + k) * 6;
+          double sx = p.ego_hl + o[4] / 2 + p.safe_l;  // PKG/MPC_CBF_optimize_kin_pre.py:246-249
+          double sy = p.ego_hw + o[5] / 2 + p.safe_w;
+          at(L::OCX + j, k) = o[0];
+          at(L::OCY + j, k) = o[1];
+          at(L::ISX + j, k) = 1.0 / (sx * sx);
+          at(L::ISY + j, k) = 1.0 / (sy * sy);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 2; i++) {

@@ -47,7 +47,7 @@ def horizon_steps(config: dict) -> int:
 
 def make_cfg(kind: str, config: dict, N: int | None = None, M: int = 1, weights: Weights | None = None,
              init_mode: int = _lib.INIT_ROLLOUT, mu_init: float = 100.0, max_iter: int = 100, tol: float = 1e-8,
-             bounds: dict | None = None) -> _lib.MpcbCfg:
+             bounds: dict | None = None, obs_input: int = _lib.OBS_TRAJECTORY) -> _lib.MpcbCfg:
     """Fill an mpcb_cfg from the YAML dict with the reference's hard-coded constants.
 
     `bounds` optionally overrides {'u_lo','u_hi','x_lo','x_hi','rate_lo','rate_hi'} (used by the
@@ -105,4 +105,5 @@ def make_cfg(kind: str, config: dict, N: int | None = None, M: int = 1, weights:
     c.init_mode = init_mode
     c.max_iter = max_iter
     c.tol, c.mu_init, c.bound_relax = tol, mu_init, 1e-8
+    c.obs_input = obs_input
     return c

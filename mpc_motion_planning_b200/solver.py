@@ -28,16 +28,20 @@ class BatchSolver:
 
     def __init__(self, kind: str = "kin_cbf_pre", config: dict | None = None, N: int | None = None, M: int = 1,
                  init: str = "rollout", mu_init: float = 100.0, max_iter: int = 100, tol: float = 1e-8,
-                 weights=None, bounds: dict | None = None):
+                 weights=None, bounds: dict | None = None, obs_input: str = "trajectory"):
         self.lib = _lib.load()
         self.kind = kind
         self.config = config if config is not None else load_config(PACKAGE_PARAMS)
         init_mode = {"rollout": _lib.INIT_ROLLOUT, "as_given": _lib.INIT_AS_GIVEN}[init]
+        self.obs_initial = {"trajectory": False, "initial": True}[obs_input]
         self.cfg = make_cfg(kind, self.config, N=N, M=M, weights=weights, init_mode=init_mode, mu_init=mu_init,
-                            max_iter=max_iter, tol=tol, bounds=bounds)
+                            max_iter=max_iter, tol=tol, bounds=bounds,
+                            obs_input=_lib.OBS_INITIAL if self.obs_initial else _lib.OBS_TRAJECTORY)
         self.N, self.M = int(self.cfg.N), int(self.cfg.M)
         self.nx = _nx(kind)
         self.nv = 2 * self.N + self.nx * (self.N + 1)
+        # obs argument: (B,M,N+1,6) obs_prediction rows, or (B,M,6) obstacle states when obs_input="initial"
+        self.obs_shape = (self.M, 6) if self.obs_initial else (self.M, self.N + 1, 6)
         self._h = C.c_void_p()
         _lib.check(self.lib.mpcb_create(C.byref(self.cfg), C.byref(self._h)), "mpcb_create")
 
@@ -78,7 +82,7 @@ class BatchSolver:
 
         x0 = prep(x0, (B, self.nx))
         xs = prep(xs, (B, self.nx))
-        obs = prep(obs, (B, self.M, self.N + 1, 6)) if self.M > 0 else None
+        obs = prep(obs, (B,) + self.obs_shape) if self.M > 0 else None
         z_init = prep(z_init, (B, self.nv))
         u0 = torch.empty((B, 2), dtype=torch.float64, device=dev)
         cost = torch.empty((B,), dtype=torch.float64, device=dev)
@@ -105,7 +109,7 @@ class BatchSolver:
         f64 = lambda a, shape: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(shape)
         x0 = f64(x0, (B, self.nx))
         xs = f64(xs, (B, self.nx))
-        obs = f64(obs, (B, self.M, self.N + 1, 6)) if self.M > 0 else None
+        obs = f64(obs, (B,) + self.obs_shape) if self.M > 0 else None
         z_init = f64(z_init, (B, self.nv))
         u0 = np.empty((B, 2))
         cost = np.empty(B)

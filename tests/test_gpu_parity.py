@@ -378,3 +378,27 @@ def test_reference_mains_run_closed_loop(dev):
         assert out.returncode == 0, out.stderr[-2000:]
         text = " ".join(out.stdout.split())  # the 6-state summary wraps over two lines
         assert f"{name}: {steps} MPC steps, {steps} solved" in text, text[-400:]
+
+
+def test_in_kernel_obstacle_prediction_equals_host_trajectories(dev):
+    """cfg.obs_input = MPCB_OBS_INITIAL: the library runs PKG/Obs_prediction.py's recursion itself."""
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+
+    B = 200
+    x0, xs, obs = scenarios.kin_cbf_moving(B, seed=21)
+    a = _gpu(BatchSolver("kin_cbf_pre"), dev, x0, xs, obs)
+    s2 = BatchSolver("kin_cbf_pre", obs_input="initial")
+    import torch
+
+    t = lambda v: torch.from_numpy(np.ascontiguousarray(v)).to(dev)
+    o = s2.solve(t(x0), t(xs), t(obs[:, :, 0, :]))
+    torch.cuda.synchronize()
+    b = {k: v.cpu().numpy() for k, v in o.items()}
+    same = (a["status"] <= 1) & (b["status"] <= 1)
+    assert ((a["status"] <= 1) == (b["status"] <= 1)).mean() >= 0.98 and same.mean() > 0.8
+    # identical up to the last ulp of the device cos/sin in the obstacle increments
+    assert np.abs(a["u0"] - b["u0"])[same].max() <= 1e-7
+    assert (np.abs(a["cost"] - b["cost"])[same] <= 1e-9 * np.abs(a["cost"][same])).all()
+    h = s2.solve(x0, xs, obs[:, :, 0, :])  # host entry with the compact layout
+    assert np.array_equal(h["status"], b["status"]) and np.array_equal(h["cost"], b["cost"])
