@@ -69,28 +69,47 @@ Variant make_kin_variant(int N) {
   return cand[best];
 }
 
+template <int W>
 cudaError_t launch_dyn(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-  dyn_solve_kernel<<<grid, 32, smem, st>>>(p);
+  dyn_solve_kernel<W><<<grid, 32 * W, smem, st>>>(p);
   return cudaGetLastError();
 }
 
-Variant make_dyn_variant() {
+template <int W>
+Variant make_dyn_variant_w() {
   Variant v;
-  v.launch = &launch_dyn;
-  v.kernel = (const void *)&dyn_solve_kernel;
+  v.launch = &launch_dyn<W>;
+  v.kernel = (const void *)&dyn_solve_kernel<W>;
   v.smem_bytes = [](int N) { return DynLayout::bytes(N); };
   v.nx = 6;
   v.nbx = 3;
-  v.slab_doubles = 0;
-  v.warps = 1;
+  v.slab_doubles = DynLayout::slab_doubles();
+  v.warps = W;
   return v;
+}
+
+Variant pick_by_occupancy(Variant *cand, int n, int N) {
+  int best = 0, best_warps = -1;
+  for (int i = 0; i < n; i++) {
+    size_t smem = cand[i].smem_bytes(N) * cand[i].warps;
+    int bps = 0;
+    if (cudaFuncSetAttribute(cand[i].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, cand[i].kernel, 32 * cand[i].warps, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (bps * cand[i].warps > best_warps) { best_warps = bps * cand[i].warps; best = i; }
+  }
+  return cand[best];
+}
+
+Variant make_dyn_variant(int N) {
+  Variant cand[3] = {make_dyn_variant_w<4>(), make_dyn_variant_w<2>(), make_dyn_variant_w<1>()};
+  return pick_by_occupancy(cand, 3, N);
 }
 
 bool select_variant(const mpcb_cfg &c, Variant &v) {
   const int M = c.obs_mode == MPCB_OBS_NONE ? 0 : c.M;
   if (c.model == MPCB_MODEL_DYN) {
     // the reference's dyn NLP: both rate rows (df, ax in that order), one obstacle, sqrt rows
-    if (c.obs_mode == MPCB_OBS_SQRT && c.n_rate == 2 && M == 1 && c.rate_ctrl[0] == 0 && c.rate_ctrl[1] == 1) { v = make_dyn_variant(); return true; }
+    if (c.obs_mode == MPCB_OBS_SQRT && c.n_rate == 2 && M == 1 && c.rate_ctrl[0] == 0 && c.rate_ctrl[1] == 1) { v = make_dyn_variant(c.N); return true; }
     return false;
   }
   if (c.model == MPCB_MODEL_KIN) {

@@ -6,12 +6,32 @@
 #pragma once
 #include "mpcb_kernel.cuh"
 #include "dyn_model.cuh"
+#include "dyn_riccati.cuh"
 
 namespace mpcb {
 
 struct DynLayout {
   static constexpr int NX = 6, NBX = 3, NR = 2, MO = 1, NJ = DYN_NJ;
-  static constexpr int X = 0;
+  // ---- shared memory: working set of the serial sweeps (stage-major records, see KinLayout)
+  static constexpr int CDEF = 0;
+  static constexpr int LAMP = CDEF;  // alias
+  static constexpr int JAC = CDEF + NX;
+  static constexpr int HXX = JAC + NJ;     // packed upper triangle 6x6 (21)
+  static constexpr int HUX = HXX + 21;     // d2L/(d delta d x_j), 6 entries (the ax row is zero)
+  static constexpr int GX = HUX + NX;
+  static constexpr int R18 = GX + NX;      // [HUU(2) EE(2) GU(2) TK(2) ...] -> gains [KX(12) KW(4) KK(2)] -> slack steps
+  static constexpr int HUU = R18, EE = R18 + 2, GU = R18 + 4, TK = R18 + 6;
+  static constexpr int KX = R18, KW = R18 + 12, KK = R18 + 16;
+  static constexpr int DSR = R18, LRP = DSR + NR, DSO = LRP + NR, LOP = DSO + MO;
+  static constexpr int CDEFT = R18 + 8;  // defects of the trial point (6 slots)
+  static constexpr int DX = R18 + 18;
+  static constexpr int DU = DX + NX;
+  static constexpr int NSH = DU + 2;
+  static constexpr int NF = NSH | 1;
+  // ---- global-memory slab: the primal-dual iterate and the obstacle centre (stage-parallel phases only)
+  static constexpr int G0 = 96;
+  static_assert(NF <= G0, "field id spaces overlap");
+  static constexpr int X = G0;
   static constexpr int U = X + NX;
   static constexpr int LAM = U + 2;
   static constexpr int ZLX = LAM + NX;
@@ -27,22 +47,10 @@ struct DynLayout {
   static constexpr int LO = VLO + MO;
   static constexpr int OCX = LO + MO;
   static constexpr int OCY = OCX + MO;
-  static constexpr int CDEF = OCY + MO;
-  static constexpr int LAMP = CDEF;  // alias, see KinLayout
-  static constexpr int JAC = CDEF + NX;
-  static constexpr int HXX = JAC + NJ;     // packed upper triangle 6x6 (21)
-  static constexpr int HUX = HXX + 21;     // d2L/(d delta d x_j), 6 entries (the ax row is zero)
-  static constexpr int GX = HUX + NX;
-  static constexpr int R18 = GX + NX;      // [HUU(2) EE(2) GU(2) TK(2) ...] -> gains [KX(12) KW(4) KK(2)] -> slack steps
-  static constexpr int HUU = R18, EE = R18 + 2, GU = R18 + 4, TK = R18 + 6;
-  static constexpr int KX = R18, KW = R18 + 12, KK = R18 + 16;
-  static constexpr int DSR = R18, LRP = DSR + NR, DSO = LRP + NR, LOP = DSO + MO;
-  static constexpr int CDEFT = R18 + 8;  // defects of the trial point (6 slots), see KinLayout
-  static constexpr int DX = R18 + 18;
-  static constexpr int DU = DX + NX;
-  static constexpr int NFIELDS = DU + 2;
-  static constexpr int NF = NFIELDS | 1;
+  static constexpr int NG = OCY + MO - G0;
+  static constexpr int SG = 132;
   __host__ __device__ static constexpr size_t bytes(int N) { return sizeof(double) * (size_t)NF * (size_t)(N + 1); }
+  __host__ __device__ static constexpr size_t slab_doubles() { return (size_t)NG * SG; }
 };
 
 __device__ __forceinline__ int pidx6(int i, int j) { return i * 6 - i * (i - 1) / 2 + (j - i); }  // i <= j
@@ -54,13 +62,19 @@ struct DynSolver {
   __device__ static __forceinline__ constexpr int bx(int i) { return i == 0 ? 1 : (i == 1 ? 3 : 4); }  // y, vx, vy
 
   const KParams &p;
+  double *gs;  // this warp's slab in global memory
+  int woff;    // this warp's offset into the block's shared memory (in doubles)
+  int &tick;
   int N, lane;
   double sigma;
   double x0[NX], xs[NX];
 
-  __device__ DynSolver(const KParams &p_, int lane_) : p(p_), N(p_.N), lane(lane_) {}
+  __device__ DynSolver(const KParams &p_, double *gs_, int woff_, int &tick_, int lane_)
+      : p(p_), gs(gs_), woff(woff_), tick(tick_), N(p_.N), lane(lane_) {}
 
-  __device__ __forceinline__ double &at(int field, int k) { return g_smem[k * L::NF + field]; }
+  __device__ __forceinline__ double &at(int field, int k) {
+    return field >= L::G0 ? gs[(field - L::G0) * L::SG + k] : g_smem[woff + k * L::NF + field];
+  }
   __device__ __forceinline__ bool has_rate(int k) const { return k >= 1 && k <= N - 1; }
 
   __device__ __forceinline__ double grad_u(int k, int i, double uk, double ukm1, double ukp1) const {
@@ -376,150 +390,87 @@ struct DynSolver {
     __syncwarp();
   }
 
-  // dense Riccati on the state augmented with the previous control (see KinSolver)
+  // Riccati on the state augmented with the previous control (see KinSolver).  The first half of
+  // a stage (F = H + [A B]' V [A B], ~300 FMAs) is generated for the sparsity of this model's
+  // A and B (dyn_riccati.cuh); the pivot, gains and value-function update are generic.
   __device__ __forceinline__ bool riccati_backward() {
-    double Pxx[NX][NX], Pxw[NX][2], Pww[2][2], px[NX], pw[2];
+    double P[21], W[12], Q[3] = {0, 0, 0}, px[NX], pw[2] = {0, 0};
+#pragma unroll
+    for (int q = 0; q < 21; q++) P[q] = at(L::HXX + q, N);
 #pragma unroll
     for (int i = 0; i < NX; i++) {
-#pragma unroll
-      for (int j = 0; j < NX; j++) Pxx[i][j] = at(L::HXX + sidx6(i, j), N);
       px[i] = at(L::GX + i, N);
-      Pxw[i][0] = Pxw[i][1] = 0;
+      W[2 * i] = W[2 * i + 1] = 0;
     }
-    Pww[0][0] = Pww[0][1] = Pww[1][0] = Pww[1][1] = 0;
-    pw[0] = pw[1] = 0;
     bool ok = true;
 #pragma unroll 1
     for (int k = N - 1; k >= 0; k--) {
-      double A[NX][NX], B[NX][2];
+      double a_[NJ], hx[DYN_NHX], hu[DYN_NHU], gx[NX], b[NX];
+#pragma unroll
+      for (int i = 0; i < NJ; i++) a_[i] = p.T * at(L::JAC + i, k);
+      // structurally nonzero Hessian entries: (x,y) block, (phi..r) block, steering row vs (vx,vy,r)
+      hx[0] = at(L::HXX + pidx6(0, 0), k);
+      hx[1] = at(L::HXX + pidx6(0, 1), k);
+      hx[2] = at(L::HXX + pidx6(1, 1), k);
       {
-        double J[NJ];
+        int q = 3;
 #pragma unroll
-        for (int i = 0; i < NJ; i++) J[i] = at(L::JAC + i, k);
-        dyn_expand(J, p.T, A, B);
+        for (int i = 2; i < 6; i++)
+#pragma unroll
+          for (int j = i; j < 6; j++) hx[q++] = at(L::HXX + pidx6(i, j), k);
       }
-      double E[2] = {at(L::EE + 0, k), at(L::EE + 1, k)};
-      double t[2] = {at(L::TK + 0, k), at(L::TK + 1, k)};
-      double b[NX], Pb[NX];
-#pragma unroll
-      for (int i = 0; i < NX; i++) b[i] = -at(L::CDEF + i, k + 1);
+      hu[0] = at(L::HUX + 3, k);
+      hu[1] = at(L::HUX + 4, k);
+      hu[2] = at(L::HUX + 5, k);
 #pragma unroll
       for (int i = 0; i < NX; i++) {
-        double s = px[i];
-#pragma unroll
-        for (int j = 0; j < NX; j++) s += Pxx[i][j] * b[j];
-        Pb[i] = s;
+        gx[i] = at(L::GX + i, k);
+        b[i] = -at(L::CDEF + i, k + 1);
       }
-      double PA[NX][NX], PB[NX][2];
+      const double Ed = at(L::EE + 0, k), Ea = at(L::EE + 1, k), td = at(L::TK + 0, k), ta = at(L::TK + 1, k);
+      double Fxx[21], Fux[12], Fuu[3], fx[NX], fu[2];
+      dyn_riccati_F(P, W, Q, px, pw, a_, p.T, hx, hu, at(L::HUU + 0, k), at(L::HUU + 1, k), Ed, Ea, td, ta, gx, at(L::GU + 0, k),
+                    at(L::GU + 1, k), b, Fxx, Fux, Fuu, fx, fu);
+      const double det = Fuu[0] * Fuu[2] - Fuu[1] * Fuu[1];
+      if (!(Fuu[0] > 0.0) || !(det > 0.0) || !isfinite(det)) { ok = false; break; }
+      const double id = 1.0 / det;
+      const double idd = Fuu[2] * id, ida = -Fuu[1] * id, iaa = Fuu[0] * id;
+      double Kd[NX], Ka[NX];
 #pragma unroll
-      for (int i = 0; i < NX; i++) {
-#pragma unroll
-        for (int j = 0; j < NX; j++) {
-          double s = 0;
-#pragma unroll
-          for (int a = 0; a < NX; a++) s += Pxx[i][a] * A[a][j];
-          PA[i][j] = s;
-        }
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-          double s = 0;
-#pragma unroll
-          for (int a = 0; a < NX; a++) s += Pxx[i][a] * B[a][j];
-          PB[i][j] = s;
-        }
+      for (int j = 0; j < NX; j++) {
+        Kd[j] = -(idd * Fux[j] + ida * Fux[6 + j]);
+        Ka[j] = -(ida * Fux[j] + iaa * Fux[6 + j]);
       }
-      double Fxx[NX][NX], Fux[2][NX], Fuu[2][2], fx[NX], fu[2];
-#pragma unroll
-      for (int i = 0; i < NX; i++)
-#pragma unroll
-        for (int j = 0; j < NX; j++) {
-          double s = at(L::HXX + sidx6(i, j), k);
-#pragma unroll
-          for (int a = 0; a < NX; a++) s += A[a][i] * PA[a][j];
-          Fxx[i][j] = s;
-        }
-#pragma unroll
-      for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int j = 0; j < NX; j++) {
-          double s = i == 0 ? at(L::HUX + j, k) : 0.0;
-#pragma unroll
-          for (int a = 0; a < NX; a++) s += B[a][i] * PA[a][j] + Pxw[a][i] * A[a][j];
-          Fux[i][j] = s;
-        }
-#pragma unroll
-      for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-          double s = Pww[i][j];
-          if (i == j) s += at(L::HUU + i, k) + E[i];
-#pragma unroll
-          for (int a = 0; a < NX; a++) s += B[a][i] * PB[a][j] + B[a][i] * Pxw[a][j] + Pxw[a][i] * B[a][j];
-          Fuu[i][j] = s;
-        }
-#pragma unroll
-      for (int i = 0; i < NX; i++) {
-        double s = at(L::GX + i, k);
-#pragma unroll
-        for (int a = 0; a < NX; a++) s += A[a][i] * Pb[a];
-        fx[i] = s;
-      }
-#pragma unroll
-      for (int i = 0; i < 2; i++) {
-        double s = at(L::GU + i, k) + t[i] + pw[i];
-#pragma unroll
-        for (int a = 0; a < NX; a++) s += B[a][i] * Pb[a] + Pxw[a][i] * b[a];
-        fu[i] = s;
-      }
-      double det = Fuu[0][0] * Fuu[1][1] - Fuu[0][1] * Fuu[1][0];
-      if (!(Fuu[0][0] > 0.0) || !(det > 0.0) || !isfinite(det)) { ok = false; break; }
-      double id = 1.0 / det;
-      double Fi[2][2] = {{Fuu[1][1] * id, -Fuu[0][1] * id}, {-Fuu[1][0] * id, Fuu[0][0] * id}};
-      double Kx[2][NX], Kw[2][2], kk[2];
-#pragma unroll
-      for (int i = 0; i < 2; i++) {
-#pragma unroll
-        for (int j = 0; j < NX; j++) Kx[i][j] = -(Fi[i][0] * Fux[0][j] + Fi[i][1] * Fux[1][j]);
-#pragma unroll
-        for (int j = 0; j < 2; j++) Kw[i][j] = Fi[i][j] * E[j];
-        kk[i] = -(Fi[i][0] * fu[0] + Fi[i][1] * fu[1]);
-      }
+      const double wdd = idd * Ed, wda = ida * Ea, wad = ida * Ed, waa = iaa * Ea;
+      const double kkd = -(idd * fu[0] + ida * fu[1]), kka = -(ida * fu[0] + iaa * fu[1]);
       __syncwarp();  // every lane has consumed the QP slots of this stage before lane 0 reuses them
       if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-#pragma unroll
-          for (int j = 0; j < NX; j++) at(L::KX + i * NX + j, k) = Kx[i][j];
-          at(L::KW + i * 2 + 0, k) = Kw[i][0];
-          at(L::KW + i * 2 + 1, k) = Kw[i][1];
-          at(L::KK + i, k) = kk[i];
+        for (int j = 0; j < NX; j++) {
+          at(L::KX + j, k) = Kd[j];
+          at(L::KX + NX + j, k) = Ka[j];
         }
+        at(L::KW + 0, k) = wdd; at(L::KW + 1, k) = wda; at(L::KW + 2, k) = wad; at(L::KW + 3, k) = waa;
+        at(L::KK + 0, k) = kkd; at(L::KK + 1, k) = kka;
+      }
+      {
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < NX; i++)
+#pragma unroll
+          for (int j = i; j < NX; j++, q++) P[q] = Fxx[q] + Fux[i] * Kd[j] + Fux[6 + i] * Ka[j];
       }
 #pragma unroll
       for (int i = 0; i < NX; i++) {
-#pragma unroll
-        for (int j = 0; j < NX; j++) Pxx[i][j] = Fxx[i][j] + Fux[0][i] * Kx[0][j] + Fux[1][i] * Kx[1][j];
-#pragma unroll
-        for (int j = 0; j < 2; j++) Pxw[i][j] = Fux[0][i] * Kw[0][j] + Fux[1][i] * Kw[1][j];
-        px[i] = fx[i] + Fux[0][i] * kk[0] + Fux[1][i] * kk[1];
+        W[2 * i] = Fux[i] * wdd + Fux[6 + i] * wad;
+        W[2 * i + 1] = Fux[i] * wda + Fux[6 + i] * waa;
+        px[i] = fx[i] + Fux[i] * kkd + Fux[6 + i] * kka;
       }
-#pragma unroll
-      for (int i = 0; i < NX; i++)
-#pragma unroll
-        for (int j = i + 1; j < NX; j++) {
-          double mm = 0.5 * (Pxx[i][j] + Pxx[j][i]);
-          Pxx[i][j] = mm;
-          Pxx[j][i] = mm;
-        }
-#pragma unroll
-      for (int i = 0; i < 2; i++) {
-#pragma unroll
-        for (int j = 0; j < 2; j++) Pww[i][j] = (i == j ? E[i] : 0.0) - E[i] * Kw[i][j];
-        pw[i] = -t[i] - E[i] * kk[i];
-      }
-      double mm = 0.5 * (Pww[0][1] + Pww[1][0]);
-      Pww[0][1] = mm;
-      Pww[1][0] = mm;
+      Q[0] = Ed - Ed * wdd;
+      Q[1] = -0.5 * (Ed * wda + Ea * wad);
+      Q[2] = Ea - Ea * waa;
+      pw[0] = -td - Ed * kkd;
+      pw[1] = -ta - Ea * kka;
     }
     __syncwarp();
     return ok;
@@ -862,17 +813,28 @@ struct DynSolver {
     return __all_sync(0xffffffffu, fin);
   }
 
-#define MPCB_ITER_SYNC() ((void)0)
+#define MPCB_ITER_SYNC() do { if (((++tick) & (MPCB_SYNC_EVERY - 1)) == 0) __syncthreads_and(0); } while (0)
 #include "mpcb_run_loop.inc"
 #undef MPCB_ITER_SYNC
 };
 
-__global__ void __launch_bounds__(32) dyn_solve_kernel(const __grid_constant__ KParams p) {
-  const int lane = threadIdx.x;
-  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-    DynSolver s(p, lane);
+// persistent, W warps per block in step, see kin_solve_kernel
+template <int W>
+__global__ void __launch_bounds__(32 * W) dyn_solve_kernel(const __grid_constant__ KParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *gs = p.slab + ((size_t)blockIdx.x * W + warp) * DynLayout::slab_doubles();
+  const int woff = warp * DynLayout::NF * (p.N + 1);
+  int tick = 0;
+  for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(p.counter, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= p.B) break;
+    DynSolver s(p, gs, woff, tick, lane);
     s.run(b);
     __syncwarp();
+  }
+  while (!__syncthreads_and(1)) {
   }
 }
 
