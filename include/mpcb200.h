@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MPCB_VERSION 100 /* 0.1.0 */
+#define MPCB_VERSION 101 /* 0.1.1: cfg gained ref_mode (was reserved) and cbf_gamma */
 #define MPCB_NMAX 128    /* maximum horizon N */
 #define MPCB_MMAX 2      /* maximum obstacles per scenario in this build */
 
@@ -33,8 +33,15 @@ extern "C" {
 enum { MPCB_MODEL_KIN = 0, MPCB_MODEL_DYN = 1 };
 /* obstacle rows: NONE = MPC_optimize_kin (no CBF); ELLIPSE = h(X_i) >= 0, i=0..N-1
  * (PKG/MPC_CBF_optimize_kin.py:236-247, _kin_pre.py:236-253); SQRT = sqrt(ellipse-1) >= 1,
- * i=0..N (PKG/MPC_CBF_optimize_dyn.py:238-243) */
-enum { MPCB_OBS_NONE = 0, MPCB_OBS_ELLIPSE = 1, MPCB_OBS_SQRT = 2 };
+ * i=0..N (PKG/MPC_CBF_optimize_dyn.py:238-243); DCBF = the discrete-time control-barrier row the
+ * reference carries commented out, `gamma*h_func + h_dot` with h_dot = h(X_{i+1}) - h(X_i), both at
+ * the step-i obstacle (PKG/MPC_CBF_optimize_kin.py:244-248, _kin_pre.py:250-254), i.e.
+ * h(X_{i+1}; obs_i) - (1-gamma) h(X_i; obs_i) >= 0, i=0..N-1 (kinematic model) */
+enum { MPCB_OBS_NONE = 0, MPCB_OBS_ELLIPSE = 1, MPCB_OBS_SQRT = 2, MPCB_OBS_DCBF = 3 };
+/* cost target: TERMINAL = xs [B][nx], every stage tracks xs (the reference's aa = 0,
+ * PKG/MPC_CBF_optimize_kin.py:194-199); TRAJECTORY = xs [B][N][nx], stage i tracks row i =
+ * aa*ref_state[i+1] + (1-aa)*xs, blended by the host (kinematic model) */
+enum { MPCB_REF_TERMINAL = 0, MPCB_REF_TRAJECTORY = 1 };
 /* how `z_init` (the `x0=` argument of the CasADi call, PKG/main_cbf_kin_c_sim.py:92,100) is used:
  * AS_GIVEN = controls and states as passed; ROLLOUT = controls as passed, states re-integrated
  * from the parameter x0 with the Euler step of PKG/MPC_CBF_optimize_kin.py:207 */
@@ -89,7 +96,8 @@ typedef struct mpcb_cfg {
   double mu_init;       /* initial barrier parameter (IPOPT default 0.1; this library's default 100) */
   double bound_relax;   /* ipopt.bound_relax_factor (1e-8) */
   int32_t obs_input;    /* MPCB_OBS_TRAJECTORY (default) or MPCB_OBS_INITIAL */
-  int32_t reserved;
+  int32_t ref_mode;     /* MPCB_REF_TERMINAL (default) or MPCB_REF_TRAJECTORY */
+  double cbf_gamma;     /* gamma in (0,1] of the MPCB_OBS_DCBF rows (the reference's `gamma = 1.00`, :235) */
 } mpcb_cfg;
 
 typedef struct mpcb_handle mpcb_handle;
@@ -113,7 +121,8 @@ int mpcb_workspace_bytes(const mpcb_cfg *cfg, int B, size_t *bytes);
 
 /* Replaces optimize_problem + solver(...) for B independent scenarios.  DEVICE pointers,
  * row-major, float64:
- *   x0 [B][nx], xs [B][nx]        = the parameter vector p=[x0;xs] (PKG/main_cbf_kin_c_sim.py:89)
+ *   x0 [B][nx], xs [B][nx]        = the parameter vector p=[x0;xs] (PKG/main_cbf_kin_c_sim.py:89);
+ *                                   xs [B][N][nx] with cfg.ref_mode = MPCB_REF_TRAJECTORY
  *   obs [B][M][N+1][6]            = obs_prediction rows [x,y,theta,v,l,w] (PKG/Obs_prediction.py:3-40);
  *                                   static obstacles repeat the row; dyn uses columns 0,1 only.
  *                                   With cfg.obs_input = MPCB_OBS_INITIAL: [B][M][6] (see above)

@@ -9,9 +9,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("MPCB200_LIB") or os.path.join(HERE, "libmpcb200.so")  # env override: A/B builds
 
 MODEL_KIN, MODEL_DYN = 0, 1
-OBS_NONE, OBS_ELLIPSE, OBS_SQRT = 0, 1, 2
+OBS_NONE, OBS_ELLIPSE, OBS_SQRT, OBS_DCBF = 0, 1, 2, 3
 INIT_AS_GIVEN, INIT_ROLLOUT = 0, 1
 OBS_TRAJECTORY, OBS_INITIAL = 0, 1
+REF_TERMINAL, REF_TRAJECTORY = 0, 1
 ST_CONVERGED, ST_ACCEPTABLE, ST_MAXITER, ST_INFEASIBLE, ST_NAN = 0, 1, 2, 3, 4
 
 # IPOPT return_status strings (CasADi `solver.stats()['return_status']`)
@@ -40,7 +41,7 @@ class MpcbCfg(C.Structure):
         ("Veh_Iz", C.c_double), ("aopt_f", C.c_double), ("aopt_r", C.c_double),
         ("Fymax_f", C.c_double), ("Fymax_r", C.c_double),
         ("tol", C.c_double), ("mu_init", C.c_double), ("bound_relax", C.c_double),
-        ("obs_input", C.c_int32), ("reserved", C.c_int32),
+        ("obs_input", C.c_int32), ("ref_mode", C.c_int32), ("cbf_gamma", C.c_double),
     ]
 
 

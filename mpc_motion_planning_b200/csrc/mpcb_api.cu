@@ -46,10 +46,10 @@ Variant make_kin_variant_w() {
   Variant v;
   v.launch = &launch_kin<NR, MO, OBS, W>;
   v.kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, W>;
-  v.smem_bytes = [](int N) { return KinLayout<NR, MO>::bytes(N); };
+  v.smem_bytes = [](int N) { return KinLayout<NR, MO, OBS == 3>::bytes(N); };
   v.nx = 4;
   v.nbx = 2;
-  v.slab_doubles = KinLayout<NR, MO>::slab_doubles();
+  v.slab_doubles = KinLayout<NR, MO, OBS == 3>::slab_doubles();
   v.warps = W;
   return v;
 }
@@ -117,6 +117,8 @@ bool select_variant(const mpcb_cfg &c, Variant &v) {
     if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 1) { v = make_kin_variant<1, 0, 0>(c.N); return true; }
     if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 1) { v = make_kin_variant<1, 1, 1>(c.N); return true; }
     if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 2) { v = make_kin_variant<1, 2, 1>(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 1) { v = make_kin_variant<1, 1, 3>(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 2) { v = make_kin_variant<1, 2, 3>(c.N); return true; }
   }
   return false;
 }
@@ -189,6 +191,9 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   if (!(c.T > 0) || !(c.tol > 0) || !(c.mu_init > 0) || !(c.bound_relax >= 0)) return MPCB_E_ARG;
   if (c.obs_mode != MPCB_OBS_NONE && c.M < 1) return MPCB_E_ARG;
   if (c.obs_input != MPCB_OBS_TRAJECTORY && c.obs_input != MPCB_OBS_INITIAL) return MPCB_E_ARG;
+  if (c.ref_mode != MPCB_REF_TERMINAL && c.ref_mode != MPCB_REF_TRAJECTORY) return MPCB_E_ARG;
+  if (c.ref_mode == MPCB_REF_TRAJECTORY && c.model != MPCB_MODEL_KIN) return MPCB_E_ARG;
+  if (c.obs_mode == MPCB_OBS_DCBF && !(c.cbf_gamma > 0.0 && c.cbf_gamma <= 1.0)) return MPCB_E_ARG;
   Variant var;
   if (!select_variant(c, var)) return MPCB_E_ARG;
   // the kernels assume: both controls two-sided; the model's bounded states (kin: y, vx; dyn: + vy)
@@ -217,9 +222,11 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   memset(&k, 0, sizeof k);
   const int M = c.obs_mode == MPCB_OBS_NONE ? 0 : c.M;
   k.obs_input = c.obs_input;
+  k.ref_mode = c.ref_mode;
+  k.cbf_g1 = 1.0 - c.cbf_gamma;
   k.N = c.N; k.obs_mode = c.obs_mode; k.du0_cost = c.du0_cost; k.init_mode = c.init_mode; k.max_iter = c.max_iter;
   k.rate_ctrl[0] = c.rate_ctrl[0]; k.rate_ctrl[1] = c.rate_ctrl[1];
-  const int n_obs_st = c.obs_mode == MPCB_OBS_ELLIPSE ? c.N : (c.obs_mode == MPCB_OBS_SQRT ? c.N + 1 : 0);
+  const int n_obs_st = (c.obs_mode == MPCB_OBS_ELLIPSE || c.obs_mode == MPCB_OBS_DCBF) ? c.N : (c.obs_mode == MPCB_OBS_SQRT ? c.N + 1 : 0);
   k.n_eq = var.nx * (c.N + 1) + c.n_rate * (c.N - 1) + M * n_obs_st;
   k.n_bm = 4 * c.N + 2 * var.nbx * (c.N + 1) + 2 * c.n_rate * (c.N - 1) + M * n_obs_st;
   k.T = c.T;
@@ -322,11 +329,12 @@ int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double 
   const int M = h->cfg.obs_mode == MPCB_OBS_NONE ? 0 : h->cfg.M;
   const size_t nv = 2 * (size_t)N + (size_t)nx * (N + 1);
   const size_t so = (size_t)M * (h->cfg.obs_input == MPCB_OBS_INITIAL ? 1 : (N + 1)) * 6;
+  const size_t sxs = h->cfg.ref_mode == MPCB_REF_TRAJECTORY ? (size_t)nx * N : (size_t)nx;
   if (M > 0 && !obs) return MPCB_E_ARG;
   if (B > h->cap_B) {
     free_bufs(h);
     size_t b = (size_t)B;
-    bool ok = cuda_ok(cudaMalloc(&h->d_x0, b * nx * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_xs, b * nx * 8), "cudaMalloc") &&
+    bool ok = cuda_ok(cudaMalloc(&h->d_x0, b * nx * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_xs, b * sxs * 8), "cudaMalloc") &&
               cuda_ok(cudaMalloc(&h->d_obs, b * (so ? so : 1) * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_zin, b * nv * 8), "cudaMalloc") &&
               cuda_ok(cudaMalloc(&h->d_u0, b * 2 * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_cost, b * 8), "cudaMalloc") &&
               cuda_ok(cudaMalloc(&h->d_z, b * nv * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_lam, b * nx * (N + 1) * 8), "cudaMalloc") &&
@@ -337,7 +345,7 @@ int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double 
   cudaStream_t st = h->stream;
   size_t b = (size_t)B;
   bool ok = cuda_ok(cudaMemcpyAsync(h->d_x0, x0, b * nx * 8, cudaMemcpyHostToDevice, st), "H2D x0") &&
-            cuda_ok(cudaMemcpyAsync(h->d_xs, xs, b * nx * 8, cudaMemcpyHostToDevice, st), "H2D xs");
+            cuda_ok(cudaMemcpyAsync(h->d_xs, xs, b * sxs * 8, cudaMemcpyHostToDevice, st), "H2D xs");
   if (ok && so) ok = cuda_ok(cudaMemcpyAsync(h->d_obs, obs, b * so * 8, cudaMemcpyHostToDevice, st), "H2D obs");
   if (ok && z_init) ok = cuda_ok(cudaMemcpyAsync(h->d_zin, z_init, b * nv * 8, cudaMemcpyHostToDevice, st), "H2D z_init");
   if (!ok) return MPCB_E_CUDA;

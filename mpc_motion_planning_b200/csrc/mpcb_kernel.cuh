@@ -62,6 +62,8 @@ namespace mpcb {
 
 struct KParams {
   int B, N, obs_mode, du0_cost, init_mode, max_iter, obs_input;
+  int ref_mode;   // 1: xs holds [B][N][nx] per-stage cost targets (kinematic kernels)
+  double cbf_g1;  // 1 - gamma of the discrete-time CBF rows (obs_mode 3)
   int rate_ctrl[2];
   int n_eq, n_bm;  // counts used by the IPOPT error scaling
   double T;
@@ -139,15 +141,18 @@ struct KinModel {
 // ------------------------------------------------------------------------------------
 // shared-memory layout of one scenario (rows of S = N+1 doubles)
 // ------------------------------------------------------------------------------------
-template <int NR, int MO>
+// FH: the stage Hessian Hxx is stored full (10 entries) - needed by the discrete-time CBF rows,
+// whose rank-one barrier term couples all four states of a stage (see build_qp).
+template <int NR, int MO, bool FH = false>
 struct KinLayout {
   static constexpr int NX = 4, NBX = 2;
   // ---- shared memory: the working set of the serial sweeps (one record of NF doubles per stage)
   static constexpr int CDEF = 0;         // c_0 = X0 - x0, c_k = defect into stage k
   static constexpr int LAMP = CDEF;      // alias: new dynamics multipliers (written after the forward sweep)
   static constexpr int JAC = CDEF + NX;  // a02 a03 a12 a13 a23 b2  (A = I + T df/dx, B = T df/du)
-  static constexpr int HXX = JAC + 6;    // h00 h01 h11 h22 h23 h33
-  static constexpr int HUX = HXX + 6;    // d2L/(d delta d v)
+  static constexpr int HXX = JAC + 6;    // h00 h01 h11 h22 h23 h33 [h02 h03 h12 h13 when FH]
+  static constexpr int NH = FH ? 10 : 6;
+  static constexpr int HUX = HXX + NH;   // d2L/(d delta d v)
   static constexpr int GX = HUX + 1;
   // 14-slot region: [HUU(2) EE(2) GU(2) TK(2) -(6)] before the backward sweep of a stage,
   // the Riccati gains [KX(8) KW(4) KK(2)] after it, the slack steps after the forward sweep
@@ -187,7 +192,8 @@ struct KinLayout {
   static constexpr int OCY = OCX + MO;
   static constexpr int ISX = OCY + MO;
   static constexpr int ISY = ISX + MO;
-  static constexpr int NG = ISY + MO - G0;
+  static constexpr int XR = ISY + MO;   // per-stage cost target (only with ref_mode)
+  static constexpr int NG = XR + NX - G0;
   static constexpr int SG = 132;        // row stride (>= MPCB_NMAX + 1)
   __host__ __device__ static constexpr size_t bytes(int N) { return sizeof(double) * (size_t)NF * (size_t)(N + 1); }
   __host__ __device__ static constexpr size_t slab_doubles() { return (size_t)NG * SG; }
@@ -212,7 +218,8 @@ __device__ __forceinline__ double clampz(double z, double mu, double rgap) {
 // ------------------------------------------------------------------------------------
 template <int NR, int MO, int OBS_MODE>
 struct KinSolver {
-  using L = KinLayout<NR, MO>;
+  static constexpr bool DCBF = OBS_MODE == 3;  // rows h(X_{k+1};obs_k) - (1-gamma) h(X_k;obs_k) >= 0
+  using L = KinLayout<NR, MO, DCBF>;
   static constexpr int NX = 4, NBX = 2;
 
   const KParams &p;
@@ -231,7 +238,10 @@ struct KinSolver {
     return field >= L::G0 ? gs[(field - L::G0) * L::SG + k] : g_smem[woff + k * L::NF + field];
   }
   __device__ __forceinline__ bool has_rate(int k) const { return NR > 0 && k >= 1 && k <= N - 1; }
-  __device__ __forceinline__ bool has_obs(int k) const { return OBS_MODE == 1 && k <= N - 1; }
+  __device__ __forceinline__ bool has_obs(int k) const { return (OBS_MODE == 1 || DCBF) && k <= N - 1; }
+  // cost target of stage k: xs, or the per-stage reference ref_X = aa*ref_state[k+1] + (1-aa)*xs
+  // (PKG/MPC_CBF_optimize_kin.py:194-199) that the host passes as [B][N][nx]
+  __device__ __forceinline__ double xref(int i, int k) { return p.ref_mode ? at(L::XR + i, k) : xs[i]; }
 
   // gradient of the unscaled objective wrt u_k[i]  (PKG/MPC_CBF_optimize_kin.py:199-205)
   __device__ __forceinline__ double grad_u(int k, int i, double uk, double ukm1, double ukp1) const {
@@ -252,7 +262,7 @@ struct KinSolver {
     double th = 0, fo = 0, br = 0, ln = 0;
     #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
-      double xk[NX], uk[2] = {0, 0};
+      double xk[NX], uk[2] = {0, 0}, xnext[2] = {0, 0};
       double gp = 1.0;  // product of the bound gaps of this stage: sum of logs = log of the product
 #pragma unroll
       for (int i = 0; i < NX; i++) xk[i] = at(L::X + i, k) + alpha * at(L::DX + i, k);
@@ -285,10 +295,11 @@ struct KinSolver {
 #pragma unroll
         for (int i = 0; i < NX; i++) {
           double xn = at(L::X + i, k + 1) + alpha * at(L::DX + i, k + 1);
+          if (i < 2) xnext[i] = xn;
           double d = xn - (xk[i] + p.T * f[i]);
           th += fabs(d);
           at(cdst + i, k + 1) = d;
-          double e = xk[i] - xs[i];
+          double e = xk[i] - xref(i, k);
           fo += p.Q[i] * e * e;
         }
 #pragma unroll
@@ -326,6 +337,10 @@ struct KinSolver {
         for (int j = 0; j < MO; j++) {
           double dx = xk[0] - at(L::OCX + j, k), dy = xk[1] - at(L::OCY + j, k);
           double d = dx * dx * at(L::ISX + j, k) + dy * dy * at(L::ISY + j, k) - 1.0;  // PKG/..._kin.py:244,247
+          if (DCBF) {  // gamma*h_func + h_dot, PKG/..._kin.py:245-248
+            double ex = xnext[0] - at(L::OCX + j, k), ey = xnext[1] - at(L::OCY + j, k);
+            d = (ex * ex * at(L::ISX + j, k) + ey * ey * at(L::ISY + j, k) - 1.0) - p.cbf_g1 * d;
+          }
           double s = at(L::SO + j, k) + (alpha != 0.0 ? alpha * at(L::DSO + j, k) : 0.0);
           th += fabs(d - s);
           gp *= s - p.obs_lo;
@@ -365,7 +380,7 @@ struct KinSolver {
 #pragma unroll
         for (int i = 0; i < NX; i++) {
           l1[i] = at(L::LAM + i, k + 1);
-          rx[i] += sigma * 2 * p.Q[i] * (xk[i] - xs[i]);
+          rx[i] += sigma * 2 * p.Q[i] * (xk[i] - xref(i, k));
         }
         // - A' lam_{k+1}
         rx[0] -= l1[0];
@@ -388,12 +403,27 @@ struct KinSolver {
           double a = at(L::ISX + j, k), b = at(L::ISY + j, k);
           double d = dx * dx * a + dy * dy * b - 1.0;
           double lo = at(L::LO + j, k), vl = at(L::VLO + j, k), s = at(L::SO + j, k);
-          rx[0] += lo * (2 * dx * a);
-          rx[1] += lo * (2 * dy * b);
+          if (DCBF) {
+            double ex = at(L::X + 0, k + 1) - at(L::OCX + j, k), ey = at(L::X + 1, k + 1) - at(L::OCY + j, k);
+            d = (ex * ex * a + ey * ey * b - 1.0) - p.cbf_g1 * d;
+            rx[0] -= p.cbf_g1 * lo * (2 * dx * a);
+            rx[1] -= p.cbf_g1 * lo * (2 * dy * b);
+          } else {
+            rx[0] += lo * (2 * dx * a);
+            rx[1] += lo * (2 * dy * b);
+          }
           dual = fmax(dual, fabs(-lo - vl));
           prim = fmax(prim, fabs(d - s));
           MPCB_COMPL(s - p.obs_lo, vl);
           sl += fabs(lo);
+        }
+      }
+      if (DCBF && k >= 1) {  // row k-1 also depends on X_k
+#pragma unroll
+        for (int j = 0; j < MO; j++) {
+          double lo = at(L::LO + j, k - 1);
+          rx[0] += lo * (2 * (xk[0] - at(L::OCX + j, k - 1)) * at(L::ISX + j, k - 1));
+          rx[1] += lo * (2 * (xk[1] - at(L::OCY + j, k - 1)) * at(L::ISY + j, k - 1));
         }
       }
 #pragma unroll
@@ -458,11 +488,13 @@ struct KinSolver {
       for (int i = 0; i < NX; i++) xk[i] = at(L::X + i, k);
       double h[NX] = {dw, dw, dw, dw};  // diagonal of Hxx
       double h01 = 0, h23 = 0, hdv = 0, hdd_f = 0;
+      double h02 = 0, h03 = 0, h12 = 0, h13 = 0;  // only the discrete-time CBF rows fill these
       double gx[NX] = {0, 0, 0, 0};
+      double a02 = 0, a03 = 0, a12 = 0, a13 = 0;
       if (k < N) {
         // - T sum_i lam_i d2 f_i, written with the stored Jacobian entries
         double l0 = at(L::LAM + 0, k + 1), l1 = at(L::LAM + 1, k + 1), l2 = at(L::LAM + 2, k + 1);
-        double a02 = at(L::JAC + 0, k), a03 = at(L::JAC + 1, k), a12 = at(L::JAC + 2, k), a13 = at(L::JAC + 3, k);
+        a02 = at(L::JAC + 0, k); a03 = at(L::JAC + 1, k); a12 = at(L::JAC + 2, k); a13 = at(L::JAC + 3, k);
         double a23 = at(L::JAC + 4, k), b2 = at(L::JAC + 5, k);
         double t = a23 * (p.Veh_l / p.T);               // tan(delta)
         double jd = (p.T / p.Veh_l) * (1.0 + t * t);    // T sec^2(delta) / L
@@ -473,7 +505,7 @@ struct KinSolver {
 #pragma unroll
         for (int i = 0; i < NX; i++) {
           h[i] += sigma * 2 * p.Q[i];
-          gx[i] = sigma * 2 * p.Q[i] * (xk[i] - xs[i]);
+          gx[i] = sigma * 2 * p.Q[i] * (xk[i] - xref(i, k));
         }
       }
 #pragma unroll
@@ -494,13 +526,45 @@ struct KinSolver {
           double D = at(L::VLO + j, k) * rg + dw;
           double gs = -mu * rg + MPCB_KAPPA_D * mu;
           double lo = at(L::LO + j, k);
-          double t = D * (d - s) + gs;
-          h[0] += lo * (2 * a) + D * ox * ox;
-          h01 += D * ox * oy;
-          h[1] += lo * (2 * b) + D * oy * oy;
-          gx[0] += ox * t;
-          gx[1] += oy * t;
+          if (DCBF) {
+            // Row k is linear in (dx_k, dx_{k+1}).  The Euler step moves the position by states
+            // only (B has no entries in rows 0,1), so with dx_{k+1} = A dx_k + B du_k + b the row
+            // becomes v'dx_k + res with v = g_k + A' g_next: a rank-one term on the stage's own
+            // states, which keeps the Riccati structure.
+            double ex = at(L::X + 0, k + 1) - at(L::OCX + j, k), ey = at(L::X + 1, k + 1) - at(L::OCY + j, k);
+            double nx_ = 2 * ex * a, ny_ = 2 * ey * b;
+            d = (ex * ex * a + ey * ey * b - 1.0) - p.cbf_g1 * d;
+            double v0 = nx_ - p.cbf_g1 * ox, v1 = ny_ - p.cbf_g1 * oy;
+            double v2 = nx_ * a02 + ny_ * a12, v3 = nx_ * a03 + ny_ * a13;
+            double res = (d - s) - nx_ * at(L::CDEF + 0, k + 1) - ny_ * at(L::CDEF + 1, k + 1);
+            double t = D * res + gs;
+            h[0] += D * v0 * v0 - p.cbf_g1 * lo * (2 * a);
+            h[1] += D * v1 * v1 - p.cbf_g1 * lo * (2 * b);
+            h[2] += D * v2 * v2;
+            h[3] += D * v3 * v3;
+            h01 += D * v0 * v1; h02 += D * v0 * v2; h03 += D * v0 * v3;
+            h12 += D * v1 * v2; h13 += D * v1 * v3; h23 += D * v2 * v3;
+            gx[0] += v0 * t; gx[1] += v1 * t; gx[2] += v2 * t; gx[3] += v3 * t;
+          } else {
+            double t = D * (d - s) + gs;
+            h[0] += lo * (2 * a) + D * ox * ox;
+            h01 += D * ox * oy;
+            h[1] += lo * (2 * b) + D * oy * oy;
+            gx[0] += ox * t;
+            gx[1] += oy * t;
+          }
         }
+      }
+      if (DCBF && k >= 1) {  // curvature of row k-1 in X_k
+#pragma unroll
+        for (int j = 0; j < MO; j++) {
+          double lo = at(L::LO + j, k - 1);
+          h[0] += lo * (2 * at(L::ISX + j, k - 1));
+          h[1] += lo * (2 * at(L::ISY + j, k - 1));
+        }
+      }
+      if (L::NH == 10) {
+        at(L::HXX + 6, k) = h02; at(L::HXX + 7, k) = h03; at(L::HXX + 8, k) = h12; at(L::HXX + 9, k) = h13;
       }
       at(L::HXX + 0, k) = h[0];
       at(L::HXX + 1, k) = h01;
@@ -584,7 +648,8 @@ struct KinSolver {
       const double m33 = p33 + a03 * p03 + a13 * p13 + a23 * p23;
       // Fxx = Hxx + A' M (upper triangle)
       const double f00 = at(L::HXX + 0, k) + p00, f01 = at(L::HXX + 1, k) + p01, f11 = at(L::HXX + 2, k) + p11;
-      const double f02 = m02, f03 = m03, f12 = m12, f13 = m13;
+      const double f02 = L::NH == 10 ? m02 + at(L::HXX + 6, k) : m02, f03 = L::NH == 10 ? m03 + at(L::HXX + 7, k) : m03;
+      const double f12 = L::NH == 10 ? m12 + at(L::HXX + 8, k) : m12, f13 = L::NH == 10 ? m13 + at(L::HXX + 9, k) : m13;
       const double f22 = at(L::HXX + 3, k) + m22 + a02 * m02 + a12 * m12;
       const double f23 = at(L::HXX + 4, k) + m23 + a02 * m03 + a12 * m13;
       const double f33 = at(L::HXX + 5, k) + m33 + a03 * m03 + a13 * m13 + a23 * m23;
@@ -705,6 +770,13 @@ struct KinSolver {
       double r1 = at(L::GX + 1, k) + h01 * d0 + h11 * d1;
       double r2 = at(L::GX + 2, k) + h22 * d2 + h23 * d3;
       double r3 = at(L::GX + 3, k) + h23 * d2 + h33 * d3 + hdv * ud;
+      if (L::NH == 10) {
+        double h02 = at(L::HXX + 6, k), h03 = at(L::HXX + 7, k), h12 = at(L::HXX + 8, k), h13 = at(L::HXX + 9, k);
+        r0 += h02 * d2 + h03 * d3;
+        r1 += h12 * d2 + h13 * d3;
+        r2 += h02 * d0 + h12 * d1;
+        r3 += h03 * d0 + h13 * d1;
+      }
       at(L::LAMP + 0, k) = r0; at(L::LAMP + 1, k) = r1; at(L::LAMP + 2, k) = r2; at(L::LAMP + 3, k) = r3;
     }
     __syncwarp();
@@ -739,7 +811,7 @@ struct KinSolver {
       for (int i = 0; i < NX; i++) {
         xk[i] = at(L::X + i, k);
         dx[i] = at(L::DX + i, k);
-        if (k < N) gd += sigma * 2 * p.Q[i] * (xk[i] - xs[i]) * dx[i];
+        if (k < N) gd += sigma * 2 * p.Q[i] * (xk[i] - xref(i, k)) * dx[i];
       }
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
@@ -789,7 +861,20 @@ struct KinSolver {
           double s = at(L::SO + j, k), rg = fast_rcp(s - p.obs_lo), vl = at(L::VLO + j, k);
           double D = vl * rg + dw;
           double gs = -mu * rg + MPCB_KAPPA_D * mu;
-          double ds = (2 * ex * a) * dx[0] + (2 * ey * b) * dx[1] + (d - s);
+          double ds;
+          if (DCBF) {
+            double fx = at(L::X + 0, k + 1) - at(L::OCX + j, k), fy = at(L::X + 1, k + 1) - at(L::OCY + j, k);
+            double nx_ = 2 * fx * a, ny_ = 2 * fy * b;
+            d = (fx * fx * a + fy * fy * b - 1.0) - p.cbf_g1 * d;
+            ds = nx_ * at(L::DX + 0, k + 1) + ny_ * at(L::DX + 1, k + 1) - p.cbf_g1 * ((2 * ex * a) * dx[0] + (2 * ey * b) * dx[1]) + (d - s);
+            // The adjoint sweep ran on the condensed stage costs (row k folded into stage k); the
+            // multipliers of the original problem differ by the row's pull on X_{k+1}.
+            double l = D * ds + gs;
+            at(L::LAMP + 0, k + 1) -= nx_ * l;
+            at(L::LAMP + 1, k + 1) -= ny_ * l;
+          } else {
+            ds = (2 * ex * a) * dx[0] + (2 * ey * b) * dx[1] + (d - s);
+          }
           dso[j] = ds;
           lop[j] = D * ds + gs;
           gd += gs * ds;
@@ -930,6 +1015,11 @@ struct KinSolver {
         at(L::ZUU + i, k) = 1.0;
         at(L::DU + i, k) = 0.0;
       }
+      if (p.ref_mode) {
+        const double *xr = p.xs + ((size_t)b * N + (k < N ? k : N - 1)) * NX;
+#pragma unroll
+        for (int i = 0; i < NX; i++) at(L::XR + i, k) = xr[i];
+      }
 #pragma unroll
       for (int i = 0; i < NX; i++) {
         if (p.init_mode == 0) at(L::X + i, k) = zi ? zi[2 * N + NX * k + i] : 0.0;
@@ -985,6 +1075,10 @@ struct KinSolver {
         for (int j = 0; j < MO; j++) {
           double dx = at(L::X + 0, k) - at(L::OCX + j, k), dy = at(L::X + 1, k) - at(L::OCY + j, k);
           double d = dx * dx * at(L::ISX + j, k) + dy * dy * at(L::ISY + j, k) - 1.0;
+          if (DCBF) {
+            double ex = at(L::X + 0, k + 1) - at(L::OCX + j, k), ey = at(L::X + 1, k + 1) - at(L::OCY + j, k);
+            d = (ex * ex * at(L::ISX + j, k) + ey * ey * at(L::ISY + j, k) - 1.0) - p.cbf_g1 * d;
+          }
           at(L::SO + j, k) = push_lo(d, p.obs_lo);
           at(L::VLO + j, k) = 1.0;
           at(L::LO + j, k) = 0.0;
@@ -999,7 +1093,7 @@ struct KinSolver {
           gmax = fmax(gmax, fabs(grad_u(k, i, uk, um, up)));
         }
 #pragma unroll
-        for (int i = 0; i < NX; i++) gmax = fmax(gmax, fabs(2 * p.Q[i] * (at(L::X + i, k) - xs[i])));
+        for (int i = 0; i < NX; i++) gmax = fmax(gmax, fabs(2 * p.Q[i] * (at(L::X + i, k) - xref(i, k))));
       }
     }
     gmax = warp_max(gmax);
@@ -1034,8 +1128,9 @@ struct KinSolver {
 template <int NR, int MO, int OBS_MODE, int W>
 __global__ void __launch_bounds__(32 * W, MPCB_KIN_RESIDENT_WARPS / W) kin_solve_kernel(const __grid_constant__ KParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *gs = p.slab + ((size_t)blockIdx.x * W + warp) * KinLayout<NR, MO>::slab_doubles();
-  const int woff = warp * KinLayout<NR, MO>::NF * (p.N + 1);
+  using L = KinLayout<NR, MO, OBS_MODE == 3>;
+  double *gs = p.slab + ((size_t)blockIdx.x * W + warp) * L::slab_doubles();
+  const int woff = warp * L::NF * (p.N + 1);
   int tick = 0;
   for (;;) {
     int b = 0;

@@ -47,11 +47,15 @@ def horizon_steps(config: dict) -> int:
 
 def make_cfg(kind: str, config: dict, N: int | None = None, M: int = 1, weights: Weights | None = None,
              init_mode: int = _lib.INIT_ROLLOUT, mu_init: float = 100.0, max_iter: int = 100, tol: float = 1e-8,
-             bounds: dict | None = None, obs_input: int = _lib.OBS_TRAJECTORY) -> _lib.MpcbCfg:
+             bounds: dict | None = None, obs_input: int = _lib.OBS_TRAJECTORY, cbf_gamma: float | None = None,
+             ref_mode: int = _lib.REF_TERMINAL) -> _lib.MpcbCfg:
     """Fill an mpcb_cfg from the YAML dict with the reference's hard-coded constants.
 
     `bounds` optionally overrides {'u_lo','u_hi','x_lo','x_hi','rate_lo','rate_hi'} (used by the
-    reference-surface shim, which receives lbx/ubx/lbg/ubg lists at call time)."""
+    reference-surface shim, which receives lbx/ubx/lbg/ubg lists at call time).
+    `cbf_gamma` switches the obstacle rows of the kin-CBF kinds to the discrete-time CBF form the
+    reference carries commented out (PKG/MPC_CBF_optimize_kin.py:244-248); `ref_mode` =
+    REF_TRAJECTORY makes `xs` a per-stage target array (the `aa` blend of :194-199)."""
     if kind not in KINDS:
         raise ValueError(f"unknown kind {kind!r}")
     mp, vp = config["mpc_params"], config["vehicle_params"]
@@ -106,4 +110,11 @@ def make_cfg(kind: str, config: dict, N: int | None = None, M: int = 1, weights:
     c.max_iter = max_iter
     c.tol, c.mu_init, c.bound_relax = tol, mu_init, 1e-8
     c.obs_input = obs_input
+    c.ref_mode = ref_mode
+    if cbf_gamma is not None:
+        if kind not in ("kin_cbf", "kin_cbf_pre"):
+            raise ValueError("cbf_gamma applies to the kinematic CBF kinds only")
+        c.obs_mode, c.cbf_gamma = _lib.OBS_DCBF, float(cbf_gamma)
+    if ref_mode == _lib.REF_TRAJECTORY and kind == "dyn":
+        raise ValueError("per-stage references are implemented for the kinematic kinds only")
     return c

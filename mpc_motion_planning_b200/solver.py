@@ -28,20 +28,26 @@ class BatchSolver:
 
     def __init__(self, kind: str = "kin_cbf_pre", config: dict | None = None, N: int | None = None, M: int = 1,
                  init: str = "rollout", mu_init: float = 100.0, max_iter: int = 100, tol: float = 1e-8,
-                 weights=None, bounds: dict | None = None, obs_input: str = "trajectory"):
+                 weights=None, bounds: dict | None = None, obs_input: str = "trajectory", cbf_gamma: float | None = None,
+                 ref: str = "terminal"):
         self.lib = _lib.load()
         self.kind = kind
         self.config = config if config is not None else load_config(PACKAGE_PARAMS)
         init_mode = {"rollout": _lib.INIT_ROLLOUT, "as_given": _lib.INIT_AS_GIVEN}[init]
         self.obs_initial = {"trajectory": False, "initial": True}[obs_input]
+        self.ref_trajectory = {"terminal": False, "trajectory": True}[ref]
         self.cfg = make_cfg(kind, self.config, N=N, M=M, weights=weights, init_mode=init_mode, mu_init=mu_init,
                             max_iter=max_iter, tol=tol, bounds=bounds,
-                            obs_input=_lib.OBS_INITIAL if self.obs_initial else _lib.OBS_TRAJECTORY)
+                            obs_input=_lib.OBS_INITIAL if self.obs_initial else _lib.OBS_TRAJECTORY,
+                            cbf_gamma=cbf_gamma,
+                            ref_mode=_lib.REF_TRAJECTORY if self.ref_trajectory else _lib.REF_TERMINAL)
         self.N, self.M = int(self.cfg.N), int(self.cfg.M)
         self.nx = _nx(kind)
         self.nv = 2 * self.N + self.nx * (self.N + 1)
         # obs argument: (B,M,N+1,6) obs_prediction rows, or (B,M,6) obstacle states when obs_input="initial"
         self.obs_shape = (self.M, 6) if self.obs_initial else (self.M, self.N + 1, 6)
+        # xs argument: (B,nx) target, or (B,N,nx) per-stage targets when ref="trajectory"
+        self.xs_shape = (self.N, self.nx) if self.ref_trajectory else (self.nx,)
         self._h = C.c_void_p()
         _lib.check(self.lib.mpcb_create(C.byref(self.cfg), C.byref(self._h)), "mpcb_create")
 
@@ -58,7 +64,7 @@ class BatchSolver:
 
     # ------------------------------------------------------------------ device path
     def solve(self, x0, xs, obs=None, z_init=None, return_z: bool = False, return_lam: bool = False):
-        """x0,xs (B,nx); obs (B,M,N+1,6) or None; z_init (B,nv) or None.
+        """x0 (B,nx); xs (B,nx) [(B,N,nx) with ref="trajectory"]; obs (B,M,N+1,6) or None; z_init (B,nv) or None.
 
         torch CUDA tensors -> asynchronous on the current stream, returns torch tensors;
         numpy arrays -> synchronous host entry, returns numpy arrays.
@@ -81,7 +87,7 @@ class BatchSolver:
             return t
 
         x0 = prep(x0, (B, self.nx))
-        xs = prep(xs, (B, self.nx))
+        xs = prep(xs, (B,) + self.xs_shape)
         obs = prep(obs, (B,) + self.obs_shape) if self.M > 0 else None
         z_init = prep(z_init, (B, self.nv))
         u0 = torch.empty((B, 2), dtype=torch.float64, device=dev)
@@ -108,7 +114,7 @@ class BatchSolver:
         B = x0.shape[0]
         f64 = lambda a, shape: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(shape)
         x0 = f64(x0, (B, self.nx))
-        xs = f64(xs, (B, self.nx))
+        xs = f64(xs, (B,) + self.xs_shape)
         obs = f64(obs, (B,) + self.obs_shape) if self.M > 0 else None
         z_init = f64(z_init, (B, self.nv))
         u0 = np.empty((B, 2))

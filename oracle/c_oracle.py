@@ -33,6 +33,7 @@ class OrcCfg(C.Structure):
         ("Veh_Iz", C.c_double), ("aopt_f", C.c_double), ("aopt_r", C.c_double),
         ("Fymax_f", C.c_double), ("Fymax_r", C.c_double),
         ("tol", C.c_double), ("mu_init", C.c_double), ("bound_relax", C.c_double),
+        ("cbf_gamma", C.c_double), ("ref_mode", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -65,7 +66,8 @@ def lib():
 
 
 def make_cfg(kind: str, N: int | None = None, M: int = 1, params: Params | None = None, init_mode: int = 1,
-             mu_init: float = 100.0, max_iter: int = 100, tol: float = 1e-8) -> OrcCfg:
+             mu_init: float = 100.0, max_iter: int = 100, tol: float = 1e-8, cbf_gamma: float | None = None,
+             ref_trajectory: bool = False) -> OrcCfg:
     p = params or Params()
     w = reference_weights(kind)
     c = OrcCfg()
@@ -104,7 +106,17 @@ def make_cfg(kind: str, N: int | None = None, M: int = 1, params: Params | None 
     c.init_mode = init_mode
     c.max_iter = max_iter
     c.tol, c.mu_init, c.bound_relax = tol, mu_init, 1e-8
+    if cbf_gamma is not None:  # the commented row of PKG/MPC_CBF_optimize_kin.py:244-248
+        assert kind in ("kin_cbf", "kin_cbf_pre")
+        c.obs_mode, c.cbf_gamma = 3, cbf_gamma
+    c.ref_mode = int(ref_trajectory)  # xs is (N, nx) per-stage cost targets
     return c
+
+
+def _xs(cfg, xs, B=None):
+    nx = 6 if cfg.model == 1 else 4
+    shape = (cfg.N, nx) if cfg.ref_mode else (nx,)
+    return np.ascontiguousarray(xs, dtype=np.float64).reshape(shape if B is None else (B,) + shape)
 
 
 def _dp(a):
@@ -116,7 +128,7 @@ def solve(cfg: OrcCfg, x0, xs, obs, z_init=None):
     N = cfg.N
     nv = 2 * N + nx * (N + 1)
     x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(nx)
-    xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(nx)
+    xs = _xs(cfg, xs)
     obs = None if obs is None or cfg.obs_mode == 0 else np.ascontiguousarray(obs, dtype=np.float64).reshape(cfg.M, N + 1, 6)
     zi = None if z_init is None else np.ascontiguousarray(z_init, dtype=np.float64).reshape(nv)
     z = np.zeros(nv)
@@ -133,7 +145,7 @@ def solve_batch(cfg: OrcCfg, x0, xs, obs, z_init=None, want_z=False, nthreads=1)
     nv = 2 * N + nx * (N + 1)
     x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, nx)
     B = x0.shape[0]
-    xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(B, nx)
+    xs = _xs(cfg, xs, B)
     obs = None if obs is None or cfg.obs_mode == 0 else np.ascontiguousarray(obs, dtype=np.float64).reshape(B, cfg.M, N + 1, 6)
     zi = None if z_init is None else np.ascontiguousarray(z_init, dtype=np.float64).reshape(B, nv)
     u0 = np.zeros((B, 2))
@@ -153,7 +165,7 @@ def newton_step(cfg: OrcCfg, x0, xs, obs, z, mu, dw, obj_scale):
     N = cfg.N
     nv = 2 * N + nx * (N + 1)
     x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(nx)
-    xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(nx)
+    xs = _xs(cfg, xs)
     obs = None if obs is None or cfg.obs_mode == 0 else np.ascontiguousarray(obs, dtype=np.float64).reshape(cfg.M, N + 1, 6)
     z = np.ascontiguousarray(z, dtype=np.float64).reshape(nv)
     dz = np.zeros(nv)

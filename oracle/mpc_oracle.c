@@ -45,7 +45,7 @@ typedef struct {
 typedef struct {
   const orc_cfg *c;
   int nx, N, M;
-  double x0[NXM], xs[NXM];
+  double x0[NXM], xr[NST][NXM]; /* start state, per-stage cost target */
   double ocx[NST][ORC_MMAX], ocy[NST][ORC_MMAX], isx2[NST][ORC_MMAX], isy2[NST][ORC_MMAX]; /* centre, 1/sX^2, 1/sY^2 */
   double xlo[NXM], xhi[NXM], ulo[2], uhi[2], rlo[2], rhi[2], olo; /* relaxed bounds */
   int xbl[NXM], xbu[NXM];
@@ -57,6 +57,8 @@ typedef struct {
   double A[NST][NXM][NXM], B[NST][NXM][2];
   double dobs[NST][ORC_MMAX], gox[NST][ORC_MMAX], goy[NST][ORC_MMAX]; /* row value and gradient */
   double hoxx[NST][ORC_MMAX], hoxy[NST][ORC_MMAX], hoyy[NST][ORC_MMAX]; /* row Hessian */
+  /* ORC_OBS_DCBF: row k also depends on x_{k+1}: gradient and (diagonal) Hessian wrt its (x,y) */
+  double gnx[NST][ORC_MMAX], gny[NST][ORC_MMAX], hnxx[NST][ORC_MMAX], hnyy[NST][ORC_MMAX];
   double reso[NST][ORC_MMAX], resr[NST][2];
   /* QP data */
   double Hxx[NST][NXM][NXM], Hux[NST][2][NXM], Huu[NST][2][2], E[NST][2];
@@ -149,7 +151,7 @@ static double push_in(double v, double lo, double hi) {
 
 static int has_rate(const ws_t *w, int k) { return k >= 1 && k <= w->N - 1; }
 static int has_obs(const ws_t *w, int k) {
-  if (w->c->obs_mode == ORC_OBS_ELLIPSE) return k <= w->N - 1;
+  if (w->c->obs_mode == ORC_OBS_ELLIPSE || w->c->obs_mode == ORC_OBS_DCBF) return k <= w->N - 1;
   if (w->c->obs_mode == ORC_OBS_SQRT) return k <= w->N;
   return 0;
 }
@@ -160,7 +162,7 @@ static int obs_row(const ws_t *w, int k, int j, double px, double py, double *d,
   double dx = px - w->ocx[k][j], dy = py - w->ocy[k][j];
   double a = w->isx2[k][j], b = w->isy2[k][j];
   double e = dx * dx * a + dy * dy * b - 1.0;
-  if (w->c->obs_mode == ORC_OBS_ELLIPSE) { /* PKG/MPC_CBF_optimize_kin.py:244,247 */
+  if (w->c->obs_mode != ORC_OBS_SQRT) { /* PKG/MPC_CBF_optimize_kin.py:244,247 */
     *d = e;
     if (gx) { *gx = 2 * dx * a; *gy = 2 * dy * b; *hxx = 2 * a; *hxy = 0; *hyy = 2 * b; }
     return isfinite(e);
@@ -181,12 +183,35 @@ static int obs_row(const ws_t *w, int k, int j, double px, double py, double *d,
   return 1;
 }
 
+/* ORC_OBS_DCBF row k: h(X_{k+1}; obs_k) - (1-gamma) h(X_k; obs_k), the commented
+ * `gamma*h_func + h_dot` of PKG/MPC_CBF_optimize_kin.py:244-248 (both terms at the step-k obstacle,
+ * PKG/MPC_CBF_optimize_kin_pre.py:250-254).  With store != 0 the derivatives go to the workspace. */
+static int dcbf_row(ws_t *w, const iterate_t *q, int k, int j, double *d, int store) {
+  double g1 = 1.0 - w->c->cbf_gamma;
+  double e0, e1, gx, gy, hxx, hxy, hyy, nx_, ny_, nxx, nxy, nyy;
+  obs_row(w, k, j, q->x[k][0], q->x[k][1], &e0, &gx, &gy, &hxx, &hxy, &hyy);
+  /* the obstacle of step k evaluated at the next state */
+  double dx = q->x[k + 1][0] - w->ocx[k][j], dy = q->x[k + 1][1] - w->ocy[k][j];
+  double a = w->isx2[k][j], b = w->isy2[k][j];
+  e1 = dx * dx * a + dy * dy * b - 1.0;
+  nx_ = 2 * dx * a; ny_ = 2 * dy * b; nxx = 2 * a; nxy = 0; nyy = 2 * b;
+  (void)nxy;
+  *d = e1 - g1 * e0;
+  if (store) {
+    w->gox[k][j] = -g1 * gx; w->goy[k][j] = -g1 * gy;
+    w->hoxx[k][j] = -g1 * hxx; w->hoxy[k][j] = -g1 * hxy; w->hoyy[k][j] = -g1 * hyy;
+    w->gnx[k][j] = nx_; w->gny[k][j] = ny_; w->hnxx[k][j] = nxx; w->hnyy[k][j] = nyy;
+  }
+  return isfinite(*d);
+}
+#define IS_DCBF(w) ((w)->c->obs_mode == ORC_OBS_DCBF)
+
 /* unscaled objective of the primal part of an iterate (PKG/MPC_CBF_optimize_kin.py:195-205) */
 static double objective(const ws_t *w, const iterate_t *q) {
   const orc_cfg *c = w->c;
   double f = 0;
   for (int k = 0; k < w->N; k++) {
-    for (int i = 0; i < w->nx; i++) { double e = q->x[k][i] - w->xs[i]; f += c->Q[i] * e * e; }
+    for (int i = 0; i < w->nx; i++) { double e = q->x[k][i] - w->xr[k][i]; f += c->Q[i] * e * e; }
     for (int i = 0; i < 2; i++) {
       f += c->R[i] * q->u[k][i] * q->u[k][i];
       if (k > 0) { double e = q->u[k][i] - q->u[k - 1][i]; f += c->DR[i] * e * e; }
@@ -230,7 +255,8 @@ static int eval_primal(ws_t *w, const iterate_t *q, double mu, double *theta, do
     if (has_obs(w, k))
       for (int j = 0; j < M; j++) {
         double d;
-        if (!obs_row(w, k, j, q->x[k][0], q->x[k][1], &d, 0, 0, 0, 0, 0)) return 0;
+        if (IS_DCBF(w)) { if (!dcbf_row(w, q, k, j, &d, 0)) return 0; }
+        else if (!obs_row(w, k, j, q->x[k][0], q->x[k][1], &d, 0, 0, 0, 0, 0)) return 0;
         double r_ = d - q->so[k][j];
         th += fabs(r_);
         if (store) { w->reso[k][j] = r_; w->dobs[k][j] = d; }
@@ -261,9 +287,12 @@ static void eval_lin(ws_t *w) {
       }
     }
     if (has_obs(w, k))
-      for (int j = 0; j < w->M; j++)
-        obs_row(w, k, j, q->x[k][0], q->x[k][1], &w->dobs[k][j], &w->gox[k][j], &w->goy[k][j], &w->hoxx[k][j],
-                &w->hoxy[k][j], &w->hoyy[k][j]);
+      for (int j = 0; j < w->M; j++) {
+        if (IS_DCBF(w)) dcbf_row(w, q, k, j, &w->dobs[k][j], 1);
+        else
+          obs_row(w, k, j, q->x[k][0], q->x[k][1], &w->dobs[k][j], &w->gox[k][j], &w->goy[k][j], &w->hoxx[k][j],
+                  &w->hoxy[k][j], &w->hoyy[k][j]);
+      }
   }
 }
 
@@ -294,13 +323,15 @@ static void kkt_pieces(ws_t *w, kkt_t *o) {
     for (int i = 0; i < nx; i++) {
       double r = q->lam[k][i];
       if (k < N) {
-        r += w->sigma * 2 * c->Q[i] * (q->x[k][i] - w->xs[i]);
+        r += w->sigma * 2 * c->Q[i] * (q->x[k][i] - w->xr[k][i]);
         for (int a = 0; a < nx; a++) r -= w->A[k][a][i] * q->lam[k + 1][a];
       }
       if (w->xbl[i]) { r -= q->zlx[k][i]; COMPL(q->x[k][i] - w->xlo[i], q->zlx[k][i]); }
       if (w->xbu[i]) { r += q->zux[k][i]; COMPL(w->xhi[i] - q->x[k][i], q->zux[k][i]); }
       if (i < 2 && has_obs(w, k))
         for (int j = 0; j < M; j++) r += q->lo[k][j] * (i == 0 ? w->gox[k][j] : w->goy[k][j]);
+      if (i < 2 && IS_DCBF(w) && k >= 1) /* row k-1 also depends on x_k */
+        for (int j = 0; j < M; j++) r += q->lo[k - 1][j] * (i == 0 ? w->gnx[k - 1][j] : w->gny[k - 1][j]);
       dual = fmax(dual, fabs(r));
       prim = fmax(prim, fabs(w->cdef[k][i]));
       sl += fabs(q->lam[k][i]);
@@ -374,7 +405,7 @@ static void build_qp(ws_t *w, double mu) {
     /* state block */
     for (int i = 0; i < nx; i++) {
       double g = 0;
-      if (k < N) { H[i][i] += w->sigma * 2 * c->Q[i]; g += w->sigma * 2 * c->Q[i] * (q->x[k][i] - w->xs[i]); }
+      if (k < N) { H[i][i] += w->sigma * 2 * c->Q[i]; g += w->sigma * 2 * c->Q[i] * (q->x[k][i] - w->xr[k][i]); }
       if (w->xbl[i]) { double gap = q->x[k][i] - w->xlo[i]; H[i][i] += q->zlx[k][i] / gap; g -= mu / gap; }
       if (w->xbu[i]) { double gap = w->xhi[i] - q->x[k][i]; H[i][i] += q->zux[k][i] / gap; g += mu / gap; }
       w->gx[k][i] = g;
@@ -388,6 +419,11 @@ static void build_qp(ws_t *w, double mu) {
         H[0][1] += q->lo[k][j] * w->hoxy[k][j];
         H[1][0] += q->lo[k][j] * w->hoxy[k][j];
         H[1][1] += q->lo[k][j] * w->hoyy[k][j];
+      }
+    if (IS_DCBF(w) && k >= 1)
+      for (int j = 0; j < M; j++) {
+        H[0][0] += q->lo[k - 1][j] * w->hnxx[k - 1][j];
+        H[1][1] += q->lo[k - 1][j] * w->hnyy[k - 1][j];
       }
     for (int i = 0; i < nx; i++)
       for (int j = 0; j < nx; j++) w->Hxx[k][i][j] = H[i][j];
@@ -458,13 +494,35 @@ static int riccati(ws_t *w, double dw) {
     double (*A)[NXM] = w->A[k];
     double (*B)[2] = w->B[k];
     double Hxx[NXM][NXM], gxk[NXM], guk[2], E[2], t[2];
+    double dHux[2][NXM] = {{0}}, dHuu[2][2] = {{0}}, dgu[2] = {0, 0}; /* DCBF rows reach u_k through x_{k+1} */
     for (int i = 0; i < nx; i++) { gxk[i] = w->gx[k][i]; for (int j = 0; j < nx; j++) Hxx[i][j] = w->Hxx[k][i][j]; Hxx[i][i] += dw; }
-    if (has_obs(w, k))
+    if (has_obs(w, k) && !IS_DCBF(w))
       for (int j = 0; j < M; j++) {
         double D = w->Do[k][j] + dw, gx_ = w->gox[k][j], gy_ = w->goy[k][j];
         double tt = D * w->reso[k][j] + w->gso[k][j];
         Hxx[0][0] += D * gx_ * gx_; Hxx[0][1] += D * gx_ * gy_; Hxx[1][0] += D * gx_ * gy_; Hxx[1][1] += D * gy_ * gy_;
         gxk[0] += gx_ * tt; gxk[1] += gy_ * tt;
+      }
+    if (has_obs(w, k) && IS_DCBF(w))
+      for (int j = 0; j < M; j++) {
+        /* row k is linear in (dx_k, dx_{k+1}); with dx_{k+1} = A dx_k + B du_k + b it becomes a row
+         * in (dx_k, du_k): v = [g_k + A' g_next ; B' g_next], residual + g_next' b */
+        double D = w->Do[k][j] + dw;
+        double gn[2] = {w->gnx[k][j], w->gny[k][j]};
+        double v[NXM + 2];
+        for (int i = 0; i < nx; i++) v[i] = (i == 0 ? w->gox[k][j] : i == 1 ? w->goy[k][j] : 0.0) + gn[0] * A[0][i] + gn[1] * A[1][i];
+        for (int i = 0; i < 2; i++) v[nx + i] = gn[0] * B[0][i] + gn[1] * B[1][i];
+        double res = w->reso[k][j] - gn[0] * w->cdef[k + 1][0] - gn[1] * w->cdef[k + 1][1];
+        double tt = D * res + w->gso[k][j];
+        for (int i = 0; i < nx; i++) {
+          for (int l = 0; l < nx; l++) Hxx[i][l] += D * v[i] * v[l];
+          gxk[i] += v[i] * tt;
+        }
+        for (int i = 0; i < 2; i++) {
+          for (int l = 0; l < nx; l++) dHux[i][l] += D * v[nx + i] * v[l];
+          for (int l = 0; l < 2; l++) dHuu[i][l] += D * v[nx + i] * v[nx + l];
+          dgu[i] += v[nx + i] * tt;
+        }
       }
     for (int i = 0; i < 2; i++) { E[i] = w->E[k][i]; t[i] = w->tk[k][i]; guk[i] = w->gu[k][i]; }
     if (has_rate(w, k))
@@ -489,20 +547,20 @@ static int riccati(ws_t *w, double dw) {
       for (int j = 0; j < nx; j++) { double s = Hxx[i][j]; for (int a = 0; a < nx; a++) s += A[a][i] * PA[a][j]; Fxx[i][j] = s; }
     for (int i = 0; i < 2; i++)
       for (int j = 0; j < nx; j++) {
-        double s = w->Hux[k][i][j];
+        double s = w->Hux[k][i][j] + dHux[i][j];
         for (int a = 0; a < nx; a++) s += B[a][i] * PA[a][j] + Pxw[a][i] * A[a][j];
         Fux[i][j] = s;
       }
     for (int i = 0; i < 2; i++)
       for (int j = 0; j < 2; j++) {
-        double s = w->Huu[k][i][j] + Pww[i][j];
+        double s = w->Huu[k][i][j] + dHuu[i][j] + Pww[i][j];
         if (i == j) s += dw + E[i];
         for (int a = 0; a < nx; a++) s += B[a][i] * PB[a][j] + B[a][i] * Pxw[a][j] + Pxw[a][i] * B[a][j];
         Fuu[i][j] = s;
       }
     for (int i = 0; i < nx; i++) { double s = gxk[i]; for (int a = 0; a < nx; a++) s += A[a][i] * Pb[a]; fx[i] = s; }
     for (int i = 0; i < 2; i++) {
-      double s = guk[i] + t[i] + pw[i];
+      double s = guk[i] + dgu[i] + t[i] + pw[i];
       for (int a = 0; a < nx; a++) s += B[a][i] * Pb[a] + Pxw[a][i] * b[a];
       fu[i] = s;
     }
@@ -557,6 +615,7 @@ static int riccati(ws_t *w, double dw) {
       for (int j = 0; j < M; j++) {
         double D = w->Do[k][j] + dw;
         w->dso[k][j] = w->gox[k][j] * w->dx[k][0] + w->goy[k][j] * w->dx[k][1] + w->reso[k][j];
+        if (IS_DCBF(w)) w->dso[k][j] += w->gnx[k][j] * w->dx[k + 1][0] + w->gny[k][j] * w->dx[k + 1][1];
         w->lop[k][j] = D * w->dso[k][j] + w->gso[k][j];
       }
   }
@@ -568,6 +627,8 @@ static int riccati(ws_t *w, double dw) {
       if (k < N) s += w->Hux[k][0][i] * w->du[k][0] + w->Hux[k][1][i] * w->du[k][1];
       if (i < 2 && has_obs(w, k))
         for (int j = 0; j < M; j++) s += (i == 0 ? w->gox[k][j] : w->goy[k][j]) * w->lop[k][j];
+      if (i < 2 && IS_DCBF(w) && k >= 1)
+        for (int j = 0; j < M; j++) s += (i == 0 ? w->gnx[k - 1][j] : w->gny[k - 1][j]) * w->lop[k - 1][j];
       s = -s;
       if (k < N) for (int a = 0; a < nx; a++) s += w->A[k][a][i] * w->lamp[k + 1][a];
       w->lamp[k][i] = s;
@@ -618,7 +679,7 @@ static double barrier_dir(ws_t *w, double mu) {
   for (int k = 0; k <= N; k++) {
     for (int i = 0; i < nx; i++) {
       double g = 0;
-      if (k < N) g += w->sigma * 2 * c->Q[i] * (q->x[k][i] - w->xs[i]);
+      if (k < N) g += w->sigma * 2 * c->Q[i] * (q->x[k][i] - w->xr[k][i]);
       if (w->xbl[i]) g -= mu / (q->x[k][i] - w->xlo[i]);
       if (w->xbu[i]) g += mu / (w->xhi[i] - q->x[k][i]);
       gd += g * w->dx[k][i];
@@ -695,7 +756,8 @@ static void setup(ws_t *w, const orc_cfg *c, const double *x0, const double *xs,
   w->M = c->obs_mode == ORC_OBS_NONE ? 0 : c->M;
   for (int i = 0; i < w->nx; i++) {
     w->x0[i] = x0[i];
-    w->xs[i] = xs[i];
+    for (int k = 0; k <= c->N; k++) /* row N is never read (the cost runs over stages 0..N-1) */
+      w->xr[k][i] = c->ref_mode == ORC_REF_TRAJECTORY ? xs[(size_t)(k < c->N ? k : c->N - 1) * w->nx + i] : xs[i];
     w->xlo[i] = relax_lo(c->x_lo[i], c->bound_relax);
     w->xhi[i] = relax_hi(c->x_hi[i], c->bound_relax);
     w->xbl[i] = isfinite(c->x_lo[i]);
@@ -714,7 +776,7 @@ static void setup(ws_t *w, const orc_cfg *c, const double *x0, const double *xs,
       w->ocx[k][j] = o[0];
       w->ocy[k][j] = o[1];
       double sx, sy;
-      if (c->obs_mode == ORC_OBS_ELLIPSE) { /* PKG/MPC_CBF_optimize_kin_pre.py:246-249 */
+      if (c->obs_mode != ORC_OBS_SQRT) { /* PKG/MPC_CBF_optimize_kin_pre.py:246-249 */
         sx = c->ego_hl + o[4] / 2 + c->safe_l;
         sy = c->ego_hw + o[5] / 2 + c->safe_w;
       } else {
@@ -764,7 +826,8 @@ static int init_iterate(ws_t *w, const double *z_init) {
     if (has_obs(w, k))
       for (int j = 0; j < M; j++) {
         double d;
-        if (!obs_row(w, k, j, q->x[k][0], q->x[k][1], &d, 0, 0, 0, 0, 0)) return 0;
+        if (IS_DCBF(w)) { if (!dcbf_row(w, q, k, j, &d, 0)) return 0; }
+        else if (!obs_row(w, k, j, q->x[k][0], q->x[k][1], &d, 0, 0, 0, 0, 0)) return 0;
         q->so[k][j] = push_in(d, w->olo, INFINITY);
         q->vlo[k][j] = 1.0;
       }
@@ -775,7 +838,7 @@ static int init_iterate(ws_t *w, const double *z_init) {
     double g[2];
     grad_u(w, q, k, g);
     gmax = fmax(gmax, fmax(fabs(g[0]), fabs(g[1])));
-    for (int i = 0; i < nx; i++) gmax = fmax(gmax, fabs(2 * c->Q[i] * (q->x[k][i] - w->xs[i])));
+    for (int i = 0; i < nx; i++) gmax = fmax(gmax, fabs(2 * c->Q[i] * (q->x[k][i] - w->xr[k][i])));
   }
   w->sigma = gmax > OBJ_SCALE_MAX_GRAD ? OBJ_SCALE_MAX_GRAD / gmax : 1.0;
   if (w->sigma < 1e-8) w->sigma = 1e-8;
@@ -937,7 +1000,8 @@ static void *batch_worker(void *arg) {
     int b = atomic_fetch_add(&j->next, 1);
     if (b >= j->B) break;
     orc_info info;
-    setup(w, cfg, j->x0 + (size_t)b * nx, j->xs + (size_t)b * nx, j->obs ? j->obs + (size_t)b * so : 0);
+    size_t sxs = cfg->ref_mode == ORC_REF_TRAJECTORY ? (size_t)nx * cfg->N : (size_t)nx;
+    setup(w, cfg, j->x0 + (size_t)b * nx, j->xs + (size_t)b * sxs, j->obs ? j->obs + (size_t)b * so : 0);
     solve_ws(w, j->z_init ? j->z_init + (size_t)b * nv : 0, z, 0, &info);
     j->u0[2 * b] = z[0];
     j->u0[2 * b + 1] = z[1];

@@ -24,7 +24,8 @@ extern "C" {
 #define ORC_MMAX 4   /* max obstacles */
 
 enum { ORC_MODEL_KIN = 0, ORC_MODEL_DYN = 1 };
-enum { ORC_OBS_NONE = 0, ORC_OBS_ELLIPSE = 1, ORC_OBS_SQRT = 2 };
+enum { ORC_OBS_NONE = 0, ORC_OBS_ELLIPSE = 1, ORC_OBS_SQRT = 2, ORC_OBS_DCBF = 3 };
+enum { ORC_REF_TERMINAL = 0, ORC_REF_TRAJECTORY = 1 };
 enum { ORC_INIT_AS_GIVEN = 0, ORC_INIT_ROLLOUT = 1 };
 enum { ORC_CONVERGED = 0, ORC_ACCEPTABLE = 1, ORC_MAXITER = 2, ORC_INFEASIBLE = 3, ORC_NAN = 4 };
 
@@ -50,6 +51,12 @@ typedef struct {
   double Veh_l, Veh_lf, Veh_lr, Veh_m, Veh_Iz, aopt_f, aopt_r, Fymax_f, Fymax_r;
   /* interior-point options */
   double tol, mu_init, bound_relax;
+  /* options the reference ships switched off */
+  double cbf_gamma;   /* ORC_OBS_DCBF: rows h(X_{k+1};obs_k) - (1-gamma) h(X_k;obs_k) >= 0, k=0..N-1
+                         (the commented row of PKG/MPC_CBF_optimize_kin.py:244-248) */
+  int32_t ref_mode;   /* ORC_REF_TRAJECTORY: xs is (N, nx) per-stage cost targets
+                         (ref_X of PKG/MPC_CBF_optimize_kin.py:194-199 with aa != 0) */
+  int32_t reserved;
 } orc_cfg;
 
 typedef struct {
@@ -60,7 +67,8 @@ typedef struct {
   int32_t status, iters, n_reg, n_backtrack;
 } orc_info;
 
-/* one scenario.  obs: (M, N+1, 6) rows [x,y,theta,v,l,w]; z_init: nv or NULL (zeros);
+/* one scenario.  xs: nx, or (N, nx) with ORC_REF_TRAJECTORY; obs: (M, N+1, 6) rows [x,y,theta,v,l,w];
+ * z_init: nv or NULL (zeros);
  * z_out: nv = 2N + nx(N+1) in the reference order [vec(U); vec(X)]; lam_g_out: nullable,
  * multipliers of [X0-x0 ; defects] (nx(N+1)), unscaled. */
 int orc_solve(const orc_cfg *cfg, const double *x0, const double *xs, const double *obs,

@@ -22,6 +22,15 @@ What is restated (reference file:line, PKG = CasaDi_MPC_Optimize_Multishoot):
 * dyn model        tire model + rhs + rows            PKG/MPC_CBF_optimize_dyn.py:156-243
 * no-CBF kin       recovered from PKG/__pycache__/MPC_optimize_kin.cpython-37.pyc
                    
+
+Two options the reference carries but ships switched off:
+
+* `cbf_gamma`      the commented row `gamma*h_func + h_dot` with
+                   h_dot = h(X_{i+1}; obs_i) - h(X_i; obs_i)       PKG/MPC_CBF_optimize_kin.py:244-248
+                   i.e. h(X_{i+1}; obs_i) - (1-gamma) h(X_i; obs_i) >= 0, i = 0..N-1
+                   (both terms use the step-i obstacle, PKG/MPC_CBF_optimize_kin_pre.py:250-254)
+* `xref`           per-stage cost targets ref_X = aa*ref_state[i+1] + (1-aa)*xs
+                                                      PKG/MPC_CBF_optimize_kin.py:194-199
 """
 from __future__ import annotations
 
@@ -238,8 +247,10 @@ class NLP:
     """
 
     def __init__(self, kind: str, x0, xs, obstacles=None, params: Params | None = None, N: int | None = None,
-                 weights: Weights | None = None):
+                 weights: Weights | None = None, cbf_gamma: float | None = None, xref=None):
         assert kind in KINDS
+        assert cbf_gamma is None or kind in ("kin_cbf", "kin_cbf_pre")
+        self.cbf_gamma = cbf_gamma
         self.kind = kind
         self.p = params or Params()
         self.N = N if N is not None else self.p.N_p
@@ -250,6 +261,8 @@ class NLP:
         self.xs = np.asarray(xs, dtype=float).reshape(self.nx)
         self.w = weights or reference_weights(kind)
         N, nx = self.N, self.nx
+        # per-stage cost target (rows 0..N-1); the reference's aa = 0 makes every row xs
+        self.xr = np.repeat(self.xs[None, :], N, axis=0) if xref is None else np.asarray(xref, dtype=float).reshape(N, nx)
         self.nv = 2 * N + nx * (N + 1)
         self.n_eq = nx * (N + 1)
         p = self.p
@@ -348,7 +361,7 @@ class NLP:
     def objective(self, z):
         U, X = self.split(z)
         w = self.w
-        dX = X[: self.N] - self.xs
+        dX = X[: self.N] - self.xr
         f = float(np.sum(w.Q * dX * dX) + np.sum(w.R * U * U))
         dU = np.diff(U, axis=0)
         f += float(np.sum(w.DR * dU * dU))
@@ -369,7 +382,7 @@ class NLP:
             gU[0] += 2 * w.DR * U[0]
         g[: 2 * N] = gU.reshape(-1)
         gX = np.zeros_like(X)
-        gX[:N] = 2 * w.Q * (X[:N] - self.xs)
+        gX[:N] = 2 * w.Q * (X[:N] - self.xr)
         g[2 * N:] = gX.reshape(-1)
         return g
 
@@ -397,9 +410,11 @@ class NLP:
         return J
 
     # ---- inequality rows --------------------------------------------------------
-    def _ell(self, X, i, j):
-        dx = X[i, 0] - self.oc[j, i, 0]
-        dy = X[i, 1] - self.oc[j, i, 1]
+    def _ell(self, X, i, j, at=None):
+        """ellipse function of obstacle j at its step-i position, evaluated at X[at] (default X[i])."""
+        at = i if at is None else at
+        dx = X[at, 0] - self.oc[j, i, 0]
+        dy = X[at, 1] - self.oc[j, i, 1]
         return dx, dy, dx * dx / self.osx[j, i] ** 2 + dy * dy / self.osy[j, i] ** 2 - 1.0
 
     def ineq(self, z):
@@ -413,6 +428,9 @@ class NLP:
                 _, _, e = self._ell(X, i, k)
                 if self.kind == "dyn":
                     d[r] = math.sqrt(e) if e >= 0 else float("nan")
+                elif self.cbf_gamma is not None:
+                    _, _, en = self._ell(X, i, k, at=i + 1)
+                    d[r] = en - (1.0 - self.cbf_gamma) * e
                 else:
                     d[r] = e
         return d
@@ -432,6 +450,11 @@ class NLP:
                 if self.kind == "dyn":
                     q = math.sqrt(e) if e > 0 else float("nan")
                     gx, gy = gx / (2 * q), gy / (2 * q)
+                if self.cbf_gamma is not None:
+                    dxn, dyn_, _ = self._ell(X, i, k, at=i + 1)
+                    J[r, self.ix(i + 1) + 0] = 2 * dxn / self.osx[k, i] ** 2
+                    J[r, self.ix(i + 1) + 1] = 2 * dyn_ / self.osy[k, i] ** 2
+                    gx, gy = -(1.0 - self.cbf_gamma) * gx, -(1.0 - self.cbf_gamma) * gy
                 J[r, self.ix(i) + 0] = gx
                 J[r, self.ix(i) + 1] = gy
         return J
@@ -475,6 +498,12 @@ class NLP:
                 H[ixx + 1, ixx + 1] += lam_in[r] * (b / (2 * q) - gy * gy / (4 * q**3))
                 H[ixx, ixx + 1] += lam_in[r] * (-gx * gy / (4 * q**3))
                 H[ixx + 1, ixx] += lam_in[r] * (-gx * gy / (4 * q**3))
+            elif self.cbf_gamma is not None:
+                ixn = self.ix(i + 1)
+                H[ixn, ixn] += lam_in[r] * a
+                H[ixn + 1, ixn + 1] += lam_in[r] * b
+                H[ixx, ixx] -= lam_in[r] * (1.0 - self.cbf_gamma) * a
+                H[ixx + 1, ixx + 1] -= lam_in[r] * (1.0 - self.cbf_gamma) * b
             else:
                 H[ixx, ixx] += lam_in[r] * a
                 H[ixx + 1, ixx + 1] += lam_in[r] * b

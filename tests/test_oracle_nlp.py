@@ -61,11 +61,15 @@ def test_objective_matches_definition():
     assert np.isclose(nlp0.objective(z), f0, rtol=1e-13)
 
 
-@pytest.mark.parametrize("kind", ["kin_nocbf", "kin_cbf", "kin_cbf_pre", "dyn"])
-def test_derivatives_against_central_differences(kind):
+@pytest.mark.parametrize("kind,opts", [("kin_nocbf", {}), ("kin_cbf", {}), ("kin_cbf_pre", {}), ("dyn", {}),
+                                       ("kin_cbf", {"cbf_gamma": 1.0}), ("kin_cbf_pre", {"cbf_gamma": 0.3, "xref": True})])
+def test_derivatives_against_central_differences(kind, opts):
     N = 6
-    nlp = default_scenario(kind, N=N)
     rng = np.random.default_rng(0)
+    opts = dict(opts)
+    if opts.get("xref"):  # per-stage cost targets (the `aa` blend of PKG/MPC_CBF_optimize_kin.py:194-199)
+        opts["xref"] = np.array([400, 3.5, 0, 30.0]) + rng.standard_normal((N, 4))
+    nlp = default_scenario(kind, N=N, **opts)
     z = nlp.rollout_start(rng.uniform(-0.1, 0.1, (N, 2))) + 0.05 * rng.standard_normal(nlp.nv)
     eps = 1e-6
 

@@ -69,6 +69,28 @@ def test_c_oracle_follows_the_dense_specification(kind):
     assert np.max(np.abs(lam - r.lam_eq)) <= 1e-8 * max(1.0, np.max(np.abs(lam)))
 
 
+@pytest.mark.parametrize("kind,gamma,xref", [("kin_cbf", 0.5, False), ("kin_cbf_pre", 1.0, False), ("kin_cbf_pre", 0.3, True),
+                                             ("kin_cbf_pre", None, True)])
+def test_c_oracle_follows_the_dense_specification_dcbf_and_stage_reference(kind, gamma, xref):
+    """The options of SURVEY.md section 8f row N3: discrete-time CBF rows (coupling X_k and X_{k+1},
+    folded into the stage by the dynamics in the Riccati form) and per-stage cost targets."""
+    N = 16
+    rng = np.random.default_rng(5)
+    ref = np.array([400, 3.5, 0, 30.0]) + np.c_[np.zeros(N), 0.3 * rng.standard_normal(N), 0.01 * rng.standard_normal(N), rng.standard_normal(N)]
+    nlp = default_scenario(kind, N=N, cbf_gamma=gamma, xref=ref if xref else None)
+    cfg = c_oracle.make_cfg(kind, N=N, cbf_gamma=gamma, ref_trajectory=xref)
+    z, lam, info = c_oracle.solve(cfg, nlp.x0, ref if xref else nlp.xs, _obs_for(nlp))
+    r = ipm_dense.solve(nlp, nlp.rollout_start(), ipm_dense.IpmOptions())
+    assert info.status == r.status == 0
+    assert info.iters == r.iters and info.n_reg == r.n_reg
+    assert np.max(np.abs(z - r.z)) <= 1e-10
+    assert abs(info.f - r.f) <= 1e-12 * abs(r.f)
+    assert np.max(np.abs(lam - r.lam_eq)) <= 1e-8 * max(1.0, np.max(np.abs(lam)))
+    if gamma is not None:  # rows hold at the solution
+        d = nlp.ineq(z)
+        assert np.all(d >= nlp.dL - 1e-7) and np.all(d <= nlp.dU + 1e-7)
+
+
 def test_c_oracle_reproduces_golden_fixtures(golden):
     """Fixtures come from the dense solver + SLSQP cross-check (tests/golden/make_golden.py)."""
     n_checked = 0
