@@ -13,6 +13,6 @@ class MPC_optimize(MPCOptimizeBase):
         return self._initialize_constraints(obs_trajectories)
 
     def optimize_problem(self, ego_state, ref_state, obs_trajectories):
-        """Returns the solver callable.  `ego_state` is unused and `ref_state` has zero weight in
-        the reference too (aa = 0.0)."""
-        return _Solver(self, self._obs_array(obs_trajectories))
+        """Returns the solver callable.  `ego_state` is unused; `ref_state` enters the stage cost
+        with weight `self.aa` (0.0 as shipped, so it has no effect unless the attribute is changed)."""
+        return _Solver(self, self._obs_array(obs_trajectories), ref_state)

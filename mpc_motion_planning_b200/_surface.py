@@ -56,9 +56,10 @@ class _ModelFunction:
 class _Solver:
     """Callable returned by optimize_problem; replaces the CasADi `Function` of `nlpsol`."""
 
-    def __init__(self, owner, obs_array):
+    def __init__(self, owner, obs_array, ref_state=None):
         self._o = owner
         self._obs = obs_array
+        self._ref = None if ref_state is None else np.asarray(ref_state, dtype=np.float64)
         self._stats = {"success": False, "return_status": "not_run", "iter_count": 0}
 
     def stats(self):
@@ -76,7 +77,13 @@ class _Solver:
             raise ValueError(f"x0 must have {nv} entries, got {z0.size}")
         bs = o._batch_solver(lbx, ubx, lbg, ubg, self._obs)
         obs = self._obs[None] if self._obs is not None else None
-        out = bs.solve(p[None, :nx].copy(), p[None, nx:].copy(), obs, z0[None], return_z=True, return_lam=True)
+        xs = p[None, nx:].copy()
+        if o._stage_reference():
+            # ref_X = aa*ref_state[i+1,:] + (1-aa)*P[n:2n], PKG/MPC_CBF_optimize_kin.py:196
+            if self._ref is None or self._ref.shape[0] < N + 1:
+                raise ValueError("aa != 0 needs a ref_state of N_p+1 rows")
+            xs = (o.aa * self._ref[1: N + 1, :nx] + (1 - o.aa) * p[None, nx:])[None]
+        out = bs.solve(p[None, :nx].copy(), xs, obs, z0[None], return_z=True, return_lam=True)
         st = int(out["status"][0])
         self._stats = {"success": st in (_lib.ST_CONVERGED, _lib.ST_ACCEPTABLE), "return_status": _lib.RETURN_STATUS[st],
                        "iter_count": int(out["iters"][0])}
@@ -102,11 +109,13 @@ class MPCOptimizeBase:
         if self.is_variable_time == True:  # noqa: E712  (the YAML value 'Flase' never equals True, :19)
             t1 = np.arange(0, self.T_horizon * self.t_ratio, self.T_S, dtype=float)
             t2 = np.arange(t1[-1] + self.T_L, t1[-1] + self.T_L + self.T_horizon * (1 - self.t_ratio), self.T_L)
+            # the two-rate grid only changes N_p and t_vector: the NLP still steps every stage with T_S
+            # (`x_next = f*T_S + X`, :207), so the same kernels serve it
             self.N_p = len(t1) + len(t2)
             self.t_vector = np.concatenate((t1, t2))
-            raise NotImplementedError("two-rate time grid: the reference computes it but always steps with T_S; not supported")
-        self.t_vector = np.arange(0, self.T_horizon + self.T_S, self.T_S, dtype=float)
-        self.N_p = len(self.t_vector) - 1
+        else:
+            self.t_vector = np.arange(0, self.T_horizon + self.T_S, self.T_S, dtype=float)
+            self.N_p = len(self.t_vector) - 1
         vp, dc, tp = self.config["vehicle_params"], self.config["dynamics_constraints"], self.config["tire_params"]
         kc = self.config["kinematics_constraints"]
         self.Veh_l, self.Veh_L = vp["Veh_l"], vp["Veh_L"]
@@ -135,6 +144,51 @@ class MPCOptimizeBase:
         self.tol = 1e-8
         self.mu_init = 100.0
         self.init = "as_given"  # the CasADi call starts IPOPT at x0= exactly
+        # Two switches the reference keeps as locals of optimize_problem (kin-CBF modules):
+        #   aa = 0.0      weight of ref_state in the stage cost target          (:194-197)
+        #   gamma = 1.00  with `g.append(h_func)` live and `gamma*h_func + h_dot` commented out (:235-248)
+        # `cbf_rows = "dcbf"` activates the commented row with this gamma.
+        self.aa = 0.0
+        self.gamma = 1.00
+        self.cbf_rows = "h"
+
+    def _stage_reference(self):
+        return self.aa != 0.0 and self.KIND != "dyn"
+
+    def _dcbf(self):
+        return self.cbf_rows == "dcbf" and self.KIND in ("kin_cbf", "kin_cbf_pre")
+
+    def generate_ref_path(self, x0, xs):
+        """Quintic lane-change reference, PKG/MPC_CBF_optimize_kin.py:258-308 (unused by the mains):
+        position/velocity/acceleration boundary conditions over T = 3 s (end point xs moved to
+        x0.x + xs.v*T), heading in DEGREES from the polynomial's velocity, speed xs.v, then a straight
+        extension to the horizon.  Returns (N1 + N2 + 1, 4) rows [x, y, phi_deg, v]."""
+        x0 = np.asarray(x0, dtype=np.float64).reshape(-1)
+        xs = np.asarray(xs, dtype=np.float64).reshape(-1)
+        T, dt = 3.0, 0.1
+        n1, n2 = int(T / dt), int((self.T_horizon - T) / dt)
+        t = np.linspace(0, T, n1)
+        t2 = np.linspace(T, self.T_horizon, n2 + 1)
+        # rows: value, first and second derivative of sum c_k t^k at t = 0 and t = T
+        pw = np.arange(6)
+        rows = []
+        for tt in (0.0, T):
+            for d in range(3):
+                coef = np.array([np.prod(np.arange(k, k - d, -1)) if k >= d else 0.0 for k in pw], dtype=float)
+                rows.append(coef * np.array([tt ** (k - d) if k >= d else 0.0 for k in pw]))
+        A = np.array(rows)
+        x_end = xs[3] * T + x0[0]
+        cx = np.linalg.solve(A, np.array([x0[0], x0[3], 0, x_end, xs[3], 0]))
+        cy = np.linalg.solve(A, np.array([x0[1], 0, 0, xs[1], 0, 0]))
+        poly = lambda c: c[0] + c[1] * t + c[2] * t**2 + c[3] * t**3 + c[4] * t**4 + c[5] * t**5
+        dpoly = lambda c: c[1] + 2 * c[2] * t + 3 * c[3] * t**2 + 4 * c[4] * t**3 + 5 * c[5] * t**4
+        xt, yt = poly(cx), poly(cy)
+        phi = np.arctan2(dpoly(cy), dpoly(cx)) * 180 / np.pi
+        v = np.full(n1, xs[3])
+        return np.column_stack((np.concatenate((xt, xt[-1] + v[-1] * (t2 - t[-1]))),
+                                np.concatenate((yt, np.full_like(t2, yt[-1]))),
+                                np.concatenate((phi, np.full_like(t2, phi[-1]))),
+                                np.concatenate((v, np.full_like(t2, v[-1])))))
 
     # ---- ODE right-hand side (host, float64) ---------------------------------------------
     def _rhs(self, x, u):
@@ -231,10 +285,12 @@ class MPCOptimizeBase:
                 r0 = nx * (N + 1)
                 bounds.update(rate_lo=lg[r0: r0 + 1], rate_hi=ug[r0: r0 + 1])
         M = 0 if obs_array is None else obs_array.shape[0]
-        key = (M, self.max_iter, self.tol, self.mu_init, self.init) + tuple(np.concatenate([np.ravel(v) for v in bounds.values()]).tolist() if bounds else ())
+        gamma = float(self.gamma) if self._dcbf() else None
+        ref = "trajectory" if self._stage_reference() else "terminal"
+        key = (M, self.max_iter, self.tol, self.mu_init, self.init, gamma, ref) + tuple(np.concatenate([np.ravel(v) for v in bounds.values()]).tolist() if bounds else ())
         if key not in self._solvers:
             self._solvers[key] = BatchSolver(self.KIND, config=self.config, N=N, M=max(M, 1), init=self.init, mu_init=self.mu_init,
-                                             max_iter=self.max_iter, tol=self.tol, bounds=bounds or None)
+                                             max_iter=self.max_iter, tol=self.tol, bounds=bounds or None, cbf_gamma=gamma, ref=ref)
         return self._solvers[key]
 
     # ---- g(z) in the reference's row order (host evaluation for res['g']) -----------------
@@ -262,6 +318,9 @@ class MPCOptimizeBase:
                         sx = self.Veh_L / 2 + o[4] / 2 + 1.0
                         sy = self.Veh_W / 2 + o[5] / 2 + 0.5
                     e = (X[i, 0] - o[0]) ** 2 / sx**2 + (X[i, 1] - o[1]) ** 2 / sy**2 - 1
+                    if self._dcbf():  # gamma*h_func + h_dot, h_func_next at the same obstacle row (:245-248)
+                        en = (X[i + 1, 0] - o[0]) ** 2 / sx**2 + (X[i + 1, 1] - o[1]) ** 2 / sy**2 - 1
+                        e = self.gamma * e + (en - e)
                     g.append(np.array([np.sqrt(e) if self.KIND == "dyn" else e]))
         return np.concatenate(g)
 

@@ -1,10 +1,11 @@
 /* CPU oracle for the MPC solve path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
- * PARITY UNPINNED: the reference's solve is CasADi nlpsol('ipopt')
+ * PARITY UNPINNED (solver): the reference's solve is CasADi nlpsol('ipopt')
  * (PKG/MPC_CBF_optimize_kin.py:251-254, called at PKG/main_cbf_kin_c_sim.py:100);
  * neither CasADi nor IPOPT exists in this image and the reference holds no golden
- * vectors, so this oracle restates the NLP exactly (see oracle/nlp.py for the
- * per-line citations) and IPOPT's published algorithm approximately
+ * vectors, so this oracle restates the NLP exactly (oracle/nlp.py has the per-line
+ * citations and IS pinned against the reference's own expressions, see
+ * tests/test_reference_vectors.py) and IPOPT's published algorithm approximately
  * (oracle/ipm_dense.py is the dense specification; this file solves the same Newton
  * systems with a scalar stage-wise Riccati recursion so that it is fast enough to be
  * the CPU baseline).

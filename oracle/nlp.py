@@ -1,8 +1,13 @@
 """CPU restatement of the reference NLPs (TEST INFRASTRUCTURE — not product code).
 
-PARITY UNPINNED: the reference ships no tests/golden vectors and its solver
-(CasADi + IPOPT, unpinned PyPI `casadi`) is not installable here (no network),
-so this restatement is anchored on the reference's own call sites only.
+PARITY: the NLP DEFINITION restated here is pinned - tests/test_reference_vectors.py checks
+objective, constraint rows (reference order) and bound lists against vectors the reference's own
+`optimize_problem` / `initialize_constraints` produced when run unmodified on a sympy-backed
+`casadi` stand-in (tests/golden/make_reference_vectors.py -> tests/golden/reference_nlp.npz;
+f to 1e-14 relative, g to 1e-11).  The SOLVE is UNPINNED: the reference ships no tests or golden
+vectors and CasADi + IPOPT (unpinned PyPI `casadi`) cannot be installed here (no network), so
+the interior-point method in oracle/ipm_dense.py / mpc_oracle.c follows IPOPT's published
+algorithm, not IPOPT's outputs.  The no-CBF module exists only as a CPython-3.7 .pyc: unpinned.
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
 `--impl reference` legs may import this package.

@@ -1,0 +1,153 @@
+"""Golden vectors produced by the REFERENCE'S OWN CODE, run in the build container.
+
+    python tests/golden/make_reference_vectors.py        (needs /root/reference; writes reference_nlp.npz)
+
+CasADi/IPOPT cannot be installed here, so the reference's *solve* cannot run.  Its NLP *definition*
+can: with tests/golden/casadi_stub.py registered as `casadi`, the unmodified
+`MPC_optimize.__init__`, `initialize_constraints`, `optimize_problem` and `generate_ref_path` of
+PKG/MPC_CBF_optimize_kin.py, _kin_pre.py and _dyn.py execute and hand their objective / constraint
+expressions to `nlpsol`, where the stub records them.  This script evaluates those expressions at
+seeded points and stores
+
+    z, p, f(z,p), g(z,p), lbg, ubg, lbx, ubx, the nlpsol options, N_p, T_S
+
+per module, plus outputs of `generate_ref_path`, `RefPathGenerator` and `obs_prediction`.
+tests/test_reference_vectors.py checks the restated NLP (oracle/nlp.py), the drop-in host classes
+and the bound lists against them.  (`MPC_optimize_kin`, the no-CBF module, exists only as a
+CPython-3.7 .pyc and cannot be imported by this interpreter: it stays unpinned.)
+"""
+from __future__ import annotations
+
+import importlib
+import json
+import os
+import shutil
+import sys
+import tempfile
+import types
+
+import numpy as np
+import sympy as sp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = "/root/reference/CasaDi_MPC_Optimize_Multishoot"
+K = 4  # evaluation points per module
+
+
+def load_module(name, workdir):
+    import casadi_stub
+
+    sys.modules["casadi"] = casadi_stub
+    casadi_stub.tools = sys.modules["casadi.tools"] = types.ModuleType("casadi.tools")  # imported, never used
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    os.chdir(workdir)  # the constructors read mpc_parameters.yaml from the CWD
+    return importlib.import_module(name)
+
+
+def evaluate(rec, pts_z, pts_p):
+    """numeric f and g of the recorded NLP at the given points"""
+    xs = [s for s in rec.prob["x"].a.reshape(-1, order="F")]
+    ps = [s for s in rec.prob["p"].a.reshape(-1, order="F")]
+    f = rec.prob["f"].a.reshape(-1)[0]
+    g = list(rec.prob["g"].a.reshape(-1, order="F"))
+    fun = sp.lambdify([xs, ps], [f] + g, "math", cse=True)
+    F, G = [], []
+    for z, p in zip(pts_z, pts_p):
+        out = fun(list(z), list(p))
+        F.append(float(out[0]))
+        G.append([float(v) for v in out[1:]])
+    return np.array(F), np.array(G)
+
+
+def rollout_points(mod, nx, N, x0, xs, rng):
+    """z near an Euler roll-out (keeps the dyn sqrt rows real), p = [x0; xs] perturbed"""
+    Z, P = [], []
+    for _ in range(K):
+        x = np.array(x0, float) + rng.normal(0, [1.0, 0.2, 0.01, 1.0, 0.05, 0.01][:nx])
+        U = np.c_[rng.uniform(-0.02, 0.02, N), rng.uniform(-1, 1, N)]
+        X = [x]
+        for i in range(N):
+            X.append(X[-1] + mod.T_S * mod.f(X[-1], U[i]).full().ravel())
+        X = np.array(X) + rng.normal(0, 0.01, (N + 1, nx))
+        Z.append(np.concatenate([U.reshape(-1), X.reshape(-1)]))
+        P.append(np.concatenate([x, np.array(xs, float) + rng.normal(0, 0.1, nx)]))
+    return np.array(Z), np.array(P)
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, PKG)
+    from Obs_prediction import obs_prediction
+    import RefPathGenerator
+
+    out = {}
+    rng = np.random.default_rng(20261018)
+
+    # ---------------- kin-CBF static (PKG/main_cbf_kin_c_sim.py:45-55,77,99)
+    m = load_module("MPC_CBF_optimize_kin", PKG)
+    mpc = m.MPC_optimize()
+    N = mpc.N_p
+    obs = np.array([[50, 3.5, 0, 8, 4.8, 1.8], [90, 0.5, 0, 0, 4.2, 1.7]])
+    x0, xs = [0, 3, 0, 15], [400, 3.5, 0, 30]
+    lbg, ubg, lbx, ubx = mpc.initialize_constraints(obs)
+    ref = np.tile(np.array(xs, float), (N + 1, 1))
+    rec = mpc.optimize_problem(np.array(x0).reshape(-1, 1), ref, obs)
+    Z, P = rollout_points(mpc, 4, N, x0, xs, rng)
+    F, G = evaluate(rec, Z, P)
+    out.update(kin_z=Z, kin_p=P, kin_f=F, kin_g=G, kin_lbg=np.array(lbg, float), kin_ubg=np.array(ubg, float),
+               kin_lbx=np.array(lbx, float), kin_ubx=np.array(ubx, float), kin_obs=obs, kin_opts=json.dumps(rec.opts),
+               kin_N=N, kin_T=mpc.T_S)
+    # the quintic lane-change reference (:258-308), unused by the mains
+    gr_in, gr_out = [], []
+    for a, b in [([0, 3, 0, 15], [400, 3.5, 0, 30]), ([12.5, 0.2, 0.01, 22], [400, 3.5, 0, 25]), ([100, 4.0, 0, 8], [600, 0.0, 0, 12])]:
+        a, b = np.array(a, float).reshape(-1, 1), np.array(b, float).reshape(-1, 1)
+        gr_in.append(np.concatenate([a.ravel(), b.ravel()]))
+        gr_out.append(mpc.generate_ref_path(a, b))
+    out.update(genref_in=np.array(gr_in), genref_out=np.array(gr_out))
+    out.update(attrs=json.dumps({k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in vars(mpc).items()
+                                 if isinstance(v, (int, float, str, bool, np.ndarray)) and k != "config"}))
+
+    # ---------------- kin-CBF moving (PKG/main_cbf_kin_c_sim_pre.py:45-56,77,99)
+    m = load_module("MPC_CBF_optimize_kin_pre", PKG)
+    mpc = m.MPC_optimize()
+    obs_list = [np.array([[50, 3.5, 0, 10, 4.8, 1.8]]), np.array([[80, 0.0, 0.03, 6, 3.9, 1.6]])]
+    tr = obs_prediction(obs_list, mpc.T_S, N)
+    lbg, ubg, lbx, ubx = mpc.initialize_constraints(obs_list)
+    rec = mpc.optimize_problem(np.array(x0).reshape(-1, 1), ref, tr)
+    Z, P = rollout_points(mpc, 4, N, x0, xs, rng)
+    F, G = evaluate(rec, Z, P)
+    out.update(pre_z=Z, pre_p=P, pre_f=F, pre_g=G, pre_lbg=np.array(lbg, float), pre_ubg=np.array(ubg, float),
+               pre_lbx=np.array(lbx, float), pre_ubx=np.array(ubx, float), pre_obs=np.array(tr), pre_obs0=np.array(obs_list).reshape(-1, 6),
+               pre_opts=json.dumps(rec.opts))
+
+    # ---------------- dyn (PKG/main_cbf_dyn_c_sim.py:44-51,77,89): the module reads `Veh_w`, which the
+    # shipped YAML spells `Veh_W`: run it from a copy with the key added
+    tmp = tempfile.mkdtemp()
+    with open(os.path.join(PKG, "mpc_parameters.yaml")) as fh:
+        text = fh.read()
+    with open(os.path.join(tmp, "mpc_parameters.yaml"), "w") as fh:
+        fh.write(text.replace("  Veh_W: 1.8", "  Veh_W: 1.8\n  Veh_w: 1.8"))
+    m = load_module("MPC_CBF_optimize_dyn", tmp)
+    mpc = m.MPC_optimize()
+    x0d, xsd, obsd = [0, 0, 0, 10, 0, 0], [600, 3.5, 0, 15, 0, 0], np.array([100, -3.5])
+    lbg, ubg, lbx, ubx = mpc.initialize_constraints()
+    rec = mpc.optimize_problem(np.array(x0d).reshape(-1, 1), np.tile(np.array(xsd, float), (N + 1, 1)), obsd)
+    Z, P = rollout_points(mpc, 6, N, x0d, xsd, rng)
+    F, G = evaluate(rec, Z, P)
+    out.update(dyn_z=Z, dyn_p=P, dyn_f=F, dyn_g=G, dyn_lbg=np.array(lbg, float), dyn_ubg=np.array(ubg, float),
+               dyn_lbx=np.array(lbx, float), dyn_ubx=np.array(ubx, float), dyn_obs=obsd, dyn_opts=json.dumps(rec.opts))
+    xq, uq = np.array([1.0, 0.5, 0.02, 12.0, 0.3, 0.05]), np.array([0.03, 1.2])
+    out.update(dyn_rhs_in=np.concatenate([xq, uq]), dyn_rhs_out=mpc.f(xq, uq).full().ravel())
+    shutil.rmtree(tmp)
+    os.chdir(HERE)
+
+    # ---------------- RefPathGenerator / obs_prediction (numpy only, imported as they are)
+    rp = RefPathGenerator.RefPathGenerator()
+    x0c, xsc = np.array(x0, float).reshape(-1, 1), np.array(xs, float).reshape(-1, 1)
+    glob = rp.define_ref_path(x0c, xsc, 0.1)
+    rt, idx = rp.find_ref_traj(np.array([37.3, 2.9, 0.01, 17.5]).reshape(-1, 1), xsc, 5, 0.1, 30)
+    out.update(refpath_global=glob, refpath_traj=rt, refpath_idx=idx)
+
+    np.savez_compressed(os.path.join(HERE, "reference_nlp.npz"), **out)
+    print("wrote reference_nlp.npz:", {k: np.asarray(v).shape for k, v in out.items()})
