@@ -456,3 +456,35 @@ def test_discrete_cbf_solution_satisfies_its_rows(dev):
         assert abs(nlp.objective(z) - g["cost"][b]) <= 1e-9 * abs(g["cost"][b])
         n += 1
     assert n >= 8
+
+
+def test_reference_surface_with_the_switched_off_options(dev, tmp_path, monkeypatch):
+    """The drop-in class with the reference's two dormant switches turned on: the commented
+    `gamma*h_func + h_dot` row and `aa != 0` (PKG/MPC_CBF_optimize_kin_pre.py:194-199,250-254), with
+    the reference's own `find_ref_traj` output as ref_state."""
+    monkeypatch.chdir(tmp_path)
+    from mpc_motion_planning_b200 import MPC_CBF_optimize_kin_pre, RefPathGenerator
+    from mpc_motion_planning_b200.Obs_prediction import obs_prediction
+    from oracle import c_oracle
+
+    mpc = MPC_CBF_optimize_kin_pre.MPC_optimize()
+    mpc.aa, mpc.gamma, mpc.cbf_rows, mpc.init = 0.25, 0.6, "dcbf", "rollout"
+    N = mpc.N_p
+    x0 = np.array([0, 3, 0, 15.0]).reshape(-1, 1)
+    xs = np.array([400, 3.5, 0, 30.0]).reshape(-1, 1)
+    rp = RefPathGenerator.RefPathGenerator()
+    rp.define_ref_path(x0, xs, mpc.T_S)
+    ref_traj, _ = rp.find_ref_traj(x0, xs, mpc.T_horizon, mpc.T_S, 0)
+    obs = [np.array([[50, 3.5, 0, 10, 4.8, 1.8]])]
+    tr = obs_prediction(obs, mpc.T_S, N)
+    lbg, ubg, lbx, ubx = mpc.initialize_constraints(obs)
+    solver = mpc.optimize_problem(ego_state=x0, ref_state=ref_traj, obs_trajectories=tr)
+    res = solver(x0=np.zeros((2 * N + 4 * (N + 1), 1)), p=np.concatenate((x0, xs)), lbg=lbg, lbx=lbx, ubg=ubg, ubx=ubx)
+    assert solver.stats()["success"]
+    xref = mpc.aa * ref_traj[1: N + 1] + (1 - mpc.aa) * xs.ravel()[None, :]
+    cfg = c_oracle.make_cfg("kin_cbf_pre", cbf_gamma=0.6, ref_trajectory=True)
+    zo, _, info = c_oracle.solve(cfg, x0.ravel(), xref, np.array(tr))
+    assert info.status == 0 and abs(float(res["f"]) - info.f) <= COST_RTOL * info.f
+    assert np.abs(res["x"].full().ravel()[:2] - zo[:2]).max() <= U0_ATOL
+    g = res["g"].full().ravel()
+    assert g.shape == (303,) and np.abs(g[:204]).max() <= 1e-7 and g[253:].min() >= -1e-7
