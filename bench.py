@@ -202,6 +202,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else {}
     step_ms = [a.elapsed_time(b) for a, b in ev]
     t_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    print(f"[bench rank {rank}] device ms/step: {sum(step_ms) / K:.3f} (min {min(step_ms):.3f}, max {max(step_ms):.3f}); "
+          f"mean iterations {float(out['iters'].float().mean()):.2f}", file=sys.stderr, flush=True)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     total_ms = float(t_ms.item())
