@@ -55,7 +55,8 @@ enum { MPCB_OBS_TRAJECTORY = 0, MPCB_OBS_INITIAL = 1 };
 /* per-scenario outcome, mapped to IPOPT return_status strings by the Python shim */
 enum {
   MPCB_CONVERGED = 0,  /* Solve_Succeeded */
-  MPCB_ACCEPTABLE = 1, /* Solved_To_Acceptable_Level (reserved; acceptable_tol == tol in the reference) */
+  MPCB_ACCEPTABLE = 1, /* Solved_To_Acceptable_Level: the line search failed at a point whose scaled KKT error is
+                          already <= 1e-6 (IPOPT's default acceptable_tol; the reference's 1e-8 equals tol) */
   MPCB_MAXITER = 2,    /* Maximum_Iterations_Exceeded */
   MPCB_INFEASIBLE = 3, /* line search failed / Restoration_Failed / Infeasible_Problem_Detected */
   MPCB_NAN = 4         /* Invalid_Number_Detected */

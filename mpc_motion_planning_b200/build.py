@@ -26,7 +26,8 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if force or stale():
         nvcc = os.environ.get("NVCC", "nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, os.path.join(HERE, "csrc", "mpcb_api.cu")]
+        extra = os.environ.get("MPCB_NVCC_EXTRA", "").split()  # e.g. -DMPCB_W0=12 for tuning experiments
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, os.path.join(HERE, "csrc", "mpcb_api.cu")]
         subprocess.check_call(cmd, cwd=HERE)
     return SO
 

@@ -57,7 +57,16 @@ Variant make_kin_variant_w() {
 // warps per block: the candidate that keeps the most warps resident for this horizon (ties: larger W)
 template <int NR, int MO, int OBS>
 Variant make_kin_variant(int N) {
-  Variant cand[3] = {make_kin_variant_w<NR, MO, OBS, 4>(), make_kin_variant_w<NR, MO, OBS, 2>(), make_kin_variant_w<NR, MO, OBS, 1>()};
+#ifndef MPCB_W0  // candidate warps-per-block values (compile-time tuning knob)
+#define MPCB_W0 4
+#define MPCB_W1 2
+#define MPCB_W2 1
+#endif
+  Variant cand[3] = {make_kin_variant_w<NR, MO, OBS, MPCB_W0>(), make_kin_variant_w<NR, MO, OBS, MPCB_W1>(), make_kin_variant_w<NR, MO, OBS, MPCB_W2>()};
+  if (const char *w = getenv("MPCB_FORCE_W")) {  // tuning knob: warps per block
+    for (int i = 0; i < 3; i++)
+      if (cand[i].warps == atoi(w)) return cand[i];
+  }
   int best = 0, best_warps = -1;
   for (int i = 0; i < 3; i++) {
     size_t smem = cand[i].smem_bytes(N) * cand[i].warps;
