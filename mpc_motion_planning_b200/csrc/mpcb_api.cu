@@ -98,6 +98,10 @@ Variant make_dyn_variant_w() {
 }
 
 Variant pick_by_occupancy(Variant *cand, int n, int N) {
+  if (const char *w = getenv("MPCB_FORCE_W")) {  // tuning knob: warps per block
+    for (int i = 0; i < n; i++)
+      if (cand[i].warps == atoi(w)) return cand[i];
+  }
   int best = 0, best_warps = -1;
   for (int i = 0; i < n; i++) {
     size_t smem = cand[i].smem_bytes(N) * cand[i].warps;

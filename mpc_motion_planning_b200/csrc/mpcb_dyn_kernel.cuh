@@ -16,17 +16,18 @@ struct DynLayout {
   static constexpr int CDEF = 0;
   static constexpr int LAMP = CDEF;  // alias
   static constexpr int JAC = CDEF + NX;
-  static constexpr int HXX = JAC + NJ;     // packed upper triangle 6x6 (21)
-  static constexpr int HUX = HXX + 21;     // d2L/(d delta d x_j), 6 entries (the ax row is zero)
-  static constexpr int GX = HUX + NX;
+  // structurally nonzero entries of the stage Hessian only: the (x,y) block (obstacle row + cost),
+  // the (phi,vx,vy,r) block (model + cost) - 3 + 10 of the 21 - and d2L/(d delta d{vx,vy,r})
+  static constexpr int HXX = JAC + NJ;
+  static constexpr int HUX = HXX + DYN_NHX;
+  static constexpr int GX = HUX + DYN_NHU;
   static constexpr int R18 = GX + NX;      // [HUU(2) EE(2) GU(2) TK(2) ...] -> gains [KX(12) KW(4) KK(2)] -> slack steps
   static constexpr int HUU = R18, EE = R18 + 2, GU = R18 + 4, TK = R18 + 6;
   static constexpr int KX = R18, KW = R18 + 12, KK = R18 + 16;
   static constexpr int DSR = R18, LRP = DSR + NR, DSO = LRP + NR, LOP = DSO + MO;
   static constexpr int CDEFT = R18 + 8;  // defects of the trial point (6 slots)
-  static constexpr int DX = R18 + 18;
-  static constexpr int DU = DX + NX;
-  static constexpr int NSH = DU + 2;
+  static constexpr int NSH = R18 + 18;
+  // 63 doubles per stage = 25.7 KB per scenario at N = 50: two blocks of four warps per SM
   static constexpr int NF = NSH | 1;
   // ---- global-memory slab: the primal-dual iterate and the obstacle centre (stage-parallel phases only)
   static constexpr int G0 = 96;
@@ -47,7 +48,10 @@ struct DynLayout {
   static constexpr int LO = VLO + MO;
   static constexpr int OCX = LO + MO;
   static constexpr int OCY = OCX + MO;
-  static constexpr int NG = OCY + MO - G0;
+  // the step: written by lane 0 in the forward sweep, read by the stage-parallel phases only
+  static constexpr int DX = OCY + MO;
+  static constexpr int DU = DX + NX;
+  static constexpr int NG = DU + 2 - G0;
   static constexpr int SG = 132;
   __host__ __device__ static constexpr size_t bytes(int N) { return sizeof(double) * (size_t)NF * (size_t)(N + 1); }
   __host__ __device__ static constexpr size_t slab_doubles() { return (size_t)NG * SG; }
@@ -55,6 +59,12 @@ struct DynLayout {
 
 __device__ __forceinline__ int pidx6(int i, int j) { return i * 6 - i * (i - 1) / 2 + (j - i); }  // i <= j
 __device__ __forceinline__ int sidx6(int i, int j) { return i <= j ? pidx6(i, j) : pidx6(j, i); }
+// slot of Hxx(i,j), i <= j, in the compact storage (order of dyn_riccati_F's hx argument); -1 = structural zero
+__device__ __forceinline__ constexpr int hslot(int i, int j) {
+  return j < 2 ? i + j : (i < 2 ? -1 : 3 + (i - 2) * 4 - (i - 2) * (i - 3) / 2 + (j - i));
+}
+static_assert(hslot(0, 0) == 0 && hslot(0, 1) == 1 && hslot(1, 1) == 2 && hslot(2, 2) == 3 && hslot(2, 5) == 6 && hslot(3, 3) == 7 &&
+              hslot(4, 4) == 10 && hslot(5, 5) == 12 && hslot(1, 2) == -1, "compact Hessian order");
 
 struct DynSolver {
   using L = DynLayout;
@@ -345,9 +355,10 @@ struct DynSolver {
 #pragma unroll
       for (int i = 0; i < NX; i++) {
         at(L::GX + i, k) = gx[i];
-        at(L::HUX + i, k) = hud[i];
+        if (i >= 3) at(L::HUX + i - 3, k) = hud[i];
 #pragma unroll
-        for (int j = i; j < NX; j++) at(L::HXX + pidx6(i, j), k) = Hxx[i][j];
+        for (int j = i; j < NX; j++)
+          if (hslot(i, j) >= 0) at(L::HXX + hslot(i, j), k) = Hxx[i][j];
       }
       if (k < N) {
         double E[2] = {0, 0}, t[2] = {0, 0};
@@ -396,7 +407,12 @@ struct DynSolver {
   __device__ __forceinline__ bool riccati_backward() {
     double P[21], W[12], Q[3] = {0, 0, 0}, px[NX], pw[2] = {0, 0};
 #pragma unroll
-    for (int q = 0; q < 21; q++) P[q] = at(L::HXX + q, N);
+    for (int q = 0; q < 21; q++) P[q] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NX; i++)
+#pragma unroll
+      for (int j = i; j < NX; j++)
+        if (hslot(i, j) >= 0) P[pidx6(i, j)] = at(L::HXX + hslot(i, j), N);
 #pragma unroll
     for (int i = 0; i < NX; i++) {
       px[i] = at(L::GX + i, N);
@@ -409,19 +425,10 @@ struct DynSolver {
 #pragma unroll
       for (int i = 0; i < NJ; i++) a_[i] = p.T * at(L::JAC + i, k);
       // structurally nonzero Hessian entries: (x,y) block, (phi..r) block, steering row vs (vx,vy,r)
-      hx[0] = at(L::HXX + pidx6(0, 0), k);
-      hx[1] = at(L::HXX + pidx6(0, 1), k);
-      hx[2] = at(L::HXX + pidx6(1, 1), k);
-      {
-        int q = 3;
 #pragma unroll
-        for (int i = 2; i < 6; i++)
+      for (int q = 0; q < DYN_NHX; q++) hx[q] = at(L::HXX + q, k);
 #pragma unroll
-          for (int j = i; j < 6; j++) hx[q++] = at(L::HXX + pidx6(i, j), k);
-      }
-      hu[0] = at(L::HUX + 3, k);
-      hu[1] = at(L::HUX + 4, k);
-      hu[2] = at(L::HUX + 5, k);
+      for (int q = 0; q < DYN_NHU; q++) hu[q] = at(L::HUX + q, k);
 #pragma unroll
       for (int i = 0; i < NX; i++) {
         gx[i] = at(L::GX + i, k);
@@ -533,9 +540,13 @@ struct DynSolver {
       for (int i = 0; i < NX; i++) dx[i] = at(L::DX + i, k);
 #pragma unroll
       for (int i = 0; i < NX; i++) {
-        double s = at(L::GX + i, k) + at(L::HUX + i, k) * ud;
+        double s = at(L::GX + i, k);
+        if (i >= 3) s += at(L::HUX + i - 3, k) * ud;
 #pragma unroll
-        for (int j = 0; j < NX; j++) s += at(L::HXX + sidx6(i, j), k) * dx[j];
+        for (int j = 0; j < NX; j++) {
+          const int q = i <= j ? hslot(i, j) : hslot(j, i);
+          if (q >= 0) s += at(L::HXX + q, k) * dx[j];
+        }
         r[i] = s;
       }
 #pragma unroll
