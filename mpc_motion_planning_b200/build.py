@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libmpcb200.so")
-SRCS = [os.path.join(HERE, "csrc", f) for f in ("mpcb_api.cu", "mpcb_kernel.cuh", "dyn_model.cuh")] + [
+SRCS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))) + [
     os.path.join(HERE, "..", "include", "mpcb200.h")
 ]
 NVCC_FLAGS = [
