@@ -409,6 +409,8 @@ def solve(nlp: NLP, z_init=None, opt: IpmOptions | None = None) -> IpmResult:
             break
         if not armijo:
             filt.append(((1 - o.gamma_theta) * th, phi - o.gamma_phi * th))
+        if o.verbose:
+            print(f"       step: a_max={a_max:.2e} alpha={alpha:.2e} a_dual={a_dual:.2e} dw={dw:.1e} |dz|={np.max(np.abs(dz)):.2e}")
         # IPOPT: equality multipliers move with the primal step size
         z, s = z_new, s_new
         lam_c = lam_c + alpha * dlc_use

@@ -488,3 +488,27 @@ def test_reference_surface_with_the_switched_off_options(dev, tmp_path, monkeypa
     assert np.abs(res["x"].full().ravel()[:2] - zo[:2]).max() <= U0_ATOL
     g = res["g"].full().ravel()
     assert g.shape == (303,) and np.abs(g[:204]).max() <= 1e-7 and g[253:].min() >= -1e-7
+
+
+@pytest.mark.parametrize("kind,gen,N", [("kin_cbf_pre", "kin_cbf_moving", 2), ("kin_cbf_pre", "kin_cbf_moving", 128),
+                                         ("dyn", "dyn_static", 3), ("dyn", "dyn_static", 128), ("kin_nocbf", "kin_nocbf", 128)])
+def test_horizon_limits(dev, kind, gen, N):
+    """Smallest and largest horizons the library accepts (2 <= N <= MPCB_NMAX = 128): the warps-per-block
+    choice changes with the shared-memory footprint, the results must not."""
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+    from oracle import c_oracle
+
+    B = 48
+    g_ = getattr(scenarios, gen)
+    x0, xs, obs = g_(B, N=N)
+    s = BatchSolver(kind, N=N)
+    g = _gpu(s, dev, x0, xs, obs)
+    cfg = c_oracle.make_cfg(kind, N=N)
+    u0, cost, st, it, _ = c_oracle.solve_batch(cfg, x0, xs, obs if obs.shape[1] else None, nthreads=os.cpu_count())
+    both = (g["status"] <= 1) & (st <= 1)
+    assert ((g["status"] <= 1) == (st <= 1)).mean() >= 0.85
+    assert both.sum() >= 24
+    du = np.abs(g["u0"] - u0).max(axis=1)
+    dc = np.abs(g["cost"] - cost) / np.maximum(np.abs(cost), 1.0)
+    assert np.all(du[both] <= U0_ATOL) and np.all(dc[both] <= COST_RTOL), (du[both].max(), dc[both].max())
