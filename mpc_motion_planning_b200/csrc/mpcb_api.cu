@@ -26,9 +26,9 @@ bool cuda_ok(cudaError_t e, const char *what) {
 typedef cudaError_t (*launch_fn)(const KParams &, int grid, size_t smem, cudaStream_t);
 typedef const void *kernel_ptr;
 
-template <int NR, int MO, int OBS, int W>
+template <int NR, int MO, int OBS, int W, bool GS>
 cudaError_t launch_kin(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-  kin_solve_kernel<NR, MO, OBS, W><<<grid, 32 * W, smem, st>>>(p);
+  kin_solve_kernel<NR, MO, OBS, W, GS><<<grid, 32 * W, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -41,20 +41,23 @@ struct Variant {
   int warps;            // warps (= scenarios in flight) per block
 };
 
-template <int NR, int MO, int OBS, int W>
+template <int NR, int MO, int OBS, int W, bool GS>
 Variant make_kin_variant_w() {
   Variant v;
-  v.launch = &launch_kin<NR, MO, OBS, W>;
-  v.kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, W>;
-  v.smem_bytes = [](int N) { return KinLayout<NR, MO, OBS == 3>::bytes(N); };
+  v.launch = &launch_kin<NR, MO, OBS, W, GS>;
+  v.kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, W, GS>;
+  v.smem_bytes = [](int N) { return KinLayout<NR, MO, OBS == 3, GS>::bytes(N); };
   v.nx = 4;
   v.nbx = 2;
-  v.slab_doubles = KinLayout<NR, MO, OBS == 3>::slab_doubles();
+  v.slab_doubles = KinLayout<NR, MO, OBS == 3, GS>::slab_doubles();
   v.warps = W;
   return v;
 }
 
-// warps per block: the candidate that keeps the most warps resident for this horizon (ties: larger W)
+Variant pick_by_occupancy(Variant *cand, int n, int N);
+
+// Layout and warps per block: the candidate that keeps the most warps resident for this horizon.
+// Order = preference on ties: step in shared memory before step in the slab, larger W first.
 template <int NR, int MO, int OBS>
 Variant make_kin_variant(int N) {
 #ifndef MPCB_W0  // candidate warps-per-block values (compile-time tuning knob)
@@ -62,20 +65,10 @@ Variant make_kin_variant(int N) {
 #define MPCB_W1 2
 #define MPCB_W2 1
 #endif
-  Variant cand[3] = {make_kin_variant_w<NR, MO, OBS, MPCB_W0>(), make_kin_variant_w<NR, MO, OBS, MPCB_W1>(), make_kin_variant_w<NR, MO, OBS, MPCB_W2>()};
-  if (const char *w = getenv("MPCB_FORCE_W")) {  // tuning knob: warps per block
-    for (int i = 0; i < 3; i++)
-      if (cand[i].warps == atoi(w)) return cand[i];
-  }
-  int best = 0, best_warps = -1;
-  for (int i = 0; i < 3; i++) {
-    size_t smem = cand[i].smem_bytes(N) * cand[i].warps;
-    int bps = 0;
-    if (cudaFuncSetAttribute(cand[i].kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, cand[i].kernel, 32 * cand[i].warps, smem) != cudaSuccess) { cudaGetLastError(); continue; }
-    if (bps * cand[i].warps > best_warps) { best_warps = bps * cand[i].warps; best = i; }
-  }
-  return cand[best];
+  Variant cand[6] = {make_kin_variant_w<NR, MO, OBS, MPCB_W0, false>(), make_kin_variant_w<NR, MO, OBS, MPCB_W1, false>(),
+                     make_kin_variant_w<NR, MO, OBS, MPCB_W2, false>(), make_kin_variant_w<NR, MO, OBS, MPCB_W0, true>(),
+                     make_kin_variant_w<NR, MO, OBS, MPCB_W1, true>(), make_kin_variant_w<NR, MO, OBS, MPCB_W2, true>()};
+  return pick_by_occupancy(cand, 6, N);
 }
 
 template <int W>

@@ -143,7 +143,10 @@ struct KinModel {
 // ------------------------------------------------------------------------------------
 // FH: the stage Hessian Hxx is stored full (10 entries) - needed by the discrete-time CBF rows,
 // whose rank-one barrier term couples all four states of a stage (see build_qp).
-template <int NR, int MO, bool FH = false>
+// GS: the step (dx, du) lives in the global slab instead of shared memory.  It costs ~2 % at N = 50
+// (the stage-parallel phases read it through L2) but frees 6 doubles per stage, which buys resident
+// warps at long horizons (N = 100: 8 warps per SM instead of 6, +12 %); the host picks per horizon.
+template <int NR, int MO, bool FH = false, bool GS = false>
 struct KinLayout {
   static constexpr int NX = 4, NBX = 2;
   // ---- shared memory: the working set of the serial sweeps (one record of NF doubles per stage)
@@ -162,9 +165,7 @@ struct KinLayout {
   static constexpr int DSR = R14, LRP = DSR + NR, DSO = LRP + NR, LOP = DSO + MO;
   static constexpr int CDEFT = R14 + 8;  // defects of the line-search trial point (moved to CDEF on acceptance)
   static_assert(2 * NR + 2 * MO <= 8, "slack steps and trial defects must fit the gain region");
-  static constexpr int DX = R14 + 14;
-  static constexpr int DU = DX + NX;
-  static constexpr int NSH = DU + 2;
+  static constexpr int NSH = R14 + 14 + (GS ? 0 : NX + 2);
   // stage-major storage: element (field, k) lives at k*NF + field.  NF is odd so that the
   // stage-parallel phases (lane = stage, stride NF doubles) touch 16 distinct even banks per
   // half-warp: conflict free; the serial sweeps read broadcasts.
@@ -193,7 +194,10 @@ struct KinLayout {
   static constexpr int ISX = OCY + MO;
   static constexpr int ISY = ISX + MO;
   static constexpr int XR = ISY + MO;   // per-stage cost target (only with ref_mode)
-  static constexpr int NG = XR + NX - G0;
+  // the step: written by lane 0 in the forward sweep, read by the stage-parallel phases only
+  static constexpr int DX = GS ? XR + NX : R14 + 14;
+  static constexpr int DU = DX + NX;
+  static constexpr int NG = XR + NX + (GS ? NX + 2 : 0) - G0;
   static constexpr int SG = 132;        // row stride (>= MPCB_NMAX + 1)
   __host__ __device__ static constexpr size_t bytes(int N) { return sizeof(double) * (size_t)NF * (size_t)(N + 1); }
   __host__ __device__ static constexpr size_t slab_doubles() { return (size_t)NG * SG; }
@@ -216,10 +220,10 @@ __device__ __forceinline__ double clampz(double z, double mu, double rgap) {
 // ------------------------------------------------------------------------------------
 // the solver: one warp = one scenario (kinematic model family)
 // ------------------------------------------------------------------------------------
-template <int NR, int MO, int OBS_MODE>
+template <int NR, int MO, int OBS_MODE, bool GS = false>
 struct KinSolver {
   static constexpr bool DCBF = OBS_MODE == 3;  // rows h(X_{k+1};obs_k) - (1-gamma) h(X_k;obs_k) >= 0
-  using L = KinLayout<NR, MO, DCBF>;
+  using L = KinLayout<NR, MO, DCBF, GS>;
   static constexpr int NX = 4, NBX = 2;
 
   const KParams &p;
@@ -1125,10 +1129,10 @@ struct KinSolver {
 #ifndef MPCB_KIN_RESIDENT_WARPS
 #define MPCB_KIN_RESIDENT_WARPS 12  // register budget: 65536 / (12 * 32) = 170 registers per thread
 #endif
-template <int NR, int MO, int OBS_MODE, int W>
+template <int NR, int MO, int OBS_MODE, int W, bool GS>
 __global__ void __launch_bounds__(32 * W, MPCB_KIN_RESIDENT_WARPS / W) kin_solve_kernel(const __grid_constant__ KParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  using L = KinLayout<NR, MO, OBS_MODE == 3>;
+  using L = KinLayout<NR, MO, OBS_MODE == 3, GS>;
   double *gs = p.slab + ((size_t)blockIdx.x * W + warp) * L::slab_doubles();
   const int woff = warp * L::NF * (p.N + 1);
   int tick = 0;
@@ -1137,7 +1141,7 @@ __global__ void __launch_bounds__(32 * W, MPCB_KIN_RESIDENT_WARPS / W) kin_solve
     if (lane == 0) b = atomicAdd(p.counter, 1);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= p.B) break;
-    KinSolver<NR, MO, OBS_MODE> s(p, gs, woff, tick, lane);
+    KinSolver<NR, MO, OBS_MODE, GS> s(p, gs, woff, tick, lane);
     s.run(b);
     __syncwarp();
   }
