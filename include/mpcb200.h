@@ -150,6 +150,18 @@ int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double 
  * in place on DEVICE buffers x0 [B][nx], z [B][nv]. */
 int mpcb_shift_batch(mpcb_handle *h, int B, double *x0, double *z, void *stream);
 
+/* Batched RefPathGenerator (row N2 of SURVEY.md section 8f; PKG/RefPathGenerator.py:9-59) on DEVICE
+ * buffers, kinematic model.  The straight global path of define_ref_path is implicit: points
+ * path_x0[b] + i*(+-1) towards xs.x with y/phi/v of xs (:9-24).  Per scenario: nearest-point walk
+ * from last_idx (updated in place) and preview resampling to N+1 rows (find_ref_traj, :27-59), with
+ * numpy's exact index arithmetic.  Outputs (either may be NULL):
+ *   ref [B][N+1][4]           = the `ref_traj` the mains pass as ref_state
+ *   stage_targets [B][N][4]   = aa*ref[i+1] + (1-aa)*xs, the `xs` argument of mpcb_solve_batch under
+ *                               MPCB_REF_TRAJECTORY (PKG/MPC_CBF_optimize_kin.py:196)
+ * T_horizon is the YAML `horizon` (int(T_horizon/T_S) must equal cfg.N). */
+int mpcb_ref_traj_batch(mpcb_handle *h, int B, double T_horizon, const double *x0, const double *xs, const double *path_x0,
+                        int32_t *last_idx, double aa, double *ref, double *stage_targets, void *stream);
+
 /* Diagnostics (the reference only has IPOPT's print_level log, PKG/MPC_CBF_optimize_kin.py:252):
  * when set, every later solve writes one row per interior-point iteration and scenario into the
  * DEVICE buffer trace[B][rows][8] = (mu, theta, kkt_error, dual_inf, primal_inf, compl_inf,

@@ -52,7 +52,7 @@ class MpcbLaunchInfo(C.Structure):
 
 EXPORTS = [
     "mpcb_version", "mpcb_strerror", "mpcb_last_cuda_error", "mpcb_nx", "mpcb_nv", "mpcb_create", "mpcb_destroy",
-    "mpcb_workspace_bytes", "mpcb_solve_batch", "mpcb_solve_batch_host", "mpcb_shift_batch", "mpcb_get_launch_info", "mpcb_fp64_peak_tflops", "mpcb_set_trace_buffer",
+    "mpcb_workspace_bytes", "mpcb_solve_batch", "mpcb_solve_batch_host", "mpcb_shift_batch", "mpcb_ref_traj_batch", "mpcb_get_launch_info", "mpcb_fp64_peak_tflops", "mpcb_set_trace_buffer",
 ]
 
 _lib = None
@@ -87,6 +87,7 @@ def load():
     lib.mpcb_solve_batch.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, ip, ip, dp, dp, vp]
     lib.mpcb_solve_batch_host.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, ip, ip, dp, dp]
     lib.mpcb_shift_batch.argtypes = [vp, C.c_int, dp, dp, vp]
+    lib.mpcb_ref_traj_batch.argtypes = [vp, C.c_int, C.c_double, dp, dp, dp, ip, C.c_double, dp, dp, vp]
     lib.mpcb_get_launch_info.argtypes = [vp, C.POINTER(MpcbLaunchInfo)]
     lib.mpcb_fp64_peak_tflops.argtypes = [C.POINTER(C.c_double)]
     lib.mpcb_set_trace_buffer.argtypes = [vp, dp, C.c_int]

@@ -27,8 +27,13 @@ def predict_obstacles(obs_state: torch.Tensor, dt: float, N: int) -> torch.Tenso
 
 
 def run_closed_loop(solver, x0: torch.Tensor, xs: torch.Tensor, obs_state: torch.Tensor | None, steps: int,
-                    moving: bool = True, disturbance_step: int | None = None):
+                    moving: bool = True, disturbance_step: int | None = None, aa: float | None = None,
+                    T_horizon: float | None = None):
     """Returns dict(x (steps+1,B,nx), u (steps,B,2), status (steps,B), iters (steps,B)).
+
+    aa: with a solver built with ref="trajectory", every step first runs the batched
+    `find_ref_traj` on the device (the mains call it before `optimize_problem`,
+    PKG/main_cbf_kin_c_sim_pre.py:97) and tracks aa*ref_traj[i+1] + (1-aa)*xs per stage.
 
     obs_state: (B,M,6) obstacle states (kin kinds; `moving=False` keeps them fixed as in
     main_cbf_kin_c_sim.py), (B,1,6) with only columns 0,1 used for dyn, or None for the no-CBF NLP.
@@ -43,13 +48,21 @@ def run_closed_loop(solver, x0: torch.Tensor, xs: torch.Tensor, obs_state: torch
     obs = None if obs_state is None else obs_state.clone().to(torch.float64)
     xh = [x.clone()]
     uh, sth, ith = [], [], []
+    stage_ref = aa is not None and solver.ref_trajectory
+    if stage_ref:
+        path_x0 = x[:, 0].clone()  # define_ref_path(x0, xs, T_S) before the loop (:52)
+        last_idx = torch.zeros(B, dtype=torch.int32, device=dev)
+        T_h = float(T_horizon if T_horizon is not None else solver.config["mpc_params"]["horizon"])
     for step in range(steps):
+        target = xs
+        if stage_ref:
+            _, target = solver.ref_traj(x, xs, path_x0, last_idx, T_h, aa)
         traj = None
         if obs is not None and solver.obs_initial:
             traj = obs if moving else torch.cat([obs[..., :3], torch.zeros_like(obs[..., 3:4]), obs[..., 4:]], dim=-1)  # prediction in-kernel
         elif obs is not None:
             traj = predict_obstacles(obs, dt, N) if moving else obs[:, :, None, :].repeat(1, 1, N + 1, 1).contiguous()
-        out = solver.solve(x, xs, traj, z, return_z=True)
+        out = solver.solve(x, target, traj, z, return_z=True)
         z = out["z"]
         if disturbance_step is not None and step == disturbance_step:
             z[:, 0:2] = 0.0

@@ -453,6 +453,80 @@ extern "C" int mpcb_shift_batch(mpcb_handle *h, int B, double *x0, double *z, vo
 }
 
 // ---------------------------------------------------------------------------------------
+// batched RefPathGenerator (PKG/RefPathGenerator.py:9-59): one thread per scenario
+// ---------------------------------------------------------------------------------------
+namespace {
+
+// Every floating-point step below is written with explicit round-to-nearest intrinsics so that
+// no multiply-add is contracted: the index arithmetic (nearest-point walk, linspace, truncation
+// to int) has to reproduce numpy's results exactly, not approximately.
+__global__ void ref_traj_kernel(int B, int N, double T_horizon, const double *x0, const double *xs, const double *path_x0,
+                                int32_t *last_idx, double aa, double *ref, double *stage) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double ex = x0[4 * b + 0], ey = x0[4 * b + 1], ev = x0[4 * b + 3];
+  const double tx = xs[4 * b + 0], ty = xs[4 * b + 1], tphi = xs[4 * b + 2], tv = xs[4 * b + 3];
+  // define_ref_path (:9-24): np.arange(x_start, xs.x +- 1, +-1) -> element i is x_start + i*step
+  const double start = path_x0[b];
+  const double step = tx > start ? 1.0 : -1.0;
+  const double stop = __dadd_rn(tx, step);
+  int len = (int)ceil(__ddiv_rn(__dadd_rn(stop, -start), step));
+  if (len < 1) len = 1;
+  // numpy fills arange as start + i*delta with delta = (start + step) - start, which is not exactly
+  // +-1 when start + step rounds
+  const double dlt = __dadd_rn(__dadd_rn(start, step), -start);
+  // find_ref_traj (:27-59)
+  const double pv = __dadd_rn(__dmul_rn(0.5, ev), __dmul_rn(0.5, tv));
+  const int pidx = (int)__dmul_rn(pv, T_horizon);  // step_x = 1
+  const int last = last_idx[b];
+  const int lo = max(0, last - 5), hi = min(len, last + pidx);
+  int mi = lo;
+  double best = INFINITY;
+  for (int i = lo; i < hi; i++) {
+    const double dx = __dadd_rn(__dadd_rn(start, __dmul_rn((double)i, dlt)), -ex), dy = __dadd_rn(ty, -ey);
+    const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    if (d < best) { best = d; mi = i; } else break;
+  }
+  last_idx[b] = mi;
+  // idx = np.clip(np.linspace(mi, mi + pidx, N+1), 0, len-1).astype(int)
+  const double a0 = (double)mi, a1 = (double)(mi + pidx);
+  const double ls = __ddiv_rn(__dadd_rn(a1, -a0), (double)N);
+  for (int i = 0; i <= N; i++) {
+    double v = i == N ? a1 : __dadd_rn(__dmul_rn((double)i, ls), a0);
+    v = fmin(fmax(v, 0.0), (double)(len - 1));
+    const int id = (int)v;
+    const double rx = __dadd_rn(start, __dmul_rn((double)id, dlt));
+    if (ref) {
+      double *r = ref + ((size_t)b * (N + 1) + i) * 4;
+      r[0] = rx; r[1] = ty; r[2] = tphi; r[3] = tv;
+    }
+    if (stage && i >= 1) {  // ref_X of stage i-1 = aa*ref_state[i] + (1-aa)*xs   (PKG/MPC_CBF_optimize_kin.py:196)
+      double *q = stage + ((size_t)b * N + (i - 1)) * 4;
+      const double w1 = __dadd_rn(1.0, -aa);
+      q[0] = __dadd_rn(__dmul_rn(aa, rx), __dmul_rn(w1, tx));
+      q[1] = __dadd_rn(__dmul_rn(aa, ty), __dmul_rn(w1, ty));
+      q[2] = __dadd_rn(__dmul_rn(aa, tphi), __dmul_rn(w1, tphi));
+      q[3] = __dadd_rn(__dmul_rn(aa, tv), __dmul_rn(w1, tv));
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int mpcb_ref_traj_batch(mpcb_handle *h, int B, double T_horizon, const double *x0, const double *xs, const double *path_x0,
+                                   int32_t *last_idx, double aa, double *ref, double *stage_targets, void *stream) {
+  if (!h || B < 0) return MPCB_E_ARG;
+  if (B == 0) return MPCB_OK;
+  if (!x0 || !xs || !path_x0 || !last_idx || (!ref && !stage_targets) || !(T_horizon > 0)) return MPCB_E_ARG;
+  if (h->cfg.model != MPCB_MODEL_KIN) return MPCB_E_ARG;  // the reference builds references for the 4-state mains only
+  if ((int)(T_horizon / h->cfg.T) != h->cfg.N) return MPCB_E_ARG;  // N_p = int(T_horizon/dt), RefPathGenerator.py:31
+  ref_traj_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, h->cfg.N, T_horizon, x0, xs, path_x0, last_idx, aa, ref, stage_targets);
+  if (!cuda_ok(cudaGetLastError(), "ref_traj_kernel launch")) return MPCB_E_CUDA;
+  h->info.launches++;
+  return MPCB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // FP64 FMA-pipe micro-benchmark: the roofline denominator of the solve kernel (SURVEY.md
 // section 8d asks for a measured DFMA peak; MEASURED_PEAKS.json only holds HBM and bf16).
 // ---------------------------------------------------------------------------------------

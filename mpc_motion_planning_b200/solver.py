@@ -151,6 +151,30 @@ class BatchSolver:
             rc = self.lib.mpcb_shift_batch(self._h, B, C.c_void_p(x0.data_ptr()), C.c_void_p(z.data_ptr()), stream)
         _lib.check(rc, "mpcb_shift_batch")
 
+    def ref_traj(self, x0, xs, path_x0, last_idx, T_horizon: float, aa: float | None = None):
+        """Batched `RefPathGenerator.find_ref_traj` on the device (PKG/RefPathGenerator.py:27-59) over the
+        implicit straight path of `define_ref_path` (:9-24) that starts at x = path_x0[b].
+
+        x0, xs (B,4) and path_x0 (B,) float64 CUDA tensors; last_idx (B,) int32 CUDA tensor, updated in
+        place.  Returns ref (B,N+1,4); with `aa` also the stage targets aa*ref[i+1] + (1-aa)*xs (B,N,4),
+        the `xs` argument of a solver built with ref="trajectory"."""
+        import torch
+
+        B = x0.shape[0]
+        dev = x0.device
+        assert self.nx == 4 and last_idx.dtype == torch.int32 and last_idx.is_contiguous()
+        x0, xs, path_x0 = (t.to(torch.float64).contiguous() for t in (x0, xs, path_x0))
+        ref = torch.empty((B, self.N + 1, 4), dtype=torch.float64, device=dev)
+        stage = torch.empty((B, self.N, 4), dtype=torch.float64, device=dev) if aa is not None else None
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            rc = self.lib.mpcb_ref_traj_batch(self._h, B, float(T_horizon), C.c_void_p(x0.data_ptr()), C.c_void_p(xs.data_ptr()),
+                                              C.c_void_p(path_x0.data_ptr()), C.c_void_p(last_idx.data_ptr()),
+                                              float(aa if aa is not None else 0.0), C.c_void_p(ref.data_ptr()),
+                                              C.c_void_p(stage.data_ptr()) if stage is not None else None, stream)
+        _lib.check(rc, "mpcb_ref_traj_batch")
+        return (ref, stage) if aa is not None else ref
+
     def set_trace(self, trace):
         """trace: CUDA float64 tensor (B, rows, 8) to receive the per-iteration log, or None."""
         if trace is None:

@@ -512,3 +512,85 @@ def test_horizon_limits(dev, kind, gen, N):
     du = np.abs(g["u0"] - u0).max(axis=1)
     dc = np.abs(g["cost"] - cost) / np.maximum(np.abs(cost), 1.0)
     assert np.all(du[both] <= U0_ATOL) and np.all(dc[both] <= COST_RTOL), (du[both].max(), dc[both].max())
+
+
+def test_device_ref_traj_equals_the_host_generator(dev):
+    """`mpcb_ref_traj_batch` against the host RefPathGenerator mirror (itself equal to the reference's
+    output, tests/test_reference_vectors.py): index arithmetic bit for bit, both driving directions,
+    `last_idx` carried over several calls like the mains' loops do."""
+    import torch
+
+    from mpc_motion_planning_b200 import RefPathGenerator
+    from mpc_motion_planning_b200.solver import BatchSolver
+
+    rng = np.random.default_rng(11)
+    B, N, T_h, aa = 96, 50, 5, 0.3
+    s = BatchSolver("kin_cbf_pre", ref="trajectory")
+    start = rng.uniform(0, 20, B)
+    xs = np.c_[np.where(np.arange(B) % 7 == 0, start - rng.uniform(50, 300, B), start + rng.uniform(100, 500, B)),
+               rng.uniform(0, 4, B), rng.uniform(-0.05, 0.05, B), rng.uniform(10, 30, B)]
+    gens = []
+    for b in range(B):
+        g = RefPathGenerator.RefPathGenerator()
+        g.define_ref_path(np.array([start[b], 0, 0, 0.0]).reshape(-1, 1), xs[b].reshape(-1, 1), 0.1)
+        gens.append(g)
+    last = np.zeros(B, dtype=np.int32)
+    t_last = torch.zeros(B, dtype=torch.int32, device=dev)
+    t_xs, t_start = torch.from_numpy(xs).to(dev), torch.from_numpy(start).to(dev)
+    x = np.c_[start, rng.uniform(0, 4, B), np.zeros(B), rng.uniform(5, 30, B)]
+    for it in range(6):
+        ref, stage = s.ref_traj(torch.from_numpy(x).to(dev), t_xs, t_start, t_last, T_h, aa)
+        torch.cuda.synchronize()
+        ref, stage = ref.cpu().numpy(), stage.cpu().numpy()
+        for b in range(B):
+            want, last[b] = gens[b].find_ref_traj(x[b].reshape(-1, 1), xs[b].reshape(-1, 1), T_h, 0.1, int(last[b]))
+            assert np.array_equal(ref[b], want), (it, b)
+            assert np.array_equal(stage[b], aa * want[1:] + (1 - aa) * xs[b][None, :]), (it, b)
+        assert np.array_equal(t_last.cpu().numpy(), last)
+        x[:, 0] += np.sign(xs[:, 0] - start) * rng.uniform(0.5, 6.0, B)  # drive along the path
+        x[:, 1] += rng.normal(0, 0.1, B)
+
+
+def test_closed_loop_with_stage_reference_on_device(dev):
+    """closed loop with aa != 0: find_ref_traj + solve + plant step + shift, all on the device, against
+    the same loop written with the host generator and the C oracle."""
+    import torch
+
+    from mpc_motion_planning_b200 import RefPathGenerator, scenarios
+    from mpc_motion_planning_b200.closed_loop import run_closed_loop
+    from mpc_motion_planning_b200.Obs_prediction import obs_prediction_batch
+    from mpc_motion_planning_b200.solver import BatchSolver
+    from oracle import c_oracle
+
+    B, steps, N, aa = 8, 6, 50, 0.3
+    x0, xs, obs = scenarios.kin_cbf_moving(B, seed=5)
+    obs0 = obs[:, :, 0, :].copy()
+    s = BatchSolver("kin_cbf_pre", ref="trajectory", init="rollout")
+    out = run_closed_loop(s, torch.from_numpy(x0).to(dev), torch.from_numpy(xs).to(dev), torch.from_numpy(obs0).to(dev), steps, aa=aa)
+    torch.cuda.synchronize()
+    X = out["x"].cpu().numpy()
+    cfg = c_oracle.make_cfg("kin_cbf_pre", ref_trajectory=True)
+    from mpc_motion_planning_b200 import MPC_CBF_optimize_kin_pre
+
+    f = MPC_CBF_optimize_kin_pre.MPC_optimize().f
+    ok = 0
+    for b in range(B):
+        g = RefPathGenerator.RefPathGenerator()
+        g.define_ref_path(x0[b].reshape(-1, 1), xs[b].reshape(-1, 1), 0.1)
+        x, o, z, last = x0[b].copy(), obs0[b, 0].copy(), None, 0
+        good = True
+        for k in range(steps):
+            ref, last = g.find_ref_traj(x.reshape(-1, 1), xs[b].reshape(-1, 1), 5, 0.1, last)
+            tgt = aa * ref[1:] + (1 - aa) * xs[b][None, :]
+            zz, _, info = c_oracle.solve(cfg, x, tgt, obs_prediction_batch(o, 0.1, N)[None], z)
+            if info.status > 1 or out["status"][k, b].item() > 1:
+                good = False
+                break
+            x = x + 0.1 * f(x, zz[:2]).full().ravel()
+            U, Xs = zz[: 2 * N].reshape(N, 2), zz[2 * N:].reshape(N + 1, 4)
+            z = np.concatenate([np.concatenate([U[1:], U[-1:]]).ravel(), np.concatenate([Xs[1:], Xs[-1:]]).ravel()])
+            o[0] += o[3] * np.cos(o[2]) * 0.1
+            o[1] += o[3] * np.sin(o[2]) * 0.1
+            assert np.abs(X[k + 1, b] - x).max() <= 1e-5, (b, k)
+        ok += good
+    assert ok >= B // 2
