@@ -162,6 +162,14 @@ int mpcb_shift_batch(mpcb_handle *h, int B, double *x0, double *z, void *stream)
 int mpcb_ref_traj_batch(mpcb_handle *h, int B, double T_horizon, const double *x0, const double *xs, const double *path_x0,
                         int32_t *last_idx, double aa, double *ref, double *stage_targets, void *stream);
 
+/* Scheduling hint.  The resident warps pull scenarios from a queue; iteration counts differ by 5x
+ * between scenarios, so at small batches (a few scenarios per resident warp) the makespan is set by
+ * long scenarios that start late.  `order` (DEVICE, [B] permutation of 0..B-1, read by every later
+ * solve until reset with NULL) makes queue position q process scenario order[q]: pass the scenarios
+ * sorted by expected work, longest first - in a closed loop the previous step's `iters` is a good
+ * predictor.  Results do not depend on the order. */
+int mpcb_set_order(mpcb_handle *h, const int32_t *order);
+
 /* Diagnostics (the reference only has IPOPT's print_level log, PKG/MPC_CBF_optimize_kin.py:252):
  * when set, every later solve writes one row per interior-point iteration and scenario into the
  * DEVICE buffer trace[B][rows][8] = (mu, theta, kkt_error, dual_inf, primal_inf, compl_inf,

@@ -52,7 +52,7 @@ class MpcbLaunchInfo(C.Structure):
 
 EXPORTS = [
     "mpcb_version", "mpcb_strerror", "mpcb_last_cuda_error", "mpcb_nx", "mpcb_nv", "mpcb_create", "mpcb_destroy",
-    "mpcb_workspace_bytes", "mpcb_solve_batch", "mpcb_solve_batch_host", "mpcb_shift_batch", "mpcb_ref_traj_batch", "mpcb_get_launch_info", "mpcb_fp64_peak_tflops", "mpcb_set_trace_buffer",
+    "mpcb_workspace_bytes", "mpcb_solve_batch", "mpcb_solve_batch_host", "mpcb_shift_batch", "mpcb_ref_traj_batch", "mpcb_get_launch_info", "mpcb_fp64_peak_tflops", "mpcb_set_trace_buffer", "mpcb_set_order",
 ]
 
 _lib = None
@@ -91,6 +91,7 @@ def load():
     lib.mpcb_get_launch_info.argtypes = [vp, C.POINTER(MpcbLaunchInfo)]
     lib.mpcb_fp64_peak_tflops.argtypes = [C.POINTER(C.c_double)]
     lib.mpcb_set_trace_buffer.argtypes = [vp, dp, C.c_int]
+    lib.mpcb_set_order.argtypes = [vp, ip]
     _lib = lib
     return lib
 

@@ -28,9 +28,11 @@ def predict_obstacles(obs_state: torch.Tensor, dt: float, N: int) -> torch.Tenso
 
 def run_closed_loop(solver, x0: torch.Tensor, xs: torch.Tensor, obs_state: torch.Tensor | None, steps: int,
                     moving: bool = True, disturbance_step: int | None = None, aa: float | None = None,
-                    T_horizon: float | None = None):
+                    T_horizon: float | None = None, longest_first: bool = False):
     """Returns dict(x (steps+1,B,nx), u (steps,B,2), status (steps,B), iters (steps,B)).
 
+    longest_first: order each step's work queue by the previous step's iteration counts (descending),
+    which shortens the last wave at small batches (`mpcb_set_order`).
     aa: with a solver built with ref="trajectory", every step first runs the batched
     `find_ref_traj` on the device (the mains call it before `optimize_problem`,
     PKG/main_cbf_kin_c_sim_pre.py:97) and tracks aa*ref_traj[i+1] + (1-aa)*xs per stage.
@@ -69,9 +71,13 @@ def run_closed_loop(solver, x0: torch.Tensor, xs: torch.Tensor, obs_state: torch
         uh.append(z[:, 0:2].clone())
         sth.append(out["status"])
         ith.append(out["iters"])
+        if longest_first:
+            solver.set_order(torch.argsort(out["iters"], descending=True, stable=True).to(torch.int32))
         solver.shift(x, z)  # plant Euler step with U_0 and warm-start shift, in place
         if obs is not None and moving:
             obs[..., 0] = obs[..., 0] + obs[..., 3] * torch.cos(obs[..., 2]) * dt  # main_cbf_kin_c_sim_pre.py:106
             obs[..., 1] = obs[..., 1] + obs[..., 3] * torch.sin(obs[..., 2]) * dt
         xh.append(x.clone())
+    if longest_first:
+        solver.set_order(None)
     return {"x": torch.stack(xh), "u": torch.stack(uh), "status": torch.stack(sth), "iters": torch.stack(ith)}

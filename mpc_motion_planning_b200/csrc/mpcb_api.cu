@@ -369,6 +369,12 @@ int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double 
   return MPCB_OK;
 }
 
+int mpcb_set_order(mpcb_handle *h, const int32_t *order) {
+  if (!h) return MPCB_E_ARG;
+  h->kp.order = order;
+  return MPCB_OK;
+}
+
 int mpcb_set_trace_buffer(mpcb_handle *h, double *trace, int rows) {
   if (!h || rows < 0) return MPCB_E_ARG;
   h->kp.trace = rows > 0 ? trace : nullptr;

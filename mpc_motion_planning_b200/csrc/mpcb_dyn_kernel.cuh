@@ -841,6 +841,7 @@ __global__ void __launch_bounds__(32 * W) dyn_solve_kernel(const __grid_constant
     if (lane == 0) b = atomicAdd(p.counter, 1);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= p.B) break;
+    if (p.order) b = p.order[b];  // caller-supplied processing order (longest expected first)
     DynSolver s(p, gs, woff, tick, lane);
     s.run(b);
     __syncwarp();

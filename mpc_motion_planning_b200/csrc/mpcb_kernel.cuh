@@ -80,6 +80,7 @@ struct KParams {
   int32_t *status, *iters;
   double *slab;    // per-resident-block scratch in global memory (kinematic kernels)
   int *counter;    // work queue head (persistent kernels)
+  const int32_t *order;  // optional [B] permutation: queue position -> scenario index
   double *trace;   // optional [B][trace_rows][8] per-iteration log (mu, theta, err, dual, prim, compl, alpha, dw)
   int trace_rows;
 };
@@ -1141,6 +1142,7 @@ __global__ void __launch_bounds__(32 * W, MPCB_KIN_RESIDENT_WARPS / W) kin_solve
     if (lane == 0) b = atomicAdd(p.counter, 1);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= p.B) break;
+    if (p.order) b = p.order[b];  // caller-supplied processing order (longest expected first)
     KinSolver<NR, MO, OBS_MODE, GS> s(p, gs, woff, tick, lane);
     s.run(b);
     __syncwarp();

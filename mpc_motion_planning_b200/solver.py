@@ -175,6 +175,19 @@ class BatchSolver:
         _lib.check(rc, "mpcb_ref_traj_batch")
         return (ref, stage) if aa is not None else ref
 
+    def set_order(self, order):
+        """order: CUDA int32 tensor (B,), a permutation - queue position q processes scenario order[q]
+        (longest expected first); None resets to arrival order.  Results do not depend on it."""
+        if order is None:
+            _lib.check(self.lib.mpcb_set_order(self._h, None), "mpcb_set_order")
+            self._order = None
+        else:
+            import torch
+
+            assert order.is_cuda and order.dtype == torch.int32 and order.is_contiguous()
+            _lib.check(self.lib.mpcb_set_order(self._h, C.c_void_p(order.data_ptr())), "mpcb_set_order")
+            self._order = order  # keep it alive
+
     def set_trace(self, trace):
         """trace: CUDA float64 tensor (B, rows, 8) to receive the per-iteration log, or None."""
         if trace is None:

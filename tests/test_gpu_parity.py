@@ -594,3 +594,22 @@ def test_closed_loop_with_stage_reference_on_device(dev):
             assert np.abs(X[k + 1, b] - x).max() <= 1e-5, (b, k)
         ok += good
     assert ok >= B // 2
+
+
+def test_results_do_not_depend_on_the_queue_order(dev):
+    """`mpcb_set_order` is a scheduling hint only."""
+    import torch
+
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+
+    B = 3000
+    x0, xs, obs = scenarios.kin_cbf_moving(B)
+    s = BatchSolver("kin_cbf_pre")
+    a = _gpu(s, dev, x0, xs, obs)
+    order = torch.argsort(torch.from_numpy(a["iters"]).to(dev), descending=True, stable=True).to(torch.int32)
+    s.set_order(order)
+    b = _gpu(s, dev, x0, xs, obs)
+    s.set_order(None)
+    for k in ("u0", "cost", "status", "iters"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
