@@ -1065,6 +1065,10 @@ struct KinSolver {
         at(L::ZLX + b2, k) = 1.0;
         at(L::ZUX + b2, k) = 1.0;
       }
+    }
+    if (DCBF) __syncwarp();  // the rows below read the pushed state of stage k+1 (another lane's)
+    #pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
       if (has_rate(k)) {
 #pragma unroll
         for (int r = 0; r < NR; r++) {
