@@ -174,8 +174,13 @@ def main():
     K = args.steps
     B = args.batch
 
-    x0, xs, obs = make_batch(rank, B)
-    solver = BatchSolver("kin_cbf", N=N_HORIZON, M=1)
+    x0, xs, obs_traj = make_batch(rank, B)
+    # The static-obstacle module's optimize_problem takes the obstacle rows themselves, (M,6)
+    # (PKG/MPC_CBF_optimize_kin.py:136,236-243; PKG/main_cbf_kin_c_sim.py:55,99): that is the input of the
+    # bench, [B][M][6] (MPCB_OBS_STATIC).  The CPU arm gets the same rows repeated per step.
+    obs = np.ascontiguousarray(obs_traj[:, :, 0, :])
+    assert np.array_equal(obs_traj, np.repeat(obs[:, :, None, :], N_HORIZON + 1, axis=2))
+    solver = BatchSolver("kin_cbf", N=N_HORIZON, M=1, obs_input="static")
     dx0, dxs, dobs = (torch.from_numpy(a).to(dev) for a in (x0, xs, obs))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -270,6 +275,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"kin-CBF static obstacle MPC, N={N_HORIZON}, M=1, B={B}/GPU (BASELINE configs[1])",
                        "start": "zero controls, Euler roll-out states", "mu_init": 100.0, "tol": 1e-8, "max_iter": 100,
+                       "inputs": "x0 [B][4], xs [B][4], obstacle rows [B][1][6] as optimize_problem takes them",
                        "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"scenario-sharded x{world}"},
             "solver": {"converged_frac": float((status <= 1).mean()), "acceptable_frac": float((status == 1).mean()), "mean_iters": float(iters.mean()),
                        "p99_iters": float(np.percentile(iters, 99))},
@@ -289,7 +295,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             sample = min(B, 4000)
-            dt, st_c, it_c = cpu_solve(x0[:sample], xs[:sample], obs[:sample], cores)
+            dt, st_c, it_c = cpu_solve(x0[:sample], xs[:sample], obs_traj[:sample], cores)
             line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {sample} scenarios of the same batch, restated CPU IPM (oracle/mpc_oracle.c, "
                                               "scalar Riccati, one scenario per thread), not CasADi+IPOPT"}

@@ -50,7 +50,10 @@ enum { MPCB_INIT_AS_GIVEN = 0, MPCB_INIT_ROLLOUT = 1 };
  * (PKG/Obs_prediction.py:3-40); INITIAL = [B][M][6], the obstacle states themselves - the library
  * then runs the same constant-velocity recursion (x += v cos(theta) dt, step by step, :27-28) on the
  * device while staging the trajectory, so nothing per-step crosses PCIe or HBM */
-enum { MPCB_OBS_TRAJECTORY = 0, MPCB_OBS_INITIAL = 1 };
+/* STATIC = [B][M][6], obstacle rows that hold at every step - what the static-obstacle module's
+ * `optimize_problem(ego_state, ref_state, obstacle)` takes (PKG/MPC_CBF_optimize_kin.py:136,236-243;
+ * PKG/main_cbf_kin_c_sim.py:55,99); identical results to TRAJECTORY with the row repeated */
+enum { MPCB_OBS_TRAJECTORY = 0, MPCB_OBS_INITIAL = 1, MPCB_OBS_STATIC = 2 };
 
 /* per-scenario outcome, mapped to IPOPT return_status strings by the Python shim */
 enum {
@@ -96,7 +99,7 @@ typedef struct mpcb_cfg {
   double tol;           /* ipopt.tol (default 1e-8) */
   double mu_init;       /* initial barrier parameter (IPOPT default 0.1; this library's default 100) */
   double bound_relax;   /* ipopt.bound_relax_factor (1e-8) */
-  int32_t obs_input;    /* MPCB_OBS_TRAJECTORY (default) or MPCB_OBS_INITIAL */
+  int32_t obs_input;    /* MPCB_OBS_TRAJECTORY (default), MPCB_OBS_INITIAL or MPCB_OBS_STATIC */
   int32_t ref_mode;     /* MPCB_REF_TERMINAL (default) or MPCB_REF_TRAJECTORY */
   double cbf_gamma;     /* gamma in (0,1] of the MPCB_OBS_DCBF rows (the reference's `gamma = 1.00`, :235) */
 } mpcb_cfg;
@@ -126,7 +129,7 @@ int mpcb_workspace_bytes(const mpcb_cfg *cfg, int B, size_t *bytes);
  *                                   xs [B][N][nx] with cfg.ref_mode = MPCB_REF_TRAJECTORY
  *   obs [B][M][N+1][6]            = obs_prediction rows [x,y,theta,v,l,w] (PKG/Obs_prediction.py:3-40);
  *                                   static obstacles repeat the row; dyn uses columns 0,1 only.
- *                                   With cfg.obs_input = MPCB_OBS_INITIAL: [B][M][6] (see above)
+ *                                   With cfg.obs_input = MPCB_OBS_INITIAL or MPCB_OBS_STATIC: [B][M][6] (see above)
  *   z_init [B][nv] or NULL        = `x0=` warm start [vec(U);vec(X)] (NULL = zeros, :47-50)
  * outputs:
  *   u0 [B][2]                     = first control, res['x'][0:2]

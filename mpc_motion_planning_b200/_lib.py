@@ -11,7 +11,7 @@ SO_PATH = os.environ.get("MPCB200_LIB") or os.path.join(HERE, "libmpcb200.so")  
 MODEL_KIN, MODEL_DYN = 0, 1
 OBS_NONE, OBS_ELLIPSE, OBS_SQRT, OBS_DCBF = 0, 1, 2, 3
 INIT_AS_GIVEN, INIT_ROLLOUT = 0, 1
-OBS_TRAJECTORY, OBS_INITIAL = 0, 1
+OBS_TRAJECTORY, OBS_INITIAL, OBS_STATIC = 0, 1, 2
 REF_TERMINAL, REF_TRAJECTORY = 0, 1
 ST_CONVERGED, ST_ACCEPTABLE, ST_MAXITER, ST_INFEASIBLE, ST_NAN = 0, 1, 2, 3, 4
 

@@ -196,7 +196,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
     if (c.rate_ctrl[r] < 0 || c.rate_ctrl[r] > 1 || !(c.rate_lo[r] < c.rate_hi[r])) return MPCB_E_ARG;
   if (!(c.T > 0) || !(c.tol > 0) || !(c.mu_init > 0) || !(c.bound_relax >= 0)) return MPCB_E_ARG;
   if (c.obs_mode != MPCB_OBS_NONE && c.M < 1) return MPCB_E_ARG;
-  if (c.obs_input != MPCB_OBS_TRAJECTORY && c.obs_input != MPCB_OBS_INITIAL) return MPCB_E_ARG;
+  if (c.obs_input != MPCB_OBS_TRAJECTORY && c.obs_input != MPCB_OBS_INITIAL && c.obs_input != MPCB_OBS_STATIC) return MPCB_E_ARG;
   if (c.ref_mode != MPCB_REF_TERMINAL && c.ref_mode != MPCB_REF_TRAJECTORY) return MPCB_E_ARG;
   if (c.ref_mode == MPCB_REF_TRAJECTORY && c.model != MPCB_MODEL_KIN) return MPCB_E_ARG;
   if (c.obs_mode == MPCB_OBS_DCBF && !(c.cbf_gamma > 0.0 && c.cbf_gamma <= 1.0)) return MPCB_E_ARG;
@@ -334,7 +334,7 @@ int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double 
   const int nx = h->var.nx, N = h->cfg.N;
   const int M = h->cfg.obs_mode == MPCB_OBS_NONE ? 0 : h->cfg.M;
   const size_t nv = 2 * (size_t)N + (size_t)nx * (N + 1);
-  const size_t so = (size_t)M * (h->cfg.obs_input == MPCB_OBS_INITIAL ? 1 : (N + 1)) * 6;
+  const size_t so = (size_t)M * (h->cfg.obs_input != MPCB_OBS_TRAJECTORY ? 1 : (N + 1)) * 6;
   const size_t sxs = h->cfg.ref_mode == MPCB_REF_TRAJECTORY ? (size_t)nx * N : (size_t)nx;
   if (M > 0 && !obs) return MPCB_E_ARG;
   if (B > h->cap_B) {

@@ -988,7 +988,10 @@ struct KinSolver {
       for (int j = 0; j < MO; j++) {
         const double *o = ob + (size_t)j * 6;
         double x = o[0], y = o[1];
-        const double dx = o[3] * cos(o[2]) * p.T, dy = o[3] * sin(o[2]) * p.T;
+        // MPCB_OBS_STATIC: the row is the obstacle at every step (PKG/MPC_CBF_optimize_kin.py:236-243 reads
+        // columns 0,1,4,5 only); adding +0.0 per step leaves x, y bit-identical to a repeated row
+        const bool moving = p.obs_input == 1;
+        const double dx = moving ? o[3] * cos(o[2]) * p.T : 0.0, dy = moving ? o[3] * sin(o[2]) * p.T : 0.0;
         const double sx = p.ego_hl + o[4] / 2 + p.safe_l, sy = p.ego_hw + o[5] / 2 + p.safe_w;
         const double isx = 1.0 / (sx * sx), isy = 1.0 / (sy * sy);
 #pragma unroll 1

@@ -34,11 +34,13 @@ class BatchSolver:
         self.kind = kind
         self.config = config if config is not None else load_config(PACKAGE_PARAMS)
         init_mode = {"rollout": _lib.INIT_ROLLOUT, "as_given": _lib.INIT_AS_GIVEN}[init]
-        self.obs_initial = {"trajectory": False, "initial": True}[obs_input]
+        # "initial": obstacle states, rolled out in the kernel; "static": rows that hold at every step
+        self.obs_initial = {"trajectory": False, "initial": True, "static": True}[obs_input]
+        obs_code = {"trajectory": _lib.OBS_TRAJECTORY, "initial": _lib.OBS_INITIAL, "static": _lib.OBS_STATIC}[obs_input]
         self.ref_trajectory = {"terminal": False, "trajectory": True}[ref]
         self.cfg = make_cfg(kind, self.config, N=N, M=M, weights=weights, init_mode=init_mode, mu_init=mu_init,
                             max_iter=max_iter, tol=tol, bounds=bounds,
-                            obs_input=_lib.OBS_INITIAL if self.obs_initial else _lib.OBS_TRAJECTORY,
+                            obs_input=obs_code,
                             cbf_gamma=cbf_gamma,
                             ref_mode=_lib.REF_TRAJECTORY if self.ref_trajectory else _lib.REF_TERMINAL)
         self.N, self.M = int(self.cfg.N), int(self.cfg.M)

@@ -613,3 +613,48 @@ def test_results_do_not_depend_on_the_queue_order(dev):
     s.set_order(None)
     for k in ("u0", "cost", "status", "iters"):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_static_obstacle_rows_equal_repeated_trajectories(dev):
+    """`obs_input="static"` ([B][M][6], what the static module's optimize_problem takes) gives bit-identical
+    results to the same rows repeated over the horizon; the velocity column is ignored."""
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+
+    B = 256
+    x0, xs, obs = scenarios.kin_cbf_static(B)
+    a = _gpu(BatchSolver("kin_cbf"), dev, x0, xs, obs)
+    rows = obs[:, :, 0, :].copy()
+    rows[:, :, 3] = 7.0  # a velocity must not move a static obstacle
+    b = _gpu(BatchSolver("kin_cbf", obs_input="static"), dev, x0, xs, rows)
+    for k in ("u0", "cost", "status", "iters"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_the_binding_stub_of_integration_md_runs(dev, tmp_path, monkeypatch):
+    """INTEGRATION.md, option B: the ctypes stub a maintainer would add to the reference, executed as
+    written (only the library path is made absolute) against the reference's default scenario."""
+    import re
+
+    monkeypatch.chdir(tmp_path)
+    from mpc_motion_planning_b200 import MPC_CBF_optimize_kin, _lib
+
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    code = re.search(r"```python\n# PKG/mpcb_binding.py.*?\n(.*?)```", text, re.S).group(1)
+    code = code.replace('C.CDLL("libmpcb200.so")', f'C.CDLL("{_lib.SO_PATH}")')
+    ns = {}
+    exec(compile(code, "mpcb_binding.py", "exec"), ns)
+    ns["lib"].mpcb_strerror.restype = __import__("ctypes").c_char_p
+    mpc = MPC_CBF_optimize_kin.MPC_optimize()
+    h = ns["make_handle"](mpc)
+    N = mpc.N_p
+    x0, xs = np.array([0, 3, 0, 15.0]), np.array([400, 3.5, 0, 30.0])
+    obs = np.array([[50, 3.5, 0, 8, 4.8, 1.8]])
+    z0 = np.zeros(2 * N + 4 * (N + 1))
+    X = [x0]
+    for _ in range(N):  # dynamically consistent first guess (the stub starts the solver exactly at x0=)
+        X.append(X[-1] + mpc.T_S * mpc.f(X[-1], [0.0, 0.0]).full().ravel())
+    z0[2 * N:] = np.array(X).ravel()
+    z, f, status = ns["solve"](h, N, x0, xs, obs, z0)
+    assert status == 0 and z.shape == (304, 1)
+    assert abs(f - 1.0947508480e8) <= 1e-6 * 1.1e8 and np.allclose(z[:2, 0], [0.03564617, 3.0], atol=1e-6)
