@@ -7,7 +7,8 @@ objective, constraint rows (reference order) and bound lists against vectors the
 f to 1e-14 relative, g to 1e-11).  The SOLVE is UNPINNED: the reference ships no tests or golden
 vectors and CasADi + IPOPT (unpinned PyPI `casadi`) cannot be installed here (no network), so
 the interior-point method in oracle/ipm_dense.py / mpc_oracle.c follows IPOPT's published
-algorithm, not IPOPT's outputs.  The no-CBF module exists only as a CPython-3.7 .pyc: unpinned.
+algorithm, not IPOPT's outputs.  (The no-CBF module exists only as a CPython-3.7 .pyc; the
+generator executes its bytecode with tests/golden/pyc37.py, so it is pinned the same way.)
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
 `--impl reference` legs may import this package.

@@ -13,8 +13,9 @@ seeded points and stores
 
 per module, plus outputs of `generate_ref_path`, `RefPathGenerator` and `obs_prediction`.
 tests/test_reference_vectors.py checks the restated NLP (oracle/nlp.py), the drop-in host classes
-and the bound lists against them.  (`MPC_optimize_kin`, the no-CBF module, exists only as a
-CPython-3.7 .pyc and cannot be imported by this interpreter: it stays unpinned.)
+and the bound lists against them.  `MPC_optimize_kin`, the no-CBF module, exists only as a
+CPython-3.7 .pyc that this interpreter cannot import: its three methods are executed from the
+bytecode by the small 3.7 interpreter in tests/golden/pyc37.py.
 """
 from __future__ import annotations
 
@@ -139,6 +140,35 @@ if __name__ == "__main__":
                dyn_lbx=np.array(lbx, float), dyn_ubx=np.array(ubx, float), dyn_obs=obsd, dyn_opts=json.dumps(rec.opts))
     xq, uq = np.array([1.0, 0.5, 0.02, 12.0, 0.3, 0.05]), np.array([0.03, 1.2])
     out.update(dyn_rhs_in=np.concatenate([xq, uq]), dyn_rhs_out=mpc.f(xq, uq).full().ravel())
+    shutil.rmtree(tmp)
+    os.chdir(HERE)
+
+    # ---------------- no-CBF kin module: only PKG/__pycache__/MPC_optimize_kin.cpython-37.pyc exists.  Its three
+    # methods are executed from the bytecode (tests/golden/pyc37.py) on the same casadi stand-in
+    # (PKG/main_kin_c_sim.py:42-46,68,83 for the call protocol).  Its __init__ reads `Veh_w` like the dyn module.
+    import math
+    import yaml
+    import pyc37
+    import casadi_stub
+    from helpers import load_config
+
+    tmp = tempfile.mkdtemp()
+    with open(os.path.join(tmp, "mpc_parameters.yaml"), "w") as fh:
+        fh.write(text.replace("  Veh_W: 1.8", "  Veh_W: 1.8\n  Veh_w: 1.8"))
+    os.chdir(tmp)
+    mod = pyc37.load_pyc(os.path.join(PKG, "__pycache__", "MPC_optimize_kin.cpython-37.pyc"))
+    glb = {"ca": casadi_stub, "np": np, "math": math, "yaml": yaml, "load_config": load_config, "PARAMS_FILE": "mpc_parameters.yaml"}
+    me = types.SimpleNamespace()
+    pyc37.run(pyc37.find_code(mod, "MPC_optimize", "__init__"), glb, me)
+    lbg, ubg, lbx, ubx = pyc37.run(pyc37.find_code(mod, "MPC_optimize", "initialize_constraints"), glb, me)
+    x0n, xsn = [0, 0, 0, 20], [500, 3.5, 0, 30]
+    rec = pyc37.run(pyc37.find_code(mod, "MPC_optimize", "optimize_problem"), glb, me, np.array(x0n).reshape(-1, 1),
+                    np.tile(np.array(xsn, float), (N + 1, 1)))
+    Z, P = rollout_points(me, 4, N, x0n, xsn, rng)
+    F, G = evaluate(rec, Z, P)
+    out.update(nocbf_z=Z, nocbf_p=P, nocbf_f=F, nocbf_g=G, nocbf_lbg=np.array(lbg, float), nocbf_ubg=np.array(ubg, float),
+               nocbf_lbx=np.array(lbx, float), nocbf_ubx=np.array(ubx, float), nocbf_opts=json.dumps(rec.opts),
+               nocbf_attrs=json.dumps({k: v for k, v in vars(me).items() if isinstance(v, (int, float, str, bool))}))
     shutil.rmtree(tmp)
     os.chdir(HERE)
 

@@ -1,7 +1,7 @@
 """The restated NLP, the bound lists and the host helpers against vectors produced by the
 reference's OWN code (tests/golden/make_reference_vectors.py ran PKG/MPC_CBF_optimize_kin.py,
-_kin_pre.py and _dyn.py unmodified on a sympy-backed `casadi` stand-in and stored what they
-hand to `nlpsol`).  The IPOPT solve itself is not covered by these vectors."""
+_kin_pre.py and _dyn.py unmodified - and the bytecode of the .pyc-only MPC_optimize_kin - on a
+sympy-backed `casadi` stand-in and stored what they hand to `nlpsol`).  The IPOPT solve itself is not covered by these vectors."""
 import json
 import os
 
@@ -25,10 +25,12 @@ def _nlp(ref, tag, k):
         return NLP("kin_cbf", p[:nx], p[nx:], ref["kin_obs"])
     if tag == "pre":
         return NLP("kin_cbf_pre", p[:nx], p[nx:], list(ref["pre_obs"]))
+    if tag == "nocbf":
+        return NLP("kin_nocbf", p[:nx], p[nx:])
     return NLP("dyn", p[:nx], p[nx:], ref["dyn_obs"])
 
 
-@pytest.mark.parametrize("tag", ["kin", "pre", "dyn"])
+@pytest.mark.parametrize("tag", ["kin", "pre", "dyn", "nocbf"])
 def test_objective_and_constraints_equal_the_reference_expressions(ref, tag):
     """f(z,p) and g(z,p) in the reference's row order, two obstacles for the kinematic modules."""
     for k in range(ref[f"{tag}_z"].shape[0]):
@@ -47,6 +49,24 @@ def test_bound_lists_equal_initialize_constraints(ref, tag):
     assert np.array_equal(nlp.zL, ref[f"{tag}_lbx"]) and np.array_equal(nlp.zU, ref[f"{tag}_ubx"])
 
 
+def test_no_cbf_module_executed_from_its_bytecode(ref):
+    """`MPC_optimize_kin` ships only as a CPython-3.7 .pyc; the generator ran its three methods through a
+    3.7 bytecode interpreter (tests/golden/pyc37.py).  Scalar lbg/ubg, the lbx/ubx lists, the constructor
+    attributes and the weights (through f) must match the restatement and the drop-in class."""
+    from mpc_motion_planning_b200 import MPC_optimize_kin
+
+    nlp = _nlp(ref, "nocbf", 0)
+    assert float(ref["nocbf_lbg"]) == 0.0 and float(ref["nocbf_ubg"]) == 0.0 and nlp.n_ineq == 0
+    assert np.array_equal(nlp.zL, ref["nocbf_lbx"]) and np.array_equal(nlp.zU, ref["nocbf_ubx"])
+    m = MPC_optimize_kin.MPC_optimize()
+    lbg, ubg, lbx, ubx = m.initialize_constraints()
+    assert lbg == 0.0 and ubg == 0.0 and np.array_equal(lbx, ref["nocbf_lbx"]) and np.array_equal(ubx, ref["nocbf_ubx"])
+    for k, v in json.loads(str(ref["nocbf_attrs"])).items():
+        assert getattr(m, k) == v, k
+    g = m._g_of(ref["nocbf_z"][0], ref["nocbf_p"][0], None)
+    assert np.max(np.abs(g - ref["nocbf_g"][0])) <= 1e-11
+
+
 def test_dyn_bound_lists_and_the_shipped_misalignment(ref):
     """the shipped lbg/ubg are a permutation of the aligned lists that pairs
     196 rows with the wrong bounds.  The aligned lists are what every implementation here solves."""
@@ -58,7 +78,7 @@ def test_dyn_bound_lists_and_the_shipped_misalignment(ref):
 
 
 def test_nlpsol_options_are_the_ones_the_solvers_assume(ref):
-    for tag in ("kin", "pre", "dyn"):
+    for tag in ("kin", "pre", "dyn", "nocbf"):
         o = json.loads(str(ref[f"{tag}_opts"]))
         assert o == {"ipopt.max_iter": 100, "ipopt.print_level": 5, "print_time": 0, "ipopt.acceptable_tol": 1e-8,
                      "ipopt.acceptable_obj_change_tol": 1e-6}
