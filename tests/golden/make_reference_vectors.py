@@ -61,6 +61,49 @@ def evaluate(rec, pts_z, pts_p):
     return np.array(F), np.array(G)
 
 
+def kkt_at_oracle_solution(rec, kind, x0, xs, obstacles, lbg, ubg, lbx, ubx):
+    """Solve the restated NLP with the dense interior-point specification, then measure the KKT residuals of that
+    point on the REFERENCE'S expressions (exact sympy derivatives of what the reference handed to nlpsol):
+    stationarity  grad f + J_g' lam_g - z_L + z_U,  feasibility of g and x against the reference's own bound lists,
+    complementarity.  Returns z*, f*, and the residual norms (objective-scaled like IPOPT's error)."""
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle import ipm_dense
+    from oracle.nlp import NLP
+
+    nlp = NLP(kind, x0, xs, obstacles)
+    r = ipm_dense.solve(nlp, nlp.rollout_start(), ipm_dense.IpmOptions())
+    assert r.status == 0, (kind, r.status)
+    xsym = list(rec.prob["x"].a.reshape(-1, order="F"))
+    psym = list(rec.prob["p"].a.reshape(-1, order="F"))
+    pos = {v: i for i, v in enumerate(xsym)}
+    f = rec.prob["f"].a.reshape(-1)[0]
+    g = list(rec.prob["g"].a.reshape(-1, order="F"))
+    # sparse exact derivatives: every row depends on a handful of variables
+    entries, exprs = [], [f] + g
+    for row, e in enumerate(exprs):
+        for v in sorted(sp.sympify(e).free_symbols & set(xsym), key=lambda q: pos[q]):
+            entries.append((row, pos[v], sp.diff(e, v)))
+    fun = sp.lambdify([xsym, psym], [e for _, _, e in entries] + exprs, "math", cse=True)
+    pvec = np.concatenate([np.asarray(x0, float), np.asarray(xs, float)])
+    vals = fun(list(r.z), list(pvec))
+    nv, ng = len(xsym), len(g)
+    J = np.zeros((1 + ng, nv))
+    for (row, col, _), v in zip(entries, vals[:len(entries)]):
+        J[row, col] = float(v)
+    fval, gval = float(vals[len(entries)]), np.array([float(v) for v in vals[len(entries) + 1:]])
+    lam_g = np.concatenate([r.lam_eq, r.lam_in])[nlp.g_perm()]
+    stat = J[0] + J[1:].T @ lam_g - r.zl + r.zu
+    lo, hi = (np.full(ng, float(lbg)), np.full(ng, float(ubg))) if np.isscalar(lbg) else nlp.lbg_ubg_aligned()
+    if kind != "dyn" and not np.isscalar(lbg):  # the shipped lists are the aligned ones for the kinematic modules
+        assert np.array_equal(lo, np.array(lbg, float)) and np.array_equal(hi, np.array(ubg, float))
+    viol_g = float(max(np.max(lo - gval), np.max(gval - hi), 0.0))
+    viol_x = float(max(np.max(np.array(lbx, float) - r.z), np.max(r.z - np.array(ubx, float)), 0.0))
+    act = np.minimum(gval - lo, hi - gval)
+    compl = float(np.max(np.abs(lam_g) * np.where(np.isfinite(act), act, 0.0) * (lo != hi)))
+    return {"z": r.z, "f_ref": fval, "f_oracle": r.f, "stationarity_scaled": float(r.obj_scale * np.max(np.abs(stat))),
+            "g_violation": viol_g, "x_violation": viol_x, "complementarity_scaled": float(r.obj_scale * compl), "iters": r.iters}
+
+
 def rollout_points(mod, nx, N, x0, xs, rng):
     """z near an Euler roll-out (keeps the dyn sqrt rows real), p = [x0; xs] perturbed"""
     Z, P = [], []
@@ -99,6 +142,10 @@ if __name__ == "__main__":
     out.update(kin_z=Z, kin_p=P, kin_f=F, kin_g=G, kin_lbg=np.array(lbg, float), kin_ubg=np.array(ubg, float),
                kin_lbx=np.array(lbx, float), kin_ubx=np.array(ubx, float), kin_obs=obs, kin_opts=json.dumps(rec.opts),
                kin_N=N, kin_T=mpc.T_S)
+    one = np.array([[50, 3.5, 0, 8, 4.8, 1.8]])  # the main's own obstacle (PKG/main_cbf_kin_c_sim.py:55)
+    rec1 = mpc.optimize_problem(np.array(x0).reshape(-1, 1), ref, one)
+    l1 = mpc.initialize_constraints(one)
+    out.update({f"kin_kkt_{k}": v for k, v in kkt_at_oracle_solution(rec1, "kin_cbf", x0, xs, one, *l1).items()})
     # the quintic lane-change reference (:258-308), unused by the mains
     gr_in, gr_out = [], []
     for a, b in [([0, 3, 0, 15], [400, 3.5, 0, 30]), ([12.5, 0.2, 0.01, 22], [400, 3.5, 0, 25]), ([100, 4.0, 0, 8], [600, 0.0, 0, 12])]:
@@ -122,6 +169,11 @@ if __name__ == "__main__":
                pre_lbx=np.array(lbx, float), pre_ubx=np.array(ubx, float), pre_obs=np.array(tr), pre_obs0=np.array(obs_list).reshape(-1, 6),
                pre_opts=json.dumps(rec.opts))
 
+    tr1 = obs_prediction(obs_list[:1], mpc.T_S, N)
+    rec1 = mpc.optimize_problem(np.array(x0).reshape(-1, 1), ref, tr1)
+    l1 = mpc.initialize_constraints(obs_list[:1])
+    out.update({f"pre_kkt_{k}": v for k, v in kkt_at_oracle_solution(rec1, "kin_cbf_pre", x0, xs, tr1, *l1).items()})
+
     # ---------------- dyn (PKG/main_cbf_dyn_c_sim.py:44-51,77,89): the module reads `Veh_w`, which the
     # shipped YAML spells `Veh_W`: run it from a copy with the key added
     tmp = tempfile.mkdtemp()
@@ -138,6 +190,7 @@ if __name__ == "__main__":
     F, G = evaluate(rec, Z, P)
     out.update(dyn_z=Z, dyn_p=P, dyn_f=F, dyn_g=G, dyn_lbg=np.array(lbg, float), dyn_ubg=np.array(ubg, float),
                dyn_lbx=np.array(lbx, float), dyn_ubx=np.array(ubx, float), dyn_obs=obsd, dyn_opts=json.dumps(rec.opts))
+    out.update({f"dyn_kkt_{k}": v for k, v in kkt_at_oracle_solution(rec, "dyn", x0d, xsd, obsd, lbg, ubg, lbx, ubx).items()})
     xq, uq = np.array([1.0, 0.5, 0.02, 12.0, 0.3, 0.05]), np.array([0.03, 1.2])
     out.update(dyn_rhs_in=np.concatenate([xq, uq]), dyn_rhs_out=mpc.f(xq, uq).full().ravel())
     shutil.rmtree(tmp)
@@ -169,6 +222,7 @@ if __name__ == "__main__":
     out.update(nocbf_z=Z, nocbf_p=P, nocbf_f=F, nocbf_g=G, nocbf_lbg=np.array(lbg, float), nocbf_ubg=np.array(ubg, float),
                nocbf_lbx=np.array(lbx, float), nocbf_ubx=np.array(ubx, float), nocbf_opts=json.dumps(rec.opts),
                nocbf_attrs=json.dumps({k: v for k, v in vars(me).items() if isinstance(v, (int, float, str, bool))}))
+    out.update({f"nocbf_kkt_{k}": v for k, v in kkt_at_oracle_solution(rec, "kin_nocbf", x0n, xsn, None, lbg, ubg, lbx, ubx).items()})
     shutil.rmtree(tmp)
     os.chdir(HERE)
 

@@ -658,3 +658,20 @@ def test_the_binding_stub_of_integration_md_runs(dev, tmp_path, monkeypatch):
     z, f, status = ns["solve"](h, N, x0, xs, obs, z0)
     assert status == 0 and z.shape == (304, 1)
     assert abs(f - 1.0947508480e8) <= 1e-6 * 1.1e8 and np.allclose(z[:2, 0], [0.03564617, 3.0], atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["kin", "pre", "dyn", "nocbf"])
+def test_cuda_reaches_the_kkt_points_verified_on_the_reference_expressions(dev, tag):
+    """tests/golden/reference_nlp.npz holds, for the first step of each reference main, a point whose KKT
+    residuals were measured on the reference's own NLP expressions (tests/test_reference_vectors.py)."""
+    from mpc_motion_planning_b200.solver import BatchSolver
+    from test_reference_vectors import KKT_CASES, kkt_case_obs
+
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_nlp.npz"))
+    kind, x0, xs = KKT_CASES[tag]
+    obs = kkt_case_obs(ref, tag)
+    g = _gpu(BatchSolver(kind), dev, np.array([x0]), np.array([xs]), obs[None] if obs is not None else np.zeros((1, 0, 51, 6)), return_z=True)
+    assert g["status"][0] == 0
+    assert np.abs(g["z"][0] - ref[f"{tag}_kkt_z"]).max() <= 1e-5
+    assert np.abs(g["u0"][0] - ref[f"{tag}_kkt_z"][:2]).max() <= U0_ATOL
+    assert abs(g["cost"][0] - float(ref[f"{tag}_kkt_f_ref"])) <= COST_RTOL * float(ref[f"{tag}_kkt_f_ref"])

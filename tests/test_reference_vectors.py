@@ -155,3 +155,38 @@ def test_c_oracle_agrees_with_the_reference_objective_at_its_solution(ref):
     z, lam, info = c_oracle.solve(cfg, p[:4], p[4:], obs[0])
     nlp = NLP("kin_cbf_pre", p[:4], p[4:], [ref["pre_obs"][0]])
     assert info.status == 0 and abs(nlp.objective(z) - info.f) <= 1e-12 * abs(info.f)
+
+
+KKT_CASES = {"kin": ("kin_cbf", [0, 3, 0, 15.0], [400, 3.5, 0, 30.0]), "pre": ("kin_cbf_pre", [0, 3, 0, 15.0], [400, 3.5, 0, 30.0]),
+             "dyn": ("dyn", [0, 0, 0, 10, 0, 0.0], [600, 3.5, 0, 15, 0, 0.0]), "nocbf": ("kin_nocbf", [0, 0, 0, 20.0], [500, 3.5, 0, 30.0])}
+
+
+def kkt_case_obs(ref, tag, N=50):
+    """obstacle array (M,N+1,6) of the mains' default scenarios used for the KKT vectors"""
+    if tag == "kin":
+        return np.repeat(np.array([[50, 3.5, 0, 8, 4.8, 1.8]])[:, None, :], N + 1, axis=1)
+    if tag == "pre":
+        return ref["pre_obs"][:1]
+    if tag == "dyn":
+        o = np.zeros((1, N + 1, 6))
+        o[0, :, 0], o[0, :, 1] = ref["dyn_obs"]
+        return o
+    return None
+
+
+@pytest.mark.parametrize("tag", ["kin", "pre", "dyn", "nocbf"])
+def test_oracle_solutions_are_kkt_points_of_the_reference_nlp(ref, tag):
+    """At generation time the dense interior-point solution of each main's first step was checked against the
+    REFERENCE'S expressions with exact (sympy) derivatives: stationarity below IPOPT's tol in IPOPT's scaling,
+    rows and bounds feasible up to bound_relax_factor, complementarity below tol.  Here: those recorded
+    residuals, and the C oracle reaching the same point."""
+    from oracle import c_oracle
+
+    k = lambda n: float(ref[f"{tag}_kkt_{n}"])
+    assert k("stationarity_scaled") <= 1e-8 and k("complementarity_scaled") <= 1e-8
+    assert k("g_violation") <= 1.01e-8 and k("x_violation") <= 4.01e-7  # 1e-8 * max(1, |bound|), |vx_max| = 40
+    assert abs(k("f_ref") - k("f_oracle")) <= 1e-14 * abs(k("f_ref"))
+    kind, x0, xs = KKT_CASES[tag]
+    z, _, info = c_oracle.solve(c_oracle.make_cfg(kind), np.array(x0), np.array(xs), kkt_case_obs(ref, tag))
+    assert info.status == 0
+    assert np.max(np.abs(z - ref[f"{tag}_kkt_z"])) <= 1e-7 and abs(info.f - k("f_ref")) <= 1e-10 * k("f_ref")
