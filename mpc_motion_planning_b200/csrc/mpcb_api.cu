@@ -123,8 +123,10 @@ bool select_variant(const mpcb_cfg &c, Variant &v) {
     if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 1) { v = make_kin_variant<1, 0, 0>(c.N); return true; }
     if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 1) { v = make_kin_variant<1, 1, 1>(c.N); return true; }
     if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 2) { v = make_kin_variant<1, 2, 1>(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 3) { v = make_kin_variant<1, 3, 1>(c.N); return true; }
     if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 1) { v = make_kin_variant<1, 1, 3>(c.N); return true; }
     if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 2) { v = make_kin_variant<1, 2, 3>(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 3) { v = make_kin_variant<1, 3, 3>(c.N); return true; }
   }
   return false;
 }
