@@ -1,19 +1,22 @@
-"""Build libmpcb200.so (sm_100a) in-tree with nvcc.  `python -m mpc_motion_planning_b200.build`."""
+"""Build libmpcb200.so (sm_100a) in-tree with nvcc.  `python -m mpc_motion_planning_b200.build`.
+
+The kernel families are separate translation units (csrc/mpcb_variants.cu compiled once per
+-DMPCB_FAMILY=k) so that the compile runs on all host cores; objects go to _obj/ (git-ignored)."""
 from __future__ import annotations
 
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libmpcb200.so")
+OBJ = os.path.join(HERE, "_obj")
 SRCS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))) + [
     os.path.join(HERE, "..", "include", "mpcb200.h")
 ]
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+N_FAMILIES = 9  # csrc/mpcb_variants.cu: 8 kinematic families + the dynamic bicycle
 
 
 def stale() -> bool:
@@ -24,11 +27,28 @@ def stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if force or stale():
-        nvcc = os.environ.get("NVCC", "nvcc")
-        extra = os.environ.get("MPCB_NVCC_EXTRA", "").split()  # e.g. -DMPCB_W0=12 for tuning experiments
-        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, os.path.join(HERE, "csrc", "mpcb_api.cu")]
-        subprocess.check_call(cmd, cwd=HERE)
+    if not (force or stale()):
+        return SO
+    nvcc = os.environ.get("NVCC", "nvcc")
+    extra = os.environ.get("MPCB_NVCC_EXTRA", "").split()  # e.g. -DMPCB_W0=12 for tuning experiments
+    flags = NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else [])
+    os.makedirs(OBJ, exist_ok=True)
+    jobs = [(os.path.join(HERE, "csrc", "mpcb_api.cu"), os.path.join(OBJ, "api.o"), [])]
+    jobs += [(os.path.join(HERE, "csrc", "mpcb_variants.cu"), os.path.join(OBJ, f"family{k}.o"), [f"-DMPCB_FAMILY={k}"]) for k in range(N_FAMILIES)]
+
+    def compile_one(job):
+        src, obj, defs = job
+        r = subprocess.run([nvcc] + flags + defs + ["-c", "-o", obj, src], cwd=HERE, capture_output=True, text=True)
+        return job, r
+
+    with ThreadPoolExecutor(max_workers=max(1, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, jobs))
+    for (src, obj, defs), r in results:
+        if verbose or r.returncode != 0:
+            sys.stderr.write(f"---- nvcc {' '.join(defs)} {os.path.basename(src)}\n{r.stdout}{r.stderr}")
+        if r.returncode != 0:
+            raise subprocess.CalledProcessError(r.returncode, r.args)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + [obj for _, obj, _ in jobs], cwd=HERE)
     return SO
 
 

@@ -2,8 +2,8 @@
 // exceptions across the boundary.  There is no CPU fallback: without a CUDA device
 // mpcb_create fails with MPCB_E_NODEVICE.
 #include "../../include/mpcb200.h"
-#include "mpcb_kernel.cuh"
-#include "mpcb_dyn_kernel.cuh"
+#include "mpcb_variants.h"
+#include "dyn_model.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -23,73 +23,10 @@ bool cuda_ok(cudaError_t e, const char *what) {
   return false;
 }
 
-typedef cudaError_t (*launch_fn)(const KParams &, int grid, size_t smem, cudaStream_t);
-typedef const void *kernel_ptr;
+}  // namespace
 
-template <int NR, int MO, int OBS, int W, bool GS>
-cudaError_t launch_kin(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-  kin_solve_kernel<NR, MO, OBS, W, GS><<<grid, 32 * W, smem, st>>>(p);
-  return cudaGetLastError();
-}
-
-struct Variant {
-  launch_fn launch;
-  kernel_ptr kernel;
-  size_t (*smem_bytes)(int N);
-  int nx, nbx;
-  size_t slab_doubles;  // per resident warp; 0 = one block per scenario, no slab
-  int warps;            // warps (= scenarios in flight) per block
-};
-
-template <int NR, int MO, int OBS, int W, bool GS>
-Variant make_kin_variant_w() {
-  Variant v;
-  v.launch = &launch_kin<NR, MO, OBS, W, GS>;
-  v.kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, W, GS>;
-  v.smem_bytes = [](int N) { return KinLayout<NR, MO, OBS == 3, GS>::bytes(N); };
-  v.nx = 4;
-  v.nbx = 2;
-  v.slab_doubles = KinLayout<NR, MO, OBS == 3, GS>::slab_doubles();
-  v.warps = W;
-  return v;
-}
-
-Variant pick_by_occupancy(Variant *cand, int n, int N);
-
-// Layout and warps per block: the candidate that keeps the most warps resident for this horizon.
-// Order = preference on ties: step in shared memory before step in the slab, larger W first.
-template <int NR, int MO, int OBS>
-Variant make_kin_variant(int N) {
-#ifndef MPCB_W0  // candidate warps-per-block values (compile-time tuning knob)
-#define MPCB_W0 4
-#define MPCB_W1 2
-#define MPCB_W2 1
-#endif
-  Variant cand[6] = {make_kin_variant_w<NR, MO, OBS, MPCB_W0, false>(), make_kin_variant_w<NR, MO, OBS, MPCB_W1, false>(),
-                     make_kin_variant_w<NR, MO, OBS, MPCB_W2, false>(), make_kin_variant_w<NR, MO, OBS, MPCB_W0, true>(),
-                     make_kin_variant_w<NR, MO, OBS, MPCB_W1, true>(), make_kin_variant_w<NR, MO, OBS, MPCB_W2, true>()};
-  return pick_by_occupancy(cand, 6, N);
-}
-
-template <int W>
-cudaError_t launch_dyn(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-  dyn_solve_kernel<W><<<grid, 32 * W, smem, st>>>(p);
-  return cudaGetLastError();
-}
-
-template <int W>
-Variant make_dyn_variant_w() {
-  Variant v;
-  v.launch = &launch_dyn<W>;
-  v.kernel = (const void *)&dyn_solve_kernel<W>;
-  v.smem_bytes = [](int N) { return DynLayout::bytes(N); };
-  v.nx = 6;
-  v.nbx = 3;
-  v.slab_doubles = DynLayout::slab_doubles();
-  v.warps = W;
-  return v;
-}
-
+namespace mpcb {
+// shared by the kernel-family translation units (mpcb_variants.cu)
 Variant pick_by_occupancy(Variant *cand, int n, int N) {
   if (const char *w = getenv("MPCB_FORCE_W")) {  // tuning knob: warps per block
     for (int i = 0; i < n; i++)
@@ -105,28 +42,26 @@ Variant pick_by_occupancy(Variant *cand, int n, int N) {
   }
   return cand[best];
 }
+}  // namespace mpcb
 
-Variant make_dyn_variant(int N) {
-  Variant cand[3] = {make_dyn_variant_w<4>(), make_dyn_variant_w<2>(), make_dyn_variant_w<1>()};
-  return pick_by_occupancy(cand, 3, N);
-}
+namespace {
 
 bool select_variant(const mpcb_cfg &c, Variant &v) {
   const int M = c.obs_mode == MPCB_OBS_NONE ? 0 : c.M;
   if (c.model == MPCB_MODEL_DYN) {
     // the reference's dyn NLP: both rate rows (df, ax in that order), one obstacle, sqrt rows
-    if (c.obs_mode == MPCB_OBS_SQRT && c.n_rate == 2 && M == 1 && c.rate_ctrl[0] == 0 && c.rate_ctrl[1] == 1) { v = make_dyn_variant(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_SQRT && c.n_rate == 2 && M == 1 && c.rate_ctrl[0] == 0 && c.rate_ctrl[1] == 1) { v = variant_dyn(c.N); return true; }
     return false;
   }
   if (c.model == MPCB_MODEL_KIN) {
-    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 0) { v = make_kin_variant<0, 0, 0>(c.N); return true; }
-    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 1) { v = make_kin_variant<1, 0, 0>(c.N); return true; }
-    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 1) { v = make_kin_variant<1, 1, 1>(c.N); return true; }
-    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 2) { v = make_kin_variant<1, 2, 1>(c.N); return true; }
-    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 3) { v = make_kin_variant<1, 3, 1>(c.N); return true; }
-    if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 1) { v = make_kin_variant<1, 1, 3>(c.N); return true; }
-    if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 2) { v = make_kin_variant<1, 2, 3>(c.N); return true; }
-    if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 3) { v = make_kin_variant<1, 3, 3>(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 0) { v = variant_kin_0_0_0(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_NONE && c.n_rate == 1) { v = variant_kin_1_0_0(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 1) { v = variant_kin_1_1_1(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 2) { v = variant_kin_1_2_1(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 3) { v = variant_kin_1_3_1(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 1) { v = variant_kin_1_1_3(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 2) { v = variant_kin_1_2_3(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 3) { v = variant_kin_1_3_3(c.N); return true; }
   }
   return false;
 }

@@ -101,9 +101,9 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return r;
 }
 
-__device__ __noinline__ double d_log(double x) { return log(x); }
-__device__ __noinline__ double d_pow(double x, double y) { return pow(x, y); }
-__device__ __noinline__ double3 d_trig3(double phi, double delta) {  // (sin phi, cos phi, tan delta)
+static __device__ __noinline__ double d_log(double x) { return log(x); }
+static __device__ __noinline__ double d_pow(double x, double y) { return pow(x, y); }
+static __device__ __noinline__ double3 d_trig3(double phi, double delta) {  // (sin phi, cos phi, tan delta)
   double s, c;
   sincos(phi, &s, &c);
   return make_double3(s, c, tan(delta));

@@ -1,0 +1,96 @@
+// One kernel family per compilation: nvcc -DMPCB_FAMILY=k -c mpcb_variants.cu (see build.py).
+#include "mpcb_variants.h"
+
+#ifndef MPCB_FAMILY
+#error "compile with -DMPCB_FAMILY=0..8"
+#endif
+
+#if MPCB_FAMILY == 8
+#include "mpcb_dyn_kernel.cuh"
+#endif
+
+namespace mpcb {
+
+#if MPCB_FAMILY < 8
+
+template <int NR, int MO, int OBS, int W, bool GS>
+static cudaError_t launch_kin(const KParams &p, int grid, size_t smem, cudaStream_t st) {
+  kin_solve_kernel<NR, MO, OBS, W, GS><<<grid, 32 * W, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int NR, int MO, int OBS, int W, bool GS>
+static Variant make_kin_variant_w() {
+  Variant v;
+  v.launch = &launch_kin<NR, MO, OBS, W, GS>;
+  v.kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, W, GS>;
+  v.smem_bytes = [](int N) { return KinLayout<NR, MO, OBS == 3, GS>::bytes(N); };
+  v.nx = 4;
+  v.nbx = 2;
+  v.slab_doubles = KinLayout<NR, MO, OBS == 3, GS>::slab_doubles();
+  v.warps = W;
+  return v;
+}
+
+// Layout and warps per block: the candidate that keeps the most warps resident for this horizon.
+// Order = preference on ties: step in shared memory before step in the slab, larger W first.
+template <int NR, int MO, int OBS>
+static Variant make_kin_variant(int N) {
+#ifndef MPCB_W0  // candidate warps-per-block values (compile-time tuning knob)
+#define MPCB_W0 4
+#define MPCB_W1 2
+#define MPCB_W2 1
+#endif
+  Variant cand[6] = {make_kin_variant_w<NR, MO, OBS, MPCB_W0, false>(), make_kin_variant_w<NR, MO, OBS, MPCB_W1, false>(),
+                     make_kin_variant_w<NR, MO, OBS, MPCB_W2, false>(), make_kin_variant_w<NR, MO, OBS, MPCB_W0, true>(),
+                     make_kin_variant_w<NR, MO, OBS, MPCB_W1, true>(), make_kin_variant_w<NR, MO, OBS, MPCB_W2, true>()};
+  return pick_by_occupancy(cand, 6, N);
+}
+
+#if MPCB_FAMILY == 0
+Variant variant_kin_0_0_0(int N) { return make_kin_variant<0, 0, 0>(N); }
+#elif MPCB_FAMILY == 1
+Variant variant_kin_1_0_0(int N) { return make_kin_variant<1, 0, 0>(N); }
+#elif MPCB_FAMILY == 2
+Variant variant_kin_1_1_1(int N) { return make_kin_variant<1, 1, 1>(N); }
+#elif MPCB_FAMILY == 3
+Variant variant_kin_1_2_1(int N) { return make_kin_variant<1, 2, 1>(N); }
+#elif MPCB_FAMILY == 4
+Variant variant_kin_1_3_1(int N) { return make_kin_variant<1, 3, 1>(N); }
+#elif MPCB_FAMILY == 5
+Variant variant_kin_1_1_3(int N) { return make_kin_variant<1, 1, 3>(N); }
+#elif MPCB_FAMILY == 6
+Variant variant_kin_1_2_3(int N) { return make_kin_variant<1, 2, 3>(N); }
+#elif MPCB_FAMILY == 7
+Variant variant_kin_1_3_3(int N) { return make_kin_variant<1, 3, 3>(N); }
+#endif
+
+#else  // MPCB_FAMILY == 8: dynamic bicycle
+
+template <int W>
+static cudaError_t launch_dyn(const KParams &p, int grid, size_t smem, cudaStream_t st) {
+  dyn_solve_kernel<W><<<grid, 32 * W, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int W>
+static Variant make_dyn_variant_w() {
+  Variant v;
+  v.launch = &launch_dyn<W>;
+  v.kernel = (const void *)&dyn_solve_kernel<W>;
+  v.smem_bytes = [](int N) { return DynLayout::bytes(N); };
+  v.nx = 6;
+  v.nbx = 3;
+  v.slab_doubles = DynLayout::slab_doubles();
+  v.warps = W;
+  return v;
+}
+
+Variant variant_dyn(int N) {
+  Variant cand[3] = {make_dyn_variant_w<4>(), make_dyn_variant_w<2>(), make_dyn_variant_w<1>()};
+  return pick_by_occupancy(cand, 3, N);
+}
+
+#endif
+
+}  // namespace mpcb

@@ -1,0 +1,34 @@
+// Kernel families and the host-side description of one launchable variant.  Every family is its own
+// translation unit (mpcb_variants.cu compiled with -DMPCB_FAMILY=k) so that the build runs in parallel.
+#pragma once
+#include "mpcb_kernel.cuh"
+
+namespace mpcb {
+
+typedef cudaError_t (*launch_fn)(const KParams &, int grid, size_t smem, cudaStream_t);
+typedef const void *kernel_ptr;
+
+struct Variant {
+  launch_fn launch;
+  kernel_ptr kernel;
+  size_t (*smem_bytes)(int N);
+  int nx, nbx;
+  size_t slab_doubles;  // per resident warp; 0 = one block per scenario, no slab
+  int warps;            // warps (= scenarios in flight) per block
+};
+
+// the candidate that keeps the most warps resident for horizon N (first one wins ties); mpcb_api.cu
+Variant pick_by_occupancy(Variant *cand, int n, int N);
+
+// variant_kin_<NR>_<MO>_<OBS>: rate rows, obstacles, obstacle-row mode (0 none, 1 h >= 0, 3 discrete-time CBF)
+Variant variant_kin_0_0_0(int N);
+Variant variant_kin_1_0_0(int N);
+Variant variant_kin_1_1_1(int N);
+Variant variant_kin_1_2_1(int N);
+Variant variant_kin_1_3_1(int N);
+Variant variant_kin_1_1_3(int N);
+Variant variant_kin_1_2_3(int N);
+Variant variant_kin_1_3_3(int N);
+Variant variant_dyn(int N);
+
+}  // namespace mpcb
