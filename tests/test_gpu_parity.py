@@ -694,3 +694,54 @@ def test_three_obstacles(dev, gamma):
     g = _gpu(BatchSolver("kin_cbf_pre", M=3, cbf_gamma=gamma), dev, x0, xs, obs3)
     u0, cost, st, it, _ = c_oracle.solve_batch(c_oracle.make_cfg("kin_cbf_pre", M=3, cbf_gamma=gamma), x0, xs, obs3, nthreads=os.cpu_count())
     _check(g, u0, cost, st, 0.5, 0.93)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_parity_under_randomised_problem_data(dev, seed):
+    """Nothing in the kernels is specialised to the reference's constants: weights, bounds, margins, step
+    and horizon are drawn at random (every mpcb_cfg field the reference hard-codes) and the CUDA path is
+    compared with the oracle configured with the same numbers."""
+    import ctypes as C
+
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+    from oracle import c_oracle
+
+    rng = np.random.default_rng(1000 + seed)
+    kind = ["kin_cbf_pre", "kin_nocbf", "dyn", "kin_cbf_pre", "kin_cbf", "kin_cbf_pre"][seed - 1]
+    gamma = 0.7 if seed == 4 else None
+    N = int(rng.choice([24, 40, 64]))
+    nx = 6 if kind == "dyn" else 4
+    base = BatchSolver(kind, N=N).cfg
+    sc = lambda a, lo=-0.7, hi=0.7: [float(v * 10 ** rng.uniform(lo, hi)) for v in a]
+    ov = {"T": float(rng.choice([0.08, 0.1, 0.12])), "Q": sc(list(base.Q)[:nx]), "R": sc(list(base.R)), "DR": sc(list(base.DR)),
+          "u_lo": [-rng.uniform(0.45, 0.7), -rng.uniform(2.0, 4.0)], "u_hi": [rng.uniform(0.45, 0.7), rng.uniform(2.0, 4.0)],
+          "safe_l": float(rng.uniform(0.5, 1.5)), "safe_w": float(rng.uniform(0.3, 0.8)), "mu_init": float(rng.choice([10.0, 100.0, 1000.0]))}
+    xl, xh = list(base.x_lo)[:nx], list(base.x_hi)[:nx]
+    xl[1], xh[1], xh[3] = -rng.uniform(0.8, 1.5), rng.uniform(4.8, 6.0), rng.uniform(32.0, 45.0)
+    ov["x_lo"], ov["x_hi"] = xl, xh
+    if base.n_rate:
+        k = rng.uniform(0.6, 2.0)
+        ov["rate_lo"], ov["rate_hi"] = [v * k for v in list(base.rate_lo)], [v * k for v in list(base.rate_hi)]
+    s = BatchSolver(kind, N=N, cbf_gamma=gamma, cfg_overrides=ov)
+    ocfg = c_oracle.make_cfg(kind, N=N, cbf_gamma=gamma)
+    for name, _ in c_oracle.OrcCfg._fields_:  # same numbers on both sides, field by field
+        if name in ("obs_mode", "cbf_gamma", "ref_mode", "reserved", "init_mode"):
+            continue
+        v = getattr(s.cfg, name)
+        if hasattr(v, "__len__"):
+            for i in range(len(v)):
+                getattr(ocfg, name)[i] = v[i]
+        else:
+            setattr(ocfg, name, v)
+    gen = {"kin_cbf_pre": scenarios.kin_cbf_moving, "kin_cbf": scenarios.kin_cbf_static, "kin_nocbf": scenarios.kin_nocbf, "dyn": scenarios.dyn_static}[kind]
+    B = 160
+    x0, xs, obs = gen(B, N=N, seed=500 + seed)
+    g = _gpu(s, dev, x0, xs, obs)
+    u0, cost, st, it, _ = c_oracle.solve_batch(ocfg, x0, xs, obs if obs.shape[1] else None, nthreads=os.cpu_count())
+    both = (g["status"] <= 1) & (st <= 1)
+    assert both.sum() >= 0.4 * B, both.sum()
+    assert ((g["status"] <= 1) == (st <= 1)).mean() >= 0.9
+    du = np.abs(g["u0"] - u0).max(axis=1)
+    dc = np.abs(g["cost"] - cost) / np.maximum(np.abs(cost), 1.0)
+    assert np.all(du[both] <= U0_ATOL) and np.all(dc[both] <= COST_RTOL), (du[both].max(), dc[both].max())
