@@ -7,7 +7,7 @@ from mpc_motion_planning_b200.solver import BatchSolver
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2960
 kind = sys.argv[2] if len(sys.argv) > 2 else "kin_cbf"
-gen = {"kin_cbf": scenarios.kin_cbf_static, "kin_cbf_pre": scenarios.kin_cbf_moving, "kin_nocbf": scenarios.kin_nocbf}[kind]
+gen = {"kin_cbf": scenarios.kin_cbf_static, "kin_cbf_pre": scenarios.kin_cbf_moving, "kin_nocbf": scenarios.kin_nocbf, "dyn": scenarios.dyn_static}[kind]
 x0, xs, obs = gen(B)
 dev = torch.device("cuda:0")
 s = BatchSolver(kind)
