@@ -120,7 +120,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out);
 void mpcb_destroy(mpcb_handle *h);
 
 /* upper bound of the device scratch mpcb_create allocates for this configuration (independent of
- * B: a slab per RESIDENT warp of the persistent kernel; 0 for the dyn kernel) */
+ * B: a slab per RESIDENT warp of the persistent kernel) */
 int mpcb_workspace_bytes(const mpcb_cfg *cfg, int B, size_t *bytes);
 
 /* Replaces optimize_problem + solver(...) for B independent scenarios.  DEVICE pointers,

@@ -110,9 +110,9 @@ int mpcb_nv(const mpcb_cfg *cfg) { return cfg ? 2 * cfg->N + mpcb_nx(cfg) * (cfg
 
 int mpcb_workspace_bytes(const mpcb_cfg *cfg, int B, size_t *bytes) {
   if (!cfg || !bytes || B < 0) return MPCB_E_ARG;
-  // Independent of B: the kinematic kernels are persistent and keep the primal-dual iterate of each
-  // RESIDENT warp in a global-memory slab (allocated by mpcb_create, sized by the occupancy of the
-  // device: at most 32 warps x #SMs).  The dyn kernel keeps everything in shared memory.
+  // Independent of B: the kernels are persistent and keep the primal-dual iterate of each RESIDENT
+  // warp in a global-memory slab (allocated by mpcb_create, sized by the occupancy of the device:
+  // at most 32 warps x #SMs).
   Variant v;
   if (!select_variant(*cfg, v)) return MPCB_E_ARG;
   int ndev = 0, dev = 0, sms = 0;
