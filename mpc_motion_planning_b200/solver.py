@@ -59,6 +59,15 @@ class BatchSolver:
         self.xs_shape = (self.N, self.nx) if self.ref_trajectory else (self.nx,)
         self._h = C.c_void_p()
         _lib.check(self.lib.mpcb_create(C.byref(self.cfg), C.byref(self._h)), "mpcb_create")
+        # the handle (slab, work queue) lives on the CUDA device that was current at creation
+        self.device_index = None
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                self.device_index = torch.cuda.current_device()
+        except ImportError:
+            pass
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -86,6 +95,8 @@ class BatchSolver:
         dev = x0.device
         if dev.type != "cuda":
             raise _lib.MpcbError("solve() needs CUDA tensors or numpy arrays; there is no CPU fallback")
+        if self.device_index is not None and dev.index is not None and dev.index != self.device_index:
+            raise _lib.MpcbError(f"this handle was created on cuda:{self.device_index}, the tensors are on cuda:{dev.index}")
 
         def prep(t, shape):
             if t is None:
