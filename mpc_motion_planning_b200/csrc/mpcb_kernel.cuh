@@ -681,11 +681,7 @@ struct KinSolver {
       const double fua = at(L::GU + 1, k) + ta + pwa + T * Pb3 + w0a * b0 + w1a * b1 + w2a * b2_ + w3a * b3;
       const double det = Fdd * Faa - Fda * Fda;
       if (!(Fdd > 0.0) || !(det > 0.0) || !isfinite(det)) { ok = false; break; }
-      #ifdef MPCB_EXACT_PIVOT
-      const double id = 1.0 / det;
-#else
       const double id = fast_rcp(det);
-#endif
       const double idd = Faa * id, ida = -Fda * id, iaa = Fdd * id;  // Fuu^{-1}
       // gains: u = Kx x + Kw w + kk
       const double kd0 = -(idd * ud0 + ida * ua0), kd1 = -(idd * ud1 + ida * ua1), kd2 = -(idd * ud2 + ida * ua2), kd3 = -(idd * ud3 + ida * ua3);
@@ -704,21 +700,12 @@ struct KinSolver {
       p11 = f11 + ud1 * kd1 + ua1 * ka1;
       p22 = f22 + ud2 * kd2 + ua2 * ka2;
       p33 = f33 + ud3 * kd3 + ua3 * ka3;
-#ifdef MPCB_SYM_P
-      p01 = f01 + 0.5 * ((ud0 * kd1 + ua0 * ka1) + (ud1 * kd0 + ua1 * ka0));
-      p02 = f02 + 0.5 * ((ud0 * kd2 + ua0 * ka2) + (ud2 * kd0 + ua2 * ka0));
-      p03 = f03 + 0.5 * ((ud0 * kd3 + ua0 * ka3) + (ud3 * kd0 + ua3 * ka0));
-      p12 = f12 + 0.5 * ((ud1 * kd2 + ua1 * ka2) + (ud2 * kd1 + ua2 * ka1));
-      p13 = f13 + 0.5 * ((ud1 * kd3 + ua1 * ka3) + (ud3 * kd1 + ua3 * ka1));
-      p23 = f23 + 0.5 * ((ud2 * kd3 + ua2 * ka3) + (ud3 * kd2 + ua3 * ka2));
-#else
       p01 = f01 + ud0 * kd1 + ua0 * ka1;
       p02 = f02 + ud0 * kd2 + ua0 * ka2;
       p03 = f03 + ud0 * kd3 + ua0 * ka3;
       p12 = f12 + ud1 * kd2 + ua1 * ka2;
       p13 = f13 + ud1 * kd3 + ua1 * ka3;
       p23 = f23 + ud2 * kd3 + ua2 * ka3;
-#endif
       w0d = ud0 * wdd + ua0 * wad; w0a = ud0 * wda + ua0 * waa;
       w1d = ud1 * wdd + ua1 * wad; w1a = ud1 * wda + ua1 * waa;
       w2d = ud2 * wdd + ua2 * wad; w2a = ud2 * wda + ua2 * waa;
