@@ -591,3 +591,72 @@ def predict_obstacles(obs_list, dt, N_p):
         tr[:, 2], tr[:, 3], tr[:, 4], tr[:, 5] = th, v, l, w
         out.append(tr)
     return out
+
+
+class ShippedDynNLP(NLP):
+    """The dyn NLP with the bound lists exactly as `initialize_constraints` ships them
+    (PKG/MPC_CBF_optimize_dyn.py:112-133), which do not line up with the rows of g (:215,227-243):
+    the rate-bound pair of block i lands on the x and y defects of stage i, and the rate rows
+    themselves meet the zeros of the next block.  The problem IPOPT would be given is therefore
+
+        U_i = U_{i-1}, i = 1..N-1          (every rate row is an equality: one control pair for the horizon)
+        x, y defects into stages 2..N within [df_dot_min*T, df_dot_max*T], [jerk_min*T, jerk_max*T]
+        everything else as in the aligned problem.
+
+    Rows are re-partitioned by their shipped bounds: lo == hi -> equality row, else inequality row.
+    Oracle-level only (numpy NLP + dense interior point): the CUDA kernels and the C oracle solve the
+    aligned problem."""
+
+    def __init__(self, x0, xs, obstacles, **kw):
+        super().__init__("dyn", x0, xs, obstacles, **kw)
+        N, p = self.N, self.p
+        lo, hi = [], []
+        for i in range(N + 1):  # the reference's own loop, :112-129
+            lo += [0.0] * 6
+            hi += [0.0] * 6
+            if 0 < i < N:
+                lo += [p.df_dot_min * self.T, p.jerk_min * self.T]
+                hi += [p.df_dot_max * self.T, p.jerk_max * self.T]
+        lo += [1.0] * (N + 1)  # :131-133
+        hi += [INF] * (N + 1)
+        self.lbg_shipped, self.ubg_shipped = np.array(lo), np.array(hi)
+        self._perm = super().g_perm()                 # reference row r = base row perm[r]
+        self._is_eq = self.lbg_shipped == self.ubg_shipped
+        self._rows_eq = np.where(self._is_eq)[0]
+        self._rows_in = np.where(~self._is_eq)[0]
+        self._base_n_eq, self._base_n_ineq = self.n_eq, self.n_ineq
+        self.n_eq, self.n_ineq = len(self._rows_eq), len(self._rows_in)
+        self._eq_target = self.lbg_shipped[self._rows_eq]
+        self.dL, self.dU = self.lbg_shipped[self._rows_in], self.ubg_shipped[self._rows_in]
+
+    def _g_base(self, z):
+        return np.concatenate([NLP.eq(self, z), NLP.ineq(self, z)])[self._perm]
+
+    def _J_base(self, z):
+        return np.vstack([NLP.jac_eq(self, z), NLP.jac_ineq(self, z)])[self._perm]
+
+    def eq(self, z):
+        return self._g_base(z)[self._rows_eq] - self._eq_target
+
+    def ineq(self, z):
+        return self._g_base(z)[self._rows_in]
+
+    def jac_eq(self, z):
+        return self._J_base(z)[self._rows_eq]
+
+    def jac_ineq(self, z):
+        return self._J_base(z)[self._rows_in]
+
+    def hess_lag(self, z, lam_eq, lam_in, sigma=1.0):
+        lam_ref = np.zeros(len(self._perm))
+        lam_ref[self._rows_eq] = lam_eq
+        lam_ref[self._rows_in] = lam_in
+        lam_base = np.zeros(len(self._perm))
+        lam_base[self._perm] = lam_ref
+        return NLP.hess_lag(self, z, lam_base[: self._base_n_eq], lam_base[self._base_n_eq:], sigma)
+
+    def g_ref(self, z):
+        return self._g_base(z)
+
+    def g_perm(self):
+        raise NotImplementedError("rows are partitioned by the shipped bounds; use lbg_shipped / ubg_shipped")

@@ -190,3 +190,22 @@ def test_oracle_solutions_are_kkt_points_of_the_reference_nlp(ref, tag):
     z, _, info = c_oracle.solve(c_oracle.make_cfg(kind), np.array(x0), np.array(xs), kkt_case_obs(ref, tag))
     assert info.status == 0
     assert np.max(np.abs(z - ref[f"{tag}_kkt_z"])) <= 1e-7 and abs(info.f - k("f_ref")) <= 1e-10 * k("f_ref")
+
+
+def test_dyn_problem_as_shipped_at_oracle_level(ref):
+    """The dyn bound lists exactly as shipped define a different problem:
+    every rate row becomes an equality (one control pair for the whole horizon) and the x/y defects of
+    stages 2..N are relaxed.  `ShippedDynNLP` reproduces the shipped lists bit for bit and the dense
+    interior point solves it; the CUDA path solves the aligned problem."""
+    from oracle import ipm_dense
+    from oracle.nlp import ShippedDynNLP
+
+    nlp = ShippedDynNLP([0, 0, 0, 10, 0, 0.0], [600, 3.5, 0, 15, 0, 0.0], ref["dyn_obs"], N=20)
+    full = ShippedDynNLP([0, 0, 0, 10, 0, 0.0], [600, 3.5, 0, 15, 0, 0.0], ref["dyn_obs"])
+    assert np.array_equal(full.lbg_shipped, ref["dyn_lbg"]) and np.array_equal(full.ubg_shipped, ref["dyn_ubg"])
+    assert full.n_eq == 306 and full.n_ineq == 98 + 51  # 49 rate pairs -> equalities, 49 x/y defect pairs -> ranges, 51 obstacle rows
+    r = ipm_dense.solve(nlp, nlp.rollout_start(), ipm_dense.IpmOptions())
+    U, X = nlp.split(r.z)
+    assert r.status == 0 and np.abs(U - U[0]).max() <= 1e-10
+    g = nlp.g_ref(r.z)
+    assert np.all(g >= nlp.lbg_shipped - 1e-7) and np.all(g <= nlp.ubg_shipped + 1e-7)
