@@ -33,7 +33,7 @@ class OrcCfg(C.Structure):
         ("Veh_Iz", C.c_double), ("aopt_f", C.c_double), ("aopt_r", C.c_double),
         ("Fymax_f", C.c_double), ("Fymax_r", C.c_double),
         ("tol", C.c_double), ("mu_init", C.c_double), ("bound_relax", C.c_double),
-        ("cbf_gamma", C.c_double), ("ref_mode", C.c_int32), ("reserved", C.c_int32),
+        ("cbf_gamma", C.c_double), ("ref_mode", C.c_int32), ("rows_as_shipped", C.c_int32),
     ]
 
 
@@ -67,7 +67,7 @@ def lib():
 
 def make_cfg(kind: str, N: int | None = None, M: int = 1, params: Params | None = None, init_mode: int = 1,
              mu_init: float = 100.0, max_iter: int = 100, tol: float = 1e-8, cbf_gamma: float | None = None,
-             ref_trajectory: bool = False) -> OrcCfg:
+             ref_trajectory: bool = False, rows_as_shipped: bool = False) -> OrcCfg:
     p = params or Params()
     w = reference_weights(kind)
     c = OrcCfg()
@@ -110,6 +110,7 @@ def make_cfg(kind: str, N: int | None = None, M: int = 1, params: Params | None 
         assert kind in ("kin_cbf", "kin_cbf_pre")
         c.obs_mode, c.cbf_gamma = 3, cbf_gamma
     c.ref_mode = int(ref_trajectory)  # xs is (N, nx) per-stage cost targets
+    c.rows_as_shipped = int(rows_as_shipped)  # dyn: bound lists as PKG/MPC_CBF_optimize_dyn.py:112-133 ships them
     return c
 
 

@@ -150,6 +150,10 @@ static double push_in(double v, double lo, double hi) {
 }
 
 static int has_rate(const ws_t *w, int k) { return k >= 1 && k <= w->N - 1; }
+/* dyn with the bound lists as shipped: at stages k = 1..N-1 the slack sr[k][c] (bounds = the rate bounds)
+ * relaxes component c = 0,1 (x, y) of the defect into stage k+1, its row multiplier is lam[k+1][c]; the
+ * rate rows U_k - U_{k-1} are equalities with multipliers lr[k][c]. */
+#define SHIPPED(w) ((w)->c->rows_as_shipped && (w)->c->model == ORC_MODEL_DYN && (w)->c->n_rate == 2)
 static int has_obs(const ws_t *w, int k) {
   if (w->c->obs_mode == ORC_OBS_ELLIPSE || w->c->obs_mode == ORC_OBS_DCBF) return k <= w->N - 1;
   if (w->c->obs_mode == ORC_OBS_SQRT) return k <= w->N;
@@ -235,6 +239,7 @@ static int eval_primal(ws_t *w, const iterate_t *q, double mu, double *theta, do
       model_f(w, q->x[k], q->u[k], f);
       for (int i = 0; i < nx; i++) {
         double d = q->x[k + 1][i] - (q->x[k][i] + c->T * f[i]);
+        if (SHIPPED(w) && i < 2 && has_rate(w, k)) d -= q->sr[k][i]; /* relaxed row: defect - slack */
         th += fabs(d);
         if (store) w->cdef[k + 1][i] = d;
       }
@@ -247,7 +252,7 @@ static int eval_primal(ws_t *w, const iterate_t *q, double mu, double *theta, do
     if (has_rate(w, k))
       for (int r = 0; r < c->n_rate; r++) {
         int ci = c->rate_ctrl[r];
-        double d = q->u[k][ci] - q->u[k - 1][ci] - q->sr[k][r];
+        double d = q->u[k][ci] - q->u[k - 1][ci] - (SHIPPED(w) ? 0.0 : q->sr[k][r]);
         th += fabs(d);
         if (store) w->resr[k][r] = d;
         bar += log(q->sr[k][r] - w->rlo[r]) + log(w->rhi[r] - q->sr[k][r]);
@@ -355,7 +360,7 @@ static void kkt_pieces(ws_t *w, kkt_t *o) {
     }
     if (has_rate(w, k))
       for (int r = 0; r < c->n_rate; r++) {
-        dual = fmax(dual, fabs(-q->lr[k][r] - q->vlr[k][r] + q->vur[k][r]));
+        dual = fmax(dual, fabs(-(SHIPPED(w) ? q->lam[k + 1][r] : q->lr[k][r]) - q->vlr[k][r] + q->vur[k][r]));
         prim = fmax(prim, fabs(w->resr[k][r]));
         COMPL(q->sr[k][r] - w->rlo[r], q->vlr[k][r]);
         COMPL(w->rhi[r] - q->sr[k][r], q->vur[k][r]);
@@ -637,6 +642,175 @@ static int riccati(ws_t *w, double dw) {
   return 1;
 }
 
+/* Newton system of the dyn problem with the bound lists as shipped.  Stage 0 has the free control U_0;
+ * at stages k >= 1 the control is tied to the previous one (dU_k = dU_{k-1} - e_k, e_k = U_k - U_{k-1}) and the
+ * free inputs are the two slacks that relax the x/y defects, entering x_{k+1} additively.  The value function
+ * keeps the same (x, w = previous control) form as in riccati(). */
+static int riccati_shipped(ws_t *w, double dw) {
+  const int nx = w->nx, N = w->N, M = w->M;
+  double Pxx[NXM][NXM], Pxw[NXM][2], Pww[2][2], px[NXM], pw[2];
+  {
+    int k = N;
+    double gxk[NXM];
+    for (int i = 0; i < nx; i++) { gxk[i] = w->gx[k][i]; for (int j = 0; j < nx; j++) Pxx[i][j] = w->Hxx[k][i][j]; Pxx[i][i] += dw; }
+    if (has_obs(w, k))
+      for (int j = 0; j < M; j++) {
+        double D = w->Do[k][j] + dw, gx_ = w->gox[k][j], gy_ = w->goy[k][j];
+        double t = D * w->reso[k][j] + w->gso[k][j];
+        Pxx[0][0] += D * gx_ * gx_; Pxx[0][1] += D * gx_ * gy_; Pxx[1][0] += D * gx_ * gy_; Pxx[1][1] += D * gy_ * gy_;
+        gxk[0] += gx_ * t; gxk[1] += gy_ * t;
+      }
+    for (int i = 0; i < nx; i++) { px[i] = gxk[i]; Pxw[i][0] = Pxw[i][1] = 0; }
+    Pww[0][0] = Pww[0][1] = Pww[1][0] = Pww[1][1] = 0; pw[0] = pw[1] = 0;
+  }
+  for (int k = N - 1; k >= 0; k--) {
+    double (*A)[NXM] = w->A[k];
+    double (*B)[2] = w->B[k];
+    double Hxx[NXM][NXM], gxk[NXM];
+    for (int i = 0; i < nx; i++) { gxk[i] = w->gx[k][i]; for (int j = 0; j < nx; j++) Hxx[i][j] = w->Hxx[k][i][j]; Hxx[i][i] += dw; }
+    if (has_obs(w, k))
+      for (int j = 0; j < M; j++) {
+        double D = w->Do[k][j] + dw, gx_ = w->gox[k][j], gy_ = w->goy[k][j];
+        double tt = D * w->reso[k][j] + w->gso[k][j];
+        Hxx[0][0] += D * gx_ * gx_; Hxx[0][1] += D * gx_ * gy_; Hxx[1][0] += D * gx_ * gy_; Hxx[1][1] += D * gy_ * gy_;
+        gxk[0] += gx_ * tt; gxk[1] += gy_ * tt;
+      }
+    double b[NXM], Pb[NXM];
+    for (int i = 0; i < nx; i++) b[i] = -w->cdef[k + 1][i];
+    for (int i = 0; i < nx; i++) { double s = px[i]; for (int j = 0; j < nx; j++) s += Pxx[i][j] * b[j]; Pb[i] = s; }
+    double PA[NXM][NXM], PB[NXM][2];
+    for (int i = 0; i < nx; i++) {
+      for (int j = 0; j < nx; j++) { double s = 0; for (int a = 0; a < nx; a++) s += Pxx[i][a] * A[a][j]; PA[i][j] = s; }
+      for (int j = 0; j < 2; j++) { double s = 0; for (int a = 0; a < nx; a++) s += Pxx[i][a] * B[a][j]; PB[i][j] = s; }
+    }
+    /* quadratic over (dx_k, dU_k) of the stage cost plus V_{k+1}(A dx + B dU + b, w+ = dU); the DR cost
+     * couples dU_k with dU_{k-1} only through dU_k - dU_{k-1} = -e_k, a constant on this manifold */
+    double Fxx[NXM][NXM], Fux[2][NXM], Fuu[2][2], fx[NXM], fu[2];
+    for (int i = 0; i < nx; i++)
+      for (int j = 0; j < nx; j++) { double s = Hxx[i][j]; for (int a = 0; a < nx; a++) s += A[a][i] * PA[a][j]; Fxx[i][j] = s; }
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < nx; j++) {
+        double s = w->Hux[k][i][j];
+        for (int a = 0; a < nx; a++) s += B[a][i] * PA[a][j] + Pxw[a][i] * A[a][j];
+        Fux[i][j] = s;
+      }
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 2; j++) {
+        double s = w->Huu[k][i][j] + Pww[i][j];
+        if (i == j) s += dw;
+        for (int a = 0; a < nx; a++) s += B[a][i] * PB[a][j] + B[a][i] * Pxw[a][j] + Pxw[a][i] * B[a][j];
+        Fuu[i][j] = s;
+      }
+    for (int i = 0; i < nx; i++) { double s = gxk[i]; for (int a = 0; a < nx; a++) s += A[a][i] * Pb[a]; fx[i] = s; }
+    for (int i = 0; i < 2; i++) {
+      double s = w->gu[k][i] + pw[i];
+      for (int a = 0; a < nx; a++) s += B[a][i] * Pb[a] + Pxw[a][i] * b[a];
+      fu[i] = s;
+    }
+    if (k == 0) {
+      double Fi[2][2];
+      if (!inv2(Fuu, Fi)) return 0;
+      for (int i = 0; i < 2; i++) {
+        for (int j = 0; j < nx; j++) w->Kx[k][i][j] = -(Fi[i][0] * Fux[0][j] + Fi[i][1] * Fux[1][j]);
+        w->Kw[k][i][0] = w->Kw[k][i][1] = 0.0;
+        w->kk[k][i] = -(Fi[i][0] * fu[0] + Fi[i][1] * fu[1]);
+      }
+      break;
+    }
+    /* k >= 1: inputs are the two slacks; they reach x_{k+1} rows 0,1 */
+    const double *e = w->resr[k];
+    double Hss[2][2], Hi[2][2], Cm[2][2], c0[2];
+    for (int a = 0; a < 2; a++) {
+      for (int j = 0; j < 2; j++) { Cm[a][j] = PB[a][j] + Pxw[a][j]; Hss[a][j] = Pxx[a][j]; }
+      Hss[a][a] += w->Dr[k][a] + dw;
+    }
+    for (int a = 0; a < 2; a++) c0[a] = Pb[a] + w->gsr[k][a] - (Cm[a][0] * e[0] + Cm[a][1] * e[1]);
+    if (!inv2(Hss, Hi)) return 0;
+    for (int a = 0; a < 2; a++) {
+      for (int j = 0; j < nx; j++) w->Kx[k][a][j] = -(Hi[a][0] * PA[0][j] + Hi[a][1] * PA[1][j]);
+      for (int j = 0; j < 2; j++) w->Kw[k][a][j] = -(Hi[a][0] * Cm[0][j] + Hi[a][1] * Cm[1][j]);
+      w->kk[k][a] = -(Hi[a][0] * c0[0] + Hi[a][1] * c0[1]);
+    }
+    double nPxx[NXM][NXM], nPxw[NXM][2], nPww[2][2], npx[NXM], npw[2];
+    for (int i = 0; i < nx; i++) {
+      for (int j = 0; j < nx; j++) nPxx[i][j] = Fxx[i][j] + PA[0][i] * w->Kx[k][0][j] + PA[1][i] * w->Kx[k][1][j];
+      for (int j = 0; j < 2; j++) nPxw[i][j] = Fux[j][i] + PA[0][i] * w->Kw[k][0][j] + PA[1][i] * w->Kw[k][1][j];
+      npx[i] = fx[i] - (Fux[0][i] * e[0] + Fux[1][i] * e[1]) + PA[0][i] * w->kk[k][0] + PA[1][i] * w->kk[k][1];
+    }
+    for (int i = 0; i < 2; i++) {
+      for (int j = 0; j < 2; j++) nPww[i][j] = Fuu[i][j] + Cm[0][i] * w->Kw[k][0][j] + Cm[1][i] * w->Kw[k][1][j];
+      npw[i] = fu[i] - (Fuu[i][0] * e[0] + Fuu[i][1] * e[1]) + Cm[0][i] * w->kk[k][0] + Cm[1][i] * w->kk[k][1];
+    }
+    for (int i = 0; i < nx; i++) {
+      for (int j = 0; j < nx; j++) Pxx[i][j] = 0.5 * (nPxx[i][j] + nPxx[j][i]);
+      Pxw[i][0] = nPxw[i][0]; Pxw[i][1] = nPxw[i][1];
+      px[i] = npx[i];
+    }
+    Pww[0][0] = nPww[0][0]; Pww[1][1] = nPww[1][1]; Pww[0][1] = Pww[1][0] = 0.5 * (nPww[0][1] + nPww[1][0]);
+    pw[0] = npw[0]; pw[1] = npw[1];
+  }
+  /* forward */
+  for (int i = 0; i < nx; i++) w->dx[0][i] = -w->cdef[0][i];
+  for (int k = 0; k < N; k++) {
+    double ds[2] = {0, 0};
+    if (k == 0) {
+      for (int i = 0; i < 2; i++) {
+        double s = w->kk[0][i];
+        for (int j = 0; j < nx; j++) s += w->Kx[0][i][j] * w->dx[0][j];
+        w->du[0][i] = s;
+      }
+    } else {
+      for (int a = 0; a < 2; a++) {
+        double s = w->kk[k][a];
+        for (int j = 0; j < nx; j++) s += w->Kx[k][a][j] * w->dx[k][j];
+        s += w->Kw[k][a][0] * w->du[k - 1][0] + w->Kw[k][a][1] * w->du[k - 1][1];
+        ds[a] = s;
+        w->dsr[k][a] = s;
+      }
+      for (int i = 0; i < 2; i++) w->du[k][i] = w->du[k - 1][i] - w->resr[k][i];
+    }
+    for (int i = 0; i < nx; i++) {
+      double s = -w->cdef[k + 1][i];
+      for (int j = 0; j < nx; j++) s += w->A[k][i][j] * w->dx[k][j];
+      s += w->B[k][i][0] * w->du[k][0] + w->B[k][i][1] * w->du[k][1];
+      if (i < 2) s += ds[i];
+      w->dx[k + 1][i] = s;
+    }
+  }
+  for (int k = 0; k <= N; k++)
+    if (has_obs(w, k))
+      for (int j = 0; j < M; j++) {
+        double D = w->Do[k][j] + dw;
+        w->dso[k][j] = w->gox[k][j] * w->dx[k][0] + w->goy[k][j] * w->dx[k][1] + w->reso[k][j];
+        w->lop[k][j] = D * w->dso[k][j] + w->gso[k][j];
+      }
+  /* adjoint recursion: multipliers of every defect row (relaxed ones included) */
+  for (int k = N; k >= 0; k--)
+    for (int i = 0; i < nx; i++) {
+      double s = w->gx[k][i] + dw * w->dx[k][i];
+      for (int j = 0; j < nx; j++) s += w->Hxx[k][i][j] * w->dx[k][j];
+      if (k < N) s += w->Hux[k][0][i] * w->du[k][0] + w->Hux[k][1][i] * w->du[k][1];
+      if (i < 2 && has_obs(w, k))
+        for (int j = 0; j < M; j++) s += (i == 0 ? w->gox[k][j] : w->goy[k][j]) * w->lop[k][j];
+      s = -s;
+      if (k < N) for (int a = 0; a < nx; a++) s += w->A[k][a][i] * w->lamp[k + 1][a];
+      w->lamp[k][i] = s;
+    }
+  /* multipliers of the rate equalities from stationarity in U_k, k = N-1..1 */
+  double nu[2] = {0, 0};
+  for (int k = N - 1; k >= 1; k--)
+    for (int i = 0; i < 2; i++) {
+      double s = w->gu[k][i] + dw * w->du[k][i] + w->Huu[k][i][0] * w->du[k][0] + w->Huu[k][i][1] * w->du[k][1];
+      for (int j = 0; j < nx; j++) s += w->Hux[k][i][j] * w->dx[k][j];
+      for (int a = 0; a < nx; a++) s -= w->B[k][a][i] * w->lamp[k + 1][a];
+      s += w->E[k][i] * (w->du[k][i] - w->du[k - 1][i]) + w->tk[k][i];
+      if (k + 1 <= N - 1) s -= w->E[k + 1][i] * (w->du[k + 1][i] - w->du[k][i]) + w->tk[k + 1][i];
+      nu[i] = nu[i] - s;
+      w->lrp[k][i] = nu[i];
+    }
+  return 1;
+}
+
 /* bound-multiplier steps; returns primal and dual fraction-to-boundary step sizes */
 static void mult_steps(ws_t *w, double mu, double tau, double *a_pr, double *a_du) {
   const orc_cfg *c = w->c;
@@ -820,7 +994,13 @@ static int init_iterate(ws_t *w, const double *z_init) {
     if (has_rate(w, k))
       for (int r = 0; r < c->n_rate; r++) {
         int ci = c->rate_ctrl[r];
-        q->sr[k][r] = push_in(q->u[k][ci] - q->u[k - 1][ci], w->rlo[r], w->rhi[r]);
+        double v0 = q->u[k][ci] - q->u[k - 1][ci];
+        if (SHIPPED(w)) { /* the slack of the relaxed defect component r */
+          double f[NXM];
+          model_f(w, q->x[k], q->u[k], f);
+          v0 = q->x[k + 1][r] - (q->x[k][r] + c->T * f[r]);
+        }
+        q->sr[k][r] = push_in(v0, w->rlo[r], w->rhi[r]);
         q->vlr[k][r] = q->vur[k][r] = 1.0;
       }
     if (has_obs(w, k))
@@ -904,12 +1084,12 @@ static int solve_ws(ws_t *w, const double *z_init, double *z_out, double *lam_eq
     if (mu_changed) eval_primal(w, &w->it, mu, &theta, &phi, &fobj, 1);
     build_qp(w, mu);
     double dw = 0.0;
-    int ok = riccati(w, 0.0);
+    int ok = SHIPPED(w) ? riccati_shipped(w, 0.0) : riccati(w, 0.0);
     if (!ok) {
       n_reg++;
       dw = dw_last == 0.0 ? DW_FIRST : fmax(DW_MIN, KW_MINUS * dw_last);
       for (;;) {
-        ok = riccati(w, dw);
+        ok = SHIPPED(w) ? riccati_shipped(w, dw) : riccati(w, dw);
         if (ok) break;
         dw *= dw_last == 0.0 ? KW_PLUS_FIRST : KW_PLUS;
         if (dw > DW_MAX) break;
@@ -1046,7 +1226,7 @@ int orc_newton_step(const orc_cfg *cfg, const double *x0, const double *xs, cons
   if (!rc) {
     eval_lin(w);
     build_qp(w, mu);
-    if (!riccati(w, dw)) rc = 2;
+    if (!(SHIPPED(w) ? riccati_shipped(w, dw) : riccati(w, dw))) rc = 2;
   }
   if (!rc) {
     int nx = w->nx, N = w->N;

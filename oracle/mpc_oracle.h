@@ -57,7 +57,10 @@ typedef struct {
                          (the commented row of PKG/MPC_CBF_optimize_kin.py:244-248) */
   int32_t ref_mode;   /* ORC_REF_TRAJECTORY: xs is (N, nx) per-stage cost targets
                          (ref_X of PKG/MPC_CBF_optimize_kin.py:194-199 with aa != 0) */
-  int32_t reserved;
+  int32_t rows_as_shipped; /* dyn only: pair the rows of g with the bound lists exactly as
+                         PKG/MPC_CBF_optimize_dyn.py:112-133 ships them: every rate row
+                         is an equality U_i = U_{i-1}, the x/y defects of stages 2..N are range rows with the
+                         rate bounds.  0 = aligned (what the code's comments intend). */
 } orc_cfg;
 
 typedef struct {

@@ -137,3 +137,22 @@ def test_batch_threads_equal_serial():
     b = c_oracle.solve_batch(cfg, x0, xs, obs, nthreads=4)
     for u, v in zip(a[:4], b[:4]):
         assert np.array_equal(u, v)
+
+
+@pytest.mark.parametrize("N", [8, 50])
+def test_c_oracle_dyn_rows_as_shipped_follows_the_dense_specification(N):
+    """dyn problem with the bound lists as shipped (oracle.nlp.ShippedDynNLP): controls tied over the horizon,
+    relaxed x/y defects as per-stage inputs in the Riccati form."""
+    from oracle.nlp import ShippedDynNLP
+
+    nlp = ShippedDynNLP([0, 0, 0, 10, 0, 0.0], [600, 3.5, 0, 15, 0, 0.0], [100, -3.5], N=N)
+    obs = np.zeros((1, N + 1, 6))
+    obs[0, :, 0], obs[0, :, 1] = 100, -3.5
+    z, lam, info = c_oracle.solve(c_oracle.make_cfg("dyn", N=N, rows_as_shipped=True), nlp.x0, nlp.xs, obs)
+    r = ipm_dense.solve(nlp, nlp.rollout_start(), ipm_dense.IpmOptions())
+    assert info.status == r.status == 0 and info.iters == r.iters and info.n_reg == r.n_reg
+    assert np.max(np.abs(z - r.z)) <= 1e-10 and abs(info.f - r.f) <= 1e-12 * abs(r.f)
+    U, X = nlp.split(z)
+    assert np.abs(U - U[0]).max() == 0.0
+    g = nlp.g_ref(z)
+    assert np.all(g >= nlp.lbg_shipped - 1e-7) and np.all(g <= nlp.ubg_shipped + 1e-7)
