@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MPCB_VERSION 101 /* 0.1.1: cfg gained ref_mode (was reserved) and cbf_gamma */
+#define MPCB_VERSION 102 /* 0.1.2: cfg gained ref_mode, cbf_gamma (0.1.1) and dyn_rows (0.1.2) */
 #define MPCB_NMAX 128    /* maximum horizon N */
 #define MPCB_MMAX 3      /* maximum obstacles per scenario in this build (the mains carry a commented 3-obstacle list) */
 
@@ -54,6 +54,13 @@ enum { MPCB_INIT_AS_GIVEN = 0, MPCB_INIT_ROLLOUT = 1 };
  * `optimize_problem(ego_state, ref_state, obstacle)` takes (PKG/MPC_CBF_optimize_kin.py:136,236-243;
  * PKG/main_cbf_kin_c_sim.py:55,99); identical results to TRAJECTORY with the row repeated */
 enum { MPCB_OBS_TRAJECTORY = 0, MPCB_OBS_INITIAL = 1, MPCB_OBS_STATIC = 2 };
+
+/* dyn model: how the rows of g are paired with bounds.  ALIGNED = as the code's comments intend (defects = 0,
+ * rate rows within the rate bounds).  AS_SHIPPED = exactly as the lists of PKG/MPC_CBF_optimize_dyn.py:112-133
+ * line up with g (:215,227-243): every rate row is an equality U_i = U_{i-1} (one control pair for the whole
+ * horizon) and the x / y defects into stages 2..N are range rows with the rate bounds - what IPOPT is actually
+ * given by the reference's dyn main. */
+enum { MPCB_DYN_ROWS_ALIGNED = 0, MPCB_DYN_ROWS_AS_SHIPPED = 1 };
 
 /* per-scenario outcome, mapped to IPOPT return_status strings by the Python shim */
 enum {
@@ -102,6 +109,8 @@ typedef struct mpcb_cfg {
   int32_t obs_input;    /* MPCB_OBS_TRAJECTORY (default), MPCB_OBS_INITIAL or MPCB_OBS_STATIC */
   int32_t ref_mode;     /* MPCB_REF_TERMINAL (default) or MPCB_REF_TRAJECTORY */
   double cbf_gamma;     /* gamma in (0,1] of the MPCB_OBS_DCBF rows (the reference's `gamma = 1.00`, :235) */
+  int32_t dyn_rows;     /* MPCB_DYN_ROWS_ALIGNED (default) or MPCB_DYN_ROWS_AS_SHIPPED */
+  int32_t reserved;
 } mpcb_cfg;
 
 typedef struct mpcb_handle mpcb_handle;

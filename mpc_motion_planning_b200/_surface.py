@@ -151,6 +151,10 @@ class MPCOptimizeBase:
         self.aa = 0.0
         self.gamma = 1.00
         self.cbf_rows = "h"
+        # dyn module: `initialize_constraints()` returns the bound lists exactly as the reference ships them
+        # ("as_shipped", the default: drop-in behaviour) or in the order of the rows of g ("aligned"); the solver
+        # call recognises which of the two it was given from lbg itself.
+        self.dyn_bounds = "as_shipped"
 
     def _stage_reference(self):
         return self.aa != 0.0 and self.KIND != "dyn"
@@ -232,18 +236,30 @@ class MPCOptimizeBase:
         if self.KIND == "kin_nocbf":  # pyc L85-86: scalar zero bounds
             return 0.0, 0.0, lbx, ubx
         if self.KIND == "dyn":
-            # Bounds in the order of the rows of g: [init, d0, d1, (ddf1, dax1), d2, (ddf2, dax2), ...].
-            # The reference's own list (PKG/MPC_CBF_optimize_dyn.py:112-129) interleaves the rate pair one
-            # block too early, which pairs 196 rows with the wrong bounds; the
-            # aligned order is what its comments intend and what the CUDA path solves.
-            lbg += [0.0] * 6
-            ubg += [0.0] * 6
-            for i in range(N):
+            rate_lo = [self.df_dot_min * self.T_S, self.jerk_min * self.T_S]
+            rate_hi = [self.df_dot_max * self.T_S, self.jerk_max * self.T_S]
+            if self.dyn_bounds == "as_shipped":
+                # The reference's own list (PKG/MPC_CBF_optimize_dyn.py:112-129): a block of six zeros per i = 0..N
+                # with the rate pair appended for 0 < i < N.  Against the rows of g (:215,227-231) this puts the rate
+                # bounds on the x / y defects of stage i and zeros on the rate rows - the
+                # problem the reference's dyn main actually hands to IPOPT, solved as such.
+                for i in range(N + 1):
+                    lbg += [0.0] * 6
+                    ubg += [0.0] * 6
+                    if 0 < i < N:
+                        lbg += rate_lo
+                        ubg += rate_hi
+            else:
+                # bounds in the order of the rows of g: [init, d0, d1, (ddf1, dax1), d2, (ddf2, dax2), ...] -
+                # what the reference's comments intend (`mpc_solver.dyn_bounds = "aligned"`)
                 lbg += [0.0] * 6
                 ubg += [0.0] * 6
-                if i > 0:
-                    lbg += [self.df_dot_min * self.T_S, self.jerk_min * self.T_S]
-                    ubg += [self.df_dot_max * self.T_S, self.jerk_max * self.T_S]
+                for i in range(N):
+                    lbg += [0.0] * 6
+                    ubg += [0.0] * 6
+                    if i > 0:
+                        lbg += rate_lo
+                        ubg += rate_hi
             for _ in range(N + 1):
                 lbg.append(1)
                 ubg.append(np.inf)
@@ -275,22 +291,27 @@ class MPCOptimizeBase:
                 raise NotImplementedError("stage-varying lbx/ubx are not supported by the CUDA path")
             bounds.update(u_lo=ul[0], u_hi=uh[0], x_lo=xl[0], x_hi=xh[0])
         n_rate = {"kin_nocbf": 0, "kin_cbf": 1, "kin_cbf_pre": 1, "dyn": 2}[self.KIND]
+        dyn_rows = "aligned"
         if lbg is not None and ubg is not None and n_rate and not np.isscalar(lbg):
             lg = np.asarray(lbg, dtype=np.float64).reshape(-1)
             ug = np.asarray(ubg, dtype=np.float64).reshape(-1)
             if self.KIND == "dyn":
-                r0 = 6 + 6 + 6  # init, d0, d1 then the first rate pair
+                # aligned: init, d0, d1 then the first rate pair (rows 18,19); as shipped: the pair sits at 12,13
+                shipped = bool(lg[12] != 0.0 or ug[12] != 0.0)
+                r0 = 12 if shipped else 18
                 bounds.update(rate_lo=lg[r0: r0 + 2], rate_hi=ug[r0: r0 + 2])
+                dyn_rows = "as_shipped" if shipped else "aligned"
             else:
                 r0 = nx * (N + 1)
                 bounds.update(rate_lo=lg[r0: r0 + 1], rate_hi=ug[r0: r0 + 1])
         M = 0 if obs_array is None else obs_array.shape[0]
         gamma = float(self.gamma) if self._dcbf() else None
         ref = "trajectory" if self._stage_reference() else "terminal"
-        key = (M, self.max_iter, self.tol, self.mu_init, self.init, gamma, ref) + tuple(np.concatenate([np.ravel(v) for v in bounds.values()]).tolist() if bounds else ())
+        key = (M, self.max_iter, self.tol, self.mu_init, self.init, gamma, ref, dyn_rows) + tuple(np.concatenate([np.ravel(v) for v in bounds.values()]).tolist() if bounds else ())
         if key not in self._solvers:
             self._solvers[key] = BatchSolver(self.KIND, config=self.config, N=N, M=max(M, 1), init=self.init, mu_init=self.mu_init,
-                                             max_iter=self.max_iter, tol=self.tol, bounds=bounds or None, cbf_gamma=gamma, ref=ref)
+                                             max_iter=self.max_iter, tol=self.tol, bounds=bounds or None, cbf_gamma=gamma, ref=ref,
+                                             dyn_bounds=dyn_rows)
         return self._solvers[key]
 
     # ---- g(z) in the reference's row order (host evaluation for res['g']) -----------------

@@ -50,7 +50,10 @@ bool select_variant(const mpcb_cfg &c, Variant &v) {
   const int M = c.obs_mode == MPCB_OBS_NONE ? 0 : c.M;
   if (c.model == MPCB_MODEL_DYN) {
     // the reference's dyn NLP: both rate rows (df, ax in that order), one obstacle, sqrt rows
-    if (c.obs_mode == MPCB_OBS_SQRT && c.n_rate == 2 && M == 1 && c.rate_ctrl[0] == 0 && c.rate_ctrl[1] == 1) { v = variant_dyn(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_SQRT && c.n_rate == 2 && M == 1 && c.rate_ctrl[0] == 0 && c.rate_ctrl[1] == 1) {
+      v = c.dyn_rows == MPCB_DYN_ROWS_AS_SHIPPED ? variant_dyn_shipped(c.N) : variant_dyn(c.N);
+      return true;
+    }
     return false;
   }
   if (c.model == MPCB_MODEL_KIN) {
@@ -137,6 +140,8 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   if (c.ref_mode != MPCB_REF_TERMINAL && c.ref_mode != MPCB_REF_TRAJECTORY) return MPCB_E_ARG;
   if (c.ref_mode == MPCB_REF_TRAJECTORY && c.model != MPCB_MODEL_KIN) return MPCB_E_ARG;
   if (c.obs_mode == MPCB_OBS_DCBF && !(c.cbf_gamma > 0.0 && c.cbf_gamma <= 1.0)) return MPCB_E_ARG;
+  if (c.dyn_rows != MPCB_DYN_ROWS_ALIGNED && c.dyn_rows != MPCB_DYN_ROWS_AS_SHIPPED) return MPCB_E_ARG;
+  if (c.dyn_rows == MPCB_DYN_ROWS_AS_SHIPPED && c.model != MPCB_MODEL_DYN) return MPCB_E_ARG;
   Variant var;
   if (!select_variant(c, var)) return MPCB_E_ARG;
   // the kernels assume: both controls two-sided; the model's bounded states (kin: y, vx; dyn: + vy)

@@ -51,7 +51,13 @@ struct DynLayout {
   // the step: written by lane 0 in the forward sweep, read by the stage-parallel phases only
   static constexpr int DX = OCY + MO;
   static constexpr int DU = DX + NX;
-  static constexpr int NG = DU + 2 - G0;
+  // rows-as-shipped mode only: Huu diagonal and gu of the stage (the shared copies are overwritten by the
+  // gains before the multipliers of the tied controls are recovered), and that stationarity residual
+  static constexpr int HUG = DU + 2;
+  static constexpr int GUG = HUG + 2;
+  static constexpr int RUG = GUG + 2;
+  static constexpr int NG = RUG + 2 - G0;
+  static constexpr int ER = R18 + 8;  // rows-as-shipped: e_k = U_k - U_{k-1} for the backward sweep
   static constexpr int SG = 132;
   __host__ __device__ static constexpr size_t bytes(int N) { return sizeof(double) * (size_t)NF * (size_t)(N + 1); }
   __host__ __device__ static constexpr size_t slab_doubles() { return (size_t)NG * SG; }
@@ -66,6 +72,11 @@ __device__ __forceinline__ constexpr int hslot(int i, int j) {
 static_assert(hslot(0, 0) == 0 && hslot(0, 1) == 1 && hslot(1, 1) == 2 && hslot(2, 2) == 3 && hslot(2, 5) == 6 && hslot(3, 3) == 7 &&
               hslot(4, 4) == 10 && hslot(5, 5) == 12 && hslot(1, 2) == -1, "compact Hessian order");
 
+// SHP: pair the rows of g with the bound lists exactly as PKG/MPC_CBF_optimize_dyn.py:112-133 ships them
+// (SURVEY.md section 0.4).  Then, for k = 1..N-1, the slack SR(r,k) with the rate bounds relaxes component
+// r = 0,1 (x, y) of the defect into stage k+1 (its row multiplier is LAM(r,k+1)) and the rate rows
+// U_k - U_{k-1} are equalities with multipliers LR(r,k): one control pair for the whole horizon.
+template <bool SHP>
 struct DynSolver {
   using L = DynLayout;
   static constexpr int NX = 6, NBX = 3, NR = 2, MO = 1, NJ = DYN_NJ;
@@ -143,6 +154,7 @@ struct DynSolver {
         for (int i = 0; i < NX; i++) {
           double xn = at(L::X + i, k + 1) + alpha * at(L::DX + i, k + 1);
           double d = xn - (xk[i] + p.T * f[i]);
+          if (SHP && i < 2 && has_rate(k)) d -= at(L::SR + i, k) + (alpha != 0.0 ? alpha * at(L::DSR + i, k) : 0.0);
           th += fabs(d);
           at(cdst + i, k + 1) = d;
           double e = xk[i] - xs[i];
@@ -171,7 +183,7 @@ struct DynSolver {
         for (int r = 0; r < NR; r++) {
           double um = at(L::U + r, k - 1) + alpha * at(L::DU + r, k - 1);
           double s = at(L::SR + r, k) + (alpha != 0.0 ? alpha * at(L::DSR + r, k) : 0.0);
-          th += fabs(uk[r] - um - s);
+          th += fabs(SHP ? uk[r] - um : uk[r] - um - s);
           gp *= (s - p.rate_lo[r]) * (p.rate_hi[r] - s);
         }
       }
@@ -266,8 +278,8 @@ struct DynSolver {
 #pragma unroll
         for (int r = 0; r < NR; r++) {
           double s = at(L::SR + r, k), vl = at(L::VLR + r, k), vu = at(L::VUR + r, k), lr = at(L::LR + r, k);
-          dual = fmax(dual, fabs(-lr - vl + vu));
-          prim = fmax(prim, fabs(at(L::U + r, k) - at(L::U + r, k - 1) - s));
+          dual = fmax(dual, fabs(-(SHP ? at(L::LAM + r, k + 1) : lr) - vl + vu));
+          prim = fmax(prim, fabs(SHP ? at(L::U + r, k) - at(L::U + r, k - 1) : at(L::U + r, k) - at(L::U + r, k - 1) - s));
           MPCB_COMPL(s - p.rate_lo[r], vl);
           MPCB_COMPL(p.rate_hi[r] - s, vu);
           sl += fabs(lr);
@@ -375,7 +387,10 @@ struct DynSolver {
           g += mu * (rh - rl);
           at(L::HUU + i, k) = hd;
           at(L::GU + i, k) = g;
-          if (k >= 1) {
+          if (SHP) {
+            at(L::HUG + i, k) = hd;
+            at(L::GUG + i, k) = g;
+          } else if (k >= 1) {
             E[i] = sigma * 2 * p.DR[i];
             t[i] = sigma * 2 * p.DR[i] * (uk[i] - at(L::U + i, k - 1));
           }
@@ -387,9 +402,15 @@ struct DynSolver {
             double rl = 1.0 / (s - p.rate_lo[r]), rh = 1.0 / (p.rate_hi[r] - s);
             double D = at(L::VLR + r, k) * rl + at(L::VUR + r, k) * rh + dw;
             double gs = mu * (rh - rl);
-            double res = uk[r] - at(L::U + r, k - 1) - s;
-            E[r] += D;
-            t[r] += D * res + gs;
+            if (SHP) {  // curvature and gradient of the relaxation slack (the stage input), and e_k
+              E[r] = D;
+              t[r] = gs;
+              at(L::ER + r, k) = uk[r] - at(L::U + r, k - 1);
+            } else {
+              double res = uk[r] - at(L::U + r, k - 1) - s;
+              E[r] += D;
+              t[r] += D * res + gs;
+            }
           }
         }
         at(L::EE + 0, k) = E[0];
@@ -436,8 +457,92 @@ struct DynSolver {
       }
       const double Ed = at(L::EE + 0, k), Ea = at(L::EE + 1, k), td = at(L::TK + 0, k), ta = at(L::TK + 1, k);
       double Fxx[21], Fux[12], Fuu[3], fx[NX], fu[2];
-      dyn_riccati_F(P, W, Q, px, pw, a_, p.T, hx, hu, at(L::HUU + 0, k), at(L::HUU + 1, k), Ed, Ea, td, ta, gx, at(L::GU + 0, k),
-                    at(L::GU + 1, k), b, Fxx, Fux, Fuu, fx, fu);
+      const bool tied = SHP && k >= 1;
+      dyn_riccati_F(P, W, Q, px, pw, a_, p.T, hx, hu, at(L::HUU + 0, k), at(L::HUU + 1, k), tied ? 0.0 : Ed, tied ? 0.0 : Ea, tied ? 0.0 : td,
+                    tied ? 0.0 : ta, gx, at(L::GU + 0, k), at(L::GU + 1, k), b, Fxx, Fux, Fuu, fx, fu);
+      if (SHP && k >= 1) {
+        // Rows as shipped: the control of this stage is tied to the previous one (dU_k = dw - e_k) and the
+        // free inputs are the two slacks that relax the x/y defects, entering x_{k+1} rows 0,1.  F above is the
+        // quadratic over (dx, dU) (EE/TK hold the slack curvature and gradient here, so E = t = 0 went in);
+        // eliminate the slack inputs and rename dU -> dw.
+        const double e0 = at(L::ER + 0, k), e1 = at(L::ER + 1, k);
+        double A[NX][NX], B[NX][2];
+        {
+          double J[NJ];
+#pragma unroll
+          for (int i = 0; i < NJ; i++) J[i] = at(L::JAC + i, k);
+          dyn_expand(J, p.T, A, B);
+        }
+        double M2[2][NX], Cm[2][2], c0[2];
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+#pragma unroll
+          for (int j = 0; j < NX; j++) {
+            double v = 0;
+#pragma unroll
+            for (int i = 0; i < NX; i++) v += P[sidx6(a, i)] * A[i][j];
+            M2[a][j] = v;
+          }
+          double pb = px[a];
+#pragma unroll
+          for (int i = 0; i < NX; i++) pb += P[sidx6(a, i)] * b[i];
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            double v = W[2 * a + j];
+#pragma unroll
+            for (int i = 0; i < NX; i++) v += P[sidx6(a, i)] * B[i][j];
+            Cm[a][j] = v;
+          }
+          c0[a] = pb + (a == 0 ? td : ta) - (Cm[a][0] * e0 + Cm[a][1] * e1);
+        }
+        const double h00 = P[pidx6(0, 0)] + Ed, h01 = P[pidx6(0, 1)], h11 = P[pidx6(1, 1)] + Ea;
+        const double dets = h00 * h11 - h01 * h01;
+        if (!(h00 > 0.0) || !(dets > 0.0) || !isfinite(dets)) { ok = false; break; }
+        const double ids = 1.0 / dets;
+        const double i00 = h11 * ids, i01 = -h01 * ids, i11 = h00 * ids;
+        double Ks[2][NX], Kw2[2][2], ks[2];
+#pragma unroll
+        for (int j = 0; j < NX; j++) {
+          Ks[0][j] = -(i00 * M2[0][j] + i01 * M2[1][j]);
+          Ks[1][j] = -(i01 * M2[0][j] + i11 * M2[1][j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          Kw2[0][j] = -(i00 * Cm[0][j] + i01 * Cm[1][j]);
+          Kw2[1][j] = -(i01 * Cm[0][j] + i11 * Cm[1][j]);
+        }
+        ks[0] = -(i00 * c0[0] + i01 * c0[1]);
+        ks[1] = -(i01 * c0[0] + i11 * c0[1]);
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < NX; j++) {
+            at(L::KX + j, k) = Ks[0][j];
+            at(L::KX + NX + j, k) = Ks[1][j];
+          }
+          at(L::KW + 0, k) = Kw2[0][0]; at(L::KW + 1, k) = Kw2[0][1]; at(L::KW + 2, k) = Kw2[1][0]; at(L::KW + 3, k) = Kw2[1][1];
+          at(L::KK + 0, k) = ks[0]; at(L::KK + 1, k) = ks[1];
+        }
+        {
+          int q = 0;
+#pragma unroll
+          for (int i = 0; i < NX; i++)
+#pragma unroll
+            for (int j = i; j < NX; j++, q++) P[q] = Fxx[q] + 0.5 * ((M2[0][i] * Ks[0][j] + M2[1][i] * Ks[1][j]) + (M2[0][j] * Ks[0][i] + M2[1][j] * Ks[1][i]));
+        }
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+          W[2 * i] = Fux[i] + M2[0][i] * Kw2[0][0] + M2[1][i] * Kw2[1][0];
+          W[2 * i + 1] = Fux[6 + i] + M2[0][i] * Kw2[0][1] + M2[1][i] * Kw2[1][1];
+          px[i] = fx[i] - (Fux[i] * e0 + Fux[6 + i] * e1) + M2[0][i] * ks[0] + M2[1][i] * ks[1];
+        }
+        Q[0] = Fuu[0] + Cm[0][0] * Kw2[0][0] + Cm[1][0] * Kw2[1][0];
+        Q[1] = Fuu[1] + 0.5 * ((Cm[0][0] * Kw2[0][1] + Cm[1][0] * Kw2[1][1]) + (Cm[0][1] * Kw2[0][0] + Cm[1][1] * Kw2[1][0]));
+        Q[2] = Fuu[2] + Cm[0][1] * Kw2[0][1] + Cm[1][1] * Kw2[1][1];
+        pw[0] = fu[0] - (Fuu[0] * e0 + Fuu[1] * e1) + Cm[0][0] * ks[0] + Cm[1][0] * ks[1];
+        pw[1] = fu[1] - (Fuu[1] * e0 + Fuu[2] * e1) + Cm[0][1] * ks[0] + Cm[1][1] * ks[1];
+        continue;
+      }
       const double det = Fuu[0] * Fuu[2] - Fuu[1] * Fuu[1];
       if (!(Fuu[0] > 0.0) || !(det > 0.0) || !isfinite(det)) { ok = false; break; }
       const double id = 1.0 / det;
@@ -500,13 +605,19 @@ struct DynSolver {
         for (int i = 0; i < NJ; i++) J[i] = at(L::JAC + i, k);
         dyn_expand(J, p.T, A, B);
       }
+      double ds[2] = {0, 0};  // rows as shipped: the relaxation slacks' step (the stage input for k >= 1)
 #pragma unroll
       for (int i = 0; i < 2; i++) {
         double s = at(L::KK + i, k);
 #pragma unroll
         for (int j = 0; j < NX; j++) s += at(L::KX + i * NX + j, k) * dx[j];
         s += at(L::KW + i * 2 + 0, k) * dum[0] + at(L::KW + i * 2 + 1, k) * dum[1];
-        du[i] = s;
+        if (SHP && k >= 1) {
+          ds[i] = s;
+          du[i] = dum[i] - (at(L::U + i, k) - at(L::U + i, k - 1));
+        } else {
+          du[i] = s;
+        }
       }
       double dn[NX];
 #pragma unroll
@@ -515,9 +626,12 @@ struct DynSolver {
 #pragma unroll
         for (int j = 0; j < NX; j++) s += A[i][j] * dx[j];
         s += B[i][0] * du[0] + B[i][1] * du[1];
+        if (i < 2) s += ds[i];
         dn[i] = s;
       }
+      if (SHP) __syncwarp();  // every lane has read the gains of this stage before lane 0 reuses two of their slots
       if (lane == 0) {
+        if (SHP && k >= 1) { at(L::DSR + 0, k) = ds[0]; at(L::DSR + 1, k) = ds[1]; }
         at(L::DU + 0, k) = du[0];
         at(L::DU + 1, k) = du[1];
 #pragma unroll
@@ -587,7 +701,45 @@ struct DynSolver {
     __syncwarp();
   }
 
+  // Rows as shipped: new multipliers of the tied-control equalities U_k - U_{k-1} = 0 from stationarity in U_k,
+  // nu_k = nu_{k+1} - [Huu dU_k + Hux dx_k + gu - B' lam+_{k+1}]  (the DR cost terms cancel: dU_k - dU_{k-1} = -e_k).
+  __device__ __forceinline__ void tied_control_multipliers() {
+#pragma unroll 1
+    for (int k = lane; k <= N - 1; k += 32) {
+      if (k < 1) continue;
+      double A[NX][NX], B[NX][2], dx[NX], l1[NX];
+      {
+        double J[NJ];
+#pragma unroll
+        for (int i = 0; i < NJ; i++) J[i] = at(L::JAC + i, k);
+        dyn_expand(J, p.T, A, B);
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) { dx[i] = at(L::DX + i, k); l1[i] = at(L::LAMP + i, k + 1); }
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        double r = at(L::GUG + i, k) + at(L::HUG + i, k) * at(L::DU + i, k);
+        if (i == 0) r += at(L::HUX + 0, k) * dx[3] + at(L::HUX + 1, k) * dx[4] + at(L::HUX + 2, k) * dx[5];
+#pragma unroll
+        for (int a = 0; a < NX; a++) r -= B[a][i] * l1[a];
+        at(L::RUG + i, k) = r;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double n0 = 0.0, n1 = 0.0;
+      for (int k = N - 1; k >= 1; k--) {
+        n0 -= at(L::RUG + 0, k);
+        n1 -= at(L::RUG + 1, k);
+        at(L::LRP + 0, k) = n0;
+        at(L::LRP + 1, k) = n1;
+      }
+    }
+    __syncwarp();
+  }
+
   __device__ __forceinline__ void slack_and_steps(double mu, double dw, double tau, double &a_pr, double &a_du, double &gd_out) {
+    if (SHP) tied_control_multipliers();
     double rp = 0.0, rd = 0.0, gd = 0.0;
 #define MPCB_LOWER(rgap, dv, z) do { double dz_ = -(z) + (mu - (z) * (dv)) * (rgap); \
     rp = fmax(rp, -(dv) * (rgap)); rd = fmax(rd, -dz_ / (z)); } while (0)
@@ -631,10 +783,16 @@ struct DynSolver {
           double vl = at(L::VLR + r, k), vu = at(L::VUR + r, k);
           double D = vl * rl + vu * rh + dw;
           double gs = mu * (rh - rl);
-          double res = at(L::U + r, k) - at(L::U + r, k - 1) - s;
-          double ds = at(L::DU + r, k) - at(L::DU + r, k - 1) + res;
+          double ds;
+          if (SHP) {  // the slack step came out of the forward sweep, the equality multiplier out of the pass above
+            ds = at(L::DSR + r, k);
+            lrp[r] = at(L::LRP + r, k);
+          } else {
+            double res = at(L::U + r, k) - at(L::U + r, k - 1) - s;
+            ds = at(L::DU + r, k) - at(L::DU + r, k - 1) + res;
+            lrp[r] = D * ds + gs;
+          }
           dsr[r] = ds;
-          lrp[r] = D * ds + gs;
           gd += gs * ds;
           MPCB_LOWER(rl, ds, vl);
           MPCB_UPPER(rh, ds, vu);
@@ -787,10 +945,23 @@ struct DynSolver {
         at(L::ZLX + b2, k) = 1.0;
         at(L::ZUX + b2, k) = 1.0;
       }
+    }
+    if (SHP) __syncwarp();  // the relaxed-defect slacks below read the pushed state of stage k+1 (another lane's)
+#pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
       if (has_rate(k)) {
+        double dfx[2] = {0, 0};
+        if (SHP) {  // the slack relaxes the x / y defect into stage k+1
+          double xk[NX], uk[2] = {at(L::U + 0, k), at(L::U + 1, k)}, f[NX];
+#pragma unroll
+          for (int i = 0; i < NX; i++) xk[i] = at(L::X + i, k);
+          dyn_f(xk, uk, p, f);
+          dfx[0] = at(L::X + 0, k + 1) - (xk[0] + p.T * f[0]);
+          dfx[1] = at(L::X + 1, k + 1) - (xk[1] + p.T * f[1]);
+        }
 #pragma unroll
         for (int r = 0; r < NR; r++) {
-          at(L::SR + r, k) = push_in(at(L::U + r, k) - at(L::U + r, k - 1), p.rate_lo[r], p.rate_hi[r]);
+          at(L::SR + r, k) = push_in(SHP ? dfx[r] : at(L::U + r, k) - at(L::U + r, k - 1), p.rate_lo[r], p.rate_hi[r]);
           at(L::VLR + r, k) = 1.0;
           at(L::VUR + r, k) = 1.0;
           at(L::LR + r, k) = 0.0;
@@ -830,7 +1001,7 @@ struct DynSolver {
 };
 
 // persistent, W warps per block in step, see kin_solve_kernel
-template <int W>
+template <int W, bool SHP>
 __global__ void __launch_bounds__(32 * W) dyn_solve_kernel(const __grid_constant__ KParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *gs = p.slab + ((size_t)blockIdx.x * W + warp) * DynLayout::slab_doubles();
@@ -842,7 +1013,7 @@ __global__ void __launch_bounds__(32 * W) dyn_solve_kernel(const __grid_constant
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= p.B) break;
     if (p.order) b = p.order[b];  // caller-supplied processing order (longest expected first)
-    DynSolver s(p, gs, woff, tick, lane);
+    DynSolver<SHP> s(p, gs, woff, tick, lane);
     s.run(b);
     __syncwarp();
   }

@@ -2,10 +2,10 @@
 #include "mpcb_variants.h"
 
 #ifndef MPCB_FAMILY
-#error "compile with -DMPCB_FAMILY=0..8"
+#error "compile with -DMPCB_FAMILY=0..9"
 #endif
 
-#if MPCB_FAMILY == 8
+#if MPCB_FAMILY >= 8
 #include "mpcb_dyn_kernel.cuh"
 #endif
 
@@ -65,11 +65,13 @@ Variant variant_kin_1_2_3(int N) { return make_kin_variant<1, 2, 3>(N); }
 Variant variant_kin_1_3_3(int N) { return make_kin_variant<1, 3, 3>(N); }
 #endif
 
-#else  // MPCB_FAMILY == 8: dynamic bicycle
+#else  // MPCB_FAMILY 8, 9: dynamic bicycle, rows aligned / rows as shipped
+
+constexpr bool kShipped = MPCB_FAMILY == 9;
 
 template <int W>
 static cudaError_t launch_dyn(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-  dyn_solve_kernel<W><<<grid, 32 * W, smem, st>>>(p);
+  dyn_solve_kernel<W, kShipped><<<grid, 32 * W, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -77,7 +79,7 @@ template <int W>
 static Variant make_dyn_variant_w() {
   Variant v;
   v.launch = &launch_dyn<W>;
-  v.kernel = (const void *)&dyn_solve_kernel<W>;
+  v.kernel = (const void *)&dyn_solve_kernel<W, kShipped>;
   v.smem_bytes = [](int N) { return DynLayout::bytes(N); };
   v.nx = 6;
   v.nbx = 3;
@@ -86,7 +88,11 @@ static Variant make_dyn_variant_w() {
   return v;
 }
 
+#if MPCB_FAMILY == 8
 Variant variant_dyn(int N) {
+#else
+Variant variant_dyn_shipped(int N) {
+#endif
   Variant cand[3] = {make_dyn_variant_w<4>(), make_dyn_variant_w<2>(), make_dyn_variant_w<1>()};
   return pick_by_occupancy(cand, 3, N);
 }

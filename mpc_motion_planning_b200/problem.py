@@ -48,7 +48,7 @@ def horizon_steps(config: dict) -> int:
 def make_cfg(kind: str, config: dict, N: int | None = None, M: int = 1, weights: Weights | None = None,
              init_mode: int = _lib.INIT_ROLLOUT, mu_init: float = 100.0, max_iter: int = 100, tol: float = 1e-8,
              bounds: dict | None = None, obs_input: int = _lib.OBS_TRAJECTORY, cbf_gamma: float | None = None,
-             ref_mode: int = _lib.REF_TERMINAL) -> _lib.MpcbCfg:
+             ref_mode: int = _lib.REF_TERMINAL, dyn_rows: int = _lib.DYN_ROWS_ALIGNED) -> _lib.MpcbCfg:
     """Fill an mpcb_cfg from the YAML dict with the reference's hard-coded constants.
 
     `bounds` optionally overrides {'u_lo','u_hi','x_lo','x_hi','rate_lo','rate_hi'} (used by the
@@ -111,6 +111,9 @@ def make_cfg(kind: str, config: dict, N: int | None = None, M: int = 1, weights:
     c.tol, c.mu_init, c.bound_relax = tol, mu_init, 1e-8
     c.obs_input = obs_input
     c.ref_mode = ref_mode
+    c.dyn_rows = dyn_rows  # dyn: bound lists aligned with g, or paired exactly as shipped
+    if dyn_rows != _lib.DYN_ROWS_ALIGNED and kind != "dyn":
+        raise ValueError("dyn_rows applies to the dyn kind only")
     if cbf_gamma is not None:
         if kind not in ("kin_cbf", "kin_cbf_pre"):
             raise ValueError("cbf_gamma applies to the kinematic CBF kinds only")

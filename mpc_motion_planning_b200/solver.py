@@ -29,7 +29,7 @@ class BatchSolver:
     def __init__(self, kind: str = "kin_cbf_pre", config: dict | None = None, N: int | None = None, M: int = 1,
                  init: str = "rollout", mu_init: float = 100.0, max_iter: int = 100, tol: float = 1e-8,
                  weights=None, bounds: dict | None = None, obs_input: str = "trajectory", cbf_gamma: float | None = None,
-                 ref: str = "terminal", cfg_overrides: dict | None = None):
+                 ref: str = "terminal", cfg_overrides: dict | None = None, dyn_bounds: str = "aligned"):
         self.lib = _lib.load()
         self.kind = kind
         self.config = config if config is not None else load_config(PACKAGE_PARAMS)
@@ -42,7 +42,8 @@ class BatchSolver:
                             max_iter=max_iter, tol=tol, bounds=bounds,
                             obs_input=obs_code,
                             cbf_gamma=cbf_gamma,
-                            ref_mode=_lib.REF_TRAJECTORY if self.ref_trajectory else _lib.REF_TERMINAL)
+                            ref_mode=_lib.REF_TRAJECTORY if self.ref_trajectory else _lib.REF_TERMINAL,
+                            dyn_rows={"aligned": _lib.DYN_ROWS_ALIGNED, "as_shipped": _lib.DYN_ROWS_AS_SHIPPED}[dyn_bounds])
         for key, val in (cfg_overrides or {}).items():  # any mpcb_cfg field, e.g. {"safe_l": 1.5, "T": 0.08, "Q": [...]}
             cur = getattr(self.cfg, key)
             if hasattr(cur, "__len__"):

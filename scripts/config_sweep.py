@@ -41,6 +41,7 @@ def run(name, kind, gen, B, N=50, chunk=None, **solver_kw):
 run("configs[1] kin-CBF static, 10k", "kin_cbf", scenarios.kin_cbf_static, 10000)
 run("configs[2] kin-CBF moving (obs_prediction), 100k", "kin_cbf_pre", scenarios.kin_cbf_moving, 100000)
 run("configs[3] dyn CBF, 100k", "dyn", lambda B, N=50: scenarios.dyn_static(B, N=N), 100000)
+run("configs[3] dyn CBF, bound lists as shipped, 100k", "dyn", lambda B, N=50: scenarios.dyn_static(B, N=N), 100000, dyn_bounds="as_shipped")
 for N in (20, 50, 100):
     run(f"configs[4] scaling sweep N={N}, 1M (one GPU share)", "kin_cbf_pre", scenarios.kin_cbf_moving, 1000000 if N < 100 else 500000, N=N)
 run("row N3: discrete-time CBF rows gamma=0.5, moving obstacle, 100k", "kin_cbf_pre", scenarios.kin_cbf_moving, 100000, cbf_gamma=0.5)

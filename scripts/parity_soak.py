@@ -23,7 +23,7 @@ def stage_ref(xs, N, seed=77):
     return ref
 
 
-def run(name, kind, gen, N=50, M=1, gamma=None, ref=False, seed=None, B=B):
+def run(name, kind, gen, N=50, M=1, gamma=None, ref=False, seed=None, B=B, shipped=False):
     kw = {} if seed is None else {"seed": seed}
     x0, xs, obs = gen(B, N=N, **kw)
     if M == 2:
@@ -31,11 +31,11 @@ def run(name, kind, gen, N=50, M=1, gamma=None, ref=False, seed=None, B=B):
         ob[:, :, :, 0] += 60.0
         obs = np.concatenate([obs, ob], axis=1)
     xs_in = stage_ref(xs, N) if ref else xs
-    s = BatchSolver(kind, N=N, M=M, cbf_gamma=gamma, ref="trajectory" if ref else "terminal")
+    s = BatchSolver(kind, N=N, M=M, cbf_gamma=gamma, ref="trajectory" if ref else "terminal", dyn_bounds="as_shipped" if shipped else "aligned")
     out = s.solve(t(x0), t(xs_in), t(obs) if obs.shape[1] else None)
     torch.cuda.synchronize()
     g = {k: v.cpu().numpy() for k, v in out.items()}
-    cfg = c_oracle.make_cfg(kind, N=N, M=max(M, 1), cbf_gamma=gamma, ref_trajectory=ref)
+    cfg = c_oracle.make_cfg(kind, N=N, M=max(M, 1), cbf_gamma=gamma, ref_trajectory=ref, rows_as_shipped=shipped)
     t0 = time.time()
     u0, cost, st, it, _ = c_oracle.solve_batch(cfg, x0, xs_in, obs if obs.shape[1] else None, nthreads=os.cpu_count())
     tc = time.time() - t0
@@ -54,6 +54,7 @@ run("kin no-CBF (MPC_optimize_kin)", "kin_nocbf", scenarios.kin_nocbf)
 run("kin-CBF static (configs[1] generator)", "kin_cbf", scenarios.kin_cbf_static)
 run("kin-CBF moving (configs[2] generator)", "kin_cbf_pre", scenarios.kin_cbf_moving)
 run("dyn (configs[3] generator)", "dyn", scenarios.dyn_static)
+run("dyn, bound lists as shipped", "dyn", scenarios.dyn_static, shipped=True)
 run("kin-CBF moving N=20", "kin_cbf_pre", scenarios.kin_cbf_moving, N=20)
 run("kin-CBF moving N=100", "kin_cbf_pre", scenarios.kin_cbf_moving, N=100, B=B // 2)
 run("kin-CBF moving, two obstacles", "kin_cbf_pre", scenarios.kin_cbf_moving, M=2)

@@ -726,7 +726,7 @@ def test_parity_under_randomised_problem_data(dev, seed):
     s = BatchSolver(kind, N=N, cbf_gamma=gamma, cfg_overrides=ov)
     ocfg = c_oracle.make_cfg(kind, N=N, cbf_gamma=gamma)
     for name, _ in c_oracle.OrcCfg._fields_:  # same numbers on both sides, field by field
-        if name in ("obs_mode", "cbf_gamma", "ref_mode", "reserved", "init_mode"):
+        if name in ("obs_mode", "cbf_gamma", "ref_mode", "rows_as_shipped", "init_mode"):
             continue
         v = getattr(s.cfg, name)
         if hasattr(v, "__len__"):
@@ -745,3 +745,57 @@ def test_parity_under_randomised_problem_data(dev, seed):
     du = np.abs(g["u0"] - u0).max(axis=1)
     dc = np.abs(g["cost"] - cost) / np.maximum(np.abs(cost), 1.0)
     assert np.all(du[both] <= U0_ATOL) and np.all(dc[both] <= COST_RTOL), (du[both].max(), dc[both].max())
+
+
+def test_dyn_rows_as_shipped_parity(dev):
+    """dyn with the bound lists exactly as the reference ships them: tied controls,
+    relaxed x/y defects.  CUDA vs the C oracle in the same mode, which follows the dense specification of
+    oracle.nlp.ShippedDynNLP (tests/test_oracle_solvers.py)."""
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+    from oracle import c_oracle
+
+    B = 256
+    x0, xs, obs = scenarios.dyn_static(B)
+    s = BatchSolver("dyn", dyn_bounds="as_shipped")
+    g = _gpu(s, dev, x0, xs, obs, return_z=True)
+    u0, cost, st, it, z = c_oracle.solve_batch(c_oracle.make_cfg("dyn", rows_as_shipped=True), x0, xs, obs, want_z=True, nthreads=os.cpu_count())
+    both, same = _check(g, u0, cost, st, 0.8)
+    assert (g["iters"][both] == it[both]).mean() >= 0.8
+    U = g["z"][both][:, :100].reshape(-1, 50, 2)
+    assert np.abs(U - U[:, :1, :]).max() <= 1e-9  # one control pair for the whole horizon
+    assert np.abs(g["z"][both] - z[both]).max() <= 1e-5
+    # the reference main's first step: constant controls (0.00804, 3.0), f = 1.7116e8 (aligned: (0.0939, 3.0), 1.7219e8)
+    o = np.zeros((1, 1, 51, 6))
+    o[0, 0, :, 0], o[0, 0, :, 1] = 100, -3.5
+    d = _gpu(s, dev, np.array([[0, 0, 0, 10, 0, 0.0]]), np.array([[600, 3.5, 0, 15, 0, 0.0]]), o)
+    assert d["status"][0] == 0 and abs(d["cost"][0] - 1.7116419462e8) <= 1e-6 * 1.7e8 and np.allclose(d["u0"][0], [0.00803901, 3.0], atol=1e-6)
+
+
+def test_dyn_drop_in_class_solves_what_it_is_given(dev, tmp_path, monkeypatch):
+    """The dyn drop-in class returns the reference's own lbg/ubg (as shipped) by default and the solver call
+    recognises from lbg which pairing it was handed: as shipped -> constant controls, aligned -> the intended NLP."""
+    monkeypatch.chdir(tmp_path)
+    from mpc_motion_planning_b200 import MPC_CBF_optimize_dyn
+
+    mpc = MPC_CBF_optimize_dyn.MPC_optimize()
+    mpc.init = "rollout"
+    x0 = np.array([0, 0, 0, 10, 0, 0.0]).reshape(-1, 1)
+    xs = np.array([600, 3.5, 0, 15, 0, 0.0]).reshape(-1, 1)
+    obs = np.array([100, -3.5])
+    N = mpc.N_p
+    z0 = np.zeros((2 * N + 6 * (N + 1), 1))
+    res = {}
+    for mode in ("as_shipped", "aligned"):
+        mpc.dyn_bounds = mode
+        lbg, ubg, lbx, ubx = mpc.initialize_constraints()
+        solver = mpc.optimize_problem(ego_state=x0, ref_state=xs, obstacle=obs)
+        r = solver(x0=z0, p=np.concatenate((x0, xs)), lbg=lbg, lbx=lbx, ubg=ubg, ubx=ubx)
+        assert solver.stats()["success"]
+        g = r["g"].full().ravel()
+        assert np.all(g >= np.array(lbg) - 1e-6) and np.all(g <= np.array(ubg) + 1e-6)  # feasible for the lists it was given
+        res[mode] = (float(r["f"]), r["x"].full().ravel())
+    assert abs(res["as_shipped"][0] - 1.7116419462e8) <= 1e-6 * 1.7e8 and abs(res["aligned"][0] - 1.7218596389e8) <= 1e-6 * 1.7e8
+    U = res["as_shipped"][1][: 2 * N].reshape(N, 2)
+    assert np.abs(U - U[0]).max() <= 1e-9 and np.allclose(U[0], [0.00803901, 3.0], atol=1e-6)
+    assert np.allclose(res["aligned"][1][:2], [0.09392595, 3.0], atol=1e-5)

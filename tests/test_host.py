@@ -19,7 +19,7 @@ def test_library_exports_every_symbol_of_the_header():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mpcb_version() == 101
+    assert lib.mpcb_version() == 102
 
 
 def test_cfg_struct_layout_matches_the_header_field_order():
@@ -111,7 +111,11 @@ def test_initialize_constraints_lengths_and_values(tmp_path, monkeypatch):
     md = MPC_CBF_optimize_dyn.MPC_optimize()
     lbg, ubg, lbx, ubx = md.initialize_constraints()
     assert (len(lbg), len(lbx)) == (455, 406)
-    assert lbg[18:20] == [pytest.approx(-0.008726646259971648), pytest.approx(-0.3)] and lbg[-1] == 1
+    # as shipped (default): the rate pair sits at 12,13 (on the x/y defect of stage 1); aligned: at the rate rows 18,19
+    assert lbg[12:14] == [pytest.approx(-0.008726646259971648), pytest.approx(-0.3)] and lbg[18:20] == [0.0, 0.0] and lbg[-1] == 1
+    md.dyn_bounds = "aligned"
+    lbg, ubg, lbx, ubx = md.initialize_constraints()
+    assert lbg[18:20] == [pytest.approx(-0.008726646259971648), pytest.approx(-0.3)] and lbg[12:14] == [0.0, 0.0] and lbg[-1] == 1
     mk = MPC_optimize_kin.MPC_optimize()
     lbg, ubg, lbx, ubx = mk.initialize_constraints()
     assert lbg == 0.0 and ubg == 0.0 and len(lbx) == 304

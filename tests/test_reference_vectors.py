@@ -112,7 +112,9 @@ def test_host_classes_reproduce_the_reference_attributes_lists_and_g(ref):
     md = MPC_CBF_optimize_dyn.MPC_optimize()
     lbg, ubg, lbx, ubx = md.initialize_constraints()
     assert np.array_equal(lbx, ref["dyn_lbx"]) and np.array_equal(ubx, ref["dyn_ubx"])
-    assert np.array_equal(np.sort(lbg), np.sort(ref["dyn_lbg"]))  # aligned order, see the test above
+    assert np.array_equal(lbg, ref["dyn_lbg"]) and np.array_equal(ubg, ref["dyn_ubg"])  # exactly as shipped (default)
+    md.dyn_bounds = "aligned"
+    assert np.array_equal(np.sort(md.initialize_constraints()[0]), np.sort(ref["dyn_lbg"]))
     g = md._g_of(ref["dyn_z"][2], ref["dyn_p"][2], md._obs_array(ref["dyn_obs"]))
     assert np.max(np.abs(g - ref["dyn_g"][2])) <= 1e-11
     q = ref["dyn_rhs_in"]
