@@ -26,7 +26,7 @@ extern "C" {
 
 #define MPCB_VERSION 102 /* 0.1.2: cfg gained ref_mode, cbf_gamma (0.1.1) and dyn_rows (0.1.2) */
 #define MPCB_NMAX 128    /* maximum horizon N */
-#define MPCB_MMAX 3      /* maximum obstacles per scenario in this build (the mains carry a commented 3-obstacle list) */
+#define MPCB_MMAX 4      /* maximum obstacles per scenario in this build (the mains carry a commented 3-obstacle list) */
 
 /* vehicle model: replaces the CasADi `rhs` of PKG/MPC_CBF_optimize_kin.py:153-156 (KIN) and
  * PKG/MPC_CBF_optimize_dyn.py:156-170 (DYN) */

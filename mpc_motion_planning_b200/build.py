@@ -16,7 +16,7 @@ SRCS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HER
     os.path.join(HERE, "..", "include", "mpcb200.h")
 ]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
-N_FAMILIES = 10  # csrc/mpcb_variants.cu: 8 kinematic families + the dynamic bicycle (rows aligned, rows as shipped)
+N_FAMILIES = 12  # csrc/mpcb_variants.cu: 10 kinematic families + the dynamic bicycle (rows aligned, rows as shipped)
 
 
 def stale() -> bool:

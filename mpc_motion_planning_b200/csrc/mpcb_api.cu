@@ -62,9 +62,11 @@ bool select_variant(const mpcb_cfg &c, Variant &v) {
     if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 1) { v = variant_kin_1_1_1(c.N); return true; }
     if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 2) { v = variant_kin_1_2_1(c.N); return true; }
     if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 3) { v = variant_kin_1_3_1(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_ELLIPSE && c.n_rate == 1 && M == 4) { v = variant_kin_1_4_1(c.N); return true; }
     if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 1) { v = variant_kin_1_1_3(c.N); return true; }
     if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 2) { v = variant_kin_1_2_3(c.N); return true; }
     if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 3) { v = variant_kin_1_3_3(c.N); return true; }
+    if (c.obs_mode == MPCB_OBS_DCBF && c.n_rate == 1 && M == 4) { v = variant_kin_1_4_3(c.N); return true; }
   }
   return false;
 }

@@ -164,8 +164,8 @@ struct KinLayout {
   static constexpr int HUU = R14, EE = R14 + 2, GU = R14 + 4, TK = R14 + 6;
   static constexpr int KX = R14, KW = R14 + 8, KK = R14 + 12;
   static constexpr int DSR = R14, LRP = DSR + NR, DSO = LRP + NR, LOP = DSO + MO;
-  static constexpr int CDEFT = R14 + 8;  // defects of the line-search trial point (moved to CDEF on acceptance)
-  static_assert(2 * NR + 2 * MO <= 8, "slack steps and trial defects must fit the gain region");
+  static constexpr int CDEFT = R14 + 10;  // defects of the line-search trial point (moved to CDEF on acceptance)
+  static_assert(2 * NR + 2 * MO <= 10, "slack steps and trial defects must fit the gain region");
   static constexpr int NSH = R14 + 14 + (GS ? 0 : NX + 2);
   // stage-major storage: element (field, k) lives at k*NF + field.  NF is odd so that the
   // stage-parallel phases (lane = stage, stride NF doubles) touch 16 distinct even banks per

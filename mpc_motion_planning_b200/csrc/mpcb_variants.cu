@@ -2,16 +2,16 @@
 #include "mpcb_variants.h"
 
 #ifndef MPCB_FAMILY
-#error "compile with -DMPCB_FAMILY=0..9"
+#error "compile with -DMPCB_FAMILY=0..11"
 #endif
 
-#if MPCB_FAMILY >= 8
+#if MPCB_FAMILY == 8 || MPCB_FAMILY == 9
 #include "mpcb_dyn_kernel.cuh"
 #endif
 
 namespace mpcb {
 
-#if MPCB_FAMILY < 8
+#if MPCB_FAMILY < 8 || MPCB_FAMILY >= 10
 
 template <int NR, int MO, int OBS, int W, bool GS>
 static cudaError_t launch_kin(const KParams &p, int grid, size_t smem, cudaStream_t st) {
@@ -63,6 +63,10 @@ Variant variant_kin_1_1_3(int N) { return make_kin_variant<1, 1, 3>(N); }
 Variant variant_kin_1_2_3(int N) { return make_kin_variant<1, 2, 3>(N); }
 #elif MPCB_FAMILY == 7
 Variant variant_kin_1_3_3(int N) { return make_kin_variant<1, 3, 3>(N); }
+#elif MPCB_FAMILY == 10
+Variant variant_kin_1_4_1(int N) { return make_kin_variant<1, 4, 1>(N); }
+#elif MPCB_FAMILY == 11
+Variant variant_kin_1_4_3(int N) { return make_kin_variant<1, 4, 3>(N); }
 #endif
 
 #else  // MPCB_FAMILY 8, 9: dynamic bicycle, rows aligned / rows as shipped

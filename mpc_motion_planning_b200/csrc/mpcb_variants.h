@@ -29,6 +29,8 @@ Variant variant_kin_1_3_1(int N);
 Variant variant_kin_1_1_3(int N);
 Variant variant_kin_1_2_3(int N);
 Variant variant_kin_1_3_3(int N);
+Variant variant_kin_1_4_1(int N);
+Variant variant_kin_1_4_3(int N);
 Variant variant_dyn(int N);
 Variant variant_dyn_shipped(int N);  // dyn rows paired with the bound lists as shipped (cfg.dyn_rows)
 

@@ -677,9 +677,9 @@ def test_cuda_reaches_the_kkt_points_verified_on_the_reference_expressions(dev, 
     assert abs(g["cost"][0] - float(ref[f"{tag}_kkt_f_ref"])) <= COST_RTOL * float(ref[f"{tag}_kkt_f_ref"])
 
 
-@pytest.mark.parametrize("gamma", [None, 0.5])
-def test_three_obstacles(dev, gamma):
-    """M = MPCB_MMAX = 3 (the mains carry a commented three-obstacle list, PKG/main_cbf_kin_c_sim.py:52-53)."""
+@pytest.mark.parametrize("gamma,M", [(None, 3), (0.5, 3), (None, 4), (0.5, 4)])
+def test_three_and_four_obstacles(dev, gamma, M):
+    """M up to MPCB_MMAX = 4 (the mains carry a commented three-obstacle list, PKG/main_cbf_kin_c_sim.py:52-53)."""
     from mpc_motion_planning_b200 import scenarios
     from mpc_motion_planning_b200.solver import BatchSolver
     from oracle import c_oracle
@@ -690,9 +690,11 @@ def test_three_obstacles(dev, gamma):
     _, _, oc = scenarios.kin_cbf_moving(B, seed=123)
     ob[:, :, :, 0] += 60.0
     oc[:, :, :, 0] += 120.0
-    obs3 = np.concatenate([oa, ob, oc], axis=1)
-    g = _gpu(BatchSolver("kin_cbf_pre", M=3, cbf_gamma=gamma), dev, x0, xs, obs3)
-    u0, cost, st, it, _ = c_oracle.solve_batch(c_oracle.make_cfg("kin_cbf_pre", M=3, cbf_gamma=gamma), x0, xs, obs3, nthreads=os.cpu_count())
+    _, _, od = scenarios.kin_cbf_moving(B, seed=321)
+    od[:, :, :, 0] += 180.0
+    obs3 = np.concatenate([oa, ob, oc, od][:M], axis=1)
+    g = _gpu(BatchSolver("kin_cbf_pre", M=M, cbf_gamma=gamma), dev, x0, xs, obs3)
+    u0, cost, st, it, _ = c_oracle.solve_batch(c_oracle.make_cfg("kin_cbf_pre", M=M, cbf_gamma=gamma), x0, xs, obs3, nthreads=os.cpu_count())
     _check(g, u0, cost, st, 0.5, 0.93)
 
 
