@@ -801,3 +801,18 @@ def test_dyn_drop_in_class_solves_what_it_is_given(dev, tmp_path, monkeypatch):
     U = res["as_shipped"][1][: 2 * N].reshape(N, 2)
     assert np.abs(U - U[0]).max() <= 1e-9 and np.allclose(U[0], [0.00803901, 3.0], atol=1e-6)
     assert np.allclose(res["aligned"][1][:2], [0.09392595, 3.0], atol=1e-5)
+
+
+def test_plain_c_example_runs(dev, tmp_path):
+    """examples/batch_solve.c: a C program against include/mpcb200.h, no Python in the loop."""
+    import subprocess
+
+    from mpc_motion_planning_b200 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "batch_solve")
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "batch_solve.c"), "-L",
+                    os.path.dirname(_lib.SO_PATH), "-lmpcb200", "-lm", "-o", exe], check=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(_lib.SO_PATH) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    run = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
+    assert run.returncode == 0 and run.stdout.strip().endswith("OK"), run.stdout + run.stderr

@@ -208,3 +208,25 @@ def test_install_reference_names_registers_flat_modules():
     assert hasattr(sys.modules["MPC_optimize_kin"], "MPC_optimize")
     for name in pkg.REFERENCE_MODULES:
         sys.modules.pop(name, None)
+
+
+def test_header_and_example_compile_as_plain_c(tmp_path):
+    """include/mpcb200.h is a C header (no C++ in the boundary): the plain-C example compiles with -std=c11
+    -pedantic and links against the library without a GPU."""
+    import subprocess
+
+    from mpc_motion_planning_b200 import _lib
+
+    _lib.load()
+    exe = str(tmp_path / "batch_solve")
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "batch_solve.c"), "-L", os.path.dirname(_lib.SO_PATH), "-lmpcb200", "-lm", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # without a device the program must fail loudly at mpcb_create (no CPU fallback)
+    import torch
+
+    if not torch.cuda.is_available():
+        env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(_lib.SO_PATH) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        run = subprocess.run([exe], capture_output=True, text=True, env=env)
+        assert run.returncode == 2 and "mpcb_create" in run.stderr
