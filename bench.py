@@ -274,7 +274,7 @@ def main():
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"kin-CBF static obstacle MPC, N={N_HORIZON}, M=1, B={B}/GPU (BASELINE configs[1])",
-                       "start": "zero controls, Euler roll-out states", "mu_init": 100.0, "tol": 1e-8, "max_iter": 100,
+                       "start": "zero controls, Euler roll-out states", "mu_init": float(solver.cfg.mu_init), "tol": 1e-8, "max_iter": 100,
                        "inputs": "x0 [B][4], xs [B][4], obstacle rows [B][1][6] as optimize_problem takes them",
                        "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"scenario-sharded x{world}"},
             "solver": {"converged_frac": float((status <= 1).mean()), "acceptable_frac": float((status == 1).mean()), "mean_iters": float(iters.mean()),

@@ -40,7 +40,7 @@ int main(void) {
   c.obs_lo = 0.0;
   c.ego_hl = 4.8 / 2; c.ego_hw = 1.8 / 2; c.safe_l = 1.0; c.safe_w = 0.5; /* :220-225 */
   c.Veh_l = 2.6;
-  c.tol = 1e-8; c.mu_init = 100.0; c.bound_relax = 1e-8;
+  c.tol = 1e-8; c.mu_init = 30.0; c.bound_relax = 1e-8;
 
   mpcb_handle *h = NULL;
   int rc = mpcb_create(&c, &h);

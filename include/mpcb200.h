@@ -104,7 +104,7 @@ typedef struct mpcb_cfg {
   double dyn_sx, dyn_sy;              /* safe_X, safe_Y of the dyn row (_dyn.py:240-241) */
   double Veh_l, Veh_lf, Veh_lr, Veh_m, Veh_Iz, aopt_f, aopt_r, Fymax_f, Fymax_r;
   double tol;           /* ipopt.tol (default 1e-8) */
-  double mu_init;       /* initial barrier parameter (IPOPT default 0.1; this library's default 100) */
+  double mu_init;       /* initial barrier parameter (IPOPT default 0.1; this library's default 30) */
   double bound_relax;   /* ipopt.bound_relax_factor (1e-8) */
   int32_t obs_input;    /* MPCB_OBS_TRAJECTORY (default), MPCB_OBS_INITIAL or MPCB_OBS_STATIC */
   int32_t ref_mode;     /* MPCB_REF_TERMINAL (default) or MPCB_REF_TRAJECTORY */

@@ -142,7 +142,7 @@ class MPCOptimizeBase:
         # solver options: IPOPT's as passed by the reference (:252-253) and this library's own
         self.max_iter = 100
         self.tol = 1e-8
-        self.mu_init = 100.0
+        self.mu_init = 30.0
         self.init = "as_given"  # the CasADi call starts IPOPT at x0= exactly
         # Two switches the reference keeps as locals of optimize_problem (kin-CBF modules):
         #   aa = 0.0      weight of ref_state in the stage cost target          (:194-197)

@@ -46,7 +46,7 @@ def horizon_steps(config: dict) -> int:
 
 
 def make_cfg(kind: str, config: dict, N: int | None = None, M: int = 1, weights: Weights | None = None,
-             init_mode: int = _lib.INIT_ROLLOUT, mu_init: float = 100.0, max_iter: int = 100, tol: float = 1e-8,
+             init_mode: int = _lib.INIT_ROLLOUT, mu_init: float = 30.0, max_iter: int = 100, tol: float = 1e-8,
              bounds: dict | None = None, obs_input: int = _lib.OBS_TRAJECTORY, cbf_gamma: float | None = None,
              ref_mode: int = _lib.REF_TERMINAL, dyn_rows: int = _lib.DYN_ROWS_ALIGNED) -> _lib.MpcbCfg:
     """Fill an mpcb_cfg from the YAML dict with the reference's hard-coded constants.

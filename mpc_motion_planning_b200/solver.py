@@ -27,7 +27,7 @@ class BatchSolver:
     """One handle on the current CUDA device for one NLP kind / horizon / obstacle count."""
 
     def __init__(self, kind: str = "kin_cbf_pre", config: dict | None = None, N: int | None = None, M: int = 1,
-                 init: str = "rollout", mu_init: float = 100.0, max_iter: int = 100, tol: float = 1e-8,
+                 init: str = "rollout", mu_init: float = 30.0, max_iter: int = 100, tol: float = 1e-8,
                  weights=None, bounds: dict | None = None, obs_input: str = "trajectory", cbf_gamma: float | None = None,
                  ref: str = "terminal", cfg_overrides: dict | None = None, dyn_bounds: str = "aligned"):
         self.lib = _lib.load()

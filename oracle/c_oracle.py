@@ -66,7 +66,7 @@ def lib():
 
 
 def make_cfg(kind: str, N: int | None = None, M: int = 1, params: Params | None = None, init_mode: int = 1,
-             mu_init: float = 100.0, max_iter: int = 100, tol: float = 1e-8, cbf_gamma: float | None = None,
+             mu_init: float = 30.0, max_iter: int = 100, tol: float = 1e-8, cbf_gamma: float | None = None,
              ref_trajectory: bool = False, rows_as_shipped: bool = False) -> OrcCfg:
     p = params or Params()
     w = reference_weights(kind)

@@ -34,7 +34,7 @@ ST_CONVERGED, ST_ACCEPTABLE, ST_MAXITER, ST_INFEASIBLE, ST_NAN = 0, 1, 2, 3, 4
 class IpmOptions:
     tol: float = 1e-8
     max_iter: int = 100
-    mu_init: float = 100.0  # IPOPT default is 0.1; see DESIGN.md (algorithm choices)
+    mu_init: float = 30.0  # IPOPT default is 0.1; see DESIGN.md (algorithm choices)
     kappa_eps: float = 10.0
     kappa_mu: float = 0.2
     theta_mu: float = 1.5

@@ -16,7 +16,7 @@ def compare(kind, gen, B, **kw):
     out = s.solve(t(x0), t(xs), t(obs) if obs.shape[1] else None, return_z=True)
     torch.cuda.synchronize()
     u0 = out['u0'].cpu().numpy(); cost = out['cost'].cpu().numpy(); st = out['status'].cpu().numpy(); it = out['iters'].cpu().numpy()
-    cfg = c_oracle.make_cfg(kind, N=s.N, M=max(s.M, 1), mu_init=kw.get('mu_init', 100.0))
+    cfg = c_oracle.make_cfg(kind, N=s.N, M=max(s.M, 1), mu_init=kw.get('mu_init', 30.0))
     ou0, ocost, ost, oit, _ = c_oracle.solve_batch(cfg, x0, xs, obs if obs.shape[1] else None, nthreads=os.cpu_count())
     same_st = (st <= 1) == (ost <= 1)
     both = (st <= 1) & (ost <= 1)
