@@ -110,17 +110,19 @@ struct DynSolver {
   __device__ __forceinline__ void obs_row(int k, double px, double py, double &d, double &gx, double &gy, double &hxx, double &hxy,
                                           double &hyy) {
     double dx = px - at(L::OCX, k), dy = py - at(L::OCY, k);
-    double a = 1.0 / (p.dyn_sx * p.dyn_sx), b = 1.0 / (p.dyn_sy * p.dyn_sy);
+    double a = 1.0 / (p.dyn_sx * p.dyn_sx), b = 1.0 / (p.dyn_sy * p.dyn_sy);  // exact for the reference's 4 and 1
     double e = dx * dx * a + dy * dy * b - 1.0;
     double q = e > 0.0 ? sqrt(e) : nan("");
     double ex = 2 * dx * a, ey = 2 * dy * b;
     d = q;
-    gx = ex / (2 * q);
-    gy = ey / (2 * q);
+    const double rq = fast_rcp(q);  // q > 0 or NaN (inside the ellipse), which propagates
+    gx = 0.5 * ex * rq;
+    gy = 0.5 * ey * rq;
     double q3 = 4 * q * q * q;
-    hxx = a / q - ex * ex / q3;
-    hxy = -ex * ey / q3;
-    hyy = b / q - ey * ey / q3;
+    const double rq3 = fast_rcp(q3);
+    hxx = a * rq - ex * ex * rq3;
+    hxy = -ex * ey * rq3;
+    hyy = b * rq - ey * ey * rq3;
   }
 
   __device__ __forceinline__ void eval_point(double alpha, bool fresh, double &theta, double &fobj, double &bar, double &lin) {
@@ -345,14 +347,14 @@ struct DynSolver {
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
         int i = bx(b);
-        double rl = 1.0 / (xk[i] - p.x_lo[i]), rh = 1.0 / (p.x_hi[i] - xk[i]);
+        double rl = fast_rcp(xk[i] - p.x_lo[i]), rh = fast_rcp(p.x_hi[i] - xk[i]);
         Hxx[i][i] += at(L::ZLX + b, k) * rl + at(L::ZUX + b, k) * rh;
         gx[i] += mu * (rh - rl);
       }
       {
         double d, ox, oy, hxx, hxy, hyy;
         obs_row(k, xk[0], xk[1], d, ox, oy, hxx, hxy, hyy);
-        double s = at(L::SO, k), rg = 1.0 / (s - p.obs_lo);
+        double s = at(L::SO, k), rg = fast_rcp(s - p.obs_lo);
         double D = at(L::VLO, k) * rg + dw;
         double gs = -mu * rg + MPCB_KAPPA_D * mu;
         double lo = at(L::LO, k);
@@ -382,7 +384,7 @@ struct DynSolver {
             hd += sigma * 2 * p.DR[i];
             g += sigma * 2 * p.DR[i] * uk[i];
           }
-          double rl = 1.0 / (uk[i] - p.u_lo[i]), rh = 1.0 / (p.u_hi[i] - uk[i]);
+          double rl = fast_rcp(uk[i] - p.u_lo[i]), rh = fast_rcp(p.u_hi[i] - uk[i]);
           hd += at(L::ZLU + i, k) * rl + at(L::ZUU + i, k) * rh;
           g += mu * (rh - rl);
           at(L::HUU + i, k) = hd;
@@ -399,7 +401,7 @@ struct DynSolver {
 #pragma unroll
           for (int r = 0; r < NR; r++) {
             double s = at(L::SR + r, k);
-            double rl = 1.0 / (s - p.rate_lo[r]), rh = 1.0 / (p.rate_hi[r] - s);
+            double rl = fast_rcp(s - p.rate_lo[r]), rh = fast_rcp(p.rate_hi[r] - s);
             double D = at(L::VLR + r, k) * rl + at(L::VUR + r, k) * rh + dw;
             double gs = mu * (rh - rl);
             if (SHP) {  // curvature and gradient of the relaxation slack (the stage input), and e_k
@@ -498,7 +500,7 @@ struct DynSolver {
         const double h00 = P[pidx6(0, 0)] + Ed, h01 = P[pidx6(0, 1)], h11 = P[pidx6(1, 1)] + Ea;
         const double dets = h00 * h11 - h01 * h01;
         if (!(h00 > 0.0) || !(dets > 0.0) || !isfinite(dets)) { ok = false; break; }
-        const double ids = 1.0 / dets;
+        const double ids = fast_rcp(dets);
         const double i00 = h11 * ids, i01 = -h01 * ids, i11 = h00 * ids;
         double Ks[2][NX], Kw2[2][2], ks[2];
 #pragma unroll
@@ -545,7 +547,7 @@ struct DynSolver {
       }
       const double det = Fuu[0] * Fuu[2] - Fuu[1] * Fuu[1];
       if (!(Fuu[0] > 0.0) || !(det > 0.0) || !isfinite(det)) { ok = false; break; }
-      const double id = 1.0 / det;
+      const double id = fast_rcp(det);
       const double idd = Fuu[2] * id, ida = -Fuu[1] * id, iaa = Fuu[0] * id;
       double Kd[NX], Ka[NX];
 #pragma unroll
@@ -742,9 +744,9 @@ struct DynSolver {
     if (SHP) tied_control_multipliers();
     double rp = 0.0, rd = 0.0, gd = 0.0;
 #define MPCB_LOWER(rgap, dv, z) do { double dz_ = -(z) + (mu - (z) * (dv)) * (rgap); \
-    rp = fmax(rp, -(dv) * (rgap)); rd = fmax(rd, -dz_ / (z)); } while (0)
+    rp = fmax(rp, -(dv) * (rgap)); rd = fmax(rd, -dz_ * fast_rcp(z)); } while (0)
 #define MPCB_UPPER(rgap, dv, z) do { double dz_ = -(z) + (mu + (z) * (dv)) * (rgap); \
-    rp = fmax(rp, (dv) * (rgap)); rd = fmax(rd, -dz_ / (z)); } while (0)
+    rp = fmax(rp, (dv) * (rgap)); rd = fmax(rd, -dz_ * fast_rcp(z)); } while (0)
 #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
       double xk[NX], dx[NX];
@@ -757,7 +759,7 @@ struct DynSolver {
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
         int i = bx(b);
-        double rl = 1.0 / (xk[i] - p.x_lo[i]), rh = 1.0 / (p.x_hi[i] - xk[i]);
+        double rl = fast_rcp(xk[i] - p.x_lo[i]), rh = fast_rcp(p.x_hi[i] - xk[i]);
         gd += mu * (rh - rl) * dx[i];
         MPCB_LOWER(rl, dx[i], at(L::ZLX + b, k));
         MPCB_UPPER(rh, dx[i], at(L::ZUX + b, k));
@@ -769,7 +771,7 @@ struct DynSolver {
           double uk = at(L::U + i, k), du = at(L::DU + i, k);
           double um = k > 0 ? at(L::U + i, k - 1) : 0.0;
           double up = k + 1 <= N - 1 ? at(L::U + i, k + 1) : 0.0;
-          double rl = 1.0 / (uk - p.u_lo[i]), rh = 1.0 / (p.u_hi[i] - uk);
+          double rl = fast_rcp(uk - p.u_lo[i]), rh = fast_rcp(p.u_hi[i] - uk);
           gd += (sigma * grad_u(k, i, uk, um, up) + mu * (rh - rl)) * du;
           MPCB_LOWER(rl, du, at(L::ZLU + i, k));
           MPCB_UPPER(rh, du, at(L::ZUU + i, k));
@@ -779,7 +781,7 @@ struct DynSolver {
 #pragma unroll
         for (int r = 0; r < NR; r++) {
           double s = at(L::SR + r, k);
-          double rl = 1.0 / (s - p.rate_lo[r]), rh = 1.0 / (p.rate_hi[r] - s);
+          double rl = fast_rcp(s - p.rate_lo[r]), rh = fast_rcp(p.rate_hi[r] - s);
           double vl = at(L::VLR + r, k), vu = at(L::VUR + r, k);
           double D = vl * rl + vu * rh + dw;
           double gs = mu * (rh - rl);
@@ -802,7 +804,7 @@ struct DynSolver {
       {
         double d, ox, oy, hxx, hxy, hyy;
         obs_row(k, xk[0], xk[1], d, ox, oy, hxx, hxy, hyy);
-        double s = at(L::SO, k), rg = 1.0 / (s - p.obs_lo), vl = at(L::VLO, k);
+        double s = at(L::SO, k), rg = fast_rcp(s - p.obs_lo), vl = at(L::VLO, k);
         double D = vl * rg + dw;
         double gs = -mu * rg + MPCB_KAPPA_D * mu;
         double ds = ox * dx[0] + oy * dx[1] + (d - s);
@@ -841,12 +843,12 @@ struct DynSolver {
       for (int b = 0; b < NBX; b++) {
         int i = bx(b);
         double x = at(L::X + i, k), dx = at(L::DX + i, k);
-        double rl = 1.0 / (x - p.x_lo[i]), rh = 1.0 / (p.x_hi[i] - x);
+        double rl = fast_rcp(x - p.x_lo[i]), rh = fast_rcp(p.x_hi[i] - x);
         double zl = at(L::ZLX + b, k), zu = at(L::ZUX + b, k);
         double dzl = -zl + (mu - zl * dx) * rl, dzu = -zu + (mu + zu * dx) * rh;
         double xn = x + a * dx;
-        at(L::ZLX + b, k) = clampz(zl + ad * dzl, mu, 1.0 / (xn - p.x_lo[i]));
-        at(L::ZUX + b, k) = clampz(zu + ad * dzu, mu, 1.0 / (p.x_hi[i] - xn));
+        at(L::ZLX + b, k) = clampz(zl + ad * dzl, mu, fast_rcp(xn - p.x_lo[i]));
+        at(L::ZUX + b, k) = clampz(zu + ad * dzu, mu, fast_rcp(p.x_hi[i] - xn));
       }
 #pragma unroll
       for (int i = 0; i < NX; i++) at(L::X + i, k) += a * at(L::DX + i, k);
@@ -854,37 +856,37 @@ struct DynSolver {
 #pragma unroll
         for (int i = 0; i < 2; i++) {
           double u = at(L::U + i, k), du = at(L::DU + i, k);
-          double rl = 1.0 / (u - p.u_lo[i]), rh = 1.0 / (p.u_hi[i] - u);
+          double rl = fast_rcp(u - p.u_lo[i]), rh = fast_rcp(p.u_hi[i] - u);
           double zl = at(L::ZLU + i, k), zu = at(L::ZUU + i, k);
           double dzl = -zl + (mu - zl * du) * rl, dzu = -zu + (mu + zu * du) * rh;
           double un = u + a * du;
           at(L::U + i, k) = un;
-          at(L::ZLU + i, k) = clampz(zl + ad * dzl, mu, 1.0 / (un - p.u_lo[i]));
-          at(L::ZUU + i, k) = clampz(zu + ad * dzu, mu, 1.0 / (p.u_hi[i] - un));
+          at(L::ZLU + i, k) = clampz(zl + ad * dzl, mu, fast_rcp(un - p.u_lo[i]));
+          at(L::ZUU + i, k) = clampz(zu + ad * dzu, mu, fast_rcp(p.u_hi[i] - un));
         }
       }
       if (has_rate(k)) {
 #pragma unroll
         for (int r = 0; r < NR; r++) {
           double s = at(L::SR + r, k), ds = at(L::DSR + r, k);
-          double rl = 1.0 / (s - p.rate_lo[r]), rh = 1.0 / (p.rate_hi[r] - s);
+          double rl = fast_rcp(s - p.rate_lo[r]), rh = fast_rcp(p.rate_hi[r] - s);
           double vl = at(L::VLR + r, k), vu = at(L::VUR + r, k);
           double dvl = -vl + (mu - vl * ds) * rl, dvu = -vu + (mu + vu * ds) * rh;
           double sn = s + a * ds;
           at(L::SR + r, k) = sn;
-          at(L::VLR + r, k) = clampz(vl + ad * dvl, mu, 1.0 / (sn - p.rate_lo[r]));
-          at(L::VUR + r, k) = clampz(vu + ad * dvu, mu, 1.0 / (p.rate_hi[r] - sn));
+          at(L::VLR + r, k) = clampz(vl + ad * dvl, mu, fast_rcp(sn - p.rate_lo[r]));
+          at(L::VUR + r, k) = clampz(vu + ad * dvu, mu, fast_rcp(p.rate_hi[r] - sn));
           double l = at(L::LR + r, k);
           at(L::LR + r, k) = l + a * (at(L::LRP + r, k) - l);
         }
       }
       {
         double s = at(L::SO, k), ds = at(L::DSO, k);
-        double rg = 1.0 / (s - p.obs_lo), vl = at(L::VLO, k);
+        double rg = fast_rcp(s - p.obs_lo), vl = at(L::VLO, k);
         double dvl = -vl + (mu - vl * ds) * rg;
         double sn = s + a * ds;
         at(L::SO, k) = sn;
-        at(L::VLO, k) = clampz(vl + ad * dvl, mu, 1.0 / (sn - p.obs_lo));
+        at(L::VLO, k) = clampz(vl + ad * dvl, mu, fast_rcp(sn - p.obs_lo));
         double l = at(L::LO, k);
         at(L::LO, k) = l + a * (at(L::LOP, k) - l);
       }
