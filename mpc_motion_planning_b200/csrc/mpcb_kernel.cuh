@@ -264,6 +264,7 @@ struct KinSolver {
   // accepted trial point needs no second evaluation.
   __device__ __forceinline__ void eval_point(double alpha, bool fresh, double &theta, double &fobj, double &bar, double &lin) {
     const int cdst = fresh ? L::CDEF : L::CDEFT;
+    const double rL = 1.0 / p.Veh_l;  // one division per call instead of three per stage
     double th = 0, fo = 0, br = 0, ln = 0;
     #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
@@ -287,15 +288,15 @@ struct KinSolver {
         double f[NX];
         f[0] = xk[3] * c;                 // PKG/MPC_CBF_optimize_kin.py:153-156
         f[1] = xk[3] * s;
-        f[2] = xk[3] * t / p.Veh_l;
+        f[2] = xk[3] * t * rL;
         f[3] = uk[1];
         {
           at(L::JAC + 0, k) = p.T * (-xk[3] * s);                       // a02 = T d f0/d phi
           at(L::JAC + 1, k) = p.T * c;                                  // a03 = T d f0/d v
           at(L::JAC + 2, k) = p.T * (xk[3] * c);                        // a12
           at(L::JAC + 3, k) = p.T * s;                                  // a13
-          at(L::JAC + 4, k) = p.T * (t / p.Veh_l);                      // a23
-          at(L::JAC + 5, k) = p.T * (xk[3] * (1.0 + t * t) / p.Veh_l);  // b2  = T d f2/d delta
+          at(L::JAC + 4, k) = p.T * (t * rL);                      // a23
+          at(L::JAC + 5, k) = p.T * (xk[3] * (1.0 + t * t) * rL);  // b2  = T d f2/d delta
         }
 #pragma unroll
         for (int i = 0; i < NX; i++) {
@@ -1036,7 +1037,7 @@ struct KinSolver {
         if (k < N) {
           double u0_ = at(L::U + 0, k), u1_ = at(L::U + 1, k), s, c, t;
           d_trig(x[2], u0_, &s, &c, &t);
-          double f0 = x[3] * c, f1 = x[3] * s, f2 = x[3] * t / p.Veh_l;
+          double f0 = x[3] * c, f1 = x[3] * s, f2 = x[3] * t * (1.0 / p.Veh_l);  // same expression as eval_point
           x[0] = x[0] + p.T * f0;
           x[1] = x[1] + p.T * f1;
           x[2] = x[2] + p.T * f2;
