@@ -478,9 +478,10 @@ struct KinSolver {
 
   __device__ __forceinline__ double kkt_error(const Kkt &o, double mu, double &co) const {
     co = p.n_bm > 0 ? fmax(fabs(o.cmax - mu), fabs(o.cmin - mu)) : 0.0;
-    double s_d = fmax(MPCB_S_MAX, (o.sum_lam + o.sum_z) / fmax(1.0, (double)(p.n_eq + p.n_bm))) / MPCB_S_MAX;
-    double s_c = fmax(MPCB_S_MAX, o.sum_z / fmax(1.0, (double)p.n_bm)) / MPCB_S_MAX;
-    return fmax(fmax(o.dual / s_d, o.prim), co / s_c);
+    // 1/s_d and 1/s_c of IPOPT's error scaling; the denominators are positive, fast_rcp is exact to ~1 ulp
+    double rs_d = MPCB_S_MAX * fast_rcp(fmax(MPCB_S_MAX, (o.sum_lam + o.sum_z) * fast_rcp(fmax(1.0, (double)(p.n_eq + p.n_bm)))));
+    double rs_c = MPCB_S_MAX * fast_rcp(fmax(MPCB_S_MAX, o.sum_z * fast_rcp(fmax(1.0, (double)p.n_bm))));
+    return fmax(fmax(o.dual * rs_d, o.prim), co * rs_c);
   }
 
   // ---------------------------------------------------------------- condensed QP (stage parallel)
@@ -888,8 +889,8 @@ struct KinSolver {
 #undef MPCB_UPPER
     rp = warp_max(rp);
     rd = warp_max(rd);
-    a_pr = rp > tau ? tau / rp : 1.0;
-    a_du = rd > tau ? tau / rd : 1.0;
+    a_pr = rp > tau ? tau * fast_rcp(rp) : 1.0;
+    a_du = rd > tau ? tau * fast_rcp(rd) : 1.0;
     gd_out = warp_sum(gd);
     __syncwarp();
   }
