@@ -33,9 +33,9 @@ N_HORIZON = 50
 FLOP_PER_ITER = 72.4e3
 BYTES_PER_SOLVE_MIN = 912  # x0, xs, per-step obstacle (x,y)+(l,w) in; u0, cost, status, iters out
 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of kin_solve_kernel<1,1,1>
-# at B = 7104 (profiles/r01_final2_solve_kernel_kin_cbf_B7104.txt): 23.08 MB + 12.93 MB -> per scenario
+# at B = 7104 (profiles/r01_final3_solve_kernel_kin_cbf_B7104.txt): 22.70 MB + 13.03 MB -> per scenario
 # (inputs 2.5 KB + the part of the iterate slab that falls out of L2; L2 hit rate 96.6 %)
-DRAM_BYTES_PER_SOLVE_NCU = (23083008 + 12932096) / 7104
+DRAM_BYTES_PER_SOLVE_NCU = (22704640 + 13032704) / 7104
 
 
 def _peaks():
@@ -285,7 +285,7 @@ def main():
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": float(peak.value), "unit": "TFLOP/s",
                          "frac": ach_tf / float(peak.value) if peak.value > 0 else None,
                          "traffic": int(B * DRAM_BYTES_PER_SOLVE_NCU),
-                         "traffic_source": "ncu --set full capture at B=7104 scaled to this batch (profiles/r01_final2_*)",
+                         "traffic_source": "ncu --set full capture at B=7104 scaled to this batch (profiles/r01_final3_*)",
                          "peak_source": "DFMA micro-benchmark measured in this run (mpcb_fp64_peak_tflops)",
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "peak_source": hbm_src + " MEASURED_PEAKS.json hbm_gbs"}},
