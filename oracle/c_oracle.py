@@ -42,11 +42,29 @@ class OrcInfo(C.Structure):
                 ("status", C.c_int32), ("iters", C.c_int32), ("n_reg", C.c_int32), ("n_backtrack", C.c_int32)]
 
 
+def _host_tag() -> str:
+    """fingerprint of the host CPU's instruction-set flags: the library is built with -march=native and travels
+    with the repo snapshot, so it must be rebuilt on a machine with a different CPU"""
+    import hashlib
+
+    try:
+        with open("/proc/cpuinfo") as fh:
+            flags = next((line for line in fh if line.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return hashlib.sha1(flags.encode()).hexdigest()
+
+
 def build(force: bool = False) -> str:
     so = os.path.join(HERE, "liboracle.so")
+    tag_file = so + ".host"
     srcs = [os.path.join(HERE, f) for f in ("mpc_oracle.c", "mpc_oracle.h", "dyn_model_gen.h")]
-    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+    tag = _host_tag()
+    same_host = os.path.exists(tag_file) and open(tag_file).read().strip() == tag
+    if force or not os.path.exists(so) or not same_host or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+        with open(tag_file, "w") as fh:
+            fh.write(tag + "\n")
     return so
 
 
