@@ -168,6 +168,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries the one JSON line only: NCCL prints its version banner on fd 1 at the first collective, so
+    # everything else that writes to fd 1 is sent to stderr and the line goes out through a saved descriptor
+    out_stream = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
@@ -209,7 +214,11 @@ def main():
     t_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     print(f"[bench rank {rank}] device ms/step: {sum(step_ms) / K:.3f} (min {min(step_ms):.3f}, max {max(step_ms):.3f}); "
           f"mean iterations {float(out['iters'].float().mean()):.2f}", file=sys.stderr, flush=True)
+    rank_ms = [float(t_ms.item()) / K]
     if world > 1:
+        gathered = [torch.zeros_like(t_ms) for _ in range(world)]
+        dist.all_gather(gathered, t_ms)
+        rank_ms = [float(g.item()) / K for g in gathered]
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     total_ms = float(t_ms.item())
     launches = solver.launch_info()["launches"] - launches0
@@ -289,6 +298,7 @@ def main():
                          "peak_source": "DFMA micro-benchmark measured in this run (mpcb_fp64_peak_tflops)",
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "peak_source": hbm_src + " MEASURED_PEAKS.json hbm_gbs"}},
+            "ranks": {"ms_per_step": [round(v, 3) for v in rank_ms], "max_over_mean": max(rank_ms) / (sum(rank_ms) / len(rank_ms))},
             "launch": solver.launch_info(),
             "latency": latency,
         }
@@ -299,7 +309,7 @@ def main():
             line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {sample} scenarios of the same batch, restated CPU IPM (oracle/mpc_oracle.c, "
                                               "scalar Riccati, one scenario per thread), not CasADi+IPOPT"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
