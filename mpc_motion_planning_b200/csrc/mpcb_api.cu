@@ -84,6 +84,8 @@ struct mpcb_handle {
   int device;
   mpcb_launch_info info;
   int persistent_grid;  // resident blocks of the persistent kernel (0: grid = B)
+  int lat_grid;         // resident blocks of the small-batch kernel (0: not available for this configuration)
+  size_t lat_smem;
   double *d_slab;
   int *d_counter;
   // device buffers for the host-pointer entry point
@@ -221,6 +223,19 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
     }
     cudaMemset(h->d_slab, 0, bytes);
   }
+  if (var.lat_kernel && !getenv("MPCB_NO_LATENCY_VARIANT")) {
+    // small-batch sibling: one warp per block, everything in shared memory
+    h->lat_smem = var.lat_smem_bytes(c.N);
+    int lb = 0;
+    if (h->lat_smem <= (size_t)prop.sharedMemPerBlockOptin &&
+        cudaFuncSetAttribute(var.lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->lat_smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lb, var.lat_kernel, 32, h->lat_smem) == cudaSuccess && lb >= 1) {
+      h->lat_grid = lb * prop.multiProcessorCount;
+      if (!h->d_counter && !cuda_ok(cudaMalloc(&h->d_counter, sizeof(int)), "cudaMalloc counter")) { delete h; return MPCB_E_NOMEM; }
+    } else {
+      cudaGetLastError();
+    }
+  }
   if (!cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete h; return MPCB_E_CUDA; }
   *out = h;
   return MPCB_OK;
@@ -255,14 +270,23 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
   k.x0 = x0; k.xs = xs; k.obs = obs; k.z_init = z_init;
   k.u0 = u0; k.cost = cost; k.status = status; k.iters = iters; k.z_out = z_out; k.lam_out = lam_out;
   int grid = B;
-  if (h->persistent_grid) {
-    const int need = (B + h->var.warps - 1) / h->var.warps;
-    grid = need < h->persistent_grid ? need : h->persistent_grid;
-    k.slab = h->d_slab;
+  cudaError_t e;
+  if (h->lat_grid && B <= h->lat_grid) {
+    // the batch fits the SMs in one wave of the small-batch kernel (one warp per block, all state in shared memory)
+    k.slab = nullptr;
     k.counter = h->d_counter;
     if (!cuda_ok(cudaMemsetAsync(h->d_counter, 0, sizeof(int), (cudaStream_t)stream), "queue reset")) return MPCB_E_CUDA;
+    e = h->var.lat_launch(k, grid, h->lat_smem, (cudaStream_t)stream);
+  } else {
+    if (h->persistent_grid) {
+      const int need = (B + h->var.warps - 1) / h->var.warps;
+      grid = need < h->persistent_grid ? need : h->persistent_grid;
+      k.slab = h->d_slab;
+      k.counter = h->d_counter;
+      if (!cuda_ok(cudaMemsetAsync(h->d_counter, 0, sizeof(int), (cudaStream_t)stream), "queue reset")) return MPCB_E_CUDA;
+    }
+    e = h->var.launch(k, grid, h->smem, (cudaStream_t)stream);
   }
-  cudaError_t e = h->var.launch(k, grid, h->smem, (cudaStream_t)stream);
   if (!cuda_ok(e, "solve_kernel launch")) return MPCB_E_CUDA;
   h->info.grid = grid;
   h->info.launches++;

@@ -147,8 +147,11 @@ struct KinModel {
 // GS: the step (dx, du) lives in the global slab instead of shared memory.  It costs ~2 % at N = 50
 // (the stage-parallel phases read it through L2) but frees 6 doubles per stage, which buys resident
 // warps at long horizons (N = 100: 8 warps per SM instead of 6, +12 %); the host picks per horizon.
-template <int NR, int MO, bool FH = false, bool GS = false>
+// AS: everything in shared memory, no slab (the small-batch variant: with a handful of scenarios per SM
+// occupancy is irrelevant and the L2 round trips of the stage-parallel phases are the latency).
+template <int NR, int MO, bool FH = false, bool GS = false, bool AS = false>
 struct KinLayout {
+  static_assert(!(GS && AS), "the step lives in the slab or everything lives in shared memory");
   static constexpr int NX = 4, NBX = 2;
   // ---- shared memory: the working set of the serial sweeps (one record of NF doubles per stage)
   static constexpr int CDEF = 0;         // c_0 = X0 - x0, c_k = defect into stage k
@@ -200,8 +203,9 @@ struct KinLayout {
   static constexpr int DU = DX + NX;
   static constexpr int NG = XR + NX + (GS ? NX + 2 : 0) - G0;
   static constexpr int SG = 132;        // row stride (>= MPCB_NMAX + 1)
-  __host__ __device__ static constexpr size_t bytes(int N) { return sizeof(double) * (size_t)NF * (size_t)(N + 1); }
-  __host__ __device__ static constexpr size_t slab_doubles() { return (size_t)NG * SG; }
+  static constexpr int NFA = AS ? ((NF + NG) | 1) : NF;  // record length in shared memory
+  __host__ __device__ static constexpr size_t bytes(int N) { return sizeof(double) * (size_t)NFA * (size_t)(N + 1); }
+  __host__ __device__ static constexpr size_t slab_doubles() { return AS ? 0 : (size_t)NG * SG; }
 };
 
 __device__ __forceinline__ double push_in(double v, double lo, double hi) {
@@ -221,10 +225,10 @@ __device__ __forceinline__ double clampz(double z, double mu, double rgap) {
 // ------------------------------------------------------------------------------------
 // the solver: one warp = one scenario (kinematic model family)
 // ------------------------------------------------------------------------------------
-template <int NR, int MO, int OBS_MODE, bool GS = false>
+template <int NR, int MO, int OBS_MODE, bool GS = false, bool AS = false>
 struct KinSolver {
   static constexpr bool DCBF = OBS_MODE == 3;  // rows h(X_{k+1};obs_k) - (1-gamma) h(X_k;obs_k) >= 0
-  using L = KinLayout<NR, MO, DCBF, GS>;
+  using L = KinLayout<NR, MO, DCBF, GS, AS>;
   static constexpr int NX = 4, NBX = 2;
 
   const KParams &p;
@@ -240,6 +244,7 @@ struct KinSolver {
 
   // field ids are compile-time constants at (almost) every use, so the space test folds away
   __device__ __forceinline__ double &at(int field, int k) {
+    if (AS) return g_smem[woff + k * L::NFA + (field >= L::G0 ? L::NF + (field - L::G0) : field)];
     return field >= L::G0 ? gs[(field - L::G0) * L::SG + k] : g_smem[woff + k * L::NF + field];
   }
   __device__ __forceinline__ bool has_rate(int k) const { return NR > 0 && k >= 1 && k <= N - 1; }
@@ -1126,12 +1131,12 @@ struct KinSolver {
 #ifndef MPCB_KIN_RESIDENT_WARPS
 #define MPCB_KIN_RESIDENT_WARPS 12  // register budget: 65536 / (12 * 32) = 170 registers per thread
 #endif
-template <int NR, int MO, int OBS_MODE, int W, bool GS>
-__global__ void __launch_bounds__(32 * W, MPCB_KIN_RESIDENT_WARPS / W) kin_solve_kernel(const __grid_constant__ KParams p) {
+template <int NR, int MO, int OBS_MODE, int W, bool GS, bool AS = false>
+__global__ void __launch_bounds__(32 * W, AS ? 1 : MPCB_KIN_RESIDENT_WARPS / W) kin_solve_kernel(const __grid_constant__ KParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  using L = KinLayout<NR, MO, OBS_MODE == 3, GS>;
-  double *gs = p.slab + ((size_t)blockIdx.x * W + warp) * L::slab_doubles();
-  const int woff = warp * L::NF * (p.N + 1);
+  using L = KinLayout<NR, MO, OBS_MODE == 3, GS, AS>;
+  double *gs = AS ? nullptr : p.slab + ((size_t)blockIdx.x * W + warp) * L::slab_doubles();
+  const int woff = warp * L::NFA * (p.N + 1);
   int tick = 0;
   for (;;) {
     int b = 0;
@@ -1139,7 +1144,7 @@ __global__ void __launch_bounds__(32 * W, MPCB_KIN_RESIDENT_WARPS / W) kin_solve
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= p.B) break;
     if (p.order) b = p.order[b];  // caller-supplied processing order (longest expected first)
-    KinSolver<NR, MO, OBS_MODE, GS> s(p, gs, woff, tick, lane);
+    KinSolver<NR, MO, OBS_MODE, GS, AS> s(p, gs, woff, tick, lane);
     s.run(b);
     __syncwarp();
   }

@@ -29,6 +29,12 @@ static Variant make_kin_variant_w() {
   v.nbx = 2;
   v.slab_doubles = KinLayout<NR, MO, OBS == 3, GS>::slab_doubles();
   v.warps = W;
+  v.lat_launch = [](const KParams &p, int grid, size_t smem, cudaStream_t st) {
+    kin_solve_kernel<NR, MO, OBS, 1, false, true><<<grid, 32, smem, st>>>(p);
+    return cudaGetLastError();
+  };
+  v.lat_kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, 1, false, true>;
+  v.lat_smem_bytes = [](int N) { return KinLayout<NR, MO, OBS == 3, false, true>::bytes(N); };
   return v;
 }
 
@@ -89,6 +95,9 @@ static Variant make_dyn_variant_w() {
   v.nbx = 3;
   v.slab_doubles = DynLayout::slab_doubles();
   v.warps = W;
+  v.lat_launch = nullptr;
+  v.lat_kernel = nullptr;
+  v.lat_smem_bytes = nullptr;
   return v;
 }
 

@@ -13,8 +13,13 @@ struct Variant {
   kernel_ptr kernel;
   size_t (*smem_bytes)(int N);
   int nx, nbx;
-  size_t slab_doubles;  // per resident warp; 0 = one block per scenario, no slab
+  size_t slab_doubles;  // per resident warp; 0 = everything in shared memory, no slab
   int warps;            // warps (= scenarios in flight) per block
+  // optional small-batch sibling (one warp per block, the whole iterate in shared memory): used when the
+  // batch fits the SMs in one wave, where the L2 round trips of the slab are pure latency
+  launch_fn lat_launch;
+  kernel_ptr lat_kernel;
+  size_t (*lat_smem_bytes)(int N);
 };
 
 // the candidate that keeps the most warps resident for horizon N (first one wins ties); mpcb_api.cu
