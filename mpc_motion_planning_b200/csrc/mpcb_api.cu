@@ -271,7 +271,9 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
   k.u0 = u0; k.cost = cost; k.status = status; k.iters = iters; k.z_out = z_out; k.lam_out = lam_out;
   int grid = B;
   cudaError_t e;
-  if (h->lat_grid && B <= h->lat_grid) {
+  static const int lat_force = getenv("MPCB_LAT_MAX_B") ? atoi(getenv("MPCB_LAT_MAX_B")) : 0;  // tuning knob
+  if (h->lat_grid && (B <= h->lat_grid || B <= lat_force)) {
+    if (grid > h->lat_grid) grid = h->lat_grid;
     // the batch fits the SMs in one wave of the small-batch kernel (one warp per block, all state in shared memory)
     k.slab = nullptr;
     k.counter = h->d_counter;
