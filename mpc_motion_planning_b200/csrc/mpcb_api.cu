@@ -229,7 +229,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
     int lb = 0;
     if (h->lat_smem <= (size_t)prop.sharedMemPerBlockOptin &&
         cudaFuncSetAttribute(var.lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->lat_smem) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lb, var.lat_kernel, 32, h->lat_smem) == cudaSuccess && lb >= 1) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lb, var.lat_kernel, 32 * var.lat_warps, h->lat_smem) == cudaSuccess && lb >= 1) {
       h->lat_grid = lb * prop.multiProcessorCount;
       if (!h->d_counter && !cuda_ok(cudaMalloc(&h->d_counter, sizeof(int)), "cudaMalloc counter")) { delete h; return MPCB_E_NOMEM; }
     } else {
@@ -272,7 +272,8 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
   int grid = B;
   cudaError_t e;
   static const int lat_force = getenv("MPCB_LAT_MAX_B") ? atoi(getenv("MPCB_LAT_MAX_B")) : 0;  // tuning knob
-  if (h->lat_grid && (B <= h->lat_grid || B <= lat_force)) {
+  if (h->lat_grid && (B <= h->lat_grid * h->var.lat_warps || B <= lat_force)) {
+    grid = (B + h->var.lat_warps - 1) / h->var.lat_warps;
     if (grid > h->lat_grid) grid = h->lat_grid;
     // the batch fits the SMs in one wave of the small-batch kernel (one warp per block, all state in shared memory)
     k.slab = nullptr;

@@ -29,12 +29,16 @@ static Variant make_kin_variant_w() {
   v.nbx = 2;
   v.slab_doubles = KinLayout<NR, MO, OBS == 3, GS>::slab_doubles();
   v.warps = W;
+#ifndef MPCB_AS_W
+#define MPCB_AS_W 1  // warps per block of the all-shared kernel (compile-time tuning knob)
+#endif
   v.lat_launch = [](const KParams &p, int grid, size_t smem, cudaStream_t st) {
-    kin_solve_kernel<NR, MO, OBS, 1, false, true><<<grid, 32, smem, st>>>(p);
+    kin_solve_kernel<NR, MO, OBS, MPCB_AS_W, false, true><<<grid, 32 * MPCB_AS_W, smem, st>>>(p);
     return cudaGetLastError();
   };
-  v.lat_kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, 1, false, true>;
-  v.lat_smem_bytes = [](int N) { return KinLayout<NR, MO, OBS == 3, false, true>::bytes(N); };
+  v.lat_kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, MPCB_AS_W, false, true>;
+  v.lat_smem_bytes = [](int N) { return KinLayout<NR, MO, OBS == 3, false, true>::bytes(N) * MPCB_AS_W; };
+  v.lat_warps = MPCB_AS_W;
   return v;
 }
 
@@ -98,6 +102,7 @@ static Variant make_dyn_variant_w() {
   v.lat_launch = nullptr;
   v.lat_kernel = nullptr;
   v.lat_smem_bytes = nullptr;
+  v.lat_warps = 0;
   return v;
 }
 

@@ -19,7 +19,8 @@ struct Variant {
   // batch fits the SMs in one wave, where the L2 round trips of the slab are pure latency
   launch_fn lat_launch;
   kernel_ptr lat_kernel;
-  size_t (*lat_smem_bytes)(int N);
+  size_t (*lat_smem_bytes)(int N);  // per block
+  int lat_warps;
 };
 
 // the candidate that keeps the most warps resident for horizon N (first one wins ties); mpcb_api.cu
