@@ -86,6 +86,7 @@ struct mpcb_handle {
   int persistent_grid;  // resident blocks of the persistent kernel (0: grid = B)
   int lat_grid;         // resident blocks of the small-batch kernel (0: not available for this configuration)
   size_t lat_smem;
+  mpcb_launch_info main_info, lat_info;  // static launch facts of the two kernels (info = the one last launched)
   double *d_slab;
   int *d_counter;
   // device buffers for the host-pointer entry point
@@ -223,6 +224,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
     }
     cudaMemset(h->d_slab, 0, bytes);
   }
+  h->main_info = h->info;
   if (var.lat_kernel && !getenv("MPCB_NO_LATENCY_VARIANT")) {
     // small-batch sibling: one warp per block, everything in shared memory
     h->lat_smem = var.lat_smem_bytes(c.N);
@@ -231,6 +233,12 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
         cudaFuncSetAttribute(var.lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->lat_smem) == cudaSuccess &&
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lb, var.lat_kernel, 32 * var.lat_warps, h->lat_smem) == cudaSuccess && lb >= 1) {
       h->lat_grid = lb * prop.multiProcessorCount;
+      cudaFuncAttributes la;
+      h->lat_info = h->info;
+      if (cudaFuncGetAttributes(&la, var.lat_kernel) == cudaSuccess) h->lat_info.regs_per_thread = la.numRegs;
+      h->lat_info.block = 32 * var.lat_warps;
+      h->lat_info.smem_bytes = (int32_t)h->lat_smem;
+      h->lat_info.blocks_per_sm = lb;
       if (!h->d_counter && !cuda_ok(cudaMalloc(&h->d_counter, sizeof(int)), "cudaMalloc counter")) { delete h; return MPCB_E_NOMEM; }
     } else {
       cudaGetLastError();
@@ -272,7 +280,8 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
   int grid = B;
   cudaError_t e;
   static const int lat_force = getenv("MPCB_LAT_MAX_B") ? atoi(getenv("MPCB_LAT_MAX_B")) : 0;  // tuning knob
-  if (h->lat_grid && (B <= h->lat_grid * h->var.lat_warps || B <= lat_force)) {
+  const bool small_batch = h->lat_grid && (B <= h->lat_grid * h->var.lat_warps || B <= lat_force);
+  if (small_batch) {
     grid = (B + h->var.lat_warps - 1) / h->var.lat_warps;
     if (grid > h->lat_grid) grid = h->lat_grid;
     // the batch fits the SMs in one wave of the small-batch kernel (one warp per block, all state in shared memory)
@@ -291,8 +300,12 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
     e = h->var.launch(k, grid, h->smem, (cudaStream_t)stream);
   }
   if (!cuda_ok(e, "solve_kernel launch")) return MPCB_E_CUDA;
-  h->info.grid = grid;
-  h->info.launches++;
+  {
+    const int64_t launches = h->info.launches + 1;
+    h->info = small_batch ? h->lat_info : h->main_info;
+    h->info.grid = grid;
+    h->info.launches = launches;
+  }
   return MPCB_OK;
 }
 
