@@ -24,8 +24,9 @@ def shift_movement(T, t0, x0, u, x_f, f):
 
 
 def rollout_guess(mpc, x0, u0):
-    """States consistent with the guessed controls (the reference starts from all-zero states, which
-    makes the first linearisation degenerate at v ~ 0)."""
+    """States consistent with the guessed controls.  Only the dyn main needs it: the reference starts every main
+    from all-zero states, which the kinematic NLPs are solved from as they are; for the dyn NLP vx = 0 makes the
+    tire model's derivatives blow up."""
     N = u0.shape[0]
     xs = np.zeros((N + 1, mpc.num_states))
     xs[0] = np.asarray(x0).ravel()

@@ -3,7 +3,7 @@
 import time
 
 import numpy as np
-from _common import PARAMS_FILE, rollout_guess, shift_movement, summary
+from _common import PARAMS_FILE, shift_movement, summary
 
 import MPC_CBF_optimize_kin
 import RefPathGenerator
@@ -19,7 +19,7 @@ if __name__ == "__main__":
     x0 = np.array([0, 3, 0, 15]).reshape(-1, 1).astype(float)
     xs = np.array([400, 3.5, 0, 30]).reshape(-1, 1).astype(float)
     u0 = np.zeros((N_p, n_controls))
-    next_states = rollout_guess(mpc_solver, x0, u0)
+    next_states = np.zeros((N_p + 1, n_states))  # the reference's literal first guess: all zeros (x_m.copy().T)
     ref = RefPathGenerator.RefPathGenerator()
     ref.define_ref_path(x0, xs, T_S)
     obs = np.array([[50, 3.5, 0, 8, 4.8, 1.8]])
