@@ -23,18 +23,6 @@ def shift_movement(T, t0, x0, u, x_f, f):
     return t, st, u_end, x_f
 
 
-def rollout_guess(mpc, x0, u0):
-    """States consistent with the guessed controls.  Only the dyn main needs it: the reference starts every main
-    from all-zero states, which the kinematic NLPs are solved from as they are; for the dyn NLP vx = 0 makes the
-    tire model's derivatives blow up."""
-    N = u0.shape[0]
-    xs = np.zeros((N + 1, mpc.num_states))
-    xs[0] = np.asarray(x0).ravel()
-    for k in range(N):
-        xs[k + 1] = xs[k] + mpc.T_S * mpc.f(xs[k], u0[k]).full().ravel()
-    return xs
-
-
 def summary(name, xh, uh, caltimeh, stats):
     np.set_printoptions(linewidth=200)
     xh = np.array(xh).reshape(len(xh), -1)

@@ -3,7 +3,7 @@
 import time
 
 import numpy as np
-from _common import PARAMS_FILE, rollout_guess, shift_movement, summary
+from _common import PARAMS_FILE, shift_movement, summary
 
 import MPC_CBF_optimize_dyn
 from helpers import load_config
@@ -18,7 +18,7 @@ if __name__ == "__main__":
     x0 = np.array([0, 0, 0, 10, 0, 0]).reshape(-1, 1).astype(float)
     xs = np.array([600, 3.5, 0, 15, 0, 0]).reshape(-1, 1).astype(float)
     u0 = np.zeros((N_p, n_controls))
-    next_states = rollout_guess(mpc_solver, x0, u0)
+    next_states = np.zeros((N_p + 1, n_states))  # the reference's literal first guess (the dyn shim re-integrates all-zero states)
     obs = np.array([100, -3.5])
     lbg, ubg, lbx, ubx = mpc_solver.initialize_constraints()
     xh, uh, caltimeh, stats = [x0], [], [0], []

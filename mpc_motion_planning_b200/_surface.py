@@ -75,6 +75,18 @@ class _Solver:
         z0 = np.zeros(nv) if x0 is None else np.asarray(x0, dtype=np.float64).reshape(-1)
         if z0.size != nv:
             raise ValueError(f"x0 must have {nv} entries, got {z0.size}")
+        if o.KIND == "dyn" and not np.any(z0[2 * N:]):
+            # The reference's literal first guess (all states zero, PKG/main_cbf_dyn_c_sim.py:47-50) puts vx at its
+            # lower bound 0, where the tire model's slip angles divide by vx: after the bound push the dynamics
+            # Jacobian has entries of 6e3 per stage and the stage-wise recursion overflows.
+            # The controls of the guess are kept; the states are re-integrated from p[:nx] instead.
+            z0 = z0.copy()
+            X = np.zeros((N + 1, nx))
+            X[0] = p[:nx]
+            U = z0[: 2 * N].reshape(N, 2)
+            for k in range(N):
+                X[k + 1] = X[k] + o.T_S * o._rhs(X[k], U[k])
+            z0[2 * N:] = X.reshape(-1)
         bs = o._batch_solver(lbx, ubx, lbg, ubg, self._obs)
         obs = self._obs[None] if self._obs is not None else None
         xs = p[None, nx:].copy()
