@@ -228,6 +228,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   if (var.lat_kernel && !getenv("MPCB_NO_LATENCY_VARIANT")) {
     // small-batch sibling: one warp per block, everything in shared memory
     h->lat_smem = var.lat_smem_bytes(c.N);
+    if (const char *pad = getenv("MPCB_LAT_SMEM_PAD")) h->lat_smem += (size_t)atoi(pad);  // tuning knob: lowers occupancy
     int lb = 0;
     if (h->lat_smem <= (size_t)prop.sharedMemPerBlockOptin &&
         cudaFuncSetAttribute(var.lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->lat_smem) == cudaSuccess &&
