@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MPCB_VERSION 102 /* 0.1.2: cfg gained ref_mode, cbf_gamma (0.1.1) and dyn_rows (0.1.2) */
+#define MPCB_VERSION 103 /* 0.1.3: mpcb_submit_batch_host / mpcb_wait; 0.1.2: cfg gained dyn_rows; 0.1.1: ref_mode, cbf_gamma */
 #define MPCB_NMAX 128    /* maximum horizon N */
 #define MPCB_MMAX 4      /* maximum obstacles per scenario in this build (the mains carry a commented 3-obstacle list) */
 
@@ -156,6 +156,19 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
 int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double *xs, const double *obs,
                           const double *z_init, double *u0, double *cost, int32_t *status, int32_t *iters,
                           double *z_out, double *lam_out);
+
+/* The same call split in two, for callers with several independent batches per control period (the reference
+ * has no counterpart: its solver(...) call, PKG/main_cbf_kin_c_sim.py:100, blocks):
+ * mpcb_submit_batch_host enqueues copy-in, solve and copy-out on the handle's own stream and returns;
+ * mpcb_wait blocks until everything submitted on the handle has finished.  The host buffers must stay valid and
+ * the outputs unread until mpcb_wait returns; use page-locked host memory for the copies to overlap.  A handle
+ * still holds one batch at a time -- a second submit on the same handle queues behind the first and reuses its
+ * device buffers -- so a pipeline uses two (or more) handles and alternates: while one batch's long scenarios
+ * finish on a few warps, the other handle's batch fills the rest of the GPU. */
+int mpcb_submit_batch_host(mpcb_handle *h, int B, const double *x0, const double *xs, const double *obs,
+                           const double *z_init, double *u0, double *cost, int32_t *status, int32_t *iters,
+                           double *z_out, double *lam_out);
+int mpcb_wait(mpcb_handle *h);
 
 /* Closed-loop helper (row N1 of SURVEY.md section 8f; PKG/main_cbf_kin_c_sim.py:16-26):
  * plant Euler step x0 <- x0 + T f(x0, U_0) and warm-start shift of z (drop first row, repeat last),

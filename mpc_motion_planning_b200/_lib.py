@@ -54,7 +54,7 @@ class MpcbLaunchInfo(C.Structure):
 
 EXPORTS = [
     "mpcb_version", "mpcb_strerror", "mpcb_last_cuda_error", "mpcb_nx", "mpcb_nv", "mpcb_create", "mpcb_destroy",
-    "mpcb_workspace_bytes", "mpcb_solve_batch", "mpcb_solve_batch_host", "mpcb_shift_batch", "mpcb_ref_traj_batch", "mpcb_get_launch_info", "mpcb_fp64_peak_tflops", "mpcb_set_trace_buffer", "mpcb_set_order",
+    "mpcb_workspace_bytes", "mpcb_solve_batch", "mpcb_solve_batch_host", "mpcb_submit_batch_host", "mpcb_wait", "mpcb_shift_batch", "mpcb_ref_traj_batch", "mpcb_get_launch_info", "mpcb_fp64_peak_tflops", "mpcb_set_trace_buffer", "mpcb_set_order",
 ]
 
 _lib = None
@@ -88,6 +88,8 @@ def load():
     lib.mpcb_workspace_bytes.argtypes = [C.POINTER(MpcbCfg), C.c_int, C.POINTER(C.c_size_t)]
     lib.mpcb_solve_batch.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, ip, ip, dp, dp, vp]
     lib.mpcb_solve_batch_host.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, ip, ip, dp, dp]
+    lib.mpcb_submit_batch_host.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, ip, ip, dp, dp]
+    lib.mpcb_wait.argtypes = [vp]
     lib.mpcb_shift_batch.argtypes = [vp, C.c_int, dp, dp, vp]
     lib.mpcb_ref_traj_batch.argtypes = [vp, C.c_int, C.c_double, dp, dp, dp, ip, C.c_double, dp, dp, vp]
     lib.mpcb_get_launch_info.argtypes = [vp, C.POINTER(MpcbLaunchInfo)]

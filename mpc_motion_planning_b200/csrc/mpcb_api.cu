@@ -310,9 +310,21 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
   return MPCB_OK;
 }
 
+int mpcb_wait(mpcb_handle *h) {
+  if (!h) return MPCB_E_ARG;
+  return cuda_ok(cudaStreamSynchronize(h->stream), "solve (stream sync)") ? MPCB_OK : MPCB_E_CUDA;
+}
+
 int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double *xs, const double *obs,
                           const double *z_init, double *u0, double *cost, int32_t *status, int32_t *iters,
                           double *z_out, double *lam_out) {
+  int rc = mpcb_submit_batch_host(h, B, x0, xs, obs, z_init, u0, cost, status, iters, z_out, lam_out);
+  return rc != MPCB_OK ? rc : mpcb_wait(h);
+}
+
+int mpcb_submit_batch_host(mpcb_handle *h, int B, const double *x0, const double *xs, const double *obs,
+                           const double *z_init, double *u0, double *cost, int32_t *status, int32_t *iters,
+                           double *z_out, double *lam_out) {
   if (!h || B < 0) return MPCB_E_ARG;
   if (B == 0) return MPCB_OK;
   if (!x0 || !xs || !u0 || !cost || !status || !iters) return MPCB_E_ARG;
@@ -323,6 +335,7 @@ int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double 
   const size_t sxs = h->cfg.ref_mode == MPCB_REF_TRAJECTORY ? (size_t)nx * N : (size_t)nx;
   if (M > 0 && !obs) return MPCB_E_ARG;
   if (B > h->cap_B) {
+    if (!cuda_ok(cudaStreamSynchronize(h->stream), "stream sync before regrowing buffers")) return MPCB_E_CUDA;
     free_bufs(h);
     size_t b = (size_t)B;
     bool ok = cuda_ok(cudaMalloc(&h->d_x0, b * nx * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_xs, b * sxs * 8), "cudaMalloc") &&
@@ -349,9 +362,7 @@ int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double 
        cuda_ok(cudaMemcpyAsync(iters, h->d_iters, b * 4, cudaMemcpyDeviceToHost, st), "D2H iters");
   if (ok && z_out) ok = cuda_ok(cudaMemcpyAsync(z_out, h->d_z, b * nv * 8, cudaMemcpyDeviceToHost, st), "D2H z");
   if (ok && lam_out) ok = cuda_ok(cudaMemcpyAsync(lam_out, h->d_lam, b * nx * (N + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H lam");
-  if (!ok) return MPCB_E_CUDA;
-  if (!cuda_ok(cudaStreamSynchronize(st), "solve (stream sync)")) return MPCB_E_CUDA;
-  return MPCB_OK;
+  return ok ? MPCB_OK : MPCB_E_CUDA;
 }
 
 int mpcb_set_order(mpcb_handle *h, const int32_t *order) {

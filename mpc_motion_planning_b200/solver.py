@@ -162,6 +162,18 @@ class BatchSolver:
                                             ptr(status), ptr(iters), None, None)
         _lib.check(rc, "mpcb_solve_batch_host")
 
+    def submit_host_ptrs(self, B, x0, xs, obs, z_init, u0, cost, status, iters):
+        """Non-blocking half of `solve_host_ptrs` (mpcb_submit_batch_host): copy-in, solve and copy-out are queued on
+        the handle's stream; the tensors (page-locked CPU tensors) must stay alive and unread until `wait()`."""
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        rc = self.lib.mpcb_submit_batch_host(self._h, B, ptr(x0), ptr(xs), ptr(obs), ptr(z_init), ptr(u0), ptr(cost),
+                                             ptr(status), ptr(iters), None, None)
+        _lib.check(rc, "mpcb_submit_batch_host")
+
+    def wait(self):
+        """Block until everything submitted on this handle has finished (mpcb_wait)."""
+        _lib.check(self.lib.mpcb_wait(self._h), "mpcb_wait")
+
     def shift(self, x0, z):
         """In-place plant Euler step + warm-start shift on CUDA tensors (PKG/main_cbf_kin_c_sim.py:16-26)."""
         import torch

@@ -820,3 +820,47 @@ def test_plain_c_example_runs(dev, tmp_path):
     env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(_lib.SO_PATH) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
     run = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
     assert run.returncode == 0 and run.stdout.strip().endswith("OK"), run.stdout + run.stderr
+
+
+@pytest.mark.gpu
+def test_pipelined_batches_equal_one_at_a_time():
+    """PipelinedSolver (two handles, batches in flight on two streams; mpcb_submit_batch_host / mpcb_wait for host
+    buffers) returns, for every batch, exactly what BatchSolver returns for it alone."""
+    import torch
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.pipeline import PipelinedSolver
+    from mpc_motion_planning_b200.solver import BatchSolver
+    dev = torch.device("cuda:0")
+    batches = [scenarios.kin_cbf_moving(B, seed=900 + i) for i, B in enumerate((700, 64, 2500, 1, 1300))]
+    one = BatchSolver("kin_cbf_pre")
+    want = []
+    for x0, xs, obs in batches:
+        o = one.solve(*(torch.from_numpy(v).to(dev) for v in (x0, xs, obs)))
+        want.append({k: v.cpu() for k, v in o.items()})
+    pipe = PipelinedSolver(2, "kin_cbf_pre")
+    # device tensors: submit everything, then collect
+    tickets, got = [], []
+    for i, (x0, xs, obs) in enumerate(batches):
+        if i >= pipe.lanes:                       # a lane holds one batch: collect before reusing it
+            got.append({k: v.clone() for k, v in pipe.result(tickets[i - pipe.lanes]).items()})
+        tickets.append(pipe.submit(*(torch.from_numpy(v).to(dev) for v in (x0, xs, obs))))
+    for t in tickets[-pipe.lanes:]:
+        got.append({k: v.clone() for k, v in pipe.result(t).items()})
+    torch.cuda.synchronize()
+    for w, g in zip(want, got):
+        for k in ("u0", "cost", "status", "iters"):
+            assert torch.equal(w[k], g[k].cpu()), k
+    # page-locked host buffers through the C-ABI pair
+    outs, tick = [], []
+    for i, (x0, xs, obs) in enumerate(batches):
+        B = x0.shape[0]
+        h = [torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for v in (x0, xs, obs)]
+        o = (torch.empty((B, 2), dtype=torch.float64).pin_memory(), torch.empty(B, dtype=torch.float64).pin_memory(),
+             torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory())
+        tick.append(pipe.submit_host(B, h[0], h[1], h[2], None, *o))
+        outs.append((h, o))
+    pipe.wait()
+    for w, (_, o) in zip(want, outs):
+        assert torch.equal(w["u0"], o[0]) and torch.equal(w["cost"], o[1])
+        assert torch.equal(w["status"], o[2]) and torch.equal(w["iters"], o[3])
+    pipe.close()
