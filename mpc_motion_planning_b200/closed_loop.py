@@ -40,6 +40,51 @@ def run_closed_loop(solver, x0: torch.Tensor, xs: torch.Tensor, obs_state: torch
     obs_state: (B,M,6) obstacle states (kin kinds; `moving=False` keeps them fixed as in
     main_cbf_kin_c_sim.py), (B,1,6) with only columns 0,1 used for dyn, or None for the no-CBF NLP.
     disturbance_step: zero the applied control at that step (PKG/main_cbf_dyn_c_sim.py:98-100)."""
+    gen = _closed_loop_steps(solver, x0, xs, obs_state, steps, moving, disturbance_step, aa, T_horizon, longest_first)
+    while True:
+        try:
+            next(gen)
+        except StopIteration as done:
+            return done.value
+
+
+def run_closed_loop_lanes(solvers, x0: torch.Tensor, xs: torch.Tensor, obs_state: torch.Tensor | None, steps: int, **kw):
+    """The same closed loop with the fleet split into len(solvers) contiguous groups, each on its own handle and
+    stream: the groups' control steps are independent, so one group's last wave of long solves overlaps the other
+    group's next step (batches in flight).  Same arguments and the same result, bit for bit, as
+    `run_closed_loop` on the whole fleet."""
+    L = len(solvers)
+    dev = x0.device
+    B = x0.shape[0]
+    cur = torch.cuda.current_stream(dev)
+    streams = [torch.cuda.Stream(dev) for _ in range(L)]
+    cuts = [(B * i) // L for i in range(L + 1)]
+    gens = []
+    for i, s in enumerate(solvers):
+        lo, hi = cuts[i], cuts[i + 1]
+        streams[i].wait_stream(cur)
+        gens.append(_closed_loop_steps(s, x0[lo:hi], xs[lo:hi], None if obs_state is None else obs_state[lo:hi], steps,
+                                       kw.get("moving", True), kw.get("disturbance_step"), kw.get("aa"), kw.get("T_horizon"),
+                                       kw.get("longest_first", False)))
+    parts = [None] * L
+    for _ in range(steps + 1):           # `steps` yields, then the return
+        for i, g in enumerate(gens):
+            if parts[i] is None:
+                with torch.cuda.stream(streams[i]):
+                    try:
+                        next(g)
+                    except StopIteration as done:
+                        parts[i] = done.value
+    for st in streams:
+        cur.wait_stream(st)
+    for part in parts:
+        for t in part.values():
+            t.record_stream(cur)
+    return {k: torch.cat([part[k] for part in parts], dim=1) for k in parts[0]}
+
+
+def _closed_loop_steps(solver, x0, xs, obs_state, steps, moving, disturbance_step, aa, T_horizon, longest_first):
+    """Generator behind both drivers: enqueues one control step per `next`, returns the histories."""
     dev = x0.device
     B = x0.shape[0]
     N, nv = solver.N, solver.nv
@@ -78,6 +123,7 @@ def run_closed_loop(solver, x0: torch.Tensor, xs: torch.Tensor, obs_state: torch
             obs[..., 0] = obs[..., 0] + obs[..., 3] * torch.cos(obs[..., 2]) * dt  # main_cbf_kin_c_sim_pre.py:106
             obs[..., 1] = obs[..., 1] + obs[..., 3] * torch.sin(obs[..., 2]) * dt
         xh.append(x.clone())
+        yield step
     if longest_first:
         solver.set_order(None)
     return {"x": torch.stack(xh), "u": torch.stack(uh), "status": torch.stack(sth), "iters": torch.stack(ith)}

@@ -864,3 +864,21 @@ def test_pipelined_batches_equal_one_at_a_time():
         assert torch.equal(w["u0"], o[0]) and torch.equal(w["cost"], o[1])
         assert torch.equal(w["status"], o[2]) and torch.equal(w["iters"], o[3])
     pipe.close()
+
+
+@pytest.mark.gpu
+def test_closed_loop_in_lanes_equals_the_single_handle_loop():
+    """run_closed_loop_lanes (fleet split over two handles/streams, steps interleaved) = run_closed_loop, bit for bit."""
+    import torch
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.closed_loop import run_closed_loop, run_closed_loop_lanes
+    from mpc_motion_planning_b200.solver import BatchSolver
+    dev = torch.device("cuda:0")
+    x0, xs, obs = scenarios.kin_cbf_moving(301, seed=4242)
+    tx0, txs = torch.from_numpy(x0).to(dev), torch.from_numpy(xs).to(dev)
+    obs0 = torch.from_numpy(obs[:, :, 0, :].copy()).to(dev)
+    one = run_closed_loop(BatchSolver("kin_cbf_pre"), tx0, txs, obs0, 6)
+    two = run_closed_loop_lanes([BatchSolver("kin_cbf_pre") for _ in range(2)], tx0, txs, obs0, 6)
+    torch.cuda.synchronize()
+    for k in ("x", "u", "status", "iters"):
+        assert one[k].shape == two[k].shape and torch.equal(one[k], two[k]), k
