@@ -56,10 +56,25 @@ int main(void) {
   if (rc != MPCB_OK) { fprintf(stderr, "mpcb_solve_batch_host: %s (%s)\n", mpcb_strerror(rc), mpcb_last_cuda_error()); return 3; }
   for (int b = 0; b < B; b++)
     printf("scenario %d: status %d, %d iterations, cost %.10e, u0 = (%.8f, %.8f)\n", b, status[b], iters[b], cost[b], u0[b][0], u0[b][1]);
+  /* the same batch twice more, in flight on two handles (mpcb_submit_batch_host / mpcb_wait) */
+  mpcb_handle *h2 = NULL;
+  rc = mpcb_create(&c, &h2);
+  if (rc != MPCB_OK) { fprintf(stderr, "mpcb_create (second handle): %s\n", mpcb_strerror(rc)); return 4; }
+  double u0a[B][2], costa[B], u0b[B][2], costb[B];
+  int32_t sta[B], ita[B], stb[B], itb[B];
+  rc = mpcb_submit_batch_host(h, B, &x0[0][0], &xs[0][0], &obs[0][0][0], NULL, &u0a[0][0], costa, sta, ita, NULL, NULL);
+  if (rc == MPCB_OK) rc = mpcb_submit_batch_host(h2, B, &x0[0][0], &xs[0][0], &obs[0][0][0], NULL, &u0b[0][0], costb, stb, itb, NULL, NULL);
+  if (rc == MPCB_OK) rc = mpcb_wait(h);
+  if (rc == MPCB_OK) rc = mpcb_wait(h2);
+  if (rc != MPCB_OK) { fprintf(stderr, "submit/wait: %s (%s)\n", mpcb_strerror(rc), mpcb_last_cuda_error()); return 5; }
+  int same = memcmp(u0a, u0, sizeof u0) == 0 && memcmp(u0b, u0, sizeof u0) == 0 && memcmp(costa, cost, sizeof cost) == 0 &&
+             memcmp(costb, cost, sizeof cost) == 0 && memcmp(sta, status, sizeof status) == 0 && memcmp(itb, iters, sizeof iters) == 0;
+  printf("two handles in flight: %s\n", same ? "identical" : "DIFFERENT");
+  mpcb_destroy(h2);
   mpcb_destroy(h);
   /* the reference's default scenario: cost 1.0947508e8, u0 = (0.0356462, 3.0) */
   int ok = status[0] == MPCB_CONVERGED && fabs(cost[0] - 1.0947508274e8) <= 1e-6 * 1.1e8 && fabs(u0[0][0] - 0.03564619) <= 1e-6 &&
-           cost[2] == cost[0] && u0[2][0] == u0[0][0];
+           cost[2] == cost[0] && u0[2][0] == u0[0][0] && same;
   printf("%s\n", ok ? "OK" : "MISMATCH");
   return ok ? 0 : 1;
 }
