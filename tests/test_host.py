@@ -46,6 +46,12 @@ def test_no_cpu_fallback_without_a_device():
 
     with pytest.raises(_lib.MpcbError, match="no CUDA device"):
         BatchSolver("kin_cbf_pre")
+    from mpc_motion_planning_b200.pipeline import PipelinedSolver
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PipelinedSolver(2, "kin_cbf_pre")
+    lib = _lib.load()
+    assert lib.mpcb_wait(None) < 0 and lib.mpcb_submit_batch_host(None, 1, *([None] * 10)) < 0   # argument errors, not crashes
 
 
 def test_create_rejects_bad_configurations():
