@@ -260,6 +260,7 @@ static void free_bufs(mpcb_handle *h) {
 
 void mpcb_destroy(mpcb_handle *h) {
   if (!h) return;
+  if (h->stream) cudaStreamSynchronize(h->stream);  // a batch submitted with mpcb_submit_batch_host may still be in flight
   free_bufs(h);
   cudaFree(h->d_slab);
   cudaFree(h->d_counter);
