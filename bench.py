@@ -113,6 +113,25 @@ def cpu_solve(x0, xs, obs, nthreads):
     return time.perf_counter() - t, st, it
 
 
+def cpu_latency():
+    """The B = 1 latency workload of `latency` (kin no-CBF closed loop, PKG/main_kin_c_sim.py) on ONE host core with the
+    restated CPU IPM: 99 warm-started solves, plant Euler step and warm-start shift in numpy (not timed)."""
+    from oracle import c_oracle
+    cfg = c_oracle.make_cfg("kin_nocbf", N=N_HORIZON)
+    N, T, L = N_HORIZON, float(cfg.T), float(cfg.Veh_l)
+    x, xs, z = np.array([0.0, 0.0, 0.0, 20.0]), np.array([500.0, 3.5, 0.0, 30.0]), np.zeros(2 * N + 4 * (N + 1))
+    lat = []
+    for _ in range(100):
+        t = time.perf_counter()
+        zz, _, _ = c_oracle.solve(cfg, x, xs, None, z)
+        lat.append((time.perf_counter() - t) * 1e3)
+        U, X = zz[:2 * N].reshape(N, 2), zz[2 * N:].reshape(N + 1, 4)
+        x = x + T * np.array([x[3] * np.cos(x[2]), x[3] * np.sin(x[2]), x[3] * np.tan(U[0, 0]) / L, U[0, 1]])
+        z = np.concatenate([np.vstack([U[1:], U[-1:]]).ravel(), np.vstack([X[1:], X[-1:]]).ravel()])
+    lat = np.array(lat[1:])
+    return float(np.percentile(lat, 50)), float(np.percentile(lat, 99))
+
+
 def run_reference(args):
     """CPU arm.  The reference's own solver (CasADi+IPOPT) is not installable here (no wheel, no
     network), so this times the oracle port on all host cores, as the tier rules say."""
@@ -356,6 +375,10 @@ def main():
             line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {sample} scenarios of the same batch, restated CPU IPM (oracle/mpc_oracle.c, "
                                               "scalar Riccati, one scenario per thread), not CasADi+IPOPT"}
+            if latency is not None:
+                p50, p99 = cpu_latency()
+                latency["cpu_port"] = {"p50_ms": p50, "p99_ms": p99, "cores": 1,
+                                       "note": "same closed loop, restated CPU IPM (oracle/mpc_oracle.c) called through ctypes, one host core"}
         print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
