@@ -9,13 +9,15 @@ from mpc_motion_planning_b200.solver import BatchSolver
 dev = torch.device("cuda:0")
 rng = np.random.default_rng(2026)
 total = bad = 0
-_equal = torch.equal
-class _T:  # bit-pattern equality: the dyn NLP reports a NaN cost for status 4, and NaN != NaN
-    @staticmethod
-    def equal(a, b):
-        if a.dtype == torch.float64:
-            return a.shape == b.shape and _equal(a.contiguous().view(torch.int64), b.contiguous().view(torch.int64))
-        return _equal(a, b)
+
+
+def same_bits(a, b):
+    """Bit-pattern equality: the dyn NLP reports a NaN cost for status 4, and NaN != NaN."""
+    if a.dtype == torch.float64:
+        return a.shape == b.shape and torch.equal(a.contiguous().view(torch.int64), b.contiguous().view(torch.int64))
+    return torch.equal(a, b)
+
+
 for kind, gen in (("kin_cbf_pre", scenarios.kin_cbf_moving), ("dyn", scenarios.dyn_static)):
     one = BatchSolver(kind)
     pipe = PipelinedSolver(3, kind)
@@ -42,15 +44,15 @@ for kind, gen in (("kin_cbf_pre", scenarios.kin_cbf_moving), ("dyn", scenarios.d
     for (h, o), dv in zip(jobs, dev_out):
         w = one.solve(*(t.to(dev) for t in h))
         torch.cuda.synchronize()
-        same = (_T.equal(w["u0"].cpu(), o[0]) and _T.equal(w["cost"].cpu(), o[1]) and _T.equal(w["status"].cpu(), o[2])
-                and _T.equal(w["iters"].cpu(), o[3]) and _T.equal(w["u0"], dv["u0"]) and _T.equal(w["iters"], dv["iters"])
-                and _T.equal(w["cost"], dv["cost"]))
+        same = (same_bits(w["u0"].cpu(), o[0]) and same_bits(w["cost"].cpu(), o[1]) and same_bits(w["status"].cpu(), o[2])
+                and same_bits(w["iters"].cpu(), o[3]) and same_bits(w["u0"], dv["u0"]) and same_bits(w["iters"], dv["iters"])
+                and same_bits(w["cost"], dv["cost"]))
         total += 1
         bad += 0 if same else 1
         if not same and bad <= 3:
             B = h[0].shape[0]
-            print("B", B, "host:", [bool(_T.equal(w[k].cpu(), o[j])) for j, k in enumerate(("u0", "cost", "status", "iters"))],
-                  "device:", [bool(_T.equal(w[k], dv[k])) for k in ("u0", "cost", "status", "iters")],
+            print("B", B, "host:", [bool(same_bits(w[k].cpu(), o[j])) for j, k in enumerate(("u0", "cost", "status", "iters"))],
+                  "device:", [bool(same_bits(w[k], dv[k])) for k in ("u0", "cost", "status", "iters")],
                   "shapes", tuple(w["u0"].shape), tuple(dv["u0"].shape), flush=True)
     print(f"{kind}: {len(jobs)} batches, sizes {sorted(set(sizes))}", flush=True)
 print(f"pipeline soak: {total} batches x (host path, device path), {bad} differ from the one-at-a-time result")
