@@ -1,7 +1,7 @@
 """GPU check of the discrete-time CBF rows / per-stage reference options + timing beside the plain rows."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from mpc_motion_planning_b200 import scenarios
 from mpc_motion_planning_b200.solver import BatchSolver

@@ -1,7 +1,7 @@
 """First-contact GPU check: CUDA path vs the C oracle on seeded scenarios + a rough timing."""
 import json, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from mpc_motion_planning_b200 import scenarios
 from mpc_motion_planning_b200.solver import BatchSolver

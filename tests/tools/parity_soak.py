@@ -3,7 +3,7 @@ points): counts, worst differences and verdict agreement per configuration.  Tol
 BASELINE.json: first control 1e-4 absolute, cost 1e-6 relative, same converged / not verdict."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from mpc_motion_planning_b200 import scenarios
 from mpc_motion_planning_b200.solver import BatchSolver
