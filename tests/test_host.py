@@ -236,3 +236,17 @@ def test_header_and_example_compile_as_plain_c(tmp_path):
         env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(_lib.SO_PATH) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
         run = subprocess.run([exe], capture_output=True, text=True, env=env)
         assert run.returncode == 2 and "mpcb_create" in run.stderr
+
+
+def test_only_the_checkers_touch_the_oracle():
+    """oracle/ is test infrastructure: the package, the mains, the examples and the scripts never import it
+    (bench.py's CPU legs and __graft_entry__'s build/smoke are the two allowed callers outside tests/)."""
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    offenders = []
+    for top in ("mpc_motion_planning_b200", "mains", "examples", "scripts"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith(".py") and pat.search(open(os.path.join(dirpath, f)).read()):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+    assert "liboracle" not in open(os.path.join(ROOT, "mpc_motion_planning_b200", "_lib.py")).read()
