@@ -24,7 +24,8 @@
 extern "C" {
 #endif
 
-#define MPCB_VERSION 103 /* 0.1.3: mpcb_submit_batch_host / mpcb_wait; 0.1.2: cfg gained dyn_rows; 0.1.1: ref_mode, cbf_gamma */
+#define MPCB_VERSION 200 /* 0.2.0: mpcb_set_order takes the length, mpcb_reserve, mpcb_set_dual_outputs, mpcb_n_g;
+                            0.1.3: mpcb_submit_batch_host / mpcb_wait; 0.1.2: cfg gained dyn_rows; 0.1.1: ref_mode, cbf_gamma */
 #define MPCB_NMAX 128    /* maximum horizon N */
 #define MPCB_MMAX 4      /* maximum obstacles per scenario in this build (the mains carry a commented 3-obstacle list) */
 
@@ -132,7 +133,10 @@ void mpcb_destroy(mpcb_handle *h);
  * B: a slab per RESIDENT warp of the persistent kernel) */
 int mpcb_workspace_bytes(const mpcb_cfg *cfg, int B, size_t *bytes);
 
-/* Replaces optimize_problem + solver(...) for B independent scenarios.  DEVICE pointers,
+/* One solve at a time per handle (it owns one work queue and one iterate slab): a call on a different stream than the
+ * previous call on the same handle first waits, on the device, for that one to finish.
+ *
+ * Replaces optimize_problem + solver(...) for B independent scenarios.  DEVICE pointers,
  * row-major, float64:
  *   x0 [B][nx], xs [B][nx]        = the parameter vector p=[x0;xs] (PKG/main_cbf_kin_c_sim.py:89);
  *                                   xs [B][N][nx] with cfg.ref_mode = MPCB_REF_TRAJECTORY
@@ -170,6 +174,26 @@ int mpcb_submit_batch_host(mpcb_handle *h, int B, const double *x0, const double
                            double *z_out, double *lam_out);
 int mpcb_wait(mpcb_handle *h);
 
+/* Sizes the device staging buffers of the *_host entry points for batches of up to B scenarios, so that no later
+ * mpcb_solve_batch_host / mpcb_submit_batch_host with a batch <= B allocates ("no allocation
+ * in solve_batch"; mpcb_solve_batch with device pointers never allocates).  Without it the first call that sees a
+ * larger batch grows them. */
+int mpcb_reserve(mpcb_handle *h, int B);
+
+/* Number of rows of g (= length of CasADi's res['g'] / res['lam_g']) for this configuration. */
+int mpcb_n_g(const mpcb_cfg *cfg);
+
+/* The rest of the CasADi result dict (`{'x','f','g','lam_x','lam_g','lam_p'}`; the mains read
+ * only 'x', PKG/main_cbf_kin_c_sim.py:100-102).  When set, every later solve on the handle also writes
+ *   lam_g [B][mpcb_n_g]  multipliers of ALL rows of g in the reference's row order - kin: X_0 - x0, defects,
+ *                        steering-rate rows, obstacle rows (PKG/MPC_CBF_optimize_kin.py:191,207-216,236-247); dyn: X_0 - x0,
+ *                        then per stage the defect and (i > 0) the two rate rows, then the obstacle rows
+ *                        (PKG/MPC_CBF_optimize_dyn.py:215,227-231,242-243)
+ *   lam_x [B][nv]        bound multipliers z_U - z_L in the order of 'x' (CasADi's sign: > 0 at an active upper bound)
+ * in the units of the unscaled objective.  on_host = 0: DEVICE buffers, written by mpcb_solve_batch; on_host = 1: HOST
+ * buffers, filled by the *_host entry points.  Either pointer may be NULL; (NULL, NULL) switches the outputs off. */
+int mpcb_set_dual_outputs(mpcb_handle *h, double *lam_g, double *lam_x, int on_host);
+
 /* Closed-loop helper (row N1 of SURVEY.md section 8f; PKG/main_cbf_kin_c_sim.py:16-26):
  * plant Euler step x0 <- x0 + T f(x0, U_0) and warm-start shift of z (drop first row, repeat last),
  * in place on DEVICE buffers x0 [B][nx], z [B][nv]. */
@@ -189,11 +213,11 @@ int mpcb_ref_traj_batch(mpcb_handle *h, int B, double T_horizon, const double *x
 
 /* Scheduling hint.  The resident warps pull scenarios from a queue; iteration counts differ by 5x
  * between scenarios, so at small batches (a few scenarios per resident warp) the makespan is set by
- * long scenarios that start late.  `order` (DEVICE, [B] permutation of 0..B-1, read by every later
- * solve until reset with NULL) makes queue position q process scenario order[q]: pass the scenarios
+ * long scenarios that start late.  `order` (DEVICE, [n] permutation of 0..n-1, read by every later
+ * solve until reset with NULL; a solve whose batch size differs from n fails with MPCB_E_ARG) makes queue position q process scenario order[q]: pass the scenarios
  * sorted by expected work, longest first - in a closed loop the previous step's `iters` is a good
  * predictor.  Results do not depend on the order. */
-int mpcb_set_order(mpcb_handle *h, const int32_t *order);
+int mpcb_set_order(mpcb_handle *h, const int32_t *order, int n);
 
 /* Diagnostics (the reference only has IPOPT's print_level log, PKG/MPC_CBF_optimize_kin.py:252):
  * when set, every later solve writes one row per interior-point iteration and scenario into the

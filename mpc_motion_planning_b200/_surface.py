@@ -95,14 +95,23 @@ class _Solver:
             if self._ref is None or self._ref.shape[0] < N + 1:
                 raise ValueError("aa != 0 needs a ref_state of N_p+1 rows")
             xs = (o.aa * self._ref[1: N + 1, :nx] + (1 - o.aa) * p[None, nx:])[None]
-        out = bs.solve(p[None, :nx].copy(), xs, obs, z0[None], return_z=True, return_lam=True)
+        out = bs.solve(p[None, :nx].copy(), xs, obs, z0[None], return_z=True, return_lam=True, return_duals=True)
         st = int(out["status"][0])
         self._stats = {"success": st in (_lib.ST_CONVERGED, _lib.ST_ACCEPTABLE), "return_status": _lib.RETURN_STATUS[st],
                        "iter_count": int(out["iters"][0])}
         z = out["z"][0]
-        res = {"x": _DM(z), "f": _DM([out["cost"][0]]), "lam_g_eq": _DM(out["lam"][0])}
+        # CasADi's result keys; 'lam_g_eq' = the [init; defects] head of lam_g, kept for callers of
+        # the first release
+        res = {"x": _DM(z), "f": _DM([out["cost"][0]]), "lam_g": _DM(out["lam_g"][0]), "lam_x": _DM(out["lam_x"][0]),
+               "lam_p": _DM(self._lam_p(out["lam"][0], nx)), "lam_g_eq": _DM(out["lam"][0])}
         res["g"] = _DM(o._g_of(z, p, self._obs))
         return res
+
+    @staticmethod
+    def _lam_p(lam_eq, nx):
+        """dL/dp for p = [x0; xs]: x0 enters only the row X_0 - P[:nx] (PKG/MPC_CBF_optimize_kin.py:191), so its part is
+        minus that row's multipliers; the xs part (cost gradient wrt the target) is not formed and reported as NaN."""
+        return np.concatenate([-np.asarray(lam_eq[:nx]), np.full(nx, np.nan)])
 
 
 class MPCOptimizeBase:
@@ -316,6 +325,9 @@ class MPCOptimizeBase:
             else:
                 r0 = nx * (N + 1)
                 bounds.update(rate_lo=lg[r0: r0 + 1], rate_hi=ug[r0: r0 + 1])
+            # everything else the caller passes in lbg/ubg must be what the kernels assume: zeros on the equality
+            # rows, ONE rate interval for all stages, [obs_lo, inf) on the obstacle rows - in the reference's row order
+            self._check_row_bounds(lg, ug, bounds, dyn_rows, 0 if obs_array is None else obs_array.shape[0])
         M = 0 if obs_array is None else obs_array.shape[0]
         gamma = float(self.gamma) if self._dcbf() else None
         ref = "trajectory" if self._stage_reference() else "terminal"
@@ -325,6 +337,32 @@ class MPCOptimizeBase:
                                              max_iter=self.max_iter, tol=self.tol, bounds=bounds or None, cbf_gamma=gamma, ref=ref,
                                              dyn_bounds=dyn_rows)
         return self._solvers[key]
+
+    def _check_row_bounds(self, lg, ug, bounds, dyn_rows, M):
+        N, nx = self.N_p, self.num_states
+        rl, rh = np.ravel(bounds["rate_lo"]), np.ravel(bounds["rate_hi"])
+        elo, ehi = [], []
+        if self.KIND == "dyn":
+            if dyn_rows == "as_shipped":
+                for i in range(N + 1):
+                    elo += [0.0] * 6; ehi += [0.0] * 6
+                    if 0 < i < N:
+                        elo += list(rl); ehi += list(rh)
+            else:
+                elo += [0.0] * 6; ehi += [0.0] * 6
+                for i in range(N):
+                    elo += [0.0] * 6; ehi += [0.0] * 6
+                    if i > 0:
+                        elo += list(rl); ehi += list(rh)
+            elo += [1.0] * (N + 1); ehi += [np.inf] * (N + 1)
+        else:
+            elo += [0.0] * (nx * (N + 1)); ehi += [0.0] * (nx * (N + 1))
+            elo += [rl[0]] * (N - 1); ehi += [rh[0]] * (N - 1)
+            elo += [0.0] * (N * M); ehi += [np.inf] * (N * M)
+        if lg.size != len(elo) or not (np.array_equal(lg, elo) and np.array_equal(ug, ehi)):
+            raise NotImplementedError("lbg/ubg differ from the pattern of initialize_constraints (zeros on the equality rows, one rate "
+                                      "interval for every stage, [lb, inf) on the obstacle rows): row-varying bounds are not supported "
+                                      "by the CUDA path")
 
     # ---- g(z) in the reference's row order (host evaluation for res['g']) -----------------
     def _g_of(self, z, p, obs):

@@ -100,30 +100,33 @@ def _closed_loop_steps(solver, x0, xs, obs_state, steps, moving, disturbance_ste
         path_x0 = x[:, 0].clone()  # define_ref_path(x0, xs, T_S) before the loop (:52)
         last_idx = torch.zeros(B, dtype=torch.int32, device=dev)
         T_h = float(T_horizon if T_horizon is not None else solver.config["mpc_params"]["horizon"])
-    for step in range(steps):
-        target = xs
-        if stage_ref:
-            _, target = solver.ref_traj(x, xs, path_x0, last_idx, T_h, aa)
-        traj = None
-        if obs is not None and solver.obs_initial:
-            traj = obs if moving else torch.cat([obs[..., :3], torch.zeros_like(obs[..., 3:4]), obs[..., 4:]], dim=-1)  # prediction in-kernel
-        elif obs is not None:
-            traj = predict_obstacles(obs, dt, N) if moving else obs[:, :, None, :].repeat(1, 1, N + 1, 1).contiguous()
-        out = solver.solve(x, target, traj, z, return_z=True)
-        z = out["z"]
-        if disturbance_step is not None and step == disturbance_step:
-            z[:, 0:2] = 0.0
-        uh.append(z[:, 0:2].clone())
-        sth.append(out["status"])
-        ith.append(out["iters"])
+    try:
+        for step in range(steps):
+            target = xs
+            if stage_ref:
+                _, target = solver.ref_traj(x, xs, path_x0, last_idx, T_h, aa)
+            traj = None
+            if obs is not None and solver.obs_initial:
+                traj = obs if moving else torch.cat([obs[..., :3], torch.zeros_like(obs[..., 3:4]), obs[..., 4:]], dim=-1)  # prediction in-kernel
+            elif obs is not None:
+                traj = predict_obstacles(obs, dt, N) if moving else obs[:, :, None, :].repeat(1, 1, N + 1, 1).contiguous()
+            out = solver.solve(x, target, traj, z, return_z=True)
+            z = out["z"]
+            if disturbance_step is not None and step == disturbance_step:
+                z[:, 0:2] = 0.0
+            uh.append(z[:, 0:2].clone())
+            sth.append(out["status"])
+            ith.append(out["iters"])
+            if longest_first:
+                solver.set_order(torch.argsort(out["iters"], descending=True, stable=True).to(torch.int32))
+            solver.shift(x, z)  # plant Euler step with U_0 and warm-start shift, in place
+            if obs is not None and moving:
+                obs[..., 0] = obs[..., 0] + obs[..., 3] * torch.cos(obs[..., 2]) * dt  # main_cbf_kin_c_sim_pre.py:106
+                obs[..., 1] = obs[..., 1] + obs[..., 3] * torch.sin(obs[..., 2]) * dt
+            xh.append(x.clone())
+            yield step
+    finally:
+        # an abandoned or failing loop must not leave its order installed on the handle
         if longest_first:
-            solver.set_order(torch.argsort(out["iters"], descending=True, stable=True).to(torch.int32))
-        solver.shift(x, z)  # plant Euler step with U_0 and warm-start shift, in place
-        if obs is not None and moving:
-            obs[..., 0] = obs[..., 0] + obs[..., 3] * torch.cos(obs[..., 2]) * dt  # main_cbf_kin_c_sim_pre.py:106
-            obs[..., 1] = obs[..., 1] + obs[..., 3] * torch.sin(obs[..., 2]) * dt
-        xh.append(x.clone())
-        yield step
-    if longest_first:
-        solver.set_order(None)
+            solver.set_order(None)
     return {"x": torch.stack(xh), "u": torch.stack(uh), "status": torch.stack(sth), "iters": torch.stack(ith)}

@@ -92,8 +92,16 @@ struct mpcb_handle {
   // device buffers for the host-pointer entry point
   cudaStream_t stream;
   int cap_B;
-  double *d_x0, *d_xs, *d_obs, *d_zin, *d_u0, *d_cost, *d_z, *d_lam;
+  double *d_x0, *d_xs, *d_obs, *d_zin, *d_u0, *d_cost, *d_z, *d_lam, *d_lamg, *d_lamx;
   int32_t *d_status, *d_iters;
+  // one solve at a time per handle: the work queue head and the slab belong to the launch in flight.  A solve
+  // issued on another stream first waits (on the device) for the previous one.
+  cudaEvent_t last_done;
+  cudaStream_t last_stream;
+  bool has_last;
+  int order_n;                    // length of the installed processing order
+  double *lam_g_out, *lam_x_out;  // optional dual outputs (mpcb_set_dual_outputs)
+  int duals_on_host;
 };
 
 extern "C" {
@@ -169,7 +177,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   memset(h, 0, sizeof *h);
   h->cfg = c;
   h->var = var;
-  if (!cuda_ok(cudaGetDevice(&h->device), "cudaGetDevice")) { delete h; return MPCB_E_CUDA; }
+  if (!cuda_ok(cudaGetDevice(&h->device), "cudaGetDevice")) { mpcb_destroy(h); return MPCB_E_CUDA; }
 
   KParams &k = h->kp;
   memset(&k, 0, sizeof k);
@@ -198,14 +206,14 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   h->smem = var.smem_bytes(c.N) * var.warps;
   if (const char *pad = getenv("MPCB_SMEM_PAD")) h->smem += (size_t)atoi(pad);  // tuning knob: lowers occupancy
   cudaDeviceProp prop;
-  if (!cuda_ok(cudaGetDeviceProperties(&prop, h->device), "cudaGetDeviceProperties")) { delete h; return MPCB_E_CUDA; }
-  if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return MPCB_E_ARG; }
+  if (!cuda_ok(cudaGetDeviceProperties(&prop, h->device), "cudaGetDeviceProperties")) { mpcb_destroy(h); return MPCB_E_CUDA; }
+  if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { mpcb_destroy(h); return MPCB_E_ARG; }
   if (!cuda_ok(cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem), "cudaFuncSetAttribute")) {
-    delete h;
+    mpcb_destroy(h);
     return MPCB_E_CUDA;
   }
   cudaFuncAttributes fa;
-  if (!cuda_ok(cudaFuncGetAttributes(&fa, var.kernel), "cudaFuncGetAttributes")) { delete h; return MPCB_E_CUDA; }
+  if (!cuda_ok(cudaFuncGetAttributes(&fa, var.kernel), "cudaFuncGetAttributes")) { mpcb_destroy(h); return MPCB_E_CUDA; }
   int bps = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, var.kernel, 32 * var.warps, h->smem);
   h->info.block = 32 * var.warps;
@@ -214,12 +222,11 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   h->info.blocks_per_sm = bps;
   h->info.num_sms = prop.multiProcessorCount;
   if (var.slab_doubles) {
-    if (bps < 1) { delete h; return MPCB_E_ARG; }
+    if (bps < 1) { mpcb_destroy(h); return MPCB_E_ARG; }
     h->persistent_grid = bps * prop.multiProcessorCount;
     size_t bytes = (size_t)h->persistent_grid * var.warps * var.slab_doubles * sizeof(double);
     if (!cuda_ok(cudaMalloc(&h->d_slab, bytes), "cudaMalloc slab") || !cuda_ok(cudaMalloc(&h->d_counter, sizeof(int)), "cudaMalloc counter")) {
-      cudaFree(h->d_slab);
-      delete h;
+      mpcb_destroy(h);
       return MPCB_E_NOMEM;
     }
     cudaMemset(h->d_slab, 0, bytes);
@@ -240,12 +247,13 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
       h->lat_info.block = 32 * var.lat_warps;
       h->lat_info.smem_bytes = (int32_t)h->lat_smem;
       h->lat_info.blocks_per_sm = lb;
-      if (!h->d_counter && !cuda_ok(cudaMalloc(&h->d_counter, sizeof(int)), "cudaMalloc counter")) { delete h; return MPCB_E_NOMEM; }
+      if (!h->d_counter && !cuda_ok(cudaMalloc(&h->d_counter, sizeof(int)), "cudaMalloc counter")) { mpcb_destroy(h); return MPCB_E_NOMEM; }
     } else {
       cudaGetLastError();
     }
   }
-  if (!cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete h; return MPCB_E_CUDA; }
+  if (!cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { mpcb_destroy(h); return MPCB_E_CUDA; }
+  if (!cuda_ok(cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming), "cudaEventCreate")) { mpcb_destroy(h); return MPCB_E_CUDA; }
   *out = h;
   return MPCB_OK;
 }
@@ -253,7 +261,8 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
 static void free_bufs(mpcb_handle *h) {
   cudaFree(h->d_x0); cudaFree(h->d_xs); cudaFree(h->d_obs); cudaFree(h->d_zin); cudaFree(h->d_u0);
   cudaFree(h->d_cost); cudaFree(h->d_z); cudaFree(h->d_lam); cudaFree(h->d_status); cudaFree(h->d_iters);
-  h->d_x0 = h->d_xs = h->d_obs = h->d_zin = h->d_u0 = h->d_cost = h->d_z = h->d_lam = nullptr;
+  cudaFree(h->d_lamg); cudaFree(h->d_lamx);
+  h->d_x0 = h->d_xs = h->d_obs = h->d_zin = h->d_u0 = h->d_cost = h->d_z = h->d_lam = h->d_lamg = h->d_lamx = nullptr;
   h->d_status = h->d_iters = nullptr;
   h->cap_B = 0;
 }
@@ -261,6 +270,8 @@ static void free_bufs(mpcb_handle *h) {
 void mpcb_destroy(mpcb_handle *h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);  // a batch submitted with mpcb_submit_batch_host may still be in flight
+  if (h->has_last) cudaEventSynchronize(h->last_done);  // ... or a solve on a caller's stream
+  if (h->last_done) cudaEventDestroy(h->last_done);
   free_bufs(h);
   cudaFree(h->d_slab);
   cudaFree(h->d_counter);
@@ -275,10 +286,17 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
   if (B == 0) return MPCB_OK;  // empty batch: nothing to read or write
   if (!x0 || !xs || !u0 || !cost || !status || !iters) return MPCB_E_ARG;
   if (h->cfg.obs_mode != MPCB_OBS_NONE && !obs) return MPCB_E_ARG;
+  if (h->kp.order && h->order_n != B) return MPCB_E_ARG;  // an installed order is a permutation of exactly this batch
   KParams k = h->kp;
   k.B = B;
   k.x0 = x0; k.xs = xs; k.obs = obs; k.z_init = z_init;
   k.u0 = u0; k.cost = cost; k.status = status; k.iters = iters; k.z_out = z_out; k.lam_out = lam_out;
+  if (!h->duals_on_host) { k.lam_g_out = h->lam_g_out; k.lam_x_out = h->lam_x_out; }
+  else if (stream == (void *)h->stream && h->d_lamg) { k.lam_g_out = h->lam_g_out ? h->d_lamg : nullptr; k.lam_x_out = h->lam_x_out ? h->d_lamx : nullptr; }
+  // The queue head and the slab are per handle: a solve issued on a different stream than the previous one
+  // queues behind it on the device (same stream: already ordered).
+  if (h->has_last && h->last_stream != (cudaStream_t)stream &&
+      !cuda_ok(cudaStreamWaitEvent((cudaStream_t)stream, h->last_done, 0), "cudaStreamWaitEvent")) return MPCB_E_CUDA;
   int grid = B;
   cudaError_t e;
   static const int lat_force = getenv("MPCB_LAT_MAX_B") ? atoi(getenv("MPCB_LAT_MAX_B")) : 0;  // tuning knob
@@ -302,6 +320,9 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
     e = h->var.launch(k, grid, h->smem, (cudaStream_t)stream);
   }
   if (!cuda_ok(e, "solve_kernel launch")) return MPCB_E_CUDA;
+  if (!cuda_ok(cudaEventRecord(h->last_done, (cudaStream_t)stream), "cudaEventRecord")) return MPCB_E_CUDA;
+  h->has_last = true;
+  h->last_stream = (cudaStream_t)stream;
   {
     const int64_t launches = h->info.launches + 1;
     h->info = small_batch ? h->lat_info : h->main_info;
@@ -323,6 +344,43 @@ int mpcb_solve_batch_host(mpcb_handle *h, int B, const double *x0, const double 
   return rc != MPCB_OK ? rc : mpcb_wait(h);
 }
 
+int mpcb_n_g(const mpcb_cfg *c) {
+  if (!c) return 0;
+  const int nx = mpcb_nx(c), M = c->obs_mode == MPCB_OBS_NONE ? 0 : c->M;
+  const int n_obs_st = (c->obs_mode == MPCB_OBS_ELLIPSE || c->obs_mode == MPCB_OBS_DCBF) ? c->N : (c->obs_mode == MPCB_OBS_SQRT ? c->N + 1 : 0);
+  return nx * (c->N + 1) + c->n_rate * (c->N - 1) + M * n_obs_st;
+}
+
+int mpcb_reserve(mpcb_handle *h, int B) {
+  if (!h || B < 0) return MPCB_E_ARG;
+  if (B <= h->cap_B) return MPCB_OK;
+  const int nx = h->var.nx, N = h->cfg.N;
+  const int M = h->cfg.obs_mode == MPCB_OBS_NONE ? 0 : h->cfg.M;
+  const size_t nv = 2 * (size_t)N + (size_t)nx * (N + 1);
+  const size_t so = (size_t)M * (h->cfg.obs_input != MPCB_OBS_TRAJECTORY ? 1 : (N + 1)) * 6;
+  const size_t sxs = h->cfg.ref_mode == MPCB_REF_TRAJECTORY ? (size_t)nx * N : (size_t)nx;
+  if (!cuda_ok(cudaStreamSynchronize(h->stream), "stream sync before regrowing buffers")) return MPCB_E_CUDA;
+  free_bufs(h);
+  size_t b = (size_t)B;
+  bool ok = cuda_ok(cudaMalloc(&h->d_x0, b * nx * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_xs, b * sxs * 8), "cudaMalloc") &&
+            cuda_ok(cudaMalloc(&h->d_obs, b * (so ? so : 1) * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_zin, b * nv * 8), "cudaMalloc") &&
+            cuda_ok(cudaMalloc(&h->d_u0, b * 2 * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_cost, b * 8), "cudaMalloc") &&
+            cuda_ok(cudaMalloc(&h->d_z, b * nv * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_lam, b * nx * (N + 1) * 8), "cudaMalloc") &&
+            cuda_ok(cudaMalloc(&h->d_lamg, b * mpcb_n_g(&h->cfg) * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_lamx, b * nv * 8), "cudaMalloc") &&
+            cuda_ok(cudaMalloc(&h->d_status, b * 4), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_iters, b * 4), "cudaMalloc");
+  if (!ok) { free_bufs(h); return MPCB_E_NOMEM; }
+  h->cap_B = B;
+  return MPCB_OK;
+}
+
+int mpcb_set_dual_outputs(mpcb_handle *h, double *lam_g, double *lam_x, int on_host) {
+  if (!h) return MPCB_E_ARG;
+  h->lam_g_out = lam_g;
+  h->lam_x_out = lam_x;
+  h->duals_on_host = on_host ? 1 : 0;
+  return MPCB_OK;
+}
+
 int mpcb_submit_batch_host(mpcb_handle *h, int B, const double *x0, const double *xs, const double *obs,
                            const double *z_init, double *u0, double *cost, int32_t *status, int32_t *iters,
                            double *z_out, double *lam_out) {
@@ -335,17 +393,9 @@ int mpcb_submit_batch_host(mpcb_handle *h, int B, const double *x0, const double
   const size_t so = (size_t)M * (h->cfg.obs_input != MPCB_OBS_TRAJECTORY ? 1 : (N + 1)) * 6;
   const size_t sxs = h->cfg.ref_mode == MPCB_REF_TRAJECTORY ? (size_t)nx * N : (size_t)nx;
   if (M > 0 && !obs) return MPCB_E_ARG;
-  if (B > h->cap_B) {
-    if (!cuda_ok(cudaStreamSynchronize(h->stream), "stream sync before regrowing buffers")) return MPCB_E_CUDA;
-    free_bufs(h);
-    size_t b = (size_t)B;
-    bool ok = cuda_ok(cudaMalloc(&h->d_x0, b * nx * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_xs, b * sxs * 8), "cudaMalloc") &&
-              cuda_ok(cudaMalloc(&h->d_obs, b * (so ? so : 1) * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_zin, b * nv * 8), "cudaMalloc") &&
-              cuda_ok(cudaMalloc(&h->d_u0, b * 2 * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_cost, b * 8), "cudaMalloc") &&
-              cuda_ok(cudaMalloc(&h->d_z, b * nv * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_lam, b * nx * (N + 1) * 8), "cudaMalloc") &&
-              cuda_ok(cudaMalloc(&h->d_status, b * 4), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_iters, b * 4), "cudaMalloc");
-    if (!ok) { free_bufs(h); return MPCB_E_NOMEM; }
-    h->cap_B = B;
+  if (B > h->cap_B) {  // grows the staging buffers (allocation); call mpcb_reserve up front to keep this path allocation-free
+    int rc = mpcb_reserve(h, B);
+    if (rc != MPCB_OK) return rc;
   }
   cudaStream_t st = h->stream;
   size_t b = (size_t)B;
@@ -363,12 +413,15 @@ int mpcb_submit_batch_host(mpcb_handle *h, int B, const double *x0, const double
        cuda_ok(cudaMemcpyAsync(iters, h->d_iters, b * 4, cudaMemcpyDeviceToHost, st), "D2H iters");
   if (ok && z_out) ok = cuda_ok(cudaMemcpyAsync(z_out, h->d_z, b * nv * 8, cudaMemcpyDeviceToHost, st), "D2H z");
   if (ok && lam_out) ok = cuda_ok(cudaMemcpyAsync(lam_out, h->d_lam, b * nx * (N + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H lam");
+  if (ok && h->duals_on_host && h->lam_g_out) ok = cuda_ok(cudaMemcpyAsync(h->lam_g_out, h->d_lamg, b * mpcb_n_g(&h->cfg) * 8, cudaMemcpyDeviceToHost, st), "D2H lam_g");
+  if (ok && h->duals_on_host && h->lam_x_out) ok = cuda_ok(cudaMemcpyAsync(h->lam_x_out, h->d_lamx, b * nv * 8, cudaMemcpyDeviceToHost, st), "D2H lam_x");
   return ok ? MPCB_OK : MPCB_E_CUDA;
 }
 
-int mpcb_set_order(mpcb_handle *h, const int32_t *order) {
-  if (!h) return MPCB_E_ARG;
+int mpcb_set_order(mpcb_handle *h, const int32_t *order, int n) {
+  if (!h || (order && n <= 0)) return MPCB_E_ARG;
   h->kp.order = order;
+  h->order_n = order ? n : 0;
   return MPCB_OK;
 }
 

@@ -12,6 +12,7 @@ namespace mpcb {
 
 struct DynLayout {
   static constexpr int NX = 6, NBX = 3, NR = 2, MO = 1, NJ = DYN_NJ;
+  static constexpr int NR_ROWS = NR, MO_ROWS = MO;
   // ---- shared memory: working set of the serial sweeps (stage-major records, see KinLayout)
   static constexpr int CDEF = 0;
   static constexpr int LAMP = CDEF;  // alias
@@ -80,6 +81,7 @@ template <bool SHP>
 struct DynSolver {
   using L = DynLayout;
   static constexpr int NX = 6, NBX = 3, NR = 2, MO = 1, NJ = DYN_NJ;
+  static constexpr bool ROWS_INTERLEAVED = true;  // g = init, then per stage: defect, rate rows; obstacle rows last
   __device__ static __forceinline__ constexpr int bx(int i) { return i == 0 ? 1 : (i == 1 ? 3 : 4); }  // y, vx, vy
 
   const KParams &p;

@@ -77,6 +77,7 @@ struct KParams {
   double tol, mu_init;
   const double *x0, *xs, *obs, *z_init;
   double *u0, *cost, *z_out, *lam_out;
+  double *lam_g_out, *lam_x_out;  // optional: res['lam_g'] [B][rows of g], res['lam_x'] [B][nv]
   int32_t *status, *iters;
   double *slab;    // per-resident-block scratch in global memory (kinematic kernels)
   int *counter;    // work queue head (persistent kernels)
@@ -153,6 +154,7 @@ template <int NR, int MO, bool FH = false, bool GS = false, bool AS = false>
 struct KinLayout {
   static_assert(!(GS && AS), "the step lives in the slab or everything lives in shared memory");
   static constexpr int NX = 4, NBX = 2;
+  static constexpr int NR_ROWS = NR, MO_ROWS = MO;
   // ---- shared memory: the working set of the serial sweeps (one record of NF doubles per stage)
   static constexpr int CDEF = 0;         // c_0 = X0 - x0, c_k = defect into stage k
   static constexpr int LAMP = CDEF;      // alias: new dynamics multipliers (written after the forward sweep)
@@ -230,6 +232,8 @@ struct KinSolver {
   static constexpr bool DCBF = OBS_MODE == 3;  // rows h(X_{k+1};obs_k) - (1-gamma) h(X_k;obs_k) >= 0
   using L = KinLayout<NR, MO, DCBF, GS, AS>;
   static constexpr int NX = 4, NBX = 2;
+  static constexpr bool ROWS_INTERLEAVED = false;  // g = [init; defects][rate rows][obstacle rows]
+  __device__ static __forceinline__ constexpr int bx(int i) { return KinModel::bx(i); }
 
   const KParams &p;
   double *gs;  // this warp's slab in global memory

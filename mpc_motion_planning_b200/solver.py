@@ -54,6 +54,7 @@ class BatchSolver:
         self.N, self.M = int(self.cfg.N), int(self.cfg.M)
         self.nx = _nx(kind)
         self.nv = 2 * self.N + self.nx * (self.N + 1)
+        self.n_g = int(self.lib.mpcb_n_g(C.byref(self.cfg)))  # rows of g = len(res['g']) = len(res['lam_g'])
         # obs argument: (B,M,N+1,6) obs_prediction rows, or (B,M,6) obstacle states when obs_input="initial"
         self.obs_shape = (self.M, 6) if self.obs_initial else (self.M, self.N + 1, 6)
         # xs argument: (B,nx) target, or (B,N,nx) per-stage targets when ref="trajectory"
@@ -82,14 +83,20 @@ class BatchSolver:
             pass
 
     # ------------------------------------------------------------------ device path
-    def solve(self, x0, xs, obs=None, z_init=None, return_z: bool = False, return_lam: bool = False):
+    def reserve(self, B: int):
+        """Size the staging buffers of the host-pointer entry points for batches up to B (mpcb_reserve): no later host
+        solve with a batch <= B allocates."""
+        _lib.check(self.lib.mpcb_reserve(self._h, int(B)), "mpcb_reserve")
+
+    def solve(self, x0, xs, obs=None, z_init=None, return_z: bool = False, return_lam: bool = False, return_duals: bool = False):
         """x0 (B,nx); xs (B,nx) [(B,N,nx) with ref="trajectory"]; obs (B,M,N+1,6) or None; z_init (B,nv) or None.
 
         torch CUDA tensors -> asynchronous on the current stream, returns torch tensors;
         numpy arrays -> synchronous host entry, returns numpy arrays.
-        dict keys: u0 (B,2), cost (B,), status (B,) int32, iters (B,) int32 [, z (B,nv)] [, lam (B,nx(N+1))]."""
+        dict keys: u0 (B,2), cost (B,), status (B,) int32, iters (B,) int32 [, z (B,nv)] [, lam (B,nx(N+1))]
+        [, lam_g (B,n_g), lam_x (B,nv) with return_duals: CasADi's res['lam_g'] / res['lam_x']]."""
         if isinstance(x0, np.ndarray):
-            return self._solve_host(x0, xs, obs, z_init, return_z, return_lam)
+            return self._solve_host(x0, xs, obs, z_init, return_z, return_lam, return_duals)
         import torch
 
         B = x0.shape[0]
@@ -117,13 +124,23 @@ class BatchSolver:
         iters = torch.empty((B,), dtype=torch.int32, device=dev)
         z = torch.empty((B, self.nv), dtype=torch.float64, device=dev) if return_z else None
         lam = torch.empty((B, self.nx * (self.N + 1)), dtype=torch.float64, device=dev) if return_lam else None
+        lam_g = torch.empty((B, self.n_g), dtype=torch.float64, device=dev) if return_duals else None
+        lam_x = torch.empty((B, self.nv), dtype=torch.float64, device=dev) if return_duals else None
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         with torch.cuda.device(dev):
-            rc = self.lib.mpcb_solve_batch(self._h, B, ptr(x0), ptr(xs), ptr(obs), ptr(z_init), ptr(u0), ptr(cost),
-                                           ptr(status), ptr(iters), ptr(z), ptr(lam), stream)
+            if return_duals:
+                _lib.check(self.lib.mpcb_set_dual_outputs(self._h, ptr(lam_g), ptr(lam_x), 0), "mpcb_set_dual_outputs")
+            try:
+                rc = self.lib.mpcb_solve_batch(self._h, B, ptr(x0), ptr(xs), ptr(obs), ptr(z_init), ptr(u0), ptr(cost),
+                                               ptr(status), ptr(iters), ptr(z), ptr(lam), stream)
+            finally:
+                if return_duals:
+                    self.lib.mpcb_set_dual_outputs(self._h, None, None, 0)
         _lib.check(rc, "mpcb_solve_batch")
         out = {"u0": u0, "cost": cost, "status": status, "iters": iters}
+        if return_duals:
+            out["lam_g"], out["lam_x"] = lam_g, lam_x
         if return_z:
             out["z"] = z
         if return_lam:
@@ -131,7 +148,7 @@ class BatchSolver:
         return out
 
     # ------------------------------------------------------------------ host path
-    def _solve_host(self, x0, xs, obs, z_init, return_z, return_lam):
+    def _solve_host(self, x0, xs, obs, z_init, return_z, return_lam, return_duals=False):
         B = x0.shape[0]
         f64 = lambda a, shape: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(shape)
         x0 = f64(x0, (B, self.nx))
@@ -144,11 +161,21 @@ class BatchSolver:
         iters = np.empty(B, dtype=np.int32)
         z = np.empty((B, self.nv)) if return_z else None
         lam = np.empty((B, self.nx * (self.N + 1))) if return_lam else None
+        lam_g = np.empty((B, self.n_g)) if return_duals else None
+        lam_x = np.empty((B, self.nv)) if return_duals else None
         ptr = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
-        rc = self.lib.mpcb_solve_batch_host(self._h, B, ptr(x0), ptr(xs), ptr(obs), ptr(z_init), ptr(u0), ptr(cost),
-                                            ptr(status), ptr(iters), ptr(z), ptr(lam))
+        if return_duals:
+            _lib.check(self.lib.mpcb_set_dual_outputs(self._h, ptr(lam_g), ptr(lam_x), 1), "mpcb_set_dual_outputs")
+        try:
+            rc = self.lib.mpcb_solve_batch_host(self._h, B, ptr(x0), ptr(xs), ptr(obs), ptr(z_init), ptr(u0), ptr(cost),
+                                                ptr(status), ptr(iters), ptr(z), ptr(lam))
+        finally:
+            if return_duals:
+                self.lib.mpcb_set_dual_outputs(self._h, None, None, 0)
         _lib.check(rc, "mpcb_solve_batch_host")
         out = {"u0": u0, "cost": cost, "status": status, "iters": iters}
+        if return_duals:
+            out["lam_g"], out["lam_x"] = lam_g, lam_x
         if return_z:
             out["z"] = z
         if return_lam:
@@ -212,13 +239,13 @@ class BatchSolver:
         """order: CUDA int32 tensor (B,), a permutation - queue position q processes scenario order[q]
         (longest expected first); None resets to arrival order.  Results do not depend on it."""
         if order is None:
-            _lib.check(self.lib.mpcb_set_order(self._h, None), "mpcb_set_order")
+            _lib.check(self.lib.mpcb_set_order(self._h, None, 0), "mpcb_set_order")
             self._order = None
         else:
             import torch
 
             assert order.is_cuda and order.dtype == torch.int32 and order.is_contiguous()
-            _lib.check(self.lib.mpcb_set_order(self._h, C.c_void_p(order.data_ptr())), "mpcb_set_order")
+            _lib.check(self.lib.mpcb_set_order(self._h, C.c_void_p(order.data_ptr()), int(order.numel())), "mpcb_set_order")
             self._order = order  # keep it alive
 
     def set_trace(self, trace):

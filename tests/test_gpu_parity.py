@@ -380,6 +380,10 @@ def test_reference_mains_run_closed_loop(dev):
         assert out.returncode == 0, out.stderr[-2000:]
         text = " ".join(out.stdout.split())  # the 6-state summary wraps over two lines
         assert f"{name}: {steps} MPC steps, {steps} solved" in text, text[-400:]
+    # the single-shot main (PKG/main_kin_s_sim.py): one solve from the all-zero guess, full result dict
+    out = subprocess.run([sys.executable, "main_kin_s_sim.py"], cwd=os.path.join(root, "mains"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "main_kin_s_sim: 1 MPC steps, 2 solved" in " ".join(out.stdout.split()), out.stdout[-400:]
 
 
 def test_in_kernel_obstacle_prediction_equals_host_trajectories(dev):
@@ -882,3 +886,97 @@ def test_closed_loop_in_lanes_equals_the_single_handle_loop():
     torch.cuda.synchronize()
     for k in ("x", "u", "status", "iters"):
         assert one[k].shape == two[k].shape and torch.equal(one[k], two[k]), k
+
+
+# --------------------------------------------------------------------------- ABI 0.2.0
+@pytest.mark.parametrize("kind,gen", [("kin_nocbf", "kin_nocbf"), ("kin_cbf", "kin_cbf_static"), ("kin_cbf_pre", "kin_cbf_moving"),
+                                      ("dyn", "dyn_static")])
+def test_lam_g_and_lam_x_satisfy_stationarity_on_the_restated_nlp(dev, kind, gen):
+    """res['lam_g'] (every row of g, the reference's order) and res['lam_x'] (CasADi's sign) of converged scenarios make
+    grad f + J_g' lam_g + lam_x vanish on the numpy restatement of the NLP, and obey the sign rules of their bounds."""
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+    from oracle import nlp as onlp
+
+    B = 24
+    x0, xs, obs = getattr(scenarios, gen)(B)
+    s = BatchSolver(kind)
+    g = _gpu(s, dev, x0, xs, obs, return_z=True, return_lam=True, return_duals=True)
+    assert g["lam_g"].shape == (B, s.n_g) and g["lam_x"].shape == (B, s.nv)
+    n = 0
+    for b in np.where(g["status"] == 0)[0][:8]:
+        if kind == "kin_cbf":
+            ob = obs[b, :, 0, :]
+        elif kind == "kin_cbf_pre":
+            ob = [obs[b, j] for j in range(obs.shape[1])]
+        elif kind == "dyn":
+            ob = obs[b, 0, 0, :2]
+        else:
+            ob = None
+        P = onlp.NLP(kind, x0[b], xs[b], ob)
+        z = g["z"][b]
+        J = np.vstack([P.jac_eq(z), P.jac_ineq(z)] if P.n_ineq else [P.jac_eq(z)])[P.g_perm()]
+        lam_g, lam_x = g["lam_g"][b], g["lam_x"][b]
+        r = P.grad(z) + J.T @ lam_g + lam_x
+        scale = max(1.0, np.abs(P.grad(z)).max())
+        assert np.abs(r).max() <= 1e-6 * scale, (kind, b, np.abs(r).max(), scale)
+        # head of lam_g = the equality multipliers already exported as lam_out
+        if kind != "dyn":
+            assert np.array_equal(lam_g[: P.n_eq], g["lam"][b])
+        lo, hi = P.lbg_ubg_aligned()
+        ineq = np.isinf(hi) & np.isfinite(lo)
+        assert np.all(lam_g[ineq] <= 1e-9 * scale)  # g >= lb rows: multiplier <= 0 in CasADi's convention
+        free = np.isinf(P.zL) & np.isinf(P.zU)
+        assert np.all(lam_x[free] == 0.0)
+        n += 1
+    assert n >= 4
+
+
+def test_two_streams_on_one_handle_are_serialised(dev):
+    """A handle owns one work queue and one slab: a solve issued on a second stream queues behind the first on the device
+    instead of racing it (include/mpcb200.h)."""
+    import torch
+
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+
+    B = 3000
+    x0, xs, obs = scenarios.kin_cbf_static(2 * B)
+    s = BatchSolver("kin_cbf")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    a = [t(v[:B]) for v in (x0, xs, obs)]
+    b = [t(v[B:]) for v in (x0, xs, obs)]
+    ref_a = {k: v.clone() for k, v in s.solve(*a).items()}
+    ref_b = {k: v.clone() for k, v in s.solve(*b).items()}
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            oa = s.solve(*a)
+        with torch.cuda.stream(s2):
+            ob = s.solve(*b)
+        torch.cuda.synchronize()
+        for k in ("u0", "cost", "status", "iters"):
+            assert torch.equal(oa[k], ref_a[k]) and torch.equal(ob[k], ref_b[k]), k
+
+
+def test_reserve_and_order_length(dev):
+    import torch
+
+    from mpc_motion_planning_b200 import _lib, scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+
+    x0, xs, obs = scenarios.kin_cbf_static(64)
+    s = BatchSolver("kin_cbf")
+    s.reserve(64)
+    free0 = torch.cuda.mem_get_info(dev)[0]
+    h = s.solve(x0, xs, obs)  # numpy -> host entry, staged through the reserved buffers
+    assert torch.cuda.mem_get_info(dev)[0] == free0, "the host entry allocated although the batch was reserved"
+    g = _gpu(s, dev, x0, xs, obs)
+    assert np.array_equal(h["status"], g["status"]) and np.array_equal(h["u0"], g["u0"])
+    # an order is a permutation of exactly one batch size
+    s.set_order(torch.arange(32, dtype=torch.int32, device=dev))
+    with pytest.raises(_lib.MpcbError):
+        _gpu(s, dev, x0, xs, obs)
+    s.set_order(None)
+    _gpu(s, dev, x0, xs, obs)

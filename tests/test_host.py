@@ -19,7 +19,7 @@ def test_library_exports_every_symbol_of_the_header():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mpcb_version() == 103
+    assert lib.mpcb_version() == 200
 
 
 def test_cfg_struct_layout_matches_the_header_field_order():
