@@ -69,8 +69,12 @@ enum {
   MPCB_ACCEPTABLE = 1, /* Solved_To_Acceptable_Level: the line search failed at a point whose scaled KKT error is
                           already <= 1e-6 (IPOPT's default acceptable_tol; the reference's 1e-8 equals tol) */
   MPCB_MAXITER = 2,    /* Maximum_Iterations_Exceeded */
-  MPCB_INFEASIBLE = 3, /* line search failed / Restoration_Failed / Infeasible_Problem_Detected */
-  MPCB_NAN = 4         /* Invalid_Number_Detected */
+  MPCB_INFEASIBLE = 3, /* Infeasible_Problem_Detected: the restoration phase converged to a stationary point of the
+                          infeasibility, or was entered more than cfg.resto_max_calls times without the regular phase
+                          converging from where it left off (a locally infeasible start); with cfg.restoration = 0, and
+                          for the dyn family: the line search failed and no restoration was attempted */
+  MPCB_NAN = 4,        /* Invalid_Number_Detected */
+  MPCB_RESTO_FAILED = 5 /* Restoration_Failed: the restoration phase's own line search / inertia correction failed */
 };
 
 /* return codes of the entry points */
@@ -111,6 +115,12 @@ typedef struct mpcb_cfg {
   int32_t ref_mode;     /* MPCB_REF_TERMINAL (default) or MPCB_REF_TRAJECTORY */
   double cbf_gamma;     /* gamma in (0,1] of the MPCB_OBS_DCBF rows (the reference's `gamma = 1.00`, :235) */
   int32_t dyn_rows;     /* MPCB_DYN_ROWS_ALIGNED (default) or MPCB_DYN_ROWS_AS_SHIPPED */
+  int32_t restoration;  /* 1: a failed line search / inertia correction enters the restoration phase (what IPOPT does behind
+                           PKG/MPC_CBF_optimize_kin.py:252-254) instead of ending the solve; kinematic families with rows.
+                           The scenarios concerned are solved again, from their start point, by a restoration-capable
+                           sibling kernel launched right after the main one on the same stream */
+  int32_t resto_max_calls; /* > 0: the (n+1)-th entry into the restoration phase ends the solve with MPCB_INFEASIBLE; 0 = no cap
+                           (IPOPT: the phases alternate until max_iter).  Library default 1, drop-in classes 0 */
   int32_t reserved;
 } mpcb_cfg;
 

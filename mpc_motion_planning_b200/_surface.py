@@ -165,6 +165,9 @@ class MPCOptimizeBase:
         self.tol = 1e-8
         self.mu_init = 30.0
         self.init = "as_given"  # the CasADi call starts IPOPT at x0= exactly
+        # IPOPT answers a failed line search with its restoration phase, as often as it takes (kin-CBF modules)
+        self.restoration = True
+        self.resto_max_calls = 0
         # Two switches the reference keeps as locals of optimize_problem (kin-CBF modules):
         #   aa = 0.0      weight of ref_state in the stage cost target          (:194-197)
         #   gamma = 1.00  with `g.append(h_func)` live and `gamma*h_func + h_dot` commented out (:235-248)
@@ -331,11 +334,11 @@ class MPCOptimizeBase:
         M = 0 if obs_array is None else obs_array.shape[0]
         gamma = float(self.gamma) if self._dcbf() else None
         ref = "trajectory" if self._stage_reference() else "terminal"
-        key = (M, self.max_iter, self.tol, self.mu_init, self.init, gamma, ref, dyn_rows) + tuple(np.concatenate([np.ravel(v) for v in bounds.values()]).tolist() if bounds else ())
+        key = (M, self.max_iter, self.tol, self.mu_init, self.init, gamma, ref, dyn_rows, self.restoration, self.resto_max_calls) + tuple(np.concatenate([np.ravel(v) for v in bounds.values()]).tolist() if bounds else ())
         if key not in self._solvers:
             self._solvers[key] = BatchSolver(self.KIND, config=self.config, N=N, M=max(M, 1), init=self.init, mu_init=self.mu_init,
                                              max_iter=self.max_iter, tol=self.tol, bounds=bounds or None, cbf_gamma=gamma, ref=ref,
-                                             dyn_bounds=dyn_rows)
+                                             dyn_bounds=dyn_rows, restoration=self.restoration, resto_max_calls=self.resto_max_calls)
         return self._solvers[key]
 
     def _check_row_bounds(self, lg, ug, bounds, dyn_rows, M):

@@ -102,6 +102,13 @@ struct mpcb_handle {
   int order_n;                    // length of the installed processing order
   double *lam_g_out, *lam_x_out;  // optional dual outputs (mpcb_set_dual_outputs)
   int duals_on_host;
+  // restoration pass: scenarios whose line search failed in the main kernel (list + count on the device), the
+  // second work-queue head, and the launch geometry of the restoration-capable sibling kernel
+  int32_t *d_resto_list;
+  int *d_resto_count;  // resto_sync of KParams: [0] entries reserved, [1] consumer tickets, [2] main warps finished
+  int resto_cap, resto_grid;
+  size_t resto_smem;
+  double *d_resto_slab;
 };
 
 extern "C" {
@@ -252,6 +259,27 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
       cudaGetLastError();
     }
   }
+  k.resto_max_calls = c.resto_max_calls;
+  k.restoration = (c.restoration && var.rs_inline) ? 1 : 0;
+  if (c.restoration && !var.rs_inline && var.resto_kernel) {
+    h->resto_smem = var.resto_smem_bytes(c.N) * var.resto_warps;
+    int rb = 0;
+    if (h->resto_smem <= (size_t)prop.sharedMemPerBlockOptin &&
+        cudaFuncSetAttribute(var.resto_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resto_smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rb, var.resto_kernel, 32 * var.resto_warps, h->resto_smem) == cudaSuccess && rb >= 1) {
+      h->resto_grid = rb * prop.multiProcessorCount;
+      // the restoration pass overlaps the main kernel's last wave: its own slab
+      size_t need = (size_t)h->resto_grid * var.resto_warps * var.resto_slab_doubles * sizeof(double);
+      if (!cuda_ok(cudaMalloc(&h->d_resto_slab, need), "cudaMalloc restoration slab")) { mpcb_destroy(h); return MPCB_E_NOMEM; }
+      cudaMemset(h->d_resto_slab, 0, need);
+      if (!cuda_ok(cudaMalloc(&h->d_resto_count, 4 * sizeof(int)), "cudaMalloc resto sync")) { mpcb_destroy(h); return MPCB_E_NOMEM; }
+      if (!h->d_counter && !cuda_ok(cudaMalloc(&h->d_counter, sizeof(int)), "cudaMalloc counter")) { mpcb_destroy(h); return MPCB_E_NOMEM; }
+    } else {
+      cudaGetLastError();
+      mpcb_destroy(h);
+      return MPCB_E_ARG;  // restoration requested but its kernel does not fit this device / horizon
+    }
+  }
   if (!cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { mpcb_destroy(h); return MPCB_E_CUDA; }
   if (!cuda_ok(cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming), "cudaEventCreate")) { mpcb_destroy(h); return MPCB_E_CUDA; }
   *out = h;
@@ -275,6 +303,9 @@ void mpcb_destroy(mpcb_handle *h) {
   free_bufs(h);
   cudaFree(h->d_slab);
   cudaFree(h->d_counter);
+  cudaFree(h->d_resto_list);
+  cudaFree(h->d_resto_count);
+  cudaFree(h->d_resto_slab);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -297,6 +328,21 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
   // queues behind it on the device (same stream: already ordered).
   if (h->has_last && h->last_stream != (cudaStream_t)stream &&
       !cuda_ok(cudaStreamWaitEvent((cudaStream_t)stream, h->last_done, 0), "cudaStreamWaitEvent")) return MPCB_E_CUDA;
+  const bool with_resto = h->resto_grid > 0;
+  if (with_resto) {
+    if (B > h->resto_cap) {  // grows the list of scenarios for the second pass (allocation; mpcb_reserve sizes it up front)
+      if (h->has_last) cudaEventSynchronize(h->last_done);
+      cudaFree(h->d_resto_list);
+      h->d_resto_list = nullptr;
+      h->resto_cap = 0;
+      if (!cuda_ok(cudaMalloc(&h->d_resto_list, (size_t)B * sizeof(int32_t)), "cudaMalloc resto list")) return MPCB_E_NOMEM;
+      h->resto_cap = B;
+    }
+    if (!cuda_ok(cudaMemsetAsync(h->d_resto_count, 0, 4 * sizeof(int), (cudaStream_t)stream), "resto queue reset") ||
+        !cuda_ok(cudaMemsetAsync(h->d_resto_list, 0xFF, (size_t)B * sizeof(int32_t), (cudaStream_t)stream), "resto list reset")) return MPCB_E_CUDA;
+    k.resto_list = h->d_resto_list;
+    k.resto_sync = h->d_resto_count;
+  }
   int grid = B;
   cudaError_t e;
   static const int lat_force = getenv("MPCB_LAT_MAX_B") ? atoi(getenv("MPCB_LAT_MAX_B")) : 0;  // tuning knob
@@ -320,11 +366,26 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
     e = h->var.launch(k, grid, h->smem, (cudaStream_t)stream);
   }
   if (!cuda_ok(e, "solve_kernel launch")) return MPCB_E_CUDA;
+  if (with_resto) {
+    // second pass: the listed scenarios again, from their start points, with the restoration-capable kernel.  Its batch
+    // size is known only on the device; blocks that find the queue empty retire at once.
+    KParams k2 = k;
+    k2.restoration = 1;
+    k2.slab = h->d_resto_slab;
+    k2.order = nullptr;
+    k2.resto_consumer = 1;
+    k2.main_warps = grid * (small_batch ? h->var.lat_warps : h->var.warps);
+    k2.trace = nullptr;
+    int g2 = (B + h->var.resto_warps - 1) / h->var.resto_warps;
+    if (g2 > h->resto_grid) g2 = h->resto_grid;
+    e = h->var.resto_launch(k2, g2, h->resto_smem, (cudaStream_t)stream);
+    if (!cuda_ok(e, "restoration kernel launch")) return MPCB_E_CUDA;
+  }
   if (!cuda_ok(cudaEventRecord(h->last_done, (cudaStream_t)stream), "cudaEventRecord")) return MPCB_E_CUDA;
   h->has_last = true;
   h->last_stream = (cudaStream_t)stream;
   {
-    const int64_t launches = h->info.launches + 1;
+    const int64_t launches = h->info.launches + (with_resto ? 2 : 1);
     h->info = small_batch ? h->lat_info : h->main_info;
     h->info.grid = grid;
     h->info.launches = launches;
@@ -370,6 +431,13 @@ int mpcb_reserve(mpcb_handle *h, int B) {
             cuda_ok(cudaMalloc(&h->d_status, b * 4), "cudaMalloc") && cuda_ok(cudaMalloc(&h->d_iters, b * 4), "cudaMalloc");
   if (!ok) { free_bufs(h); return MPCB_E_NOMEM; }
   h->cap_B = B;
+  if (h->resto_grid > 0 && B > h->resto_cap) {
+    cudaFree(h->d_resto_list);
+    h->d_resto_list = nullptr;
+    h->resto_cap = 0;
+    if (!cuda_ok(cudaMalloc(&h->d_resto_list, (size_t)B * sizeof(int32_t)), "cudaMalloc resto list")) return MPCB_E_NOMEM;
+    h->resto_cap = B;
+  }
   return MPCB_OK;
 }
 

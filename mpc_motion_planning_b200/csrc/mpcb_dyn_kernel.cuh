@@ -13,6 +13,7 @@ namespace mpcb {
 struct DynLayout {
   static constexpr int NX = 6, NBX = 3, NR = 2, MO = 1, NJ = DYN_NJ;
   static constexpr int NR_ROWS = NR, MO_ROWS = MO;
+  static constexpr int FTO = 0, FPO = 0;  // (names of the shared run loop's restoration branches, unused here)
   // ---- shared memory: working set of the serial sweeps (stage-major records, see KinLayout)
   static constexpr int CDEF = 0;
   static constexpr int LAMP = CDEF;  // alias
@@ -81,6 +82,7 @@ template <bool SHP>
 struct DynSolver {
   using L = DynLayout;
   static constexpr int NX = 6, NBX = 3, NR = 2, MO = 1, NJ = DYN_NJ;
+  static constexpr bool RS = false;  // no restoration-capable sibling for this family: a failed line search ends with status 3
   static constexpr bool ROWS_INTERLEAVED = true;  // g = init, then per stage: defect, rate rows; obstacle rows last
   __device__ static __forceinline__ constexpr int bx(int i) { return i == 0 ? 1 : (i == 1 ? 3 : 4); }  // y, vx, vy
 
@@ -91,6 +93,12 @@ struct DynSolver {
   int N, lane;
   double sigma;
   double x0[NX], xs[NX];
+
+  // names the shared run loop mentions inside its `if constexpr (RS)` branches (never executed here)
+  bool resto = false;
+  double zeta = 0.0, rmu = 0.0, o_thr = 0.0, o_f = 0.0;
+  __device__ __forceinline__ void resto_switch(bool) {}
+  __device__ __forceinline__ void resto_multipliers(double) {}
 
   __device__ DynSolver(const KParams &p_, double *gs_, int woff_, int &tick_, int lane_)
       : p(p_), gs(gs_), woff(woff_), tick(tick_), N(p_.N), lane(lane_) {}
@@ -1000,7 +1008,7 @@ struct DynSolver {
     return __all_sync(0xffffffffu, fin);
   }
 
-#define MPCB_ITER_SYNC() do { if (((++tick) & (MPCB_SYNC_EVERY - 1)) == 0) __syncthreads_and(0); } while (0)
+#define MPCB_ITER_SYNC() do { if (((++tick) & (MPCB_SYNC_EVERY - 1)) == 0) block_iteration_vote(0); } while (0)
 #include "mpcb_run_loop.inc"
 #undef MPCB_ITER_SYNC
 };
@@ -1022,7 +1030,7 @@ __global__ void __launch_bounds__(32 * W) dyn_solve_kernel(const __grid_constant
     s.run(b);
     __syncwarp();
   }
-  while (!__syncthreads_and(1)) {
+  while (!block_iteration_vote(1)) {
   }
 }
 

@@ -59,6 +59,10 @@ namespace mpcb {
  * IPOPT's default 1e-6 is used for this exit only (status MPCB_ACCEPTABLE). */
 #define MPCB_ACCEPTABLE_TOL 1e-6
 #define MPCB_FILTER_SLOTS 4 /* 4 x 32 lanes = 128 filter entries */
+/* restoration phase (IPOPT: resto_penalty_parameter, required_infeasibility_reduction, bound_mult_reset_threshold) */
+#define MPCB_RESTO_RHO 1000.0
+#define MPCB_RESTO_KAPPA 0.9
+#define MPCB_BOUND_MULT_RESET 1000.0
 
 struct KParams {
   int B, N, obs_mode, du0_cost, init_mode, max_iter, obs_input;
@@ -84,6 +88,18 @@ struct KParams {
   const int32_t *order;  // optional [B] permutation: queue position -> scenario index
   double *trace;   // optional [B][trace_rows][8] per-iteration log (mu, theta, err, dual, prim, compl, alpha, dw)
   int trace_rows;
+  // Restoration: the main kernels carry no restoration code.  A scenario whose line search fails is appended to
+  // resto_list (producer side, RS = false) and solved again, from its start point, by the restoration-capable sibling
+  // kernel (consumer side, RS = true).  The sibling is launched right behind the main kernel as a programmatic
+  // dependent launch: its blocks become resident as the main kernel's last wave releases the SMs, take tickets, and
+  // wait for list entries until every main warp has reported that its queue is empty.
+  //   resto_sync[0] = entries reserved, [1] = consumer tickets handed out, [2] = main warps that have finished
+  int32_t *resto_list;   // [B], preset to -1
+  int *resto_sync;
+  int resto_consumer;    // this launch is the restoration pass
+  int main_warps;        // warps of the main launch (consumer side: when resto_sync[2] reaches it the list is complete)
+  int resto_max_calls;
+  int restoration;       // RS kernels: enter the restoration phase in place (0: end with status 3 like the kernels without it)
 };
 
 // ------------------------------------------------------------------------------------
@@ -102,6 +118,23 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return r;
 }
 
+// l1 penalty rho*(p+n) on a row residual r = p - n, with p, n >= 0 held on their central path for the barrier
+// parameter mu (IPOPT's closed form for the start of its restoration phase, Waechter & Biegler 2006 eq. 33, applied
+// at every restoration iterate): psi' = rho - mu/p is the row's multiplier, psi'' = mu/(p^2+n^2) its curvature.
+struct Psi { double v, d1, d2; };
+static __device__ __noinline__ Psi d_psi(double r, double mu, bool want_value) {
+  const double rho = MPCB_RESTO_RHO;
+  const double b = mu * r / (2 * rho), q = sqrt(mu * mu + (rho * r) * (rho * r)) / (2 * rho);
+  const double an = (mu - rho * r) / (2 * rho), ap = (mu + rho * r) / (2 * rho);
+  const double n = an >= 0 ? an + q : b / (q - an);
+  const double pp = ap >= 0 ? ap + q : -b / (q - ap);
+  Psi o;
+  o.v = want_value ? rho * (pp + n) - mu * log(pp * n) : 0.0;
+  o.d1 = rho - mu / pp;
+  o.d2 = mu / (pp * pp + n * n);
+  return o;
+}
+
 static __device__ __noinline__ double d_log(double x) { return log(x); }
 static __device__ __noinline__ double d_pow(double x, double y) { return pow(x, y); }
 static __device__ __noinline__ double3 d_trig3(double phi, double delta) {  // (sin phi, cos phi, tan delta)
@@ -113,6 +146,13 @@ __device__ __forceinline__ void d_trig(double phi, double delta, double *s, doub
   double3 r = d_trig3(phi, delta);
   *s = r.x; *c = r.y; *t = r.z;
 }
+
+// The ONE block barrier of the solve kernels.  Protocol: every warp of a block arrives here once per round, whatever it is
+// doing - a working warp at the top of each interior-point iteration with done = 0 (from Solver::run), a warp whose queue
+// is empty with done = 1 (from the drain loop at the end of the kernel) - and the block retires when a round's votes are
+// all 1.  Both call sites go through this single out-of-line function, so all warps execute the same barrier instruction
+// (bar.red.and on barrier 0 counts arriving warps; per-warp arrival counts differ only by WHICH site called).
+static __device__ __noinline__ int block_iteration_vote(int done) { return __syncthreads_and(done); }
 
 // ------------------------------------------------------------------------------------
 // warp reductions (all lanes end with the same value)
@@ -150,7 +190,8 @@ struct KinModel {
 // warps at long horizons (N = 100: 8 warps per SM instead of 6, +12 %); the host picks per horizon.
 // AS: everything in shared memory, no slab (the small-batch variant: with a handful of scenarios per SM
 // occupancy is irrelevant and the L2 round trips of the stage-parallel phases are the latency).
-template <int NR, int MO, bool FH = false, bool GS = false, bool AS = false>
+// RS: the restoration-capable sibling keeps the reference point z_R of the proximity term in the slab as well.
+template <int NR, int MO, bool FH = false, bool GS = false, bool AS = false, bool RS = false>
 struct KinLayout {
   static_assert(!(GS && AS), "the step lives in the slab or everything lives in shared memory");
   static constexpr int NX = 4, NBX = 2;
@@ -203,7 +244,12 @@ struct KinLayout {
   // the step: written by lane 0 in the forward sweep, read by the stage-parallel phases only
   static constexpr int DX = GS ? XR + NX : R14 + 14;
   static constexpr int DU = DX + NX;
-  static constexpr int NG = XR + NX + (GS ? NX + 2 : 0) - G0;
+  static constexpr int NG0 = XR + NX + (GS ? NX + 2 : 0) - G0;
+  static constexpr int XRS = G0 + NG0;  // restoration: z_R (states, controls)
+  static constexpr int URS = XRS + NX;
+  static constexpr int FTO = URS + 2;   // restoration: the original filter (MPCB_FILTER_SLOTS rows, lane-indexed)
+  static constexpr int FPO = FTO + 4;
+  static constexpr int NG = NG0 + (RS ? NX + 2 + 8 : 0);
   static constexpr int SG = 132;        // row stride (>= MPCB_NMAX + 1)
   static constexpr int NFA = AS ? ((NF + NG) | 1) : NF;  // record length in shared memory
   __host__ __device__ static constexpr size_t bytes(int N) { return sizeof(double) * (size_t)NFA * (size_t)(N + 1); }
@@ -227,10 +273,11 @@ __device__ __forceinline__ double clampz(double z, double mu, double rgap) {
 // ------------------------------------------------------------------------------------
 // the solver: one warp = one scenario (kinematic model family)
 // ------------------------------------------------------------------------------------
-template <int NR, int MO, int OBS_MODE, bool GS = false, bool AS = false>
+template <int NR, int MO, int OBS_MODE, bool GS = false, bool AS = false, bool RS_ = false>
 struct KinSolver {
   static constexpr bool DCBF = OBS_MODE == 3;  // rows h(X_{k+1};obs_k) - (1-gamma) h(X_k;obs_k) >= 0
-  using L = KinLayout<NR, MO, DCBF, GS, AS>;
+  static constexpr bool RS = RS_;              // restoration-capable build (the second-pass kernel)
+  using L = KinLayout<NR, MO, DCBF, GS, AS, RS>;
   static constexpr int NX = 4, NBX = 2;
   static constexpr bool ROWS_INTERLEAVED = false;  // g = [init; defects][rate rows][obstacle rows]
   __device__ static __forceinline__ constexpr int bx(int i) { return KinModel::bx(i); }
@@ -242,9 +289,41 @@ struct KinSolver {
   int N, lane;
   double sigma;
   double x0[NX], xs[NX];
+  // restoration phase (RS builds): min zeta/2 ||D_R (z - z_R)||^2 + sum_rows psi_mu(row - s) s.t. the dynamics and the
+  // bounds; `resto` switches every phase below between the two problems (uniform per warp)
+  bool resto = false;
+  double zeta = 0.0;
+  double o_thr = 0.0, o_f = 0.0;  // restoration: row part of the original infeasibility, original objective
 
   __device__ KinSolver(const KParams &p_, double *gs_, int woff_, int &tick_, int lane_)
       : p(p_), gs(gs_), woff(woff_), tick(tick_), N(p_.N), lane(lane_) {}
+
+  __device__ __forceinline__ bool in_resto() const { return RS && resto; }
+  __device__ static __forceinline__ double dr2(double v) { double m = fmax(1.0, fabs(v)); return 1.0 / (m * m); }
+  // A row `row(z) - s` condensed into its stage: new row multiplier lam+ = D (J dz) + tt.
+  // regular: D = Sigma_s + dw, tt = D residual + slack barrier gradient;
+  // restoration: the row is penalised by psi: D = 1/(1/Ds + 1/psi''), tt = D (gs/Ds + psi'/psi'')
+  __device__ __forceinline__ void row_cond(double Ds, double gsl, double res, double mu, double &D, double &tt) const {
+    if (in_resto()) {
+      Psi ps = d_psi(res, mu, false);
+      D = Ds * ps.d2 / (Ds + ps.d2);
+      tt = D * (gsl / Ds + ps.d1 / ps.d2);
+    } else {
+      D = Ds;
+      tt = Ds * res + gsl;
+    }
+  }
+  __device__ __forceinline__ void row_step(double Ds, double gsl, double res, double mu, double Jdz, double &ds, double &lnew) const {
+    if (in_resto()) {
+      double D, tt;
+      row_cond(Ds, gsl, res, mu, D, tt);
+      lnew = D * Jdz + tt;
+      ds = (lnew - gsl) / Ds;
+    } else {
+      ds = Jdz + res;
+      lnew = Ds * ds + gsl;
+    }
+  }
 
   // field ids are compile-time constants at (almost) every use, so the space test folds away
   __device__ __forceinline__ double &at(int field, int k) {
@@ -271,10 +350,13 @@ struct KinSolver {
   // Jacobian of the point is always kept (the old one is dead once the step is known) and its
   // defects go to CDEF (first iterate) or CDEFT (trial point; accept_step moves them), so an
   // accepted trial point needs no second evaluation.
+  double rmu = 0.0;  // barrier parameter seen by psi (set by the run loop before every phase that needs it)
   __device__ __forceinline__ void eval_point(double alpha, bool fresh, double &theta, double &fobj, double &bar, double &lin) {
     const int cdst = fresh ? L::CDEF : L::CDEFT;
     const double rL = 1.0 / p.Veh_l;  // one division per call instead of three per stage
     double th = 0, fo = 0, br = 0, ln = 0;
+    double thr = 0, fr = 0;  // RS builds: row part of theta kept apart, restoration objective
+    const double mu_psi = rmu;
     #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
       double xk[NX], uk[2] = {0, 0}, xnext[2] = {0, 0};
@@ -289,9 +371,17 @@ struct KinSolver {
           at(cdst + i, 0) = c0;
         }
       }
+      if (in_resto()) {
+#pragma unroll
+        for (int i = 0; i < NX; i++) { double xr_ = at(L::XRS + i, k), e = xk[i] - xr_; fr += 0.5 * zeta * dr2(xr_) * e * e; }
+      }
       if (k < N) {
 #pragma unroll
         for (int i = 0; i < 2; i++) uk[i] = at(L::U + i, k) + alpha * at(L::DU + i, k);
+        if (in_resto()) {
+#pragma unroll
+          for (int i = 0; i < 2; i++) { double ur_ = at(L::URS + i, k), e = uk[i] - ur_; fr += 0.5 * zeta * dr2(ur_) * e * e; }
+        }
         double s, c, t;
         d_trig(xk[2], uk[0], &s, &c, &t);
         double f[NX];
@@ -343,7 +433,8 @@ struct KinSolver {
           double ukc = ci == 0 ? uk[0] : uk[1];
           // the slack step lives in the gain region, which holds gains while alpha == 0
           double s = at(L::SR + r, k) + (alpha != 0.0 ? alpha * at(L::DSR + r, k) : 0.0);
-          th += fabs(ukc - um - s);
+          if (RS) thr += fabs(ukc - um - s); else th += fabs(ukc - um - s);
+          if (in_resto()) fr += d_psi(ukc - um - s, mu_psi, true).v;
           gp *= (s - p.rate_lo[r]) * (p.rate_hi[r] - s);
         }
       }
@@ -357,7 +448,8 @@ struct KinSolver {
             d = (ex * ex * at(L::ISX + j, k) + ey * ey * at(L::ISY + j, k) - 1.0) - p.cbf_g1 * d;
           }
           double s = at(L::SO + j, k) + (alpha != 0.0 ? alpha * at(L::DSO + j, k) : 0.0);
-          th += fabs(d - s);
+          if (RS) thr += fabs(d - s); else th += fabs(d - s);
+          if (in_resto()) fr += d_psi(d - s, mu_psi, true).v;
           gp *= s - p.obs_lo;
           ln += s - p.obs_lo;
         }
@@ -368,6 +460,16 @@ struct KinSolver {
     fobj = warp_sum(fo);
     bar = warp_sum(br);
     lin = warp_sum(ln);
+    if (RS) {
+      thr = warp_sum(thr);
+      if (resto) {  // the rows are penalised, not constrained: theta = the equalities, objective = proximity + penalties
+        o_thr = thr;
+        o_f = fobj;
+        fobj = warp_sum(fr);
+      } else {
+        theta += thr;
+      }
+    }
     __syncwarp();
   }
 
@@ -395,13 +497,17 @@ struct KinSolver {
 #pragma unroll
         for (int i = 0; i < NX; i++) {
           l1[i] = at(L::LAM + i, k + 1);
-          rx[i] += sigma * 2 * p.Q[i] * (xk[i] - xref(i, k));
+          if (!in_resto()) rx[i] += sigma * 2 * p.Q[i] * (xk[i] - xref(i, k));
         }
         // - A' lam_{k+1}
         rx[0] -= l1[0];
         rx[1] -= l1[1];
         rx[2] -= l1[2] + a02 * l1[0] + a12 * l1[1];
         rx[3] -= l1[3] + a03 * l1[0] + a13 * l1[1] + a23 * l1[2];
+      }
+      if (in_resto()) {
+#pragma unroll
+        for (int i = 0; i < NX; i++) { double xr_ = at(L::XRS + i, k); rx[i] += zeta * dr2(xr_) * (xk[i] - xr_); }
       }
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
@@ -428,7 +534,7 @@ struct KinSolver {
             rx[1] += lo * (2 * dy * b);
           }
           dual = fmax(dual, fabs(-lo - vl));
-          prim = fmax(prim, fabs(d - s));
+          if (!in_resto()) prim = fmax(prim, fabs(d - s));
           MPCB_COMPL(s - p.obs_lo, vl);
           sl += fabs(lo);
         }
@@ -451,6 +557,7 @@ struct KinSolver {
           double up = k + 1 <= N - 1 ? at(L::U + i, k + 1) : 0.0;
           double zl = at(L::ZLU + i, k), zu = at(L::ZUU + i, k);
           double r = sigma * grad_u(k, i, uk, um, up) - zl + zu;
+          if (in_resto()) { double ur_ = at(L::URS + i, k); r = zeta * dr2(ur_) * (uk - ur_) - zl + zu; }
           r -= (i == 0) ? b2 * l1[2] : p.T * l1[3];  // - B' lam_{k+1}
 #pragma unroll
           for (int rr = 0; rr < NR; rr++)
@@ -469,7 +576,7 @@ struct KinSolver {
           int ci = p.rate_ctrl[r];
           double s = at(L::SR + r, k), vl = at(L::VLR + r, k), vu = at(L::VUR + r, k), lr = at(L::LR + r, k);
           dual = fmax(dual, fabs(-lr - vl + vu));
-          prim = fmax(prim, fabs(at(L::U + ci, k) - at(L::U + ci, k - 1) - s));
+          if (!in_resto()) prim = fmax(prim, fabs(at(L::U + ci, k) - at(L::U + ci, k - 1) - s));
           MPCB_COMPL(s - p.rate_lo[r], vl);
           MPCB_COMPL(p.rate_hi[r] - s, vu);
           sl += fabs(lr);
@@ -518,11 +625,17 @@ struct KinSolver {
         h23 = l0 * a13 - l1 * a03;                      // -T (-l0 sin + l1 cos)
         hdv = -l2 * jd;
         hdd_f = -2.0 * l2 * b2 * t;
+        if (!in_resto()) {
 #pragma unroll
-        for (int i = 0; i < NX; i++) {
-          h[i] += sigma * 2 * p.Q[i];
-          gx[i] = sigma * 2 * p.Q[i] * (xk[i] - xref(i, k));
+          for (int i = 0; i < NX; i++) {
+            h[i] += sigma * 2 * p.Q[i];
+            gx[i] = sigma * 2 * p.Q[i] * (xk[i] - xref(i, k));
+          }
         }
+      }
+      if (in_resto()) {
+#pragma unroll
+        for (int i = 0; i < NX; i++) { double xr_ = at(L::XRS + i, k), w_ = zeta * dr2(xr_); h[i] += w_; gx[i] = w_ * (xk[i] - xr_); }
       }
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
@@ -542,6 +655,15 @@ struct KinSolver {
           double D = at(L::VLO + j, k) * rg + dw;
           double gs = -mu * rg + MPCB_KAPPA_D * mu;
           double lo = at(L::LO + j, k);
+          double tcond = 0.0;
+          if (RS) {
+            if (DCBF) {
+              double ex = at(L::X + 0, k + 1) - at(L::OCX + j, k), ey = at(L::X + 1, k + 1) - at(L::OCY + j, k);
+              row_cond(D, gs, ((ex * ex * a + ey * ey * b - 1.0) - p.cbf_g1 * d) - s, mu, D, tcond);
+            } else {
+              row_cond(D, gs, d - s, mu, D, tcond);
+            }
+          }
           if (DCBF) {
             // Row k is linear in (dx_k, dx_{k+1}).  The Euler step moves the position by states
             // only (B has no entries in rows 0,1), so with dx_{k+1} = A dx_k + B du_k + b the row
@@ -554,6 +676,7 @@ struct KinSolver {
             double v2 = nx_ * a02 + ny_ * a12, v3 = nx_ * a03 + ny_ * a13;
             double res = (d - s) - nx_ * at(L::CDEF + 0, k + 1) - ny_ * at(L::CDEF + 1, k + 1);
             double t = D * res + gs;
+            if (RS) t = tcond - D * (nx_ * at(L::CDEF + 0, k + 1) + ny_ * at(L::CDEF + 1, k + 1));  // J dz = v'dx_k + g_next'b
             h[0] += D * v0 * v0 - p.cbf_g1 * lo * (2 * a);
             h[1] += D * v1 * v1 - p.cbf_g1 * lo * (2 * b);
             h[2] += D * v2 * v2;
@@ -562,7 +685,7 @@ struct KinSolver {
             h12 += D * v1 * v2; h13 += D * v1 * v3; h23 += D * v2 * v3;
             gx[0] += v0 * t; gx[1] += v1 * t; gx[2] += v2 * t; gx[3] += v3 * t;
           } else {
-            double t = D * (d - s) + gs;
+            double t = RS ? tcond : D * (d - s) + gs;
             h[0] += lo * (2 * a) + D * ox * ox;
             h01 += D * ox * oy;
             h[1] += lo * (2 * b) + D * oy * oy;
@@ -602,12 +725,17 @@ struct KinSolver {
             hd += sigma * 2 * p.DR[i];
             g += sigma * 2 * p.DR[i] * uk;
           }
+          if (in_resto()) {
+            double ur_ = at(L::URS + i, k), w_ = zeta * dr2(ur_);
+            hd = w_ + dw + (i == 0 ? hdd_f : 0.0);
+            g = w_ * (uk - ur_);
+          }
           double rl = fast_rcp(uk - p.u_lo[i]), rh = fast_rcp(p.u_hi[i] - uk);
           hd += at(L::ZLU + i, k) * rl + at(L::ZUU + i, k) * rh;
           g += mu * (rh - rl);
           at(L::HUU + i, k) = hd;
           at(L::GU + i, k) = g;
-          if (k >= 1) {
+          if (k >= 1 && !in_resto()) {
             E[i] = sigma * 2 * p.DR[i];
             t[i] = sigma * 2 * p.DR[i] * (uk - at(L::U + i, k - 1));
           }
@@ -622,6 +750,7 @@ struct KinSolver {
             double gs = mu * (rh - rl);
             double res = at(L::U + ci, k) - at(L::U + ci, k - 1) - s;
             double tt = D * res + gs;
+            if (RS) row_cond(D, gs, res, mu, D, tt);
             if (ci == 0) { E[0] += D; t[0] += tt; } else { E[1] += D; t[1] += tt; }
           }
         }
@@ -814,7 +943,8 @@ struct KinSolver {
       for (int i = 0; i < NX; i++) {
         xk[i] = at(L::X + i, k);
         dx[i] = at(L::DX + i, k);
-        if (k < N) gd += sigma * 2 * p.Q[i] * (xk[i] - xref(i, k)) * dx[i];
+        if (in_resto()) { double xr_ = at(L::XRS + i, k); gd += zeta * dr2(xr_) * (xk[i] - xr_) * dx[i]; }
+        else if (k < N) gd += sigma * 2 * p.Q[i] * (xk[i] - xref(i, k)) * dx[i];
       }
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
@@ -832,7 +962,8 @@ struct KinSolver {
           double um = k > 0 ? at(L::U + i, k - 1) : 0.0;
           double up = k + 1 <= N - 1 ? at(L::U + i, k + 1) : 0.0;
           double rl = fast_rcp(uk - p.u_lo[i]), rh = fast_rcp(p.u_hi[i] - uk);
-          gd += (sigma * grad_u(k, i, uk, um, up) + mu * (rh - rl)) * du;
+          if (in_resto()) { double ur_ = at(L::URS + i, k); gd += (zeta * dr2(ur_) * (uk - ur_) + mu * (rh - rl)) * du; }
+          else gd += (sigma * grad_u(k, i, uk, um, up) + mu * (rh - rl)) * du;
           MPCB_LOWER(rl, du, at(L::ZLU + i, k));
           MPCB_UPPER(rh, du, at(L::ZUU + i, k));
         }
@@ -850,6 +981,12 @@ struct KinSolver {
           double ds = at(L::DU + ci, k) - at(L::DU + ci, k - 1) + res;
           dsr[r] = ds;
           lrp[r] = D * ds + gs;
+          if (RS) {
+            const double Jdz = at(L::DU + ci, k) - at(L::DU + ci, k - 1);
+            row_step(D, gs, res, mu, Jdz, ds, lrp[r]);
+            dsr[r] = ds;
+            if (resto) gd += at(L::LR + r, k) * (Jdz - ds);  // psi'(r) d(row - s)
+          }
           gd += gs * ds;
           MPCB_LOWER(rl, ds, vl);
           MPCB_UPPER(rh, ds, vu);
@@ -869,17 +1006,28 @@ struct KinSolver {
             double fx = at(L::X + 0, k + 1) - at(L::OCX + j, k), fy = at(L::X + 1, k + 1) - at(L::OCY + j, k);
             double nx_ = 2 * fx * a, ny_ = 2 * fy * b;
             d = (fx * fx * a + fy * fy * b - 1.0) - p.cbf_g1 * d;
-            ds = nx_ * at(L::DX + 0, k + 1) + ny_ * at(L::DX + 1, k + 1) - p.cbf_g1 * ((2 * ex * a) * dx[0] + (2 * ey * b) * dx[1]) + (d - s);
+            const double Jdz = nx_ * at(L::DX + 0, k + 1) + ny_ * at(L::DX + 1, k + 1) - p.cbf_g1 * ((2 * ex * a) * dx[0] + (2 * ey * b) * dx[1]);
+            ds = Jdz + (d - s);
             // The adjoint sweep ran on the condensed stage costs (row k folded into stage k); the
             // multipliers of the original problem differ by the row's pull on X_{k+1}.
             double l = D * ds + gs;
+            if (RS) {
+              row_step(D, gs, d - s, mu, Jdz, ds, l);
+              if (resto) gd += at(L::LO + j, k) * (Jdz - ds);
+            }
             at(L::LAMP + 0, k + 1) -= nx_ * l;
             at(L::LAMP + 1, k + 1) -= ny_ * l;
+            lop[j] = l;
           } else {
-            ds = (2 * ex * a) * dx[0] + (2 * ey * b) * dx[1] + (d - s);
+            const double Jdz = (2 * ex * a) * dx[0] + (2 * ey * b) * dx[1];
+            ds = Jdz + (d - s);
+            lop[j] = D * ds + gs;
+            if (RS) {
+              row_step(D, gs, d - s, mu, Jdz, ds, lop[j]);
+              if (resto) gd += at(L::LO + j, k) * (Jdz - ds);
+            }
           }
           dso[j] = ds;
-          lop[j] = D * ds + gs;
           gd += gs * ds;
           MPCB_LOWER(rg, ds, vl);
         }
@@ -966,6 +1114,97 @@ struct KinSolver {
           at(L::VLO + j, k) = clampz(vl + ad * dvl, mu, fast_rcp(sn - p.obs_lo));
           double l = at(L::LO + j, k);
           at(L::LO + j, k) = l + a * (at(L::LOP + j, k) - l);
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---------------------------------------------------------------- restoration passes (RS builds)
+  // the row multipliers are not iterates in restoration: LR / LO = psi'(row residual)
+  __device__ __forceinline__ void resto_multipliers(double mu) {
+    #pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
+      if (has_rate(k)) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          int ci = p.rate_ctrl[r];
+          at(L::LR + r, k) = d_psi(at(L::U + ci, k) - at(L::U + ci, k - 1) - at(L::SR + r, k), mu, false).d1;
+        }
+      }
+      if (has_obs(k)) {
+#pragma unroll
+        for (int j = 0; j < MO; j++) {
+          double dx = at(L::X + 0, k) - at(L::OCX + j, k), dy = at(L::X + 1, k) - at(L::OCY + j, k);
+          double a = at(L::ISX + j, k), b = at(L::ISY + j, k);
+          double d = dx * dx * a + dy * dy * b - 1.0;
+          if (DCBF) {
+            double ex = at(L::X + 0, k + 1) - at(L::OCX + j, k), ey = at(L::X + 1, k + 1) - at(L::OCY + j, k);
+            d = (ex * ex * a + ey * ey * b - 1.0) - p.cbf_g1 * d;
+          }
+          at(L::LO + j, k) = d_psi(d - at(L::SO + j, k), mu, false).d1;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // entering: z_R = z, dynamics multipliers to zero, bound multipliers capped at rho
+  // leaving (enter = false): every constraint multiplier to zero (IPOPT constr_mult_reset_threshold = 0), bound
+  // multipliers back to one when any of them exceeds bound_mult_reset_threshold
+  __device__ __forceinline__ void resto_switch(bool enter) {
+    double zmax = 0.0;
+    #pragma unroll 1
+    for (int k = lane; k <= N; k += 32) {
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        if (enter) at(L::XRS + i, k) = at(L::X + i, k);
+        at(L::LAM + i, k) = 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        if (enter) at(L::URS + i, k) = k < N ? at(L::U + i, k) : 0.0;
+        if (k < N) {
+          if (enter) { at(L::ZLU + i, k) = fmin(MPCB_RESTO_RHO, at(L::ZLU + i, k)); at(L::ZUU + i, k) = fmin(MPCB_RESTO_RHO, at(L::ZUU + i, k)); }
+          zmax = fmax(zmax, fmax(at(L::ZLU + i, k), at(L::ZUU + i, k)));
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < NBX; b++) {
+        if (enter) { at(L::ZLX + b, k) = fmin(MPCB_RESTO_RHO, at(L::ZLX + b, k)); at(L::ZUX + b, k) = fmin(MPCB_RESTO_RHO, at(L::ZUX + b, k)); }
+        zmax = fmax(zmax, fmax(at(L::ZLX + b, k), at(L::ZUX + b, k)));
+      }
+      if (has_rate(k)) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          if (enter) { at(L::VLR + r, k) = fmin(MPCB_RESTO_RHO, at(L::VLR + r, k)); at(L::VUR + r, k) = fmin(MPCB_RESTO_RHO, at(L::VUR + r, k)); }
+          else at(L::LR + r, k) = 0.0;
+          zmax = fmax(zmax, fmax(at(L::VLR + r, k), at(L::VUR + r, k)));
+        }
+      }
+      if (has_obs(k)) {
+#pragma unroll
+        for (int j = 0; j < MO; j++) {
+          if (enter) at(L::VLO + j, k) = fmin(MPCB_RESTO_RHO, at(L::VLO + j, k));
+          else at(L::LO + j, k) = 0.0;
+          zmax = fmax(zmax, at(L::VLO + j, k));
+        }
+      }
+    }
+    zmax = warp_max(zmax);
+    if (!enter && zmax > MPCB_BOUND_MULT_RESET) {
+      #pragma unroll 1
+      for (int k = lane; k <= N; k += 32) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) { at(L::ZLU + i, k) = 1.0; at(L::ZUU + i, k) = 1.0; }
+#pragma unroll
+        for (int b = 0; b < NBX; b++) { at(L::ZLX + b, k) = 1.0; at(L::ZUX + b, k) = 1.0; }
+        if (has_rate(k)) {
+#pragma unroll
+          for (int r = 0; r < NR; r++) { at(L::VLR + r, k) = 1.0; at(L::VUR + r, k) = 1.0; }
+        }
+        if (has_obs(k)) {
+#pragma unroll
+          for (int j = 0; j < MO; j++) at(L::VLO + j, k) = 1.0;
         }
       }
     }
@@ -1117,7 +1356,7 @@ struct KinSolver {
 #ifndef MPCB_SYNC_EVERY
 #define MPCB_SYNC_EVERY 1  // barrier every k-th iteration (power of two)
 #endif
-#define MPCB_ITER_SYNC() do { if (((++tick) & (MPCB_SYNC_EVERY - 1)) == 0) __syncthreads_and(0); } while (0)
+#define MPCB_ITER_SYNC() do { if (((++tick) & (MPCB_SYNC_EVERY - 1)) == 0) block_iteration_vote(0); } while (0)
 #include "mpcb_run_loop.inc"
 #undef MPCB_ITER_SYNC
 };
@@ -1135,24 +1374,59 @@ struct KinSolver {
 #ifndef MPCB_KIN_RESIDENT_WARPS
 #define MPCB_KIN_RESIDENT_WARPS 12  // register budget: 65536 / (12 * 32) = 170 registers per thread
 #endif
-template <int NR, int MO, int OBS_MODE, int W, bool GS, bool AS = false>
+template <int NR, int MO, int OBS_MODE, int W, bool GS, bool AS = false, bool RS = false>
 __global__ void __launch_bounds__(32 * W, AS ? 1 : MPCB_KIN_RESIDENT_WARPS / W) kin_solve_kernel(const __grid_constant__ KParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  using L = KinLayout<NR, MO, OBS_MODE == 3, GS, AS>;
+  using L = KinLayout<NR, MO, OBS_MODE == 3, GS, AS, RS>;
   double *gs = AS ? nullptr : p.slab + ((size_t)blockIdx.x * W + warp) * L::slab_doubles();
   const int woff = warp * L::NFA * (p.N + 1);
   int tick = 0;
-  for (;;) {
-    int b = 0;
-    if (lane == 0) b = atomicAdd(p.counter, 1);
-    b = __shfl_sync(0xffffffffu, b, 0);
-    if (b >= p.B) break;
-    if (p.order) b = p.order[b];  // caller-supplied processing order (longest expected first)
-    KinSolver<NR, MO, OBS_MODE, GS, AS> s(p, gs, woff, tick, lane);
-    s.run(b);
-    __syncwarp();
+  // lets a dependent launch (the restoration pass) become resident as soon as every block of this grid has started
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (RS && p.resto_consumer) {
+    for (;;) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(p.resto_sync + 1, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= p.B) break;
+      int b = -1;
+      if (lane == 0) {
+        volatile int32_t *list = p.resto_list;
+        volatile int *sync = p.resto_sync;
+        for (;;) {
+          b = list[t];
+          if (b >= 0) break;
+          if (sync[2] >= p.main_warps) {  // every producer is done and its entries are visible: look once more
+            __threadfence();
+            b = list[t];
+            break;
+          }
+          __nanosleep(2000);
+        }
+      }
+      b = __shfl_sync(0xffffffffu, b, 0);
+      if (b < 0) break;
+      KinSolver<NR, MO, OBS_MODE, GS, AS, RS> s(p, gs, woff, tick, lane);
+      s.run(b);
+      __syncwarp();
+    }
+  } else {
+    for (;;) {
+      int b = 0;
+      if (lane == 0) b = atomicAdd(p.counter, 1);
+      b = __shfl_sync(0xffffffffu, b, 0);
+      if (b >= p.B) break;
+      if (p.order) b = p.order[b];  // caller-supplied processing order (longest expected first)
+      KinSolver<NR, MO, OBS_MODE, GS, AS, RS> s(p, gs, woff, tick, lane);
+      s.run(b);
+      __syncwarp();
+    }
+    if (p.resto_sync) {  // producer side: this warp will add no more entries
+      __threadfence();
+      if (lane == 0) atomicAdd(p.resto_sync + 2, 1);
+    }
   }
-  while (!__syncthreads_and(1)) {
+  while (!block_iteration_vote(1)) {
   }
 }
 

@@ -13,9 +13,20 @@ namespace mpcb {
 
 #if MPCB_FAMILY < 8 || MPCB_FAMILY >= 10
 
+// MPCB_RS_INLINE = 1: the main kernels of the families with inequality rows carry the restoration phase themselves (a
+// failed line search continues in place); 0 (shipped): the failed scenarios are solved again by a sibling kernel.
+// Measured at B = 10,000 kin-CBF (tests/tools/resto_check.py, profiles/r02_restoration.txt): inline costs the regular
+// path 15 % (168-register cap: the restoration branches spill) - 24.3 ms with restoration off against 21.2 ms - and
+// 30.9 ms with it on; the sibling leaves the regular path untouched and takes 33.5 ms with restoration on.
+#ifndef MPCB_RS_INLINE
+#define MPCB_RS_INLINE 0
+#endif
+template <int NR, int MO>
+constexpr bool kRsMain = MPCB_RS_INLINE && (NR + MO > 0);
+
 template <int NR, int MO, int OBS, int W, bool GS>
 static cudaError_t launch_kin(const KParams &p, int grid, size_t smem, cudaStream_t st) {
-  kin_solve_kernel<NR, MO, OBS, W, GS><<<grid, 32 * W, smem, st>>>(p);
+  kin_solve_kernel<NR, MO, OBS, W, GS, false, kRsMain<NR, MO>><<<grid, 32 * W, smem, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -23,22 +34,53 @@ template <int NR, int MO, int OBS, int W, bool GS>
 static Variant make_kin_variant_w() {
   Variant v;
   v.launch = &launch_kin<NR, MO, OBS, W, GS>;
-  v.kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, W, GS>;
-  v.smem_bytes = [](int N) { return KinLayout<NR, MO, OBS == 3, GS>::bytes(N); };
+  v.kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, W, GS, false, kRsMain<NR, MO>>;
+  v.smem_bytes = [](int N) { return KinLayout<NR, MO, OBS == 3, GS, false, kRsMain<NR, MO>>::bytes(N); };
   v.nx = 4;
   v.nbx = 2;
-  v.slab_doubles = KinLayout<NR, MO, OBS == 3, GS>::slab_doubles();
+  v.slab_doubles = KinLayout<NR, MO, OBS == 3, GS, false, kRsMain<NR, MO>>::slab_doubles();
+  v.rs_inline = kRsMain<NR, MO>;
   v.warps = W;
 #ifndef MPCB_AS_W
 #define MPCB_AS_W 1  // warps per block of the all-shared kernel (compile-time tuning knob)
 #endif
   v.lat_launch = [](const KParams &p, int grid, size_t smem, cudaStream_t st) {
-    kin_solve_kernel<NR, MO, OBS, MPCB_AS_W, false, true><<<grid, 32 * MPCB_AS_W, smem, st>>>(p);
+    kin_solve_kernel<NR, MO, OBS, MPCB_AS_W, false, true, kRsMain<NR, MO>><<<grid, 32 * MPCB_AS_W, smem, st>>>(p);
     return cudaGetLastError();
   };
-  v.lat_kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, MPCB_AS_W, false, true>;
-  v.lat_smem_bytes = [](int N) { return KinLayout<NR, MO, OBS == 3, false, true>::bytes(N) * MPCB_AS_W; };
+  v.lat_kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, MPCB_AS_W, false, true, kRsMain<NR, MO>>;
+  v.lat_smem_bytes = [](int N) { return KinLayout<NR, MO, OBS == 3, false, true, kRsMain<NR, MO>>::bytes(N) * MPCB_AS_W; };
   v.lat_warps = MPCB_AS_W;
+  // restoration-capable sibling: the step lives in the slab (smallest shared-memory record), 2 warps per block,
+  // registers uncapped.  Only the families with inequality rows have one.
+  v.resto_launch = nullptr;
+  v.resto_kernel = nullptr;
+  v.resto_smem_bytes = nullptr;
+  v.resto_slab_doubles = 0;
+  v.resto_warps = 0;
+  if constexpr (NR + MO > 0 && !kRsMain<NR, MO>) {
+    constexpr int RW = 2;
+    v.resto_launch = [](const KParams &p, int grid, size_t smem, cudaStream_t st) {
+      // programmatic dependent launch behind the main kernel (same stream): these blocks may become resident once every
+      // block of the main grid has started, i.e. as its last wave drains; they never call griddepcontrol.wait - the
+      // hand-over of scenarios goes through resto_list / resto_sync
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(32 * RW);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      return cudaLaunchKernelEx(&cfg, kin_solve_kernel<NR, MO, OBS, RW, true, false, true>, p);
+    };
+    v.resto_kernel = (const void *)&kin_solve_kernel<NR, MO, OBS, RW, true, false, true>;
+    v.resto_smem_bytes = [](int N) { return KinLayout<NR, MO, OBS == 3, true, false, true>::bytes(N); };
+    v.resto_slab_doubles = KinLayout<NR, MO, OBS == 3, true, false, true>::slab_doubles();
+    v.resto_warps = RW;
+  }
   return v;
 }
 
@@ -103,6 +145,12 @@ static Variant make_dyn_variant_w() {
   v.lat_kernel = nullptr;
   v.lat_smem_bytes = nullptr;
   v.lat_warps = 0;
+  v.rs_inline = false;
+  v.resto_launch = nullptr;
+  v.resto_kernel = nullptr;
+  v.resto_smem_bytes = nullptr;
+  v.resto_slab_doubles = 0;
+  v.resto_warps = 0;
   return v;
 }
 

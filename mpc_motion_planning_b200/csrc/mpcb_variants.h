@@ -21,6 +21,13 @@ struct Variant {
   kernel_ptr lat_kernel;
   size_t (*lat_smem_bytes)(int N);  // per block
   int lat_warps;
+  // optional restoration-capable sibling (second pass over the scenarios whose line search failed, see KParams)
+  bool rs_inline;  // the main kernels carry the restoration phase themselves (KParams.restoration switches it on)
+  launch_fn resto_launch;
+  kernel_ptr resto_kernel;
+  size_t (*resto_smem_bytes)(int N);  // per warp
+  size_t resto_slab_doubles;
+  int resto_warps;
 };
 
 // the candidate that keeps the most warps resident for horizon N (first one wins ties); mpcb_api.cu

@@ -48,7 +48,8 @@ def horizon_steps(config: dict) -> int:
 def make_cfg(kind: str, config: dict, N: int | None = None, M: int = 1, weights: Weights | None = None,
              init_mode: int = _lib.INIT_ROLLOUT, mu_init: float = 30.0, max_iter: int = 100, tol: float = 1e-8,
              bounds: dict | None = None, obs_input: int = _lib.OBS_TRAJECTORY, cbf_gamma: float | None = None,
-             ref_mode: int = _lib.REF_TERMINAL, dyn_rows: int = _lib.DYN_ROWS_ALIGNED) -> _lib.MpcbCfg:
+             ref_mode: int = _lib.REF_TERMINAL, dyn_rows: int = _lib.DYN_ROWS_ALIGNED, restoration: bool = False,
+             resto_max_calls: int = 1) -> _lib.MpcbCfg:
     """Fill an mpcb_cfg from the YAML dict with the reference's hard-coded constants.
 
     `bounds` optionally overrides {'u_lo','u_hi','x_lo','x_hi','rate_lo','rate_hi'} (used by the
@@ -112,6 +113,10 @@ def make_cfg(kind: str, config: dict, N: int | None = None, M: int = 1, weights:
     c.obs_input = obs_input
     c.ref_mode = ref_mode
     c.dyn_rows = dyn_rows  # dyn: bound lists aligned with g, or paired exactly as shipped
+    # restoration phase after a failed line search (kinematic families with rows); resto_max_calls = 0 is IPOPT's
+    # behaviour (no cap on how often the phase is entered)
+    c.restoration = int(bool(restoration) and kind in ("kin_cbf", "kin_cbf_pre"))
+    c.resto_max_calls = int(resto_max_calls)
     if dyn_rows != _lib.DYN_ROWS_ALIGNED and kind != "dyn":
         raise ValueError("dyn_rows applies to the dyn kind only")
     if cbf_gamma is not None:

@@ -24,12 +24,18 @@ def _nx(kind):
 
 
 class BatchSolver:
-    """One handle on the current CUDA device for one NLP kind / horizon / obstacle count."""
+    """One handle on the current CUDA device for one NLP kind / horizon / obstacle count.
+
+    `restoration=True` (kin-CBF kinds): a failed line search enters the restoration phase, as IPOPT does behind the
+    reference's `nlpsol` call, instead of ending the solve with status 3; `resto_max_calls` caps how often (0 = no cap,
+    IPOPT's behaviour).  Off by default here: on the benchmark batches it turns 1-2.5 % more scenarios into successes
+    for 40-60 % more time.  The drop-in `MPC_optimize` classes switch it on without a cap."""
 
     def __init__(self, kind: str = "kin_cbf_pre", config: dict | None = None, N: int | None = None, M: int = 1,
                  init: str = "rollout", mu_init: float = 30.0, max_iter: int = 100, tol: float = 1e-8,
                  weights=None, bounds: dict | None = None, obs_input: str = "trajectory", cbf_gamma: float | None = None,
-                 ref: str = "terminal", cfg_overrides: dict | None = None, dyn_bounds: str = "aligned"):
+                 ref: str = "terminal", cfg_overrides: dict | None = None, dyn_bounds: str = "aligned",
+                 restoration: bool = False, resto_max_calls: int = 1):
         self.lib = _lib.load()
         self.kind = kind
         self.config = config if config is not None else load_config(PACKAGE_PARAMS)
@@ -43,7 +49,8 @@ class BatchSolver:
                             obs_input=obs_code,
                             cbf_gamma=cbf_gamma,
                             ref_mode=_lib.REF_TRAJECTORY if self.ref_trajectory else _lib.REF_TERMINAL,
-                            dyn_rows={"aligned": _lib.DYN_ROWS_ALIGNED, "as_shipped": _lib.DYN_ROWS_AS_SHIPPED}[dyn_bounds])
+                            dyn_rows={"aligned": _lib.DYN_ROWS_ALIGNED, "as_shipped": _lib.DYN_ROWS_AS_SHIPPED}[dyn_bounds],
+                            restoration=restoration, resto_max_calls=resto_max_calls)
         for key, val in (cfg_overrides or {}).items():  # any mpcb_cfg field, e.g. {"safe_l": 1.5, "T": 0.08, "Q": [...]}
             cur = getattr(self.cfg, key)
             if hasattr(cur, "__len__"):

@@ -34,12 +34,14 @@ class OrcCfg(C.Structure):
         ("Fymax_f", C.c_double), ("Fymax_r", C.c_double),
         ("tol", C.c_double), ("mu_init", C.c_double), ("bound_relax", C.c_double),
         ("cbf_gamma", C.c_double), ("ref_mode", C.c_int32), ("rows_as_shipped", C.c_int32),
+        ("restoration", C.c_int32), ("resto_max_calls", C.c_int32),
     ]
 
 
 class OrcInfo(C.Structure):
     _fields_ = [("f", C.c_double), ("err", C.c_double), ("mu", C.c_double), ("obj_scale", C.c_double),
-                ("status", C.c_int32), ("iters", C.c_int32), ("n_reg", C.c_int32), ("n_backtrack", C.c_int32)]
+                ("status", C.c_int32), ("iters", C.c_int32), ("n_reg", C.c_int32), ("n_backtrack", C.c_int32),
+                ("n_resto", C.c_int32), ("n_resto_iter", C.c_int32)]
 
 
 def _host_tag() -> str:
@@ -85,7 +87,8 @@ def lib():
 
 def make_cfg(kind: str, N: int | None = None, M: int = 1, params: Params | None = None, init_mode: int = 1,
              mu_init: float = 30.0, max_iter: int = 100, tol: float = 1e-8, cbf_gamma: float | None = None,
-             ref_trajectory: bool = False, rows_as_shipped: bool = False) -> OrcCfg:
+             ref_trajectory: bool = False, rows_as_shipped: bool = False, restoration: bool = False,
+             resto_max_calls: int = 1) -> OrcCfg:
     p = params or Params()
     w = reference_weights(kind)
     c = OrcCfg()
@@ -129,6 +132,8 @@ def make_cfg(kind: str, N: int | None = None, M: int = 1, params: Params | None 
         c.obs_mode, c.cbf_gamma = 3, cbf_gamma
     c.ref_mode = int(ref_trajectory)  # xs is (N, nx) per-stage cost targets
     c.rows_as_shipped = int(rows_as_shipped)  # dyn: bound lists as PKG/MPC_CBF_optimize_dyn.py:112-133 ships them
+    c.restoration = int(restoration and kind in ("kin_cbf", "kin_cbf_pre"))
+    c.resto_max_calls = int(resto_max_calls)
     return c
 
 

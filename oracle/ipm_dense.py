@@ -27,7 +27,7 @@ from .nlp import NLP
 INF = float("inf")
 
 # status codes shared with include/mpcb200.h
-ST_CONVERGED, ST_ACCEPTABLE, ST_MAXITER, ST_INFEASIBLE, ST_NAN = 0, 1, 2, 3, 4
+ST_CONVERGED, ST_ACCEPTABLE, ST_MAXITER, ST_INFEASIBLE, ST_NAN, ST_RESTO_FAILED = 0, 1, 2, 3, 4, 5
 
 
 @dataclass
@@ -70,6 +70,12 @@ class IpmOptions:
     acceptable_tol: float = 1e-6
     centered_mult_init: bool = False
     verbose: bool = False
+    # restoration phase (see _psi and the `resto` branches of solve)
+    restoration: bool = False
+    resto_rho: float = 1000.0          # IPOPT resto_penalty_parameter
+    resto_kappa: float = 0.9           # IPOPT required_infeasibility_reduction
+    bound_mult_reset: float = 1000.0   # IPOPT bound_mult_reset_threshold
+    resto_max_calls: int = 1           # not IPOPT: the (n+1)-th entry ends with ST_INFEASIBLE; 0 = no cap
 
 
 @dataclass
@@ -88,6 +94,8 @@ class IpmResult:
     n_reg: int = 0
     n_soc: int = 0
     n_backtrack: int = 0
+    n_resto: int = 0        # times the restoration phase was entered
+    n_resto_iter: int = 0   # iterations spent in it (counted in `iters`)
 
 
 def _push(v, lo, hi, k1, k2):
@@ -154,6 +162,26 @@ def _inertia_from_ldl(D):
                 zero += 1
             i += 1
     return pos, neg, zero
+
+
+def _psi(r, mu, rho):
+    """The l1 penalty rho*(p + n) on a row residual r = p - n with p, n >= 0 kept on their central path:
+    (p, n) = argmin rho (p + n) - mu (log p + log n) s.t. p - n = r  -- IPOPT's closed form for the start of its
+    restoration phase (Waechter & Biegler 2006, eq. 33), used here at EVERY restoration iterate, so p and n never
+    become iterates of their own.  Returns psi, psi' (= the row's multiplier rho - mu/p), psi'' (= mu / (p^2 + n^2))."""
+    r = np.asarray(r, float)
+    b = mu * r / (2 * rho)
+    q = np.sqrt(mu * mu + (rho * r) ** 2) / (2 * rho)
+
+    def n_of(a, b_):  # a + q without cancellation when a < 0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.where(a >= 0, a + q, b_ / np.where(a >= 0, 1.0, q - a))
+
+    n = n_of((mu - rho * r) / (2 * rho), b)
+    p = n_of((mu + rho * r) / (2 * rho), -b)  # p(r) = n(-r)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        val = rho * (p + n) - mu * (np.log(p) + np.log(n))
+    return val, rho - mu / p, mu / (p * p + n * n)
 
 
 def solve(nlp: NLP, z_init=None, opt: IpmOptions | None = None) -> IpmResult:
@@ -240,27 +268,122 @@ def solve(nlp: NLP, z_init=None, opt: IpmOptions | None = None) -> IpmResult:
     err0 = INF
     it = 0
 
+    # ---- restoration phase state.  Entered when the filter line search (or the inertia correction) fails at a point
+    # that is not acceptable.  IPOPT minimises rho*||c(x) - p + n||_1-style infeasibility plus a proximity term over all
+    # rows; here (DEVIATION, stated in DESIGN.md) the shooting defects stay EQUALITIES - they can always be met, the free
+    # states x and phi absorb them - and only the inequality rows d(z) - s are relaxed:
+    #     min  zeta/2 ||D_R (z - z_R)||^2 + sum_rows psi_mu(d(z) - s)   s.t.  c(z) = 0, bounds on z and s
+    # with psi_mu the l1 penalty whose p, n are eliminated on their central path (_psi), zeta = sqrt(mu),
+    # D_R = 1/max(1,|z_R|), rho = 1000 (IPOPT's defaults).  The same interior-point loop runs on it (own filter, own mu).
+    # It returns to the regular phase when the original infeasibility has dropped to kappa_resto * theta_R at a point the
+    # original filter accepts; it ends with ST_INFEASIBLE when it converges itself (a stationary point of the
+    # infeasibility: IPOPT's "Converged to a point of local infeasibility") and ST_RESTO_FAILED when its own line search
+    # fails.
+    resto = False
+    n_resto = n_resto_it = 0
+    z_R = DR2 = None
+    zeta = 0.0
+    mu_o = tau_o = th_R = 0.0
+    filt_o: list[tuple[float, float]] = []
+    theta_min_o = theta_max_o = 0.0
+    it_resto0 = 0
+    rho = o.resto_rho
+
+    def resto_obj(zz, ss, mu_):
+        """objective of the restoration problem (without the bound barriers)"""
+        v = 0.5 * zeta * float(np.sum(DR2 * (zz - z_R) ** 2))
+        if ni:
+            pv, _, _ = _psi(nlp.ineq(zz) - ss, mu_, rho)
+            v += float(np.sum(pv))
+        return v
+
+    def bound_barrier(zz, ss, mu_):
+        v = -mu_ * (np.sum(np.log(zz[hzL] - zL[hzL])) + np.sum(np.log(zU[hzU] - zz[hzU])))
+        v -= mu_ * (np.sum(np.log(ss[hdL] - dL[hdL])) + np.sum(np.log(dU[hdU] - ss[hdU])))
+        v += o.kappa_d * mu_ * (np.sum(zz[only_lo_z] - zL[only_lo_z]) + np.sum(zU[only_hi_z] - zz[only_hi_z]))
+        v += o.kappa_d * mu_ * (np.sum(ss[only_lo_s] - dL[only_lo_s]) + np.sum(dU[only_hi_s] - ss[only_hi_s]))
+        return float(v)
+
+    def in_filter_of(flt, tmax, t_, p_):
+        if t_ >= tmax:
+            return True
+        for ft, fp in flt:
+            if t_ >= ft and p_ >= fp:
+                return True
+        return False
+
     while True:
-        gz = sigma * nlp.grad(z)
         Jc = nlp.jac_eq(z)
         Jd = nlp.jac_ineq(z) if ni else np.zeros((0, nv))
-        th, c, dd = theta_of(z, s)
-        err0, du0, pr0, co0 = kkt_error(0.0, gz, Jc, Jd, c, dd)
+        th, c, dd = theta_of(z, s)  # original measure: ||c||_1 + ||d - s||_1
+        if resto:
+            # ---- restoration: leave it?  (needs one restoration step; IPOPT: required_infeasibility_reduction 0.9
+            # and acceptability to the original filter, to which the point of entry was added)
+            if it > it_resto0 and th <= o.resto_kappa * th_R:
+                with np.errstate(all="ignore"):
+                    phi_o = barrier(z, s, mu_o)
+                if np.isfinite(phi_o) and not in_filter_of(filt_o, theta_max_o, th, phi_o):
+                    resto = False
+                    mu, tau = mu_o, tau_o
+                    filt = filt_o
+                    theta_min, theta_max = theta_min_o, theta_max_o
+                    lam_c = np.zeros(ne)   # constr_mult_reset_threshold = 0: start again from zero multipliers
+                    lam_d = np.zeros(ni)
+                    if max(zl.max(initial=0), zu.max(initial=0), vl.max(initial=0), vu.max(initial=0)) > o.bound_mult_reset:
+                        zl, zu = np.where(hzL, 1.0, 0.0), np.where(hzU, 1.0, 0.0)
+                        vl, vu = np.where(hdL, 1.0, 0.0), np.where(hdU, 1.0, 0.0)
+                    if o.verbose:
+                        print(f"   leaving restoration at it {it}: theta {th:.3e} <= {o.resto_kappa}*{th_R:.3e}")
+        if resto:
+            th_full = th
+            th = float(np.sum(np.abs(c)))  # restoration's own infeasibility: the equalities only
+            _, lam_d, psi2 = _psi(dd, mu, rho) if ni else (0, np.zeros(0), np.zeros(0))
+            gz = zeta * DR2 * (z - z_R)
+        else:
+            gz = sigma * nlp.grad(z)
+        if resto:
+            # kkt_error() with lam_d = psi'(r) and the rows not counted as primal infeasibility
+            rzv = gz + Jc.T @ lam_c + (Jd.T @ lam_d if ni else 0) - zl + zu
+            rsv = -lam_d - vl + vu
+
+            def kkt_error_r(mu_):
+                dual = max(float(np.max(np.abs(rzv))), float(np.max(np.abs(rsv))) if ni else 0.0)
+                prim = float(np.max(np.abs(c)))
+                comp = 0.0
+                for arr in ((z[hzL] - zL[hzL]) * zl[hzL], (zU[hzU] - z[hzU]) * zu[hzU], (s[hdL] - dL[hdL]) * vl[hdL], (dU[hdU] - s[hdU]) * vu[hdU]):
+                    if arr.size:
+                        comp = max(comp, float(np.max(np.abs(arr - mu_))))
+                sum_lam = float(np.sum(np.abs(lam_c)) + np.sum(np.abs(lam_d)))
+                sum_z = float(np.sum(zl) + np.sum(zu) + np.sum(vl) + np.sum(vu))
+                s_d = max(o.s_max, (sum_lam + sum_z) / max(1, ne + ni + n_bm)) / o.s_max
+                s_c = max(o.s_max, sum_z / max(1, n_bm)) / o.s_max
+                return max(dual / s_d, prim, comp / s_c), dual, prim, comp
+
+            err0, du0, pr0, co0 = kkt_error_r(0.0)
+        else:
+            err0, du0, pr0, co0 = kkt_error(0.0, gz, Jc, Jd, c, dd)
         if o.verbose:
-            print(f"it {it:3d} f={nlp.objective(z):.10e} th={th:.2e} mu={mu:.1e} err0={err0:.2e} (du {du0:.1e} pr {pr0:.1e} co {co0:.1e})")
+            print(f"it {it:3d}{' R' if resto else '  '} f={nlp.objective(z):.10e} th={th:.2e} mu={mu:.1e} err0={err0:.2e} (du {du0:.1e} pr {pr0:.1e} co {co0:.1e})")
         if err0 <= o.tol and du0 <= o.dual_inf_tol and pr0 <= o.constr_viol_tol and co0 <= o.compl_inf_tol:
-            status = ST_CONVERGED
+            # in restoration: a stationary point of the infeasibility that the original filter / reduction test rejected
+            status = ST_INFEASIBLE if resto else ST_CONVERGED
             break
         if it >= o.max_iter:
             status = ST_MAXITER
             break
         # barrier parameter update (possibly several decrements)
         while True:
-            emu, _, _, _ = kkt_error(mu, gz, Jc, Jd, c, dd)
+            emu = kkt_error_r(mu)[0] if resto else kkt_error(mu, gz, Jc, Jd, c, dd)[0]
             if emu <= o.kappa_eps * mu and mu > o.tol / 10:
                 mu = max(o.tol / 10, min(o.kappa_mu * mu, mu**o.theta_mu))
                 tau = max(o.tau_min, 1 - mu)
                 filt = []
+                if resto:  # psi_mu and zeta move with mu
+                    zeta = math.sqrt(mu)
+                    _, lam_d, psi2 = _psi(dd, mu, rho) if ni else (0, np.zeros(0), np.zeros(0))
+                    gz = zeta * DR2 * (z - z_R)
+                    rzv = gz + Jc.T @ lam_c + (Jd.T @ lam_d if ni else 0) - zl + zu
+                    rsv = -lam_d - vl + vu
             else:
                 break
 
@@ -271,7 +394,10 @@ def solve(nlp: NLP, z_init=None, opt: IpmOptions | None = None) -> IpmResult:
         su_s = np.where(hdU, dU - s, 1.0)
         Sig_z = zl / sl_z + zu / su_z
         Sig_s = vl / sl_s + vu / su_s
-        W = nlp.hess_lag(z, lam_c, lam_d, sigma)
+        if resto:
+            W = nlp.hess_lag(z, lam_c, lam_d, 0.0) + np.diag(zeta * DR2)
+        else:
+            W = nlp.hess_lag(z, lam_c, lam_d, sigma)
         gphi_z = gz - np.where(hzL, mu / sl_z, 0) + np.where(hzU, mu / su_z, 0)
         gphi_z = gphi_z + o.kappa_d * mu * (only_lo_z.astype(float) - only_hi_z.astype(float))
         gphi_s = -np.where(hdL, mu / sl_s, 0) + np.where(hdU, mu / su_s, 0)
@@ -280,13 +406,21 @@ def solve(nlp: NLP, z_init=None, opt: IpmOptions | None = None) -> IpmResult:
         rs = gphi_s - lam_d
 
         def kkt_solve(dw, c_rhs, dd_rhs):
-            D = Sig_s + dw
+            Ds = Sig_s + dw
+            if resto:
+                # rows enter through the penalty: new row multiplier lam+ = D_eff J dz + t_eff with
+                # D_eff = 1/(1/Ds + 1/psi''), t_eff = D_eff (gphi_s/Ds + psi'/psi'');  ds = (lam+ - gphi_s)/Ds
+                D = Ds * psi2 / (Ds + psi2)
+                t_eff = D * (gphi_s / Ds + lam_d / psi2)
+            else:
+                D = Ds
+                t_eff = D * dd_rhs + gphi_s
             Hc = W + np.diag(Sig_z + dw) + (Jd.T * D) @ Jd
             K = np.zeros((nv + ne, nv + ne))
             K[:nv, :nv] = Hc
             K[:nv, nv:] = Jc.T
             K[nv:, :nv] = Jc
-            rhs = np.concatenate([-rz - (Jd.T @ (D * dd_rhs + rs) if ni else 0), -c_rhs])
+            rhs = np.concatenate([-(gphi_z + Jc.T @ lam_c) - (Jd.T @ t_eff if ni else 0), -c_rhs])
             L, Dm, perm = sla.ldl(K, lower=True)
             pos, neg, zero = _inertia_from_ldl(Dm)
             if not (pos == nv and neg == ne and zero == 0):
@@ -294,8 +428,13 @@ def solve(nlp: NLP, z_init=None, opt: IpmOptions | None = None) -> IpmResult:
             sol = np.linalg.solve(K, rhs)
             dz = sol[:nv]
             dlc = sol[nv:]
-            ds = Jd @ dz + dd_rhs if ni else np.zeros(0)
-            dld = D * ds + rs if ni else np.zeros(0)
+            if resto:
+                lam_new = D * (Jd @ dz) + t_eff if ni else np.zeros(0)
+                ds = (lam_new - gphi_s) / Ds if ni else np.zeros(0)
+                dld = np.zeros(ni)  # the row multipliers are not iterates in restoration (lam_d = psi'(r))
+            else:
+                ds = Jd @ dz + dd_rhs if ni else np.zeros(0)
+                dld = D * ds + rs if ni else np.zeros(0)
             return dz, ds, dlc, dld
 
         dw = 0.0
@@ -310,111 +449,114 @@ def solve(nlp: NLP, z_init=None, opt: IpmOptions | None = None) -> IpmResult:
                 dw *= o.kw_plus_first if dw_last == 0.0 else o.kw_plus
                 if dw > o.dw_max:
                     break
-            if sol is None:
+            if sol is not None:
+                dw_last = dw
+        accepted = False
+        if sol is not None:
+            dz, ds, dlc, dld = sol
+            dzl = np.where(hzL, -zl + (mu - zl * dz) / sl_z, 0.0)
+            dzu = np.where(hzU, -zu + (mu + zu * dz) / su_z, 0.0)
+            dvl = np.where(hdL, -vl + (mu - vl * ds) / sl_s, 0.0)
+            dvu = np.where(hdU, -vu + (mu + vu * ds) / su_s, 0.0)
+
+            a_max = min(_ftb(z, dz, zL, zU, tau), _ftb(s, ds, dL, dU, tau) if ni else 1.0)
+            a_dual = min(_ftb_dual(zl, dzl, tau), _ftb_dual(zu, dzu, tau), _ftb_dual(vl, dvl, tau), _ftb_dual(vu, dvu, tau))
+
+            # ---- filter line search ----------------------------------------------------
+            if resto:
+                phi = resto_obj(z, s, mu) + bound_barrier(z, s, mu)
+                gd = float(gphi_z @ dz + gphi_s @ ds + (lam_d @ (Jd @ dz - ds) if ni else 0.0))
+            else:
+                phi = barrier(z, s, mu)
+                gd = float(gphi_z @ dz + (gphi_s @ ds if ni else 0.0))
+
+            def in_filter(t_, p_):
+                return in_filter_of(filt, theta_max, t_, p_)
+
+            def acceptable(alpha, t_, p_):
+                """returns (ok, armijo_case)"""
+                if not (np.isfinite(t_) and np.isfinite(p_)):
+                    return False, False
+                if in_filter(t_, p_):
+                    return False, False
+                sw = gd < 0 and alpha * (-gd) ** o.s_phi > o.delta * th**o.s_theta
+                if th <= theta_min and sw:
+                    ok = p_ <= phi + o.eta_phi * alpha * gd + 10 * np.finfo(float).eps * abs(phi)
+                    return ok, True
+                ok = (t_ <= (1 - o.gamma_theta) * th) or (p_ <= phi - o.gamma_phi * th + 10 * np.finfo(float).eps * abs(phi))
+                return ok, False
+
+            if gd < 0 and th <= theta_min:
+                a_min = o.gamma_alpha * min(o.gamma_theta, o.gamma_phi * th / (-gd) if th > 0 else INF,
+                                            o.delta * th**o.s_theta / (-gd) ** o.s_phi if th > 0 else INF)
+            elif gd < 0:
+                a_min = o.gamma_alpha * min(o.gamma_theta, o.gamma_phi * th / (-gd))
+            else:
+                a_min = o.gamma_alpha * o.gamma_theta
+            a_min = max(a_min, 1e-14)
+
+            alpha = a_max
+            armijo = False
+            z_new = s_new = None
+            while alpha >= a_min:
+                zt, st = z + alpha * dz, s + alpha * ds
+                with np.errstate(all="ignore"):
+                    tt, ct, ddt = theta_of(zt, st)
+                    if resto:
+                        tt = float(np.sum(np.abs(ct)))
+                        pt = resto_obj(zt, st, mu) + bound_barrier(zt, st, mu) if np.isfinite(tt) else INF
+                    else:
+                        pt = barrier(zt, st, mu) if np.isfinite(tt) else INF
+                ok, arm = acceptable(alpha, tt, pt)
+                if ok:
+                    accepted, armijo, z_new, s_new = True, arm, zt, st
+                    break
+                alpha *= 0.5
+                n_bt += 1
+        if not accepted:
+            # IPOPT returns Solved_To_Acceptable_Level when the line search fails at an acceptable point; the
+            # reference's acceptable_tol (1e-8 = tol) can never trigger, IPOPT's default 1e-6 is used for this exit only.
+            if not resto and err0 <= o.acceptable_tol:
+                status = ST_ACCEPTABLE
+                break
+            if resto or not o.restoration:
+                status = ST_RESTO_FAILED if resto else ST_INFEASIBLE
+                break
+            if o.resto_max_calls > 0 and n_resto >= o.resto_max_calls:
                 status = ST_INFEASIBLE
                 break
-            dw_last = dw
-        dz, ds, dlc, dld = sol
-        dzl = np.where(hzL, -zl + (mu - zl * dz) / sl_z, 0.0)
-        dzu = np.where(hzU, -zu + (mu + zu * dz) / su_z, 0.0)
-        dvl = np.where(hdL, -vl + (mu - vl * ds) / sl_s, 0.0)
-        dvu = np.where(hdU, -vu + (mu + vu * ds) / su_s, 0.0)
-
-        a_max = min(_ftb(z, dz, zL, zU, tau), _ftb(s, ds, dL, dU, tau) if ni else 1.0)
-        a_dual = min(_ftb_dual(zl, dzl, tau), _ftb_dual(zu, dzu, tau), _ftb_dual(vl, dvl, tau), _ftb_dual(vu, dvu, tau))
-
-        # ---- filter line search ----------------------------------------------------
-        phi = barrier(z, s, mu)
-        gd = float(gphi_z @ dz + (gphi_s @ ds if ni else 0.0))
-
-        def in_filter(t_, p_):
-            if t_ >= theta_max:
-                return True
-            for ft, fp in filt:
-                if t_ >= ft and p_ >= fp:
-                    return True
-            return False
-
-        def acceptable(alpha, t_, p_):
-            """returns (ok, armijo_case)"""
-            if not (np.isfinite(t_) and np.isfinite(p_)):
-                return False, False
-            if in_filter(t_, p_):
-                return False, False
-            sw = gd < 0 and alpha * (-gd) ** o.s_phi > o.delta * th**o.s_theta
-            if th <= theta_min and sw:
-                ok = p_ <= phi + o.eta_phi * alpha * gd + 10 * np.finfo(float).eps * abs(phi)
-                return ok, True
-            ok = (t_ <= (1 - o.gamma_theta) * th) or (p_ <= phi - o.gamma_phi * th + 10 * np.finfo(float).eps * abs(phi))
-            return ok, False
-
-        if gd < 0 and th <= theta_min:
-            a_min = o.gamma_alpha * min(o.gamma_theta, o.gamma_phi * th / (-gd) if th > 0 else INF,
-                                        o.delta * th**o.s_theta / (-gd) ** o.s_phi if th > 0 else INF)
-        elif gd < 0:
-            a_min = o.gamma_alpha * min(o.gamma_theta, o.gamma_phi * th / (-gd))
-        else:
-            a_min = o.gamma_alpha * o.gamma_theta
-        a_min = max(a_min, 1e-14)
-
-        alpha = a_max
-        accepted = False
-        armijo = False
-        first = True
-        z_new = s_new = None
-        dlc_use, dld_use = dlc, dld
-        while alpha >= a_min:
-            zt, st = z + alpha * dz, s + alpha * ds
-            with np.errstate(all="ignore"):
-                tt, ct, ddt = theta_of(zt, st)
-                pt = barrier(zt, st, mu) if np.isfinite(tt) else INF
-            ok, arm = acceptable(alpha, tt, pt)
-            if ok:
-                accepted, armijo, z_new, s_new = True, arm, zt, st
-                break
-            if first and np.isfinite(tt) and tt >= th and o.max_soc > 0:
-                # second-order correction
-                c_soc, d_soc = alpha * c + ct, alpha * dd + ddt
-                th_old = th
-                for _ in range(o.max_soc):
-                    sol2 = kkt_solve(dw, c_soc, d_soc)
-                    if sol2 is None:
-                        break
-                    dz2, ds2, dlc2, dld2 = sol2
-                    a2 = min(_ftb(z, dz2, zL, zU, tau), _ftb(s, ds2, dL, dU, tau) if ni else 1.0)
-                    zt2, st2 = z + a2 * dz2, s + a2 * ds2
-                    with np.errstate(all="ignore"):
-                        tt2, ct2, ddt2 = theta_of(zt2, st2)
-                        pt2 = barrier(zt2, st2, mu) if np.isfinite(tt2) else INF
-                    ok2, arm2 = acceptable(alpha, tt2, pt2)
-                    if ok2:
-                        accepted, armijo, z_new, s_new = True, arm2, zt2, st2
-                        dlc_use, dld_use = dlc2, dld2
-                        n_soc += 1
-                        break
-                    if not np.isfinite(tt2) or tt2 > o.kappa_soc * th_old:
-                        break
-                    th_old = tt2
-                    c_soc, d_soc = a2 * c_soc + ct2, a2 * d_soc + ddt2
-                if accepted:
-                    break
-            first = False
-            alpha *= 0.5
-            n_bt += 1
-        if not accepted:
-            # no restoration phase in this restatement.  IPOPT returns Solved_To_Acceptable_Level when the
-            # line search fails at an acceptable point; the reference's acceptable_tol (1e-8 = tol) can never
-            # trigger, IPOPT's default 1e-6 is used for this exit only.
-            status = ST_ACCEPTABLE if err0 <= o.acceptable_tol else ST_INFEASIBLE
-            break
+            # ---- enter the restoration phase at (z, s)
+            resto = True
+            n_resto += 1
+            it_resto0 = it
+            phi_e = barrier(z, s, mu)
+            filt_o = filt + [((1 - o.gamma_theta) * th, phi_e - o.gamma_phi * th)]
+            theta_min_o, theta_max_o = theta_min, theta_max
+            mu_o, tau_o, th_R = mu, tau, th
+            z_R = z.copy()
+            DR2 = 1.0 / np.maximum(1.0, np.abs(z_R)) ** 2
+            c_inf = max(float(np.max(np.abs(c))), float(np.max(np.abs(dd))) if ni else 0.0)
+            mu = max(mu_o, c_inf)
+            tau = max(o.tau_min, 1 - mu)
+            zeta = math.sqrt(mu)
+            lam_c = np.zeros(ne)
+            zl, zu, vl, vu = (np.minimum(rho, a_) for a_ in (zl, zu, vl, vu))
+            filt = []
+            thc = float(np.sum(np.abs(c)))
+            theta_min = 1e-4 * max(1.0, thc)
+            theta_max = 1e4 * max(1.0, thc)
+            dw_last = 0.0
+            if o.verbose:
+                print(f"   entering restoration at it {it}: theta_R {th_R:.3e}, mu {mu:.2e}")
+            continue
         if not armijo:
             filt.append(((1 - o.gamma_theta) * th, phi - o.gamma_phi * th))
         if o.verbose:
             print(f"       step: a_max={a_max:.2e} alpha={alpha:.2e} a_dual={a_dual:.2e} dw={dw:.1e} |dz|={np.max(np.abs(dz)):.2e}")
         # IPOPT: equality multipliers move with the primal step size
         z, s = z_new, s_new
-        lam_c = lam_c + alpha * dlc_use
-        lam_d = lam_d + alpha * dld_use
+        lam_c = lam_c + alpha * dlc
+        lam_d = lam_d + alpha * dld
         zl = zl + a_dual * dzl
         zu = zu + a_dual * dzu
         vl = vl + a_dual * dvl
@@ -424,6 +566,8 @@ def solve(nlp: NLP, z_init=None, opt: IpmOptions | None = None) -> IpmResult:
             if has.any():
                 arr[has] = np.maximum(np.minimum(arr[has], o.kappa_sigma * mu / gap[has]), mu / (o.kappa_sigma * gap[has]))
         it += 1
+        if resto:
+            n_resto_it += 1
 
     return IpmResult(z, nlp.objective(z), status, it, lam_c / sigma, lam_d / sigma, zl / sigma, zu / sigma, err0, mu, sigma,
-                     n_reg, n_soc, n_bt)
+                     n_reg, n_soc, n_bt, n_resto, n_resto_it)

@@ -31,6 +31,8 @@ static const double DW_FIRST = 1e-4, DW_MIN = 1e-20, DW_MAX = 1e40, KW_MINUS = 1
 static const double ACCEPTABLE_TOL = 1e-6; /* line-search-failure exit only, see ipm_dense.py */
 static const double DUAL_INF_TOL = 1.0, CONSTR_VIOL_TOL = 1e-4, COMPL_INF_TOL = 1e-4;
 #define FILTER_CAP 128
+/* restoration phase (specification: the `resto` branches of ipm_dense.solve) */
+static const double RESTO_RHO = 1000.0, RESTO_KAPPA = 0.9, BOUND_MULT_RESET = 1000.0;
 
 typedef struct {
   /* primal-dual iterate */
@@ -72,7 +74,27 @@ typedef struct {
   double dzlx[NST][NXM], dzux[NST][NXM], dzlu[NST][2], dzuu[NST][2], dvlr[NST][2], dvur[NST][2], dvlo[NST][ORC_MMAX];
   double filt_t[FILTER_CAP], filt_p[FILTER_CAP];
   int nfilt;
+  /* restoration phase: min zeta/2 ||D_R (z - z_R)||^2 + sum_rows psi_mu(row - s)  s.t. the dynamics, bounds */
+  int resto;
+  double zeta, mu_psi;
+  double xR[NST][NXM], uR[NST][2];       /* z_R */
+  double p2r[NST][2], p2o[NST][ORC_MMAX]; /* psi''(r) per row (psi' lives in it.lr / it.lo while in restoration) */
+  double pe_thc, pe_thr, pe_bar, pe_lin, pe_f; /* pieces of the last eval_primal: |equalities|_1, |rows|_1, log sum, damping sum, objective */
+  double filt_ot[FILTER_CAP], filt_op[FILTER_CAP];
+  int nfilt_o;
 } ws_t;
+
+/* l1 penalty on a row residual r = p - n with (p, n) on their central path for the barrier parameter mu
+ * (ipm_dense._psi): value, first and second derivative */
+static double psi_n(double a, double b, double q) { return a >= 0 ? a + q : b / (q - a); }
+static void psi_eval(double r, double mu, double *val, double *d1, double *d2) {
+  const double rho = RESTO_RHO;
+  double b = mu * r / (2 * rho), q = sqrt(mu * mu + (rho * r) * (rho * r)) / (2 * rho);
+  double n = psi_n((mu - rho * r) / (2 * rho), b, q), p = psi_n((mu + rho * r) / (2 * rho), -b, q);
+  if (val) *val = rho * (p + n) - mu * (log(p) + log(n));
+  if (d1) { *d1 = rho - mu / p; *d2 = mu / (p * p + n * n); }
+}
+static double dr2(double v) { double m = fmax(1.0, fabs(v)); return 1.0 / (m * m); }
 
 int orc_nx(const orc_cfg *c) { return c->model == ORC_MODEL_DYN ? 6 : 4; }
 
@@ -230,7 +252,7 @@ static int eval_primal(ws_t *w, const iterate_t *q, double mu, double *theta, do
                        int store) {
   const orc_cfg *c = w->c;
   int nx = w->nx, N = w->N, M = w->M;
-  double th = 0, bar = 0, lin = 0;
+  double th = 0, thr = 0, bar = 0, lin = 0, fr = 0;
   double cd[NXM];
   for (int i = 0; i < nx; i++) { cd[i] = q->x[0][i] - w->x0[i]; th += fabs(cd[i]); if (store) w->cdef[0][i] = cd[i]; }
   for (int k = 0; k <= N; k++) {
@@ -253,7 +275,8 @@ static int eval_primal(ws_t *w, const iterate_t *q, double mu, double *theta, do
       for (int r = 0; r < c->n_rate; r++) {
         int ci = c->rate_ctrl[r];
         double d = q->u[k][ci] - q->u[k - 1][ci] - (SHIPPED(w) ? 0.0 : q->sr[k][r]);
-        th += fabs(d);
+        if (SHIPPED(w)) th += fabs(d); else thr += fabs(d);
+        if (w->resto) { double v; psi_eval(d, mu, &v, 0, 0); fr += v; }
         if (store) w->resr[k][r] = d;
         bar += log(q->sr[k][r] - w->rlo[r]) + log(w->rhi[r] - q->sr[k][r]);
       }
@@ -263,7 +286,8 @@ static int eval_primal(ws_t *w, const iterate_t *q, double mu, double *theta, do
         if (IS_DCBF(w)) { if (!dcbf_row(w, q, k, j, &d, 0)) return 0; }
         else if (!obs_row(w, k, j, q->x[k][0], q->x[k][1], &d, 0, 0, 0, 0, 0)) return 0;
         double r_ = d - q->so[k][j];
-        th += fabs(r_);
+        thr += fabs(r_);
+        if (w->resto) { double v; psi_eval(r_, mu, &v, 0, 0); fr += v; }
         if (store) { w->reso[k][j] = r_; w->dobs[k][j] = d; }
         bar += log(q->so[k][j] - w->olo);
         lin += q->so[k][j] - w->olo;
@@ -271,9 +295,20 @@ static int eval_primal(ws_t *w, const iterate_t *q, double mu, double *theta, do
   }
   double f = objective(w, q);
   *fobj = f;
-  *theta = th;
-  *phi = w->sigma * f - mu * bar + KAPPA_D * mu * lin;
-  return isfinite(th) && isfinite(*phi);
+  w->pe_thc = th; w->pe_thr = thr; w->pe_bar = bar; w->pe_lin = lin; w->pe_f = f;
+  if (w->resto) {
+    /* restoration: the rows are penalised, not constrained; objective = proximity term + penalties */
+    for (int k = 0; k <= N; k++) {
+      for (int i = 0; i < nx; i++) { double e = q->x[k][i] - w->xR[k][i]; fr += 0.5 * w->zeta * dr2(w->xR[k][i]) * e * e; }
+      if (k < N) for (int i = 0; i < 2; i++) { double e = q->u[k][i] - w->uR[k][i]; fr += 0.5 * w->zeta * dr2(w->uR[k][i]) * e * e; }
+    }
+    *theta = th;
+    *phi = fr - mu * bar + KAPPA_D * mu * lin;
+  } else {
+    *theta = th + thr;
+    *phi = w->sigma * f - mu * bar + KAPPA_D * mu * lin;
+  }
+  return isfinite(th + thr) && isfinite(*phi);
 }
 
 /* Jacobians of the dynamics and the obstacle rows at the current iterate */
@@ -327,8 +362,9 @@ static void kkt_pieces(ws_t *w, kkt_t *o) {
     /* stationarity wrt x_k */
     for (int i = 0; i < nx; i++) {
       double r = q->lam[k][i];
+      if (w->resto) r += w->zeta * dr2(w->xR[k][i]) * (q->x[k][i] - w->xR[k][i]);
       if (k < N) {
-        r += w->sigma * 2 * c->Q[i] * (q->x[k][i] - w->xr[k][i]);
+        if (!w->resto) r += w->sigma * 2 * c->Q[i] * (q->x[k][i] - w->xr[k][i]);
         for (int a = 0; a < nx; a++) r -= w->A[k][a][i] * q->lam[k + 1][a];
       }
       if (w->xbl[i]) { r -= q->zlx[k][i]; COMPL(q->x[k][i] - w->xlo[i], q->zlx[k][i]); }
@@ -346,7 +382,7 @@ static void kkt_pieces(ws_t *w, kkt_t *o) {
       double g[2];
       grad_u(w, q, k, g);
       for (int i = 0; i < 2; i++) {
-        double r = w->sigma * g[i] - q->zlu[k][i] + q->zuu[k][i];
+        double r = (w->resto ? w->zeta * dr2(w->uR[k][i]) * (q->u[k][i] - w->uR[k][i]) : w->sigma * g[i]) - q->zlu[k][i] + q->zuu[k][i];
         for (int a = 0; a < nx; a++) r -= w->B[k][a][i] * q->lam[k + 1][a];
         for (int rr = 0; rr < c->n_rate; rr++)
           if (c->rate_ctrl[rr] == i) {
@@ -361,7 +397,7 @@ static void kkt_pieces(ws_t *w, kkt_t *o) {
     if (has_rate(w, k))
       for (int r = 0; r < c->n_rate; r++) {
         dual = fmax(dual, fabs(-(SHIPPED(w) ? q->lam[k + 1][r] : q->lr[k][r]) - q->vlr[k][r] + q->vur[k][r]));
-        prim = fmax(prim, fabs(w->resr[k][r]));
+        if (!w->resto) prim = fmax(prim, fabs(w->resr[k][r]));
         COMPL(q->sr[k][r] - w->rlo[r], q->vlr[k][r]);
         COMPL(w->rhi[r] - q->sr[k][r], q->vur[k][r]);
         sl += fabs(q->lr[k][r]);
@@ -370,7 +406,7 @@ static void kkt_pieces(ws_t *w, kkt_t *o) {
     if (has_obs(w, k))
       for (int j = 0; j < M; j++) {
         dual = fmax(dual, fabs(-q->lo[k][j] - q->vlo[k][j]));
-        prim = fmax(prim, fabs(w->reso[k][j]));
+        if (!w->resto) prim = fmax(prim, fabs(w->reso[k][j]));
         COMPL(q->so[k][j] - w->olo, q->vlo[k][j]);
         sl += fabs(q->lo[k][j]);
         neq++;
@@ -410,7 +446,8 @@ static void build_qp(ws_t *w, double mu) {
     /* state block */
     for (int i = 0; i < nx; i++) {
       double g = 0;
-      if (k < N) { H[i][i] += w->sigma * 2 * c->Q[i]; g += w->sigma * 2 * c->Q[i] * (q->x[k][i] - w->xr[k][i]); }
+      if (w->resto) { double d2_ = w->zeta * dr2(w->xR[k][i]); H[i][i] += d2_; g += d2_ * (q->x[k][i] - w->xR[k][i]); }
+      else if (k < N) { H[i][i] += w->sigma * 2 * c->Q[i]; g += w->sigma * 2 * c->Q[i] * (q->x[k][i] - w->xr[k][i]); }
       if (w->xbl[i]) { double gap = q->x[k][i] - w->xlo[i]; H[i][i] += q->zlx[k][i] / gap; g -= mu / gap; }
       if (w->xbu[i]) { double gap = w->xhi[i] - q->x[k][i]; H[i][i] += q->zux[k][i] / gap; g += mu / gap; }
       w->gx[k][i] = g;
@@ -437,6 +474,7 @@ static void build_qp(ws_t *w, double mu) {
         double g = w->sigma * 2 * c->R[i] * q->u[k][i];
         double hd = w->sigma * 2 * c->R[i];
         if (k == 0 && c->du0_cost) { hd += w->sigma * 2 * c->DR[i]; g += w->sigma * 2 * c->DR[i] * q->u[0][i]; }
+        if (w->resto) { hd = w->zeta * dr2(w->uR[k][i]); g = hd * (q->u[k][i] - w->uR[k][i]); }
         double gl = q->u[k][i] - w->ulo[i], gh = w->uhi[i] - q->u[k][i];
         hd += q->zlu[k][i] / gl + q->zuu[k][i] / gh;
         g += -mu / gl + mu / gh;
@@ -449,7 +487,7 @@ static void build_qp(ws_t *w, double mu) {
       }
       /* coupling with the previous control: cost DR plus rate rows */
       for (int i = 0; i < 2; i++) { w->E[k][i] = 0; w->tk[k][i] = 0; }
-      if (k >= 1)
+      if (k >= 1 && !w->resto)
         for (int i = 0; i < 2; i++) {
           w->E[k][i] = w->sigma * 2 * c->DR[i];
           w->tk[k][i] = w->sigma * 2 * c->DR[i] * (q->u[k][i] - q->u[k - 1][i]);
@@ -476,6 +514,26 @@ static int inv2(const double F[2][2], double Fi[2][2]) {
 /* Riccati factor+solve of the condensed QP with primal regularisation dw and constraint
  * right-hand side (cdef,resr,reso).  Returns 0 when some Fuu is not positive definite
  * (wrong inertia). */
+/* A row `row(z) - s (= 0)` condensed into the stage: new row multiplier lam+ = D * (J dz) + tt.
+ * regular phase: D = Sigma_s + dw, tt = D * residual + barrier gradient of the slack;
+ * restoration:   the row is penalised by psi: D = 1/(1/Ds + 1/psi''), tt = D (gs/Ds + psi'/psi'') */
+static void row_cond(const ws_t *w, double Ds, double gs, double res, double lam, double p2, double *D, double *tt) {
+  if (w->resto) { *D = Ds * p2 / (Ds + p2); *tt = *D * (gs / Ds + lam / p2); }
+  else { *D = Ds; *tt = Ds * res + gs; }
+}
+/* slack step and new row multiplier once J dz is known */
+static void row_step(const ws_t *w, double Ds, double gs, double res, double lam, double p2, double Jdz, double *ds, double *lnew) {
+  if (w->resto) {
+    double D, tt;
+    row_cond(w, Ds, gs, res, lam, p2, &D, &tt);
+    *lnew = D * Jdz + tt;
+    *ds = (*lnew - gs) / Ds;
+  } else {
+    *ds = Jdz + res;
+    *lnew = Ds * *ds + gs;
+  }
+}
+
 static int riccati(ws_t *w, double dw) {
   const orc_cfg *c = w->c;
   int nx = w->nx, N = w->N, M = w->M;
@@ -487,8 +545,8 @@ static int riccati(ws_t *w, double dw) {
     for (int i = 0; i < nx; i++) { gxk[i] = w->gx[k][i]; for (int j = 0; j < nx; j++) Pxx[i][j] = w->Hxx[k][i][j]; Pxx[i][i] += dw; }
     if (has_obs(w, k))
       for (int j = 0; j < M; j++) {
-        double D = w->Do[k][j] + dw, gx_ = w->gox[k][j], gy_ = w->goy[k][j];
-        double t = D * w->reso[k][j] + w->gso[k][j];
+        double D, t, gx_ = w->gox[k][j], gy_ = w->goy[k][j];
+        row_cond(w, w->Do[k][j] + dw, w->gso[k][j], w->reso[k][j], w->it.lo[k][j], w->p2o[k][j], &D, &t);
         Pxx[0][0] += D * gx_ * gx_; Pxx[0][1] += D * gx_ * gy_; Pxx[1][0] += D * gx_ * gy_; Pxx[1][1] += D * gy_ * gy_;
         gxk[0] += gx_ * t; gxk[1] += gy_ * t;
       }
@@ -503,8 +561,8 @@ static int riccati(ws_t *w, double dw) {
     for (int i = 0; i < nx; i++) { gxk[i] = w->gx[k][i]; for (int j = 0; j < nx; j++) Hxx[i][j] = w->Hxx[k][i][j]; Hxx[i][i] += dw; }
     if (has_obs(w, k) && !IS_DCBF(w))
       for (int j = 0; j < M; j++) {
-        double D = w->Do[k][j] + dw, gx_ = w->gox[k][j], gy_ = w->goy[k][j];
-        double tt = D * w->reso[k][j] + w->gso[k][j];
+        double D, tt, gx_ = w->gox[k][j], gy_ = w->goy[k][j];
+        row_cond(w, w->Do[k][j] + dw, w->gso[k][j], w->reso[k][j], w->it.lo[k][j], w->p2o[k][j], &D, &tt);
         Hxx[0][0] += D * gx_ * gx_; Hxx[0][1] += D * gx_ * gy_; Hxx[1][0] += D * gx_ * gy_; Hxx[1][1] += D * gy_ * gy_;
         gxk[0] += gx_ * tt; gxk[1] += gy_ * tt;
       }
@@ -512,13 +570,13 @@ static int riccati(ws_t *w, double dw) {
       for (int j = 0; j < M; j++) {
         /* row k is linear in (dx_k, dx_{k+1}); with dx_{k+1} = A dx_k + B du_k + b it becomes a row
          * in (dx_k, du_k): v = [g_k + A' g_next ; B' g_next], residual + g_next' b */
-        double D = w->Do[k][j] + dw;
+        double D, tt;
+        row_cond(w, w->Do[k][j] + dw, w->gso[k][j], w->reso[k][j], w->it.lo[k][j], w->p2o[k][j], &D, &tt);
         double gn[2] = {w->gnx[k][j], w->gny[k][j]};
         double v[NXM + 2];
         for (int i = 0; i < nx; i++) v[i] = (i == 0 ? w->gox[k][j] : i == 1 ? w->goy[k][j] : 0.0) + gn[0] * A[0][i] + gn[1] * A[1][i];
         for (int i = 0; i < 2; i++) v[nx + i] = gn[0] * B[0][i] + gn[1] * B[1][i];
-        double res = w->reso[k][j] - gn[0] * w->cdef[k + 1][0] - gn[1] * w->cdef[k + 1][1];
-        double tt = D * res + w->gso[k][j];
+        tt -= D * (gn[0] * w->cdef[k + 1][0] + gn[1] * w->cdef[k + 1][1]);  /* J dz = v'[dx_k; du_k] + g_next' b, b = -c_{k+1} */
         for (int i = 0; i < nx; i++) {
           for (int l = 0; l < nx; l++) Hxx[i][l] += D * v[i] * v[l];
           gxk[i] += v[i] * tt;
@@ -533,9 +591,10 @@ static int riccati(ws_t *w, double dw) {
     if (has_rate(w, k))
       for (int r = 0; r < c->n_rate; r++) {
         int ci = c->rate_ctrl[r];
-        double D = w->Dr[k][r] + dw;
+        double D, tt;
+        row_cond(w, w->Dr[k][r] + dw, w->gsr[k][r], w->resr[k][r], w->it.lr[k][r], w->p2r[k][r], &D, &tt);
         E[ci] += D;
-        t[ci] += D * w->resr[k][r] + w->gsr[k][r];
+        t[ci] += tt;
       }
     /* b = -c_{k+1} */
     double b[NXM], Pb[NXM];
@@ -612,16 +671,14 @@ static int riccati(ws_t *w, double dw) {
     if (has_rate(w, k))
       for (int r = 0; r < c->n_rate; r++) {
         int ci = c->rate_ctrl[r];
-        double D = w->Dr[k][r] + dw;
-        w->dsr[k][r] = w->du[k][ci] - w->du[k - 1][ci] + w->resr[k][r];
-        w->lrp[k][r] = D * w->dsr[k][r] + w->gsr[k][r];
+        row_step(w, w->Dr[k][r] + dw, w->gsr[k][r], w->resr[k][r], w->it.lr[k][r], w->p2r[k][r], w->du[k][ci] - w->du[k - 1][ci],
+                 &w->dsr[k][r], &w->lrp[k][r]);
       }
     if (has_obs(w, k))
       for (int j = 0; j < M; j++) {
-        double D = w->Do[k][j] + dw;
-        w->dso[k][j] = w->gox[k][j] * w->dx[k][0] + w->goy[k][j] * w->dx[k][1] + w->reso[k][j];
-        if (IS_DCBF(w)) w->dso[k][j] += w->gnx[k][j] * w->dx[k + 1][0] + w->gny[k][j] * w->dx[k + 1][1];
-        w->lop[k][j] = D * w->dso[k][j] + w->gso[k][j];
+        double Jdz = w->gox[k][j] * w->dx[k][0] + w->goy[k][j] * w->dx[k][1];
+        if (IS_DCBF(w)) Jdz += w->gnx[k][j] * w->dx[k + 1][0] + w->gny[k][j] * w->dx[k + 1][1];
+        row_step(w, w->Do[k][j] + dw, w->gso[k][j], w->reso[k][j], w->it.lo[k][j], w->p2o[k][j], Jdz, &w->dso[k][j], &w->lop[k][j]);
       }
   }
   /* adjoint recursion for the new dynamics multipliers */
@@ -853,7 +910,8 @@ static double barrier_dir(ws_t *w, double mu) {
   for (int k = 0; k <= N; k++) {
     for (int i = 0; i < nx; i++) {
       double g = 0;
-      if (k < N) g += w->sigma * 2 * c->Q[i] * (q->x[k][i] - w->xr[k][i]);
+      if (w->resto) g += w->zeta * dr2(w->xR[k][i]) * (q->x[k][i] - w->xR[k][i]);
+      else if (k < N) g += w->sigma * 2 * c->Q[i] * (q->x[k][i] - w->xr[k][i]);
       if (w->xbl[i]) g -= mu / (q->x[k][i] - w->xlo[i]);
       if (w->xbu[i]) g += mu / (w->xhi[i] - q->x[k][i]);
       gd += g * w->dx[k][i];
@@ -862,12 +920,24 @@ static double barrier_dir(ws_t *w, double mu) {
       double g[2];
       grad_u(w, q, k, g);
       for (int i = 0; i < 2; i++)
-        gd += (w->sigma * g[i] - mu / (q->u[k][i] - w->ulo[i]) + mu / (w->uhi[i] - q->u[k][i])) * w->du[k][i];
+        gd += ((w->resto ? w->zeta * dr2(w->uR[k][i]) * (q->u[k][i] - w->uR[k][i]) : w->sigma * g[i]) - mu / (q->u[k][i] - w->ulo[i]) +
+               mu / (w->uhi[i] - q->u[k][i])) * w->du[k][i];
     }
+    /* restoration: + psi'(r) * d(row - s) for every penalised row */
     if (has_rate(w, k))
-      for (int r = 0; r < c->n_rate; r++) gd += w->gsr[k][r] * w->dsr[k][r];
+      for (int r = 0; r < c->n_rate; r++) {
+        gd += w->gsr[k][r] * w->dsr[k][r];
+        if (w->resto) { int ci = c->rate_ctrl[r]; gd += q->lr[k][r] * (w->du[k][ci] - w->du[k - 1][ci] - w->dsr[k][r]); }
+      }
     if (has_obs(w, k))
-      for (int j = 0; j < M; j++) gd += w->gso[k][j] * w->dso[k][j];
+      for (int j = 0; j < M; j++) {
+        gd += w->gso[k][j] * w->dso[k][j];
+        if (w->resto) {
+          double Jdz = w->gox[k][j] * w->dx[k][0] + w->goy[k][j] * w->dx[k][1];
+          if (IS_DCBF(w)) Jdz += w->gnx[k][j] * w->dx[k + 1][0] + w->gny[k][j] * w->dx[k + 1][1];
+          gd += q->lo[k][j] * (Jdz - w->dso[k][j]);
+        }
+      }
   }
   return gd;
 }
@@ -1055,11 +1125,26 @@ static void write_out(const ws_t *w, double *z_out, double *lam_eq_out) {
     for (int k = 0; k <= N; k++) for (int i = 0; i < nx; i++) lam_eq_out[nx * k + i] = w->it.lam[k][i] / w->sigma;
 }
 
+/* restoration: the row multipliers are not iterates but psi'(residual); psi'' goes into the condensation */
+static void resto_multipliers(ws_t *w, double mu) {
+  const orc_cfg *c = w->c;
+  for (int k = 0; k <= w->N; k++) {
+    if (has_rate(w, k))
+      for (int r = 0; r < c->n_rate; r++) psi_eval(w->resr[k][r], mu, 0, &w->it.lr[k][r], &w->p2r[k][r]);
+    if (has_obs(w, k))
+      for (int j = 0; j < w->M; j++) psi_eval(w->reso[k][j], mu, 0, &w->it.lo[k][j], &w->p2o[k][j]);
+  }
+}
+
 static int solve_ws(ws_t *w, const double *z_init, double *z_out, double *lam_eq_out, orc_info *info) {
   const orc_cfg *c = w->c;
   double mu = c->mu_init, tau = fmax(TAU_MIN, 1 - mu);
   double tol = c->tol;
   int status = ORC_MAXITER, it = 0, n_reg = 0, n_bt = 0;
+  /* restoration phase state (see ipm_dense.solve) */
+  int n_resto = 0, n_resto_it = 0, it_resto0 = 0;
+  double mu_o = 0, tau_o = 0, th_R = 0, theta_min_o = 0, theta_max_o = 0;
+  const int nx = w->nx, N = w->N, M = w->M;
   double err0 = INFINITY, dw_last = 0.0;
   if (!init_iterate(w, z_init)) { status = ORC_NAN; goto done; }
   double theta, phi, fobj;
@@ -1067,12 +1152,49 @@ static int solve_ws(ws_t *w, const double *z_init, double *z_out, double *lam_eq
   double theta_min = 1e-4 * fmax(1.0, theta), theta_max = 1e4 * fmax(1.0, theta);
   w->nfilt = 0;
   for (;;) {
+    if (w->resto && it > it_resto0) {
+      /* leave the restoration phase?  original infeasibility reduced to kappa_resto * theta_R at a point the original
+       * filter (with the point of entry added) accepts */
+      double th_o = w->pe_thc + w->pe_thr;
+      if (th_o <= RESTO_KAPPA * th_R) {
+        double phi_o = w->sigma * w->pe_f - mu_o * w->pe_bar + KAPPA_D * mu_o * w->pe_lin;
+        int blocked = th_o >= theta_max_o;
+        for (int i = 0; i < w->nfilt_o && !blocked; i++) blocked = th_o >= w->filt_ot[i] && phi_o >= w->filt_op[i];
+        if (isfinite(phi_o) && !blocked) {
+          w->resto = 0;
+          mu = mu_o; tau = tau_o; theta_min = theta_min_o; theta_max = theta_max_o;
+          w->nfilt = w->nfilt_o;
+          memcpy(w->filt_t, w->filt_ot, sizeof w->filt_t);
+          memcpy(w->filt_p, w->filt_op, sizeof w->filt_p);
+          iterate_t *q = &w->it;
+          double zmax = 0;
+          for (int k = 0; k <= N; k++) {
+            for (int i = 0; i < nx; i++) { q->lam[k][i] = 0; zmax = fmax(zmax, fmax(q->zlx[k][i], q->zux[k][i])); }
+            for (int i = 0; i < 2; i++) { q->lr[k][i] = 0; if (k < N) zmax = fmax(zmax, fmax(q->zlu[k][i], q->zuu[k][i])); if (has_rate(w, k) && i < c->n_rate) zmax = fmax(zmax, fmax(q->vlr[k][i], q->vur[k][i])); }
+            for (int j = 0; j < M; j++) { q->lo[k][j] = 0; if (has_obs(w, k)) zmax = fmax(zmax, q->vlo[k][j]); }
+          }
+          if (zmax > BOUND_MULT_RESET)
+            for (int k = 0; k <= N; k++) {
+              for (int i = 0; i < nx; i++) { q->zlx[k][i] = w->xbl[i] ? 1.0 : 0.0; q->zux[k][i] = w->xbu[i] ? 1.0 : 0.0; }
+              if (k < N) for (int i = 0; i < 2; i++) q->zlu[k][i] = q->zuu[k][i] = 1.0;
+              if (has_rate(w, k)) for (int r = 0; r < c->n_rate; r++) q->vlr[k][r] = q->vur[k][r] = 1.0;
+              if (has_obs(w, k)) for (int j = 0; j < M; j++) q->vlo[k][j] = 1.0;
+            }
+          eval_primal(w, &w->it, mu, &theta, &phi, &fobj, 1);
+        }
+      }
+    }
     eval_lin(w);
+    if (w->resto) resto_multipliers(w, mu);
     kkt_t kk;
     kkt_pieces(w, &kk);
     double co0;
     err0 = kkt_error(&kk, 0.0, &co0);
-    if (err0 <= tol && kk.dual <= DUAL_INF_TOL && kk.prim <= CONSTR_VIOL_TOL && co0 <= COMPL_INF_TOL) { status = ORC_CONVERGED; break; }
+    if (err0 <= tol && kk.dual <= DUAL_INF_TOL && kk.prim <= CONSTR_VIOL_TOL && co0 <= COMPL_INF_TOL) {
+      /* in restoration: a stationary point of the infeasibility (IPOPT: "converged to a point of local infeasibility") */
+      status = w->resto ? ORC_INFEASIBLE : ORC_CONVERGED;
+      break;
+    }
     if (it >= c->max_iter) { status = ORC_MAXITER; break; }
     int mu_changed = 0;
     while (kkt_error(&kk, mu, 0) <= KAPPA_EPS * mu && mu > tol / 10) {
@@ -1080,6 +1202,11 @@ static int solve_ws(ws_t *w, const double *z_init, double *z_out, double *lam_eq
       tau = fmax(TAU_MIN, 1 - mu);
       w->nfilt = 0;
       mu_changed = 1;
+      if (w->resto) { /* psi_mu and zeta move with mu */
+        w->zeta = sqrt(mu);
+        resto_multipliers(w, mu);
+        kkt_pieces(w, &kk);
+      }
     }
     if (mu_changed) eval_primal(w, &w->it, mu, &theta, &phi, &fobj, 1);
     build_qp(w, mu);
@@ -1094,10 +1221,12 @@ static int solve_ws(ws_t *w, const double *z_init, double *z_out, double *lam_eq
         dw *= dw_last == 0.0 ? KW_PLUS_FIRST : KW_PLUS;
         if (dw > DW_MAX) break;
       }
-      if (!ok) { status = ORC_INFEASIBLE; break; }
-      dw_last = dw;
+      if (ok) dw_last = dw;
     }
-    double a_max, a_dual;
+    int accepted = 0, armijo = 0;
+    double a = 0, a_dual = 1;
+    if (ok) {
+    double a_max;
     mult_steps(w, mu, tau, &a_max, &a_dual);
     double gd = barrier_dir(w, mu);
     double a_min;
@@ -1113,8 +1242,7 @@ static int solve_ws(ws_t *w, const double *z_init, double *z_out, double *lam_eq
       a_min = GAMMA_THETA;
     }
     a_min = fmax(GAMMA_ALPHA * a_min, 1e-14);
-    double a = a_max;
-    int accepted = 0, armijo = 0;
+    a = a_max;
     double th_t = 0, ph_t = 0, f_t = 0;
     while (a >= a_min) {
       make_trial(w, a);
@@ -1131,11 +1259,52 @@ static int solve_ws(ws_t *w, const double *z_init, double *z_out, double *lam_eq
       a *= 0.5;
       n_bt++;
     }
-    if (!accepted) { status = err0 <= ACCEPTABLE_TOL ? ORC_ACCEPTABLE : ORC_INFEASIBLE; break; }
+    } /* ok */
+    if (!accepted) {
+      if (!w->resto && err0 <= ACCEPTABLE_TOL) { status = ORC_ACCEPTABLE; break; }
+      if (w->resto || !c->restoration || SHIPPED(w)) { status = w->resto ? ORC_RESTO_FAILED : ORC_INFEASIBLE; break; }
+      if (c->resto_max_calls > 0 && n_resto >= c->resto_max_calls) { status = ORC_INFEASIBLE; break; }
+      /* ---- enter the restoration phase at the current iterate */
+      iterate_t *q = &w->it;
+      n_resto++;
+      it_resto0 = it;
+      filter_add(w, (1 - GAMMA_THETA) * theta, phi - GAMMA_PHI * theta); /* the point of entry joins the original filter */
+      memcpy(w->filt_ot, w->filt_t, sizeof w->filt_t);
+      memcpy(w->filt_op, w->filt_p, sizeof w->filt_p);
+      w->nfilt_o = w->nfilt;
+      theta_min_o = theta_min; theta_max_o = theta_max;
+      mu_o = mu; tau_o = tau; th_R = theta;
+      double c_inf = 0;
+      for (int k = 0; k <= N; k++) {
+        for (int i = 0; i < nx; i++) { w->xR[k][i] = q->x[k][i]; c_inf = fmax(c_inf, fabs(w->cdef[k][i])); q->lam[k][i] = 0; }
+        for (int i = 0; i < 2; i++) w->uR[k][i] = k < N ? q->u[k][i] : 0.0;
+        if (has_rate(w, k)) for (int r = 0; r < c->n_rate; r++) c_inf = fmax(c_inf, fabs(w->resr[k][r]));
+        if (has_obs(w, k)) for (int j = 0; j < M; j++) c_inf = fmax(c_inf, fabs(w->reso[k][j]));
+      }
+      mu = fmax(mu_o, c_inf);
+      tau = fmax(TAU_MIN, 1 - mu);
+      w->zeta = sqrt(mu);
+      for (int k = 0; k <= N; k++) {
+        for (int i = 0; i < nx; i++) { q->zlx[k][i] = fmin(RESTO_RHO, q->zlx[k][i]); q->zux[k][i] = fmin(RESTO_RHO, q->zux[k][i]); }
+        for (int i = 0; i < 2; i++) {
+          q->zlu[k][i] = fmin(RESTO_RHO, q->zlu[k][i]); q->zuu[k][i] = fmin(RESTO_RHO, q->zuu[k][i]);
+          q->vlr[k][i] = fmin(RESTO_RHO, q->vlr[k][i]); q->vur[k][i] = fmin(RESTO_RHO, q->vur[k][i]);
+        }
+        for (int j = 0; j < M; j++) q->vlo[k][j] = fmin(RESTO_RHO, q->vlo[k][j]);
+      }
+      w->nfilt = 0;
+      w->resto = 1;
+      eval_primal(w, &w->it, mu, &theta, &phi, &fobj, 1);
+      theta_min = 1e-4 * fmax(1.0, theta);
+      theta_max = 1e4 * fmax(1.0, theta);
+      dw_last = 0.0;
+      continue;
+    }
     if (!armijo) filter_add(w, (1 - GAMMA_THETA) * theta, phi - GAMMA_PHI * theta);
     accept_step(w, a, a_dual, mu);
     eval_primal(w, &w->it, mu, &theta, &phi, &fobj, 1);
     it++;
+    if (w->resto) n_resto_it++;
   }
 done:
   write_out(w, z_out, lam_eq_out);
@@ -1143,6 +1312,7 @@ done:
     info->f = status == ORC_NAN ? NAN : objective(w, &w->it);
     info->err = err0; info->mu = mu; info->obj_scale = w->sigma;
     info->status = status; info->iters = it; info->n_reg = n_reg; info->n_backtrack = n_bt;
+    info->n_resto = n_resto; info->n_resto_iter = n_resto_it;
   }
   return 0;
 }

@@ -28,7 +28,7 @@ enum { ORC_MODEL_KIN = 0, ORC_MODEL_DYN = 1 };
 enum { ORC_OBS_NONE = 0, ORC_OBS_ELLIPSE = 1, ORC_OBS_SQRT = 2, ORC_OBS_DCBF = 3 };
 enum { ORC_REF_TERMINAL = 0, ORC_REF_TRAJECTORY = 1 };
 enum { ORC_INIT_AS_GIVEN = 0, ORC_INIT_ROLLOUT = 1 };
-enum { ORC_CONVERGED = 0, ORC_ACCEPTABLE = 1, ORC_MAXITER = 2, ORC_INFEASIBLE = 3, ORC_NAN = 4 };
+enum { ORC_CONVERGED = 0, ORC_ACCEPTABLE = 1, ORC_MAXITER = 2, ORC_INFEASIBLE = 3, ORC_NAN = 4, ORC_RESTO_FAILED = 5 };
 
 typedef struct {
   int32_t model;      /* ORC_MODEL_* */
@@ -61,6 +61,12 @@ typedef struct {
                          PKG/MPC_CBF_optimize_dyn.py:112-133 ships them: every rate row
                          is an equality U_i = U_{i-1}, the x/y defects of stages 2..N are range rows with the
                          rate bounds.  0 = aligned (what the code's comments intend). */
+  int32_t restoration; /* 1: a failed line search enters the restoration phase (ipm_dense.py) instead of ending with
+                         ORC_INFEASIBLE; not available with rows_as_shipped */
+  int32_t resto_max_calls; /* > 0: entering the restoration phase for the (resto_max_calls+1)-th time ends the solve with
+                         ORC_INFEASIBLE (restoration keeps reducing the infeasibility by the required 10 % without ever reaching a
+                         point from which the regular phase converges: a locally infeasible start).  IPOPT has no such cap and
+                         would use up max_iter; 0 = IPOPT's behaviour. */
 } orc_cfg;
 
 typedef struct {
@@ -69,6 +75,7 @@ typedef struct {
   double mu;
   double obj_scale;
   int32_t status, iters, n_reg, n_backtrack;
+  int32_t n_resto, n_resto_iter; /* restoration phases entered, iterations spent in them (part of iters) */
 } orc_info;
 
 /* one scenario.  xs: nx, or (N, nx) with ORC_REF_TRAJECTORY; obs: (M, N+1, 6) rows [x,y,theta,v,l,w];

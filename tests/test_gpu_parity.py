@@ -30,14 +30,22 @@ def _gpu(solver, dev, x0, xs, obs, z_init=None, **kw):
     return {k: v.cpu().numpy() for k, v in out.items()}
 
 
-def _check(gpu, ref_u0, ref_cost, ref_st, min_conv, min_same_verdict=0.97):
+def _check(gpu, ref_u0, ref_cost, ref_st, min_conv, min_same_verdict=None):
+    """BASELINE.json's three criteria against the oracle's answers.  Verdict: converged vs not.  Measured agreement on
+    large samples is 99.0-99.6 % (tests/tools/resto_check.py, profiles/r02_restoration.txt): the scenarios that differ
+    sit on the line-search failure boundary, where one ulp of libm/FMA difference changes the path; they are listed,
+    counted and bounded - at most 1.5 % of the batch plus one scenario - not hidden."""
     st = gpu["status"]
+    B = st.shape[0]
     both = (st <= 1) & (ref_st <= 1)  # 0 converged, 1 acceptable level: both count as success (IPOPT convention)
     assert both.mean() >= min_conv, both.mean()
-    # verdict: converged vs not.  Scenarios that sit on the line-search failure boundary are chaotic
-    # (an ulp changes the path); they are counted, reported and bounded, not hidden.
     same = (st <= 1) == (ref_st <= 1)
-    assert same.mean() >= min_same_verdict, same.mean()
+    differ = np.where(~same)[0]
+    if differ.size:
+        print(f"verdict differs on {differ.size} of {B} scenarios: ids {differ.tolist()[:40]} "
+              f"(gpu status {st[differ].tolist()[:40]}, oracle {ref_st[differ].tolist()[:40]})")
+    allowed = int(np.ceil(0.015 * B)) + 1 if min_same_verdict is None else int(np.floor((1 - min_same_verdict) * B))
+    assert differ.size <= allowed, (differ.size, allowed, differ.tolist()[:40])
     du = np.abs(gpu["u0"] - ref_u0).max(axis=1)
     dc = np.abs(gpu["cost"] - ref_cost) / np.abs(ref_cost)
     ok = (du <= U0_ATOL) & (dc <= COST_RTOL)
@@ -217,14 +225,14 @@ def test_edge_cases(dev):
         sN = BatchSolver("kin_cbf_pre", N=N)
         g = _gpu(sN, dev, x0, xs, obs)
         u0, cost, st, it, _ = c_oracle.solve_batch(c_oracle.make_cfg("kin_cbf_pre", N=N), x0, xs, obs, nthreads=os.cpu_count())
-        _check(g, u0, cost, st, 0.7, 0.93)
+        _check(g, u0, cost, st, 0.7)
     x0, xs, oa = scenarios.kin_cbf_moving(96)
     _, _, ob = scenarios.kin_cbf_moving(96, seed=99)
     ob[:, :, :, 0] += 60.0
     obs2 = np.concatenate([oa, ob], axis=1)
     g = _gpu(BatchSolver("kin_cbf_pre", M=2), dev, x0, xs, obs2)
     u0, cost, st, it, _ = c_oracle.solve_batch(c_oracle.make_cfg("kin_cbf_pre", M=2), x0, xs, obs2, nthreads=os.cpu_count())
-    _check(g, u0, cost, st, 0.6, 0.93)
+    _check(g, u0, cost, st, 0.6)
     # unsupported shapes fail loudly
     with pytest.raises(ValueError):
         s.solve(torch.zeros((2, 4), dtype=torch.float64, device=dev), torch.zeros((2, 4), dtype=torch.float64, device=dev),
@@ -254,7 +262,7 @@ def test_as_given_start_and_warm_start_shift(dev):
     z0 = np.concatenate([U.reshape(B, -1), X.reshape(B, -1)], axis=1)
     g = _gpu(s, dev, x0, xs, obs, z_init=z0, return_z=True)
     u0, cost, st, it, zc = c_oracle.solve_batch(cfg, x0, xs, obs, z_init=z0, want_z=True, nthreads=os.cpu_count())
-    _check(g, u0, cost, st, 0.7, 0.93)
+    _check(g, u0, cost, st, 0.7)
     # device-side plant step + shift equals the host formula
     tx0 = torch.from_numpy(x0).to(dev)
     tz = torch.from_numpy(g["z"]).to(dev)
@@ -513,7 +521,8 @@ def test_horizon_limits(dev, kind, gen, N):
     cfg = c_oracle.make_cfg(kind, N=N)
     u0, cost, st, it, _ = c_oracle.solve_batch(cfg, x0, xs, obs if obs.shape[1] else None, nthreads=os.cpu_count())
     both = (g["status"] <= 1) & (st <= 1)
-    assert ((g["status"] <= 1) == (st <= 1)).mean() >= 0.85
+    differ = np.where((g["status"] <= 1) != (st <= 1))[0]
+    assert differ.size <= 2, (differ.tolist(), g["status"][differ].tolist(), st[differ].tolist())  # 48 scenarios: 1.5 % + 1
     assert both.sum() >= 24
     du = np.abs(g["u0"] - u0).max(axis=1)
     dc = np.abs(g["cost"] - cost) / np.maximum(np.abs(cost), 1.0)
@@ -701,7 +710,7 @@ def test_three_and_four_obstacles(dev, gamma, M):
     obs3 = np.concatenate([oa, ob, oc, od][:M], axis=1)
     g = _gpu(BatchSolver("kin_cbf_pre", M=M, cbf_gamma=gamma), dev, x0, xs, obs3)
     u0, cost, st, it, _ = c_oracle.solve_batch(c_oracle.make_cfg("kin_cbf_pre", M=M, cbf_gamma=gamma), x0, xs, obs3, nthreads=os.cpu_count())
-    _check(g, u0, cost, st, 0.5, 0.93)
+    _check(g, u0, cost, st, 0.5)
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
@@ -980,3 +989,57 @@ def test_reserve_and_order_length(dev):
         _gpu(s, dev, x0, xs, obs)
     s.set_order(None)
     _gpu(s, dev, x0, xs, obs)
+
+
+# --------------------------------------------------------------------------- restoration phase, verdict at scale
+@pytest.mark.parametrize("kind,gen", [("kin_cbf", "kin_cbf_static"), ("kin_cbf_pre", "kin_cbf_moving")])
+@pytest.mark.parametrize("calls", [1, 0])
+def test_restoration_phase_parity(dev, kind, gen, calls):
+    """cfg.restoration: a failed line search enters the restoration phase (sibling kernel, second pass) instead of ending
+    with status 3.  Same algorithm as the C oracle / the dense specification: statuses, verdicts and answers agree, the
+    success rate does not drop, and no scenario is left with the 'no restoration attempted' exit."""
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+    from oracle import c_oracle
+
+    B = 3000
+    x0, xs, obs = getattr(scenarios, gen)(B)
+    plain = _gpu(BatchSolver(kind), dev, x0, xs, obs)
+    s = BatchSolver(kind, restoration=True, resto_max_calls=calls)
+    g = _gpu(s, dev, x0, xs, obs)
+    u0, cost, st, it, _ = c_oracle.solve_batch(c_oracle.make_cfg(kind, restoration=True, resto_max_calls=calls), x0, xs, obs,
+                                               nthreads=os.cpu_count())
+    print(f"{kind} calls={calls}: gpu {np.bincount(g['status'], minlength=6)} oracle {np.bincount(st, minlength=6)} "
+          f"without restoration {np.bincount(plain['status'], minlength=6)}")
+    both, same = _check(g, u0, cost, st, 0.8)
+    assert (g["iters"][both] == it[both]).mean() >= 0.9
+    # restoration rescues scenarios, it never loses a success of the plain run (up to the chaotic handful)
+    assert (g["status"] <= 1).sum() >= (plain["status"] <= 1).sum()
+    lost = np.where((plain["status"] <= 1) & (g["status"] > 1))[0]
+    assert lost.size <= 3, lost
+    # scenarios the plain run solves are untouched by the second pass (they never enter it)
+    keep = (plain["status"] <= 1) & (g["status"] <= 1)
+    assert np.array_equal(plain["u0"][keep], g["u0"][keep]) and np.array_equal(plain["iters"][keep], g["iters"][keep])
+    if calls == 0:  # no cap: every failure is a maximum-iterations exit, a detected local infeasibility or a failed restoration
+        assert set(np.unique(g["status"])) <= {0, 1, 2, 3, 5}
+        assert (g["status"] == 3).sum() <= (plain["status"] == 3).sum()
+    assert s.launch_info()["launches"] >= 2  # main kernel + restoration sibling
+
+
+def test_verdict_agreement_on_the_bench_batch(dev):
+    """The driver-run benchmark's exact inputs (bench.py: kin_cbf_static(10000, seed BASE+2), obstacle rows as the static
+    module takes them): nothing outside tolerance among the commonly converged scenarios, verdict equal on >= 99 %."""
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+    from oracle import c_oracle
+
+    B = 10000
+    x0, xs, obs_traj = scenarios.kin_cbf_static(B, seed=scenarios.BASE_SEED + 2)
+    obs = np.ascontiguousarray(obs_traj[:, :, 0, :])
+    g = _gpu(BatchSolver("kin_cbf", obs_input="static"), dev, x0, xs, obs)
+    u0, cost, st, it, _ = c_oracle.solve_batch(c_oracle.make_cfg("kin_cbf"), x0, xs, obs_traj, nthreads=os.cpu_count())
+    both, same = _check(g, u0, cost, st, 0.8, min_same_verdict=0.99)
+    du = np.abs(g["u0"] - u0).max(axis=1)
+    dc = np.abs(g["cost"] - cost) / np.abs(cost)
+    assert np.all(du[both] <= U0_ATOL) and np.all(dc[both] <= COST_RTOL), (du[both].max(), dc[both].max())
+    print(f"bench batch: verdict-equal {same.mean():.4f}, worst |du0| {du[both].max():.2e}, worst rel dcost {dc[both].max():.2e}")

@@ -156,3 +156,45 @@ def test_c_oracle_dyn_rows_as_shipped_follows_the_dense_specification(N):
     assert np.abs(U - U[0]).max() == 0.0
     g = nlp.g_ref(z)
     assert np.all(g >= nlp.lbg_shipped - 1e-7) and np.all(g <= nlp.ubg_shipped + 1e-7)
+
+
+def test_restoration_c_oracle_equals_dense_specification():
+    """The restoration phase (elastic l1 problem on the inequality rows, dynamics kept as equalities, p/n eliminated on
+    their central path) in the C oracle's Riccati form against the dense specification: same phases entered, same
+    iteration counts, same answers on scenarios whose plain solve ends in a line-search failure."""
+    from oracle import c_oracle, ipm_dense, nlp
+    from mpc_motion_planning_b200 import scenarios
+
+    x0, xs, obs = scenarios.kin_cbf_static(2000)
+    cfg_plain = c_oracle.make_cfg("kin_cbf")
+    cfg = c_oracle.make_cfg("kin_cbf", restoration=True, resto_max_calls=0)
+    for b, n_resto in ((99, 1), (231, 1)):
+        _, _, plain = c_oracle.solve(cfg_plain, x0[b], xs[b], obs[b])
+        assert plain.status == c_oracle_status_infeasible()
+        z, lam, info = c_oracle.solve(cfg, x0[b], xs[b], obs[b])
+        P = nlp.NLP("kin_cbf", x0[b], xs[b], obs[b, :, 0, :])
+        r = ipm_dense.solve(P, P.rollout_start(), ipm_dense.IpmOptions(restoration=True, resto_max_calls=0))
+        assert (r.status, r.iters, r.n_resto, r.n_resto_iter, r.n_reg) == (info.status, info.iters, info.n_resto, info.n_resto_iter, info.n_reg)
+        assert info.status == 0 and info.n_resto == n_resto
+        assert abs(r.f - info.f) <= 1e-9 * abs(r.f) and np.abs(r.z - z).max() <= 1e-6
+
+
+def c_oracle_status_infeasible():
+    return 3
+
+
+def test_psi_penalty_derivatives():
+    """psi_mu(r): value / first / second derivative consistent, and the implied p, n solve the centred l1 split."""
+    from oracle.ipm_dense import _psi
+
+    rho = 1000.0
+    for mu in (30.0, 0.1, 1e-5):
+        r = np.array([-3.0, -0.2, -1e-4, 0.0, 1e-4, 0.2, 3.0])
+        v, d1, d2 = _psi(r, mu, rho)
+        h = 1e-4 * np.maximum(mu / rho, np.abs(r))  # well inside the smoothing width mu/rho of the kink at r = 0
+        vp, d1p, _ = _psi(r + h, mu, rho)
+        vm, d1m, _ = _psi(r - h, mu, rho)
+        assert np.allclose((vp - vm) / (2 * h), d1, rtol=2e-4, atol=1e-6 * rho)
+        assert np.allclose((d1p - d1m) / (2 * h), d2, rtol=2e-3)
+        p_, n_ = mu / (rho - d1), mu / (rho + d1)  # central path: p z_p = mu with z_p = rho - lambda
+        assert np.allclose(p_ - n_, r, atol=1e-9 * np.maximum(1, np.abs(r)))
