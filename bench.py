@@ -4,11 +4,12 @@
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on the host cores
 
-A "step" = one pass of the hot path over one batch of synthetic scenarios: B kin-CBF NLPs
+A "step" = one pass of the hot path over one batch of synthetic scenarios: G x 10,000 kin-CBF NLPs
 (static obstacle, N=50, M=1; BASELINE.json configs[1], seeded as SURVEY.md section 8d) are
-solved from the reference's zero control guess.  One rank per GPU, each rank owns its own batch
-(weak scaling), no data-path collective; only the timing reduction is collective.
-Prints ONE JSON line on rank 0.
+solved from the reference's zero control guess.  One rank per GPU; the batch is the same on every
+rank and goes through `sharding.solve_sharded`: fixed-seed shuffle, contiguous shard per rank, local
+solve (no data-path collective), all-gather of the results (NCCL) - all inside the timed region.
+Weak scaling: 10,000 scenarios per GPU.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -105,6 +106,101 @@ def make_batch(rank: int, B: int):
     return scenarios.kin_cbf_static(B, N=N_HORIZON, seed=scenarios.BASE_SEED + 2 + 1000 * rank)
 
 
+def _stats(status, iters):
+    return {"success_frac": float((status <= 1).mean()), "mean_iters": float(iters.mean()), "p99_iters": float(np.percentile(iters, 99)),
+            "status_counts": np.bincount(status, minlength=6).tolist()}
+
+
+def protocol_legs(dev, x0, xs, obs, K):
+    """The reference's literal call protocol beside the headline (N = 1, rank 0): first guess ALL ZEROS taken as given
+    (PKG/main_cbf_kin_c_sim.py:47-50,92), IPOPT's default mu_init = 0.1, restoration after a failed line search."""
+    import torch
+
+    from mpc_motion_planning_b200.solver import BatchSolver
+
+    legs = {}
+    B = x0.shape[0]
+    for name, kw in (("rollout_mu30", dict()),
+                     ("rollout_mu30_restoration", dict(restoration=True, resto_max_calls=1)),
+                     ("zeros_mu30", dict(init="as_given")),
+                     ("zeros_mu0.1", dict(init="as_given", mu_init=0.1)),
+                     ("zeros_mu0.1_restoration_nocap", dict(init="as_given", mu_init=0.1, restoration=True, resto_max_calls=0))):
+        s = BatchSolver("kin_cbf", N=N_HORIZON, M=1, obs_input="static", **kw)
+        for _ in range(2):
+            out = s.solve(x0, xs, obs)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            out = s.solve(x0, xs, obs)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        st, it = out["status"].cpu().numpy(), out["iters"].cpu().numpy()
+        leg = _stats(st, it)
+        leg.update({"value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "successful_solves_per_s": B / ms * 1e3 * leg["success_frac"],
+                    "start": "all-zero z as given" if kw.get("init") == "as_given" else "zero controls, Euler roll-out states",
+                    "mu_init": kw.get("mu_init", 30.0), "restoration": bool(kw.get("restoration", False)),
+                    "resto_max_calls": kw.get("resto_max_calls")})
+        legs[name] = leg
+        s.close()
+    return legs
+
+
+def configs4_sweep(dev, world, rank, dist):
+    """BASELINE.json configs[4]: kin-CBF moving-obstacle MPC, N in {20, 50, 100}, 4M / 4M / 2M scenarios sharded over the
+    GPUs (strong scaling: the totals are fixed).  Obstacle states go in as [B][1][6] (prediction on the device); the shard is
+    cut on the host from the same seeded, shuffled global batch on every rank; timed: local solve + all-gather of the results."""
+    import torch
+
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.sharding import balanced_permutation, shard_range
+    from mpc_motion_planning_b200.solver import BatchSolver
+
+    lines = []
+    for N, total in ((20, 4_000_000), (50, 4_000_000), (100, 2_000_000)):
+        rng = np.random.default_rng(scenarios.BASE_SEED + 5 + N)
+        x0 = np.stack([rng.uniform(0, 20, total), rng.uniform(0, 4.5, total), rng.uniform(-0.05, 0.05, total), rng.uniform(10, 25, total)], axis=1)
+        ob = np.stack([x0[:, 0] + rng.uniform(30, 80, total), rng.uniform(0, 4, total), rng.uniform(-0.05, 0.05, total), rng.uniform(5, 12, total),
+                       np.full(total, 4.8), np.full(total, 1.8)], axis=1)[:, None, :]
+        perm = balanced_permutation(total, 0)
+        lo, hi = shard_range(total, world, rank)
+        idx = perm[lo:hi]
+        dx0 = torch.from_numpy(x0[idx]).to(dev)
+        dxs = torch.tensor([400.0, 3.5, 0.0, 30.0], dtype=torch.float64, device=dev).repeat(hi - lo, 1)
+        dob = torch.from_numpy(np.ascontiguousarray(ob[idx])).to(dev)
+        del x0, ob, perm
+        s = BatchSolver("kin_cbf_pre", N=N, M=1, obs_input="initial")
+        per = -(-total // world)
+        packed = torch.zeros((per, 5), dtype=torch.float64, device=dev)
+        full = torch.empty((world * per, 5), dtype=torch.float64, device=dev) if world > 1 else packed
+        s.solve(dx0[:20000], dxs[:20000], dob[:20000])  # warm-up
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        out = s.solve(dx0, dxs, dob)
+        e1.record()
+        n = hi - lo
+        packed[:n, 0:2] = out["u0"]; packed[:n, 2] = out["cost"]; packed[:n, 3] = out["status"].to(torch.float64); packed[:n, 4] = out["iters"].to(torch.float64)
+        if world > 1:
+            dist.all_gather_into_tensor(full, packed)
+        e2.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e2), e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        st = full[:, 3]
+        lines.append({"N": N, "scenarios": total, "ms": float(t[0]), "solve_ms_max_rank": float(t[1]), "value": total / float(t[0]) * 1e3, "unit": UNIT,
+                      "success_frac": float((st[: total if world == 1 else world * per] <= 1).double().mean()),
+                      "gather_bytes": int(world * per * 40) if world > 1 else 0})
+        s.close()
+        del dx0, dxs, dob, packed, full, out
+        torch.cuda.empty_cache()
+    return lines
+
+
 def cpu_solve(x0, xs, obs, nthreads):
     from oracle import c_oracle
     cfg = c_oracle.make_cfg("kin_cbf", N=N_HORIZON, M=1)
@@ -170,6 +266,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the literal-protocol / restoration legs")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the BASELINE configs[4] horizon sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -198,14 +296,18 @@ def main():
     K = args.steps
     B = args.batch
 
-    x0, xs, obs_traj = make_batch(rank, B)
+    from mpc_motion_planning_b200.sharding import shard_range, solve_sharded
+
+    # the SAME global batch of world x B scenarios on every rank (at world = 1: configs[1]'s 10,000)
+    GB = world * B
+    gx0, gxs, gobs_traj = make_batch(0, GB)
     # The static-obstacle module's optimize_problem takes the obstacle rows themselves, (M,6)
     # (PKG/MPC_CBF_optimize_kin.py:136,236-243; PKG/main_cbf_kin_c_sim.py:55,99): that is the input of the
     # bench, [B][M][6] (MPCB_OBS_STATIC).  The CPU arm gets the same rows repeated per step.
-    obs = np.ascontiguousarray(obs_traj[:, :, 0, :])
-    assert np.array_equal(obs_traj, np.repeat(obs[:, :, None, :], N_HORIZON + 1, axis=2))
+    gobs = np.ascontiguousarray(gobs_traj[:, :, 0, :])
+    assert np.array_equal(gobs_traj, np.repeat(gobs[:, :, None, :], N_HORIZON + 1, axis=2))
     solver = BatchSolver("kin_cbf", N=N_HORIZON, M=1, obs_input="static")
-    dx0, dxs, dobs = (torch.from_numpy(a).to(dev) for a in (x0, xs, obs))
+    dx0, dxs, dobs = (torch.from_numpy(a).to(dev) for a in (gx0, gxs, gobs))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -213,39 +315,87 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # local solve of this rank's shard with CUDA events around it: the gather's share of the step is the difference
+    solve_ev = []
+
+    def solve_local(a, b_, c, z):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        o = solver.solve(a, b_, c, z)
+        e1.record()
+        solve_ev.append((e0, e1))
+        return o
+
+    def step():
+        return solve_sharded(solve_local, dx0, dxs, dobs, shuffle_seed=0)
+
     for _ in range(W):
-        out = solver.solve(dx0, dxs, dobs)
+        out = step()
     barrier()
     launches0 = solver.launch_info()["launches"]
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    solve_ev.clear()
     barrier()
     for k in range(K):
         flush.zero_()  # L2 flush between timed iterations (not timed)
         ev[k][0].record()
-        out = solver.solve(dx0, dxs, dobs)
+        out = step()
         ev[k][1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else {}
     step_ms = [a.elapsed_time(b) for a, b in ev]
+    solve_ms = [a.elapsed_time(b) for a, b in solve_ev]
     t_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    print(f"[bench rank {rank}] device ms/step: {sum(step_ms) / K:.3f} (min {min(step_ms):.3f}, max {max(step_ms):.3f}); "
+    print(f"[bench rank {rank}] device ms/step: {sum(step_ms) / K:.3f} (min {min(step_ms):.3f}, max {max(step_ms):.3f}), local solve {sum(solve_ms) / K:.3f}; "
           f"mean iterations {float(out['iters'].float().mean()):.2f}", file=sys.stderr, flush=True)
     rank_ms = [float(t_ms.item()) / K]
+    rank_solve_ms = [sum(solve_ms) / K]
     if world > 1:
-        gathered = [torch.zeros_like(t_ms) for _ in range(world)]
-        dist.all_gather(gathered, t_ms)
-        rank_ms = [float(g.item()) / K for g in gathered]
+        both = torch.tensor([sum(step_ms) / K, sum(solve_ms) / K], dtype=torch.float64, device=dev)
+        gathered = [torch.zeros_like(both) for _ in range(world)]
+        dist.all_gather(gathered, both)
+        rank_ms = [float(g[0]) for g in gathered]
+        rank_solve_ms = [float(g[1]) for g in gathered]
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     total_ms = float(t_ms.item())
     launches = solver.launch_info()["launches"] - launches0
-    iters = out["iters"].cpu().numpy()
+    launch_info = solver.launch_info()
+    iters = out["iters"].cpu().numpy()    # the whole gathered batch, input order
     status = out["status"].cpu().numpy()
+    # same work on every rank (rank 0's shard): separates machine variance from the variance of the random shards
+    same_ms = None
+    if world > 1:
+        from mpc_motion_planning_b200.sharding import balanced_permutation
+        idx0 = torch.from_numpy(balanced_permutation(GB, 0)[: shard_range(GB, world, 0)[1]]).to(dev)
+        sx0, sxs, sobs = (t.index_select(0, idx0) for t in (dx0, dxs, dobs))
+        for _ in range(2):
+            solver.solve(sx0, sxs, sobs)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            solver.solve(sx0, sxs, sobs)
+        e1.record()
+        barrier()
+        one = torch.tensor([e0.elapsed_time(e1) / K], dtype=torch.float64, device=dev)
+        gathered = [torch.zeros_like(one) for _ in range(world)]
+        dist.all_gather(gathered, one)
+        same_ms = [round(float(g.item()), 3) for g in gathered]
+    # this rank's own shard for the end-to-end legs below (host buffers)
+    lo, hi = shard_range(GB, world, rank)
+    from mpc_motion_planning_b200.sharding import balanced_permutation as _bp
+    my = _bp(GB, 0)[lo:hi]
+    x0, xs, obs, obs_traj = gx0[my], gxs[my], gobs[my], gobs_traj[my]
+    B = hi - lo
+    my_status = status[my]
+    my_u0 = out["u0"].cpu().numpy()[my]
+    dx0, dxs, dobs = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (x0, xs, obs))
 
     # ---- end to end through the host-pointer C-ABI call (pinned host buffers, copies inside)
-    hx0, hxs, hobs = (torch.from_numpy(a).pin_memory() for a in (x0, xs, obs))
+    hx0, hxs, hobs = (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (x0, xs, obs))
     hu0 = torch.empty((B, 2), dtype=torch.float64).pin_memory()
     hcost = torch.empty((B,), dtype=torch.float64).pin_memory()
     hst = torch.empty((B,), dtype=torch.int32).pin_memory()
@@ -282,7 +432,7 @@ def main():
         dist.all_reduce(e2e_p, op=dist.ReduceOp.MAX)
     e2e_val = world * B * K / float(e2e_p.item())
     for ho in houts:
-        assert np.array_equal(ho[2].numpy(), status) and np.array_equal(ho[0].numpy(), out["u0"].cpu().numpy()), "pipelined results differ"
+        assert np.array_equal(ho[2].numpy(), my_status) and np.array_equal(ho[0].numpy(), my_u0), "pipelined results differ"
     # device-resident counterpart (inputs in HBM, CUDA events around the K submissions)
     for k in range(2 * LANES):
         pipe.submit(dx0, dxs, dobs)
@@ -303,7 +453,7 @@ def main():
     pipe_launches = pipe.launch_info()["launches"] - pl0
     h2d = int(hx0.numel() + hxs.numel() + hobs.numel()) * 8
     d2h = int(hu0.numel() + hcost.numel()) * 8 + int(hst.numel() + hit.numel()) * 4
-    assert np.array_equal(hst.numpy(), status), "host-path and device-path verdicts differ"
+    assert np.array_equal(hst.numpy(), my_status), "host-path and device-path verdicts differ"
 
     # ---- single-solve latency: BASELINE configs[0] (main_kin_c_sim.py: no-CBF kin MPC, closed loop, B = 1)
     latency = None
@@ -326,9 +476,23 @@ def main():
         latency = {"p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
                    "workload": "kin no-CBF closed loop (main_kin_c_sim.py), B=1, 99 warm-started solves, host wall clock incl. launch+sync"}
 
+    # ---- the reference's literal call protocol and the restoration phase, beside the headline (one GPU only)
+    legs = None
+    if world == 1 and not args.no_legs:
+        legs = protocol_legs(dev, dx0, dxs, dobs, max(2, min(K, 3)))
+    # ---- BASELINE configs[4]: horizon sweep, 4M / 4M / 2M scenarios sharded over the GPUs (all ranks take part)
+    sweep = None
+    if not args.no_sweep:
+        solver.close()
+        del flush
+        torch.cuda.empty_cache()
+        sweep = configs4_sweep(dev, world, rank, dist if world > 1 else None)
+
     if rank == 0:
         value = world * B * K / (total_ms * 1e-3)
-        ms_kernel = float(np.mean(step_ms))
+        ms_kernel = float(np.mean(solve_ms))  # the solve kernel of this rank's shard (CUDA events around the launch)
+        iters_all, status_all = iters, status
+        iters = iters_all[my]
         # roofline of the dominant (only) kernel: FP64 FMA pipe; HBM traffic reported beside it
         import ctypes as C
         peak = C.c_double(0.0)
@@ -344,9 +508,20 @@ def main():
             "config": {"workload": f"kin-CBF static obstacle MPC, N={N_HORIZON}, M=1, B={B}/GPU (BASELINE configs[1])",
                        "start": "zero controls, Euler roll-out states", "mu_init": float(solver.cfg.mu_init), "tol": 1e-8, "max_iter": 100,
                        "inputs": "x0 [B][4], xs [B][4], obstacle rows [B][1][6] as optimize_problem takes them",
-                       "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"scenario-sharded x{world}"},
-            "solver": {"converged_frac": float((status <= 1).mean()), "acceptable_frac": float((status == 1).mean()), "mean_iters": float(iters.mean()),
-                       "p99_iters": float(np.percentile(iters, 99))},
+                       "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"scenario-sharded x{world} (solve_sharded)", "restoration": "off"},
+            "solver": {"converged_frac": float((status_all <= 1).mean()), "acceptable_frac": float((status_all == 1).mean()),
+                       "mean_iters": float(iters_all.mean()), "p99_iters": float(np.percentile(iters_all, 99)),
+                       "status_counts": np.bincount(status_all, minlength=6).tolist(),
+                       "successful_solves_per_s": value * float((status_all <= 1).mean()),
+                       "restoration": "off (cfg.restoration = 0): a failed line search ends with status 3; see `protocol` for the legs with it"},
+            "sharding": {"path": "sharding.solve_sharded: fixed-seed shuffle, contiguous shard per rank, local solve, all_gather_into_tensor of "
+                                 "(u0, cost, status, iters) = 40 B/scenario, un-shuffle - all inside the timed step",
+                         "global_batch": int(GB), "gather_bytes_per_step": int(GB * 40) if world > 1 else 0,
+                         "solve_ms_per_rank": [round(v, 3) for v in rank_solve_ms],
+                         "gather_and_bookkeeping_ms": round(total_ms / K - max(rank_solve_ms), 3),
+                         "same_shard_on_every_rank_ms": same_ms},
+            "protocol": legs,
+            "configs4": sweep,
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "mode": f"{LANES} batches in flight: mpcb_submit_batch_host on {LANES} handles, step k+1 submitted before mpcb_wait of step k; "
@@ -365,7 +540,7 @@ def main():
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "peak_source": hbm_src + " MEASURED_PEAKS.json hbm_gbs"}},
             "ranks": {"ms_per_step": [round(v, 3) for v in rank_ms], "max_over_mean": max(rank_ms) / (sum(rank_ms) / len(rank_ms))},
-            "launch": solver.launch_info(),
+            "launch": launch_info,
             "latency": latency,
         }
         if not args.no_cpu_baseline and world == 1:
