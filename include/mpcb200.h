@@ -62,6 +62,7 @@ enum { MPCB_OBS_TRAJECTORY = 0, MPCB_OBS_INITIAL = 1, MPCB_OBS_STATIC = 2 };
  * horizon) and the x / y defects into stages 2..N are range rows with the rate bounds - what IPOPT is actually
  * given by the reference's dyn main. */
 enum { MPCB_DYN_ROWS_ALIGNED = 0, MPCB_DYN_ROWS_AS_SHIPPED = 1 };
+enum { MPCB_ENGINE_AUTO = 0, MPCB_ENGINE_WARP = 1, MPCB_ENGINE_LANE = 2 };
 
 /* per-scenario outcome, mapped to IPOPT return_status strings by the Python shim */
 enum {
@@ -121,7 +122,9 @@ typedef struct mpcb_cfg {
                            sibling kernel launched right after the main one on the same stream */
   int32_t resto_max_calls; /* > 0: the (n+1)-th entry into the restoration phase ends the solve with MPCB_INFEASIBLE; 0 = no cap
                            (IPOPT: the phases alternate until max_iter).  Library default 1, drop-in classes 0 */
-  int32_t reserved;
+  int32_t engine;       /* MPCB_ENGINE_AUTO (default), _WARP: one scenario per warp (every family), _LANE: one scenario per
+                           lane (kinematic model, plain rows, one target per scenario).  AUTO uses the
+                           lane engine where it measures faster: the families without obstacle rows from 32,768 scenarios up */
 } mpcb_cfg;
 
 typedef struct mpcb_handle mpcb_handle;

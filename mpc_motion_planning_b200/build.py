@@ -17,6 +17,7 @@ SRCS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HER
 ]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 N_FAMILIES = 12  # csrc/mpcb_variants.cu: 10 kinematic families + the dynamic bicycle (rows aligned, rows as shipped)
+N_LANE_FAMILIES = 6  # csrc/mpcb_lane.cu: the lane-per-scenario engine, kinematic families with plain rows
 
 
 def stale() -> bool:
@@ -35,6 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     jobs = [(os.path.join(HERE, "csrc", "mpcb_api.cu"), os.path.join(OBJ, "api.o"), [])]
     jobs += [(os.path.join(HERE, "csrc", "mpcb_variants.cu"), os.path.join(OBJ, f"family{k}.o"), [f"-DMPCB_FAMILY={k}"]) for k in range(N_FAMILIES)]
+    jobs += [(os.path.join(HERE, "csrc", "mpcb_lane.cu"), os.path.join(OBJ, f"lane{k}.o"), [f"-DMPCB_LANE_FAMILY={k}"]) for k in range(N_LANE_FAMILIES)]
 
     def compile_one(job):
         src, obj, defs = job

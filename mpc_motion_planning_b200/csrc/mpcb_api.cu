@@ -13,6 +13,10 @@
 
 using namespace mpcb;
 
+#ifndef MPCB_LANE_MIN_B_DEFAULT
+#define MPCB_LANE_MIN_B_DEFAULT 32768  // MPCB_ENGINE_AUTO: batches of the row-free families at least this large go to the lane engine
+#endif
+
 namespace {
 
 thread_local char g_cuda_err[256] = "";
@@ -71,6 +75,24 @@ bool select_variant(const mpcb_cfg &c, Variant &v) {
   return false;
 }
 
+// lane-per-scenario engine: kinematic model, plain rows (none / h >= 0), one target per scenario, at most one rate row
+// and that on the steering angle
+bool select_lane_variant(const mpcb_cfg &c, LaneVariant &v) {
+  if (c.model != MPCB_MODEL_KIN || c.ref_mode != MPCB_REF_TERMINAL) return false;
+  const int M = c.obs_mode == MPCB_OBS_NONE ? 0 : c.M;
+  if (c.obs_mode != MPCB_OBS_NONE && c.obs_mode != MPCB_OBS_ELLIPSE) return false;
+  if (c.n_rate == 0 && M == 0) { v = lane_variant_kin_0_0(); return true; }
+  if (c.n_rate != 1 || c.rate_ctrl[0] != 0) return false;
+  switch (M) {
+    case 0: v = lane_variant_kin_1_0(); return true;
+    case 1: v = lane_variant_kin_1_1(); return true;
+    case 2: v = lane_variant_kin_1_2(); return true;
+    case 3: v = lane_variant_kin_1_3(); return true;
+    case 4: v = lane_variant_kin_1_4(); return true;
+  }
+  return false;
+}
+
 double relax_lo(double b, double f) { return std::isfinite(b) ? b - f * std::fmax(1.0, std::fabs(b)) : b; }
 double relax_hi(double b, double f) { return std::isfinite(b) ? b + f * std::fmax(1.0, std::fabs(b)) : b; }
 
@@ -109,6 +131,12 @@ struct mpcb_handle {
   int resto_cap, resto_grid;
   size_t resto_smem;
   double *d_resto_slab;
+  // lane-per-scenario engine: workspace of one slot per resident lane, used for batches of at least lane_min_B
+  LaneVariant lane;
+  double *d_lane_ws;
+  size_t lane_nslot;
+  int lane_grid, lane_min_B;
+  mpcb_launch_info lane_info;
 };
 
 extern "C" {
@@ -143,6 +171,12 @@ int mpcb_workspace_bytes(const mpcb_cfg *cfg, int B, size_t *bytes) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   *bytes = v.slab_doubles * sizeof(double) * (size_t)sms * 32;
+  // plus the lane-per-scenario engine's workspace: one slot per resident lane (at most 2048 threads per SM)
+  LaneVariant lv;
+  const char *eng = getenv("MPCB_ENGINE");
+  if (!(eng && !strcmp(eng, "warp")) && cfg->engine != MPCB_ENGINE_WARP && select_lane_variant(*cfg, lv) &&
+      (cfg->engine == MPCB_ENGINE_LANE || cfg->obs_mode == MPCB_OBS_NONE || (eng && !strcmp(eng, "lane"))))
+    *bytes += lv.slot_doubles(cfg->N) * sizeof(double) * (size_t)sms * 2048;
   return MPCB_OK;
 }
 
@@ -162,6 +196,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   if (c.obs_mode == MPCB_OBS_DCBF && !(c.cbf_gamma > 0.0 && c.cbf_gamma <= 1.0)) return MPCB_E_ARG;
   if (c.dyn_rows != MPCB_DYN_ROWS_ALIGNED && c.dyn_rows != MPCB_DYN_ROWS_AS_SHIPPED) return MPCB_E_ARG;
   if (c.dyn_rows == MPCB_DYN_ROWS_AS_SHIPPED && c.model != MPCB_MODEL_DYN) return MPCB_E_ARG;
+  if (c.engine != MPCB_ENGINE_AUTO && c.engine != MPCB_ENGINE_WARP && c.engine != MPCB_ENGINE_LANE) return MPCB_E_ARG;
   Variant var;
   if (!select_variant(c, var)) return MPCB_E_ARG;
   // the kernels assume: both controls two-sided; the model's bounded states (kin: y, vx; dyn: + vy)
@@ -259,6 +294,42 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
       cudaGetLastError();
     }
   }
+  // ---- second engine (one scenario per lane).  cfg.engine, overridden by the environment for A/B runs: MPCB_ENGINE=warp
+  // disables it, =lane forces it for every batch size, MPCB_LANE_MIN_B moves AUTO's switch-over.  AUTO uses it only for
+  // the families without obstacle rows (it measures 19 % faster there at 100k scenarios and 2x slower on the CBF families,
+  // whose iteration counts and line searches diverge between the lanes of a warp)
+  {
+    const char *eng = getenv("MPCB_ENGINE");
+    int engine = c.engine;
+    if (eng && !strcmp(eng, "warp")) engine = MPCB_ENGINE_WARP;
+    if (eng && !strcmp(eng, "lane")) engine = MPCB_ENGINE_LANE;
+    LaneVariant lv;
+    const bool has_lane = select_lane_variant(c, lv);
+    if (engine == MPCB_ENGINE_LANE && !has_lane) { mpcb_destroy(h); return MPCB_E_ARG; }
+    const bool rows = c.obs_mode != MPCB_OBS_NONE;
+    if (has_lane && (engine == MPCB_ENGINE_LANE || (engine == MPCB_ENGINE_AUTO && !rows))) {
+      int lb = 0;
+      cudaFuncAttributes la;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lb, lv.kernel, lv.block, 0) == cudaSuccess && lb >= 1 &&
+          cudaFuncGetAttributes(&la, lv.kernel) == cudaSuccess) {
+        if (const char *cap = getenv("MPCB_LANE_BLOCKS_PER_SM")) { int v_ = atoi(cap); if (v_ >= 1 && v_ < lb) lb = v_; }
+        h->lane = lv;
+        h->lane_grid = lb * prop.multiProcessorCount;
+        h->lane_nslot = (size_t)h->lane_grid * lv.block;
+        h->lane_min_B = engine == MPCB_ENGINE_LANE ? 1 : (getenv("MPCB_LANE_MIN_B") ? atoi(getenv("MPCB_LANE_MIN_B")) : MPCB_LANE_MIN_B_DEFAULT);
+        size_t bytes = h->lane_nslot * lv.slot_doubles(c.N) * sizeof(double);
+        if (!cuda_ok(cudaMalloc(&h->d_lane_ws, bytes), "cudaMalloc lane workspace")) { mpcb_destroy(h); return MPCB_E_NOMEM; }
+        if (!h->d_counter && !cuda_ok(cudaMalloc(&h->d_counter, sizeof(int)), "cudaMalloc counter")) { mpcb_destroy(h); return MPCB_E_NOMEM; }
+        h->lane_info = h->info;
+        h->lane_info.block = lv.block;
+        h->lane_info.smem_bytes = 0;
+        h->lane_info.regs_per_thread = la.numRegs;
+        h->lane_info.blocks_per_sm = lb;
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
   k.resto_max_calls = c.resto_max_calls;
   k.restoration = (c.restoration && var.rs_inline) ? 1 : 0;
   if (c.restoration && !var.rs_inline && var.resto_kernel) {
@@ -306,6 +377,7 @@ void mpcb_destroy(mpcb_handle *h) {
   cudaFree(h->d_resto_list);
   cudaFree(h->d_resto_count);
   cudaFree(h->d_resto_slab);
+  cudaFree(h->d_lane_ws);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -347,7 +419,18 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
   cudaError_t e;
   static const int lat_force = getenv("MPCB_LAT_MAX_B") ? atoi(getenv("MPCB_LAT_MAX_B")) : 0;  // tuning knob
   const bool small_batch = h->lat_grid && (B <= h->lat_grid * h->var.lat_warps || B <= lat_force);
-  if (small_batch) {
+  const bool lane_engine = h->d_lane_ws && B >= h->lane_min_B && !k.trace;
+  int main_warps = 0;
+  if (lane_engine) {
+    // one scenario per lane: the lanes of the resident grid pull scenarios from the queue
+    const int need = (B + h->lane.block - 1) / h->lane.block;
+    grid = need < h->lane_grid ? need : h->lane_grid;
+    k.slab = nullptr;
+    k.counter = h->d_counter;
+    if (!cuda_ok(cudaMemsetAsync(h->d_counter, 0, sizeof(int), (cudaStream_t)stream), "queue reset")) return MPCB_E_CUDA;
+    e = h->lane.launch(k, h->d_lane_ws, (size_t)grid * h->lane.block, grid, (cudaStream_t)stream);
+    main_warps = grid * (h->lane.block / 32);
+  } else if (small_batch) {
     grid = (B + h->var.lat_warps - 1) / h->var.lat_warps;
     if (grid > h->lat_grid) grid = h->lat_grid;
     // the batch fits the SMs in one wave of the small-batch kernel (one warp per block, all state in shared memory)
@@ -374,7 +457,7 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
     k2.slab = h->d_resto_slab;
     k2.order = nullptr;
     k2.resto_consumer = 1;
-    k2.main_warps = grid * (small_batch ? h->var.lat_warps : h->var.warps);
+    k2.main_warps = lane_engine ? main_warps : grid * (small_batch ? h->var.lat_warps : h->var.warps);
     k2.trace = nullptr;
     int g2 = (B + h->var.resto_warps - 1) / h->var.resto_warps;
     if (g2 > h->resto_grid) g2 = h->resto_grid;
@@ -386,7 +469,7 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
   h->last_stream = (cudaStream_t)stream;
   {
     const int64_t launches = h->info.launches + (with_resto ? 2 : 1);
-    h->info = small_batch ? h->lat_info : h->main_info;
+    h->info = lane_engine ? h->lane_info : (small_batch ? h->lat_info : h->main_info);
     h->info.grid = grid;
     h->info.launches = launches;
   }

@@ -30,6 +30,21 @@ struct Variant {
   int resto_warps;
 };
 
+// second engine: one scenario per lane (mpcb_lane_kernel.cuh), kinematic families with plain rows
+typedef cudaError_t (*lane_launch_fn)(const KParams &, double *ws, size_t nslot, int grid, cudaStream_t);
+struct LaneVariant {
+  lane_launch_fn launch;
+  kernel_ptr kernel;
+  size_t (*slot_doubles)(int N);  // workspace doubles per lane
+  int block;
+};
+LaneVariant lane_variant_kin_0_0();
+LaneVariant lane_variant_kin_1_0();
+LaneVariant lane_variant_kin_1_1();
+LaneVariant lane_variant_kin_1_2();
+LaneVariant lane_variant_kin_1_3();
+LaneVariant lane_variant_kin_1_4();
+
 // the candidate that keeps the most warps resident for horizon N (first one wins ties); mpcb_api.cu
 Variant pick_by_occupancy(Variant *cand, int n, int N);
 

@@ -35,7 +35,7 @@ class BatchSolver:
                  init: str = "rollout", mu_init: float = 30.0, max_iter: int = 100, tol: float = 1e-8,
                  weights=None, bounds: dict | None = None, obs_input: str = "trajectory", cbf_gamma: float | None = None,
                  ref: str = "terminal", cfg_overrides: dict | None = None, dyn_bounds: str = "aligned",
-                 restoration: bool = False, resto_max_calls: int = 1):
+                 restoration: bool = False, resto_max_calls: int = 1, engine: str = "auto"):
         self.lib = _lib.load()
         self.kind = kind
         self.config = config if config is not None else load_config(PACKAGE_PARAMS)
@@ -51,6 +51,9 @@ class BatchSolver:
                             ref_mode=_lib.REF_TRAJECTORY if self.ref_trajectory else _lib.REF_TERMINAL,
                             dyn_rows={"aligned": _lib.DYN_ROWS_ALIGNED, "as_shipped": _lib.DYN_ROWS_AS_SHIPPED}[dyn_bounds],
                             restoration=restoration, resto_max_calls=resto_max_calls)
+        # "warp": one scenario per warp (every kind); "lane": one scenario per lane (kinematic kinds, plain rows); "auto"
+        # picks per batch size what measures faster
+        self.cfg.engine = {"auto": _lib.ENGINE_AUTO, "warp": _lib.ENGINE_WARP, "lane": _lib.ENGINE_LANE}[engine]
         for key, val in (cfg_overrides or {}).items():  # any mpcb_cfg field, e.g. {"safe_l": 1.5, "T": 0.08, "Q": [...]}
             cur = getattr(self.cfg, key)
             if hasattr(cur, "__len__"):

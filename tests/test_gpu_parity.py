@@ -1043,3 +1043,61 @@ def test_verdict_agreement_on_the_bench_batch(dev):
     dc = np.abs(g["cost"] - cost) / np.abs(cost)
     assert np.all(du[both] <= U0_ATOL) and np.all(dc[both] <= COST_RTOL), (du[both].max(), dc[both].max())
     print(f"bench batch: verdict-equal {same.mean():.4f}, worst |du0| {du[both].max():.2e}, worst rel dcost {dc[both].max():.2e}")
+
+
+# --------------------------------------------------------------------------- second engine: one scenario per lane
+@pytest.mark.parametrize("kind,gen,M,B", [("kin_nocbf", "kin_nocbf", 1, 700), ("kin_cbf", "kin_cbf_static", 1, 1500),
+                                           ("kin_cbf_pre", "kin_cbf_moving", 1, 1500), ("kin_cbf_pre", "kin_cbf_moving", 2, 300)])
+def test_lane_engine_parity(dev, kind, gen, M, B):
+    """cfg.engine = MPCB_ENGINE_LANE (csrc/mpcb_lane_kernel.cuh): every lane solves its own scenario, records
+    structure-of-arrays in global memory.  Same algorithm: BASELINE's three criteria against the oracle, and against the
+    warp-per-scenario engine on the same inputs (summation orders differ, so not bit for bit)."""
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+    from oracle import c_oracle
+
+    x0, xs, obs = getattr(scenarios, gen)(B)
+    if M == 2:
+        _, _, ob = scenarios.kin_cbf_moving(B, seed=99)
+        ob[:, :, :, 0] += 60.0
+        obs = np.concatenate([obs, ob], axis=1)
+    lane = BatchSolver(kind, M=M, engine="lane")
+    g = _gpu(lane, dev, x0, xs, obs, return_z=True, return_lam=True, return_duals=True)
+    info = lane.launch_info()
+    assert info["smem_bytes"] == 0 and info["block"] == 128  # the lane kernel ran, not the warp kernel
+    w = _gpu(BatchSolver(kind, M=M, engine="warp"), dev, x0, xs, obs, return_z=True, return_lam=True, return_duals=True)
+    u0, cost, st, it, _ = c_oracle.solve_batch(c_oracle.make_cfg(kind, M=M), x0, xs, obs if obs.shape[1] else None, nthreads=os.cpu_count())
+    both, same = _check(g, u0, cost, st, 0.6 if M == 2 else 0.8)
+    assert (g["iters"][both] == it[both]).mean() >= 0.9
+    bw = (g["status"] <= 1) & (w["status"] <= 1)
+    assert bw.mean() >= 0.6
+    for key, tol in (("z", 1e-5), ("lam", None), ("lam_g", None), ("lam_x", None)):
+        d = np.abs(g[key][bw] - w[key][bw]).max(axis=1)
+        scale = np.maximum(1.0, np.abs(w[key][bw]).max(axis=1))
+        assert np.quantile(d / scale, 0.995) <= (tol or 1e-5), (key, (d / scale).max())
+    # not applicable configurations are refused, not silently served by the other engine
+    from mpc_motion_planning_b200 import _lib
+    with pytest.raises(_lib.MpcbError):
+        BatchSolver("dyn", engine="lane")
+    with pytest.raises(_lib.MpcbError):
+        BatchSolver("kin_cbf", cbf_gamma=0.5, engine="lane")
+
+
+def test_lane_engine_with_restoration_and_order(dev):
+    """The lane engine hands failed line searches to the same restoration sibling, and honours a processing order."""
+    import torch
+
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+
+    B = 2000
+    x0, xs, obs = scenarios.kin_cbf_static(B)
+    a = _gpu(BatchSolver("kin_cbf", engine="warp", restoration=True), dev, x0, xs, obs)
+    s = BatchSolver("kin_cbf", engine="lane", restoration=True)
+    s.set_order(torch.arange(B - 1, -1, -1, dtype=torch.int32, device=dev))
+    b = _gpu(s, dev, x0, xs, obs)
+    s.set_order(None)
+    assert ((a["status"] <= 1) == (b["status"] <= 1)).mean() >= 0.985
+    both = (a["status"] <= 1) & (b["status"] <= 1)
+    assert np.abs(a["u0"][both] - b["u0"][both]).max() <= U0_ATOL
+    assert (b["status"] == 3).sum() < 0.9 * (_gpu(BatchSolver("kin_cbf", engine="lane"), dev, x0, xs, obs)["status"] == 3).sum()
