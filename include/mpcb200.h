@@ -63,6 +63,12 @@ enum { MPCB_OBS_TRAJECTORY = 0, MPCB_OBS_INITIAL = 1, MPCB_OBS_STATIC = 2 };
  * given by the reference's dyn main. */
 enum { MPCB_DYN_ROWS_ALIGNED = 0, MPCB_DYN_ROWS_AS_SHIPPED = 1 };
 enum { MPCB_ENGINE_AUTO = 0, MPCB_ENGINE_WARP = 1, MPCB_ENGINE_LANE = 2 };
+/* shooting defects: EULER = X_{k+1} - X_k - T f(X_k,U_k), what the reference builds (PKG/MPC_CBF_optimize_kin.py:207) and the
+ * only mode with reference parity; RK4 = X_{k+1} - Phi(X_k,U_k) with the classical Runge-Kutta step, forward-mode Jacobians
+ * through its four stages and the exact second-order adjoint for the Lagrangian Hessian - the option BASELINE.json's north_star
+ * names (the reference's tree has Runge-Kutta only in the tutorial Reference/MPC/sim_test.py:35-37).  RK4 is served by the
+ * lane engine: kinematic model, plain rows, at most two obstacles */
+enum { MPCB_INTEGRATOR_EULER = 0, MPCB_INTEGRATOR_RK4 = 1 };
 
 /* per-scenario outcome, mapped to IPOPT return_status strings by the Python shim */
 enum {
@@ -125,6 +131,8 @@ typedef struct mpcb_cfg {
   int32_t engine;       /* MPCB_ENGINE_AUTO (default), _WARP: one scenario per warp (every family), _LANE: one scenario per
                            lane (kinematic model, plain rows, one target per scenario).  AUTO uses the
                            lane engine where it measures faster: the families without obstacle rows from 32,768 scenarios up */
+  int32_t integrator;   /* MPCB_INTEGRATOR_EULER (default) or MPCB_INTEGRATOR_RK4 */
+  int32_t reserved;
 } mpcb_cfg;
 
 typedef struct mpcb_handle mpcb_handle;

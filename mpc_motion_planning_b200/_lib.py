@@ -15,6 +15,7 @@ OBS_TRAJECTORY, OBS_INITIAL, OBS_STATIC = 0, 1, 2
 REF_TERMINAL, REF_TRAJECTORY = 0, 1
 DYN_ROWS_ALIGNED, DYN_ROWS_AS_SHIPPED = 0, 1
 ENGINE_AUTO, ENGINE_WARP, ENGINE_LANE = 0, 1, 2
+INTEGRATOR_EULER, INTEGRATOR_RK4 = 0, 1
 ST_CONVERGED, ST_ACCEPTABLE, ST_MAXITER, ST_INFEASIBLE, ST_NAN, ST_RESTO_FAILED = 0, 1, 2, 3, 4, 5
 
 # IPOPT return_status strings (CasADi `solver.stats()['return_status']`)
@@ -45,7 +46,7 @@ class MpcbCfg(C.Structure):
         ("Fymax_f", C.c_double), ("Fymax_r", C.c_double),
         ("tol", C.c_double), ("mu_init", C.c_double), ("bound_relax", C.c_double),
         ("obs_input", C.c_int32), ("ref_mode", C.c_int32), ("cbf_gamma", C.c_double),
-        ("dyn_rows", C.c_int32), ("restoration", C.c_int32), ("resto_max_calls", C.c_int32), ("engine", C.c_int32),
+        ("dyn_rows", C.c_int32), ("restoration", C.c_int32), ("resto_max_calls", C.c_int32), ("engine", C.c_int32), ("integrator", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

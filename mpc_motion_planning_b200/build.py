@@ -17,7 +17,7 @@ SRCS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HER
 ]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 N_FAMILIES = 12  # csrc/mpcb_variants.cu: 10 kinematic families + the dynamic bicycle (rows aligned, rows as shipped)
-N_LANE_FAMILIES = 6  # csrc/mpcb_lane.cu: the lane-per-scenario engine, kinematic families with plain rows
+N_LANE_FAMILIES = 10  # csrc/mpcb_lane.cu: the lane-per-scenario engine, kinematic families with plain rows
 
 
 def stale() -> bool:

@@ -81,6 +81,16 @@ bool select_lane_variant(const mpcb_cfg &c, LaneVariant &v) {
   if (c.model != MPCB_MODEL_KIN || c.ref_mode != MPCB_REF_TERMINAL) return false;
   const int M = c.obs_mode == MPCB_OBS_NONE ? 0 : c.M;
   if (c.obs_mode != MPCB_OBS_NONE && c.obs_mode != MPCB_OBS_ELLIPSE) return false;
+  if (c.integrator == MPCB_INTEGRATOR_RK4) {
+    if (c.n_rate == 0 && M == 0) { v = lane_variant_rk4_0_0(); return true; }
+    if (c.n_rate != 1 || c.rate_ctrl[0] != 0) return false;
+    switch (M) {
+      case 0: v = lane_variant_rk4_1_0(); return true;
+      case 1: v = lane_variant_rk4_1_1(); return true;
+      case 2: v = lane_variant_rk4_1_2(); return true;
+    }
+    return false;
+  }
   if (c.n_rate == 0 && M == 0) { v = lane_variant_kin_0_0(); return true; }
   if (c.n_rate != 1 || c.rate_ctrl[0] != 0) return false;
   switch (M) {
@@ -197,6 +207,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
   if (c.dyn_rows != MPCB_DYN_ROWS_ALIGNED && c.dyn_rows != MPCB_DYN_ROWS_AS_SHIPPED) return MPCB_E_ARG;
   if (c.dyn_rows == MPCB_DYN_ROWS_AS_SHIPPED && c.model != MPCB_MODEL_DYN) return MPCB_E_ARG;
   if (c.engine != MPCB_ENGINE_AUTO && c.engine != MPCB_ENGINE_WARP && c.engine != MPCB_ENGINE_LANE) return MPCB_E_ARG;
+  if (c.integrator != MPCB_INTEGRATOR_EULER && c.integrator != MPCB_INTEGRATOR_RK4) return MPCB_E_ARG;
   Variant var;
   if (!select_variant(c, var)) return MPCB_E_ARG;
   // the kernels assume: both controls two-sided; the model's bounded states (kin: y, vx; dyn: + vy)
@@ -303,6 +314,10 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
     int engine = c.engine;
     if (eng && !strcmp(eng, "warp")) engine = MPCB_ENGINE_WARP;
     if (eng && !strcmp(eng, "lane")) engine = MPCB_ENGINE_LANE;
+    if (c.integrator == MPCB_INTEGRATOR_RK4) {  // only the lane engine integrates with Runge-Kutta
+      if (engine == MPCB_ENGINE_WARP || c.restoration) { mpcb_destroy(h); return MPCB_E_ARG; }
+      engine = MPCB_ENGINE_LANE;
+    }
     LaneVariant lv;
     const bool has_lane = select_lane_variant(c, lv);
     if (engine == MPCB_ENGINE_LANE && !has_lane) { mpcb_destroy(h); return MPCB_E_ARG; }

@@ -4,20 +4,20 @@
 #include "mpcb_lane_kernel.cuh"
 
 #ifndef MPCB_LANE_FAMILY
-#error "compile with -DMPCB_LANE_FAMILY=0..5"
+#error "compile with -DMPCB_LANE_FAMILY=0..9"
 #endif
 
 namespace mpcb {
 
-template <int NR, int MO>
+template <int NR, int MO, bool RK4 = false>
 static LaneVariant make_lane_variant() {
   LaneVariant v;
   v.launch = [](const KParams &p, double *ws, size_t nslot, int grid, cudaStream_t st) {
-    kin_lane_kernel<NR, MO><<<grid, MPCB_LANE_BLOCK, 0, st>>>(p, ws, nslot);
+    kin_lane_kernel<NR, MO, RK4><<<grid, MPCB_LANE_BLOCK, 0, st>>>(p, ws, nslot);
     return cudaGetLastError();
   };
-  v.kernel = (const void *)&kin_lane_kernel<NR, MO>;
-  v.slot_doubles = [](int N) { return LaneLayout<NR, MO>::slot_doubles(N); };
+  v.kernel = (const void *)&kin_lane_kernel<NR, MO, RK4>;
+  v.slot_doubles = [](int N) { return LaneLayout<NR, MO, RK4>::slot_doubles(N); };
   v.block = MPCB_LANE_BLOCK;
   return v;
 }
@@ -34,6 +34,15 @@ LaneVariant lane_variant_kin_1_2() { return make_lane_variant<1, 2>(); }
 LaneVariant lane_variant_kin_1_3() { return make_lane_variant<1, 3>(); }
 #elif MPCB_LANE_FAMILY == 5
 LaneVariant lane_variant_kin_1_4() { return make_lane_variant<1, 4>(); }
+// Runge-Kutta shooting defects (cfg.integrator = MPCB_INTEGRATOR_RK4)
+#elif MPCB_LANE_FAMILY == 6
+LaneVariant lane_variant_rk4_0_0() { return make_lane_variant<0, 0, true>(); }
+#elif MPCB_LANE_FAMILY == 7
+LaneVariant lane_variant_rk4_1_0() { return make_lane_variant<1, 0, true>(); }
+#elif MPCB_LANE_FAMILY == 8
+LaneVariant lane_variant_rk4_1_1() { return make_lane_variant<1, 1, true>(); }
+#elif MPCB_LANE_FAMILY == 9
+LaneVariant lane_variant_rk4_1_2() { return make_lane_variant<1, 2, true>(); }
 #endif
 
 }  // namespace mpcb

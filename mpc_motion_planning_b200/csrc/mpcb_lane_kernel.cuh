@@ -22,7 +22,10 @@
 
 namespace mpcb {
 
-template <int NR, int MO>
+// RK4: the shooting defects are X_{k+1} - Phi(X_k, U_k) with Phi the classical Runge-Kutta step (cfg.integrator): the stage
+// then keeps the 11 entries of d Phi / d(x,u) that differ from the identity instead of sin/cos/tan, and d2L/(du dx) has
+// four entries instead of one.
+template <int NR, int MO, bool RK4 = false>
 struct LaneLayout {
   static constexpr int NX = 4, NBX = 2;
   // field ids of the per-slot workspace, rows of S = N + 1 stages
@@ -33,9 +36,11 @@ struct LaneLayout {
   static constexpr int DX = ISY + MO, DU = DX + 4, DSR = DU + 2, DSO = DSR + NR;       // the step
   static constexpr int LAMP = DSO + MO, LRP = LAMP + 4, LOP = LRP + NR;                // new multipliers
   static constexpr int CDEF = LOP + MO;  // two buffers of 4: defects of the iterate / of the trial point (flipped on acceptance)
-  static constexpr int TRG = CDEF + 8;   // two buffers of 3: sin(phi), cos(phi), tan(delta) per stage
-  static constexpr int HXX = TRG + 6;    // condensed stage Hessian h00 h01 h11 h22 h23 h33, d2L/(d delta d v), gradient
-  static constexpr int HUX = HXX + 6, GX = HUX + 1;
+  static constexpr int NJ = RK4 ? 11 : 3;  // Euler: sin(phi), cos(phi), tan(delta); RK4: a02 a03 a12 a13 a23 b00 b01 b10 b11 b20 b21
+  static constexpr int TRG = CDEF + 8;   // two buffers of NJ
+  static constexpr int HXX = TRG + 2 * NJ;  // condensed stage Hessian h00 h01 h11 h22 h23 h33, d2L/(du dx), gradient
+  static constexpr int NHUX = RK4 ? 4 : 1;  // Euler: (delta, v); RK4: (delta, phi) (delta, v) (a, phi) (a, v)
+  static constexpr int HUX = HXX + 6, GX = HUX + NHUX;
   static constexpr int KX = GX + 4, KW = KX + 8, KK = KW + 4;  // Riccati gains
   static constexpr int FLT = KK + 2;     // filter: 2 rows of theta entries, 2 rows of phi entries
   static constexpr int NFIELD = FLT + 4;
@@ -44,9 +49,90 @@ struct LaneLayout {
 
 enum { LANE_IDLE = 0, LANE_EVAL = 1, LANE_ACCEPT = 2, LANE_KKT = 3, LANE_NEWTON = 4, LANE_DONE = 5 };
 
-template <int NR, int MO>
+// The classical Runge-Kutta step of the kinematic bicycle and its derivatives (oracle/nlp.py Rk4KinModel states the
+// same thing densely).  Only phi and v of the stage points matter (x, y never enter the right-hand side), so everything
+// is carried in the coordinates q = (phi, v, delta, a).
+struct Rk4Stages {
+  double v[4], sn[4], cs[4];  // stage speeds, sin / cos of the stage headings
+  double dphi[4][4], dva[4];  // d phi_s / dq; d v_s / dq = (0, 1, 0, dva[s])
+  double t, sec2;
+  __device__ __forceinline__ void point(const double *x, const double *u, double T, double rL) {
+    const double al[4] = {0.0, 0.5, 0.5, 1.0};
+    t = tan(u[0]);
+    sec2 = 1.0 + t * t;
+    double ph = x[2];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      if (s > 0) ph = x[2] + al[s] * T * (v[s - 1] * t * rL);
+      v[s] = x[3] + al[s] * T * u[1];
+      dva[s] = al[s] * T;
+      sincos(ph, &sn[s], &cs[s]);
+      // d phi_s = e_phi + al T rL (t dv_{s-1} + v_{s-1} sec2 e_delta)
+      dphi[s][0] = 1.0;
+      dphi[s][1] = s > 0 ? al[s] * T * rL * t : 0.0;
+      dphi[s][2] = s > 0 ? al[s] * T * rL * v[s - 1] * sec2 : 0.0;
+      dphi[s][3] = s > 0 ? al[s] * T * rL * t * dva[s - 1] : 0.0;
+    }
+  }
+  // Phi(x,u)
+  __device__ __forceinline__ void step(const double *x, const double *u, double T, double rL, double *xn) const {
+    const double b[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+    double k0 = 0, k1 = 0, k2 = 0;
+#pragma unroll
+    for (int s = 0; s < 4; s++) { k0 += b[s] * v[s] * cs[s]; k1 += b[s] * v[s] * sn[s]; k2 += b[s] * v[s]; }
+    xn[0] = x[0] + T * k0; xn[1] = x[1] + T * k1; xn[2] = x[2] + T * (k2 * t * rL); xn[3] = x[3] + T * u[1];
+  }
+  // the 11 entries of d Phi / d(x,u) that are not those of the identity (b31 = T)
+  __device__ __forceinline__ void jac(double T, double rL, double *J) const {
+    const double b[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+    double d0[4] = {0, 0, 0, 0}, d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      const double dv[4] = {0.0, 1.0, 0.0, dva[s]};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        d0[q] += b[s] * (cs[s] * dv[q] - v[s] * sn[s] * dphi[s][q]);
+        d1[q] += b[s] * (sn[s] * dv[q] + v[s] * cs[s] * dphi[s][q]);
+        d2[q] += b[s] * rL * (t * dv[q] + (q == 2 ? v[s] * sec2 : 0.0));
+      }
+    }
+    J[0] = T * d0[0]; J[1] = T * d0[1]; J[2] = T * d1[0]; J[3] = T * d1[1]; J[4] = T * d2[1];  // a02 a03 a12 a13 a23
+    J[5] = T * d0[2]; J[6] = T * d0[3]; J[7] = T * d1[2]; J[8] = T * d1[3]; J[9] = T * d2[2]; J[10] = T * d2[3];  // b00 b01 b10 b11 b20 b21
+  }
+  // sum_i lam_i d2 Phi_i / dq2, upper triangle in the order (phi phi, phi v, phi delta, phi a, v v, v delta, v a, delta delta, delta a, a a):
+  // second-order adjoint  sum_s Z_s' [nu_s . g''(z_s)] Z_s,  nu_s = T b_s lam + al_{s+1} T g_x(z_{s+1})' nu_{s+1}
+  __device__ __forceinline__ void hess(const double *lam, double T, double rL, double *H) const {
+    const double al[4] = {0.0, 0.5, 0.5, 1.0}, b[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+#pragma unroll
+    for (int i = 0; i < 10; i++) H[i] = 0.0;
+    double n0 = 0, n1 = 0, n2 = 0;
+#pragma unroll
+    for (int s = 3; s >= 0; s--) {
+      double m2 = T * b[s] * lam[2];
+      if (s < 3) m2 += al[s + 1] * T * (-v[s + 1] * sn[s + 1] * n0 + v[s + 1] * cs[s + 1] * n1);
+      // components 0, 1 of nu never pick up anything (x, y do not enter g): nu_s0 = T b_s lam0, nu_s1 = T b_s lam1
+      n0 = T * b[s] * lam[0]; n1 = T * b[s] * lam[1]; n2 = m2;
+      // NOTE: the recursion above needs nu_{s+1,0..1} of the NEXT stage, which are T b_{s+1} lam: recomputed here
+      const double Mpp = -v[s] * (n0 * cs[s] + n1 * sn[s]), Mpv = -n0 * sn[s] + n1 * cs[s];
+      const double Mvd = n2 * sec2 * rL, Mdd = n2 * 2.0 * v[s] * sec2 * t * rL;
+      const double r0[4] = {dphi[s][0], dphi[s][1], dphi[s][2], dphi[s][3]}, r1[4] = {0.0, 1.0, 0.0, dva[s]};
+      int e = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = i; j < 4; j++, e++) {
+          double h = Mpp * r0[i] * r0[j] + Mpv * (r0[i] * r1[j] + r1[i] * r0[j]);
+          h += Mvd * (r1[i] * (j == 2 ? 1.0 : 0.0) + (i == 2 ? 1.0 : 0.0) * r1[j]);
+          if (i == 2 && j == 2) h += Mdd;
+          H[e] += h;
+        }
+    }
+  }
+};
+
+template <int NR, int MO, bool RK4 = false>
 struct LaneSolver {
-  using L = LaneLayout<NR, MO>;
+  using L = LaneLayout<NR, MO, RK4>;
   static constexpr int NX = 4, NBX = 2;
   const KParams &p;
   double *ws;
@@ -83,7 +169,23 @@ struct LaneSolver {
   __device__ __forceinline__ bool has_obs(int k) const { return MO > 0 && k <= N - 1; }
   __device__ static __forceinline__ constexpr int bx(int i) { return i == 0 ? 1 : 3; }  // bounded states: y, vx
   __device__ __forceinline__ int cdef(int buf) const { return L::CDEF + 4 * buf; }
-  __device__ __forceinline__ int trg(int buf) const { return L::TRG + 3 * buf; }
+
+  __device__ __forceinline__ int trg(int buf) const { return L::TRG + L::NJ * buf; }
+  // A = d Phi/dx (entries a02 a03 a12 a13 a23 beside the unit diagonal) and B = d Phi/du of stage k at the current iterate
+  struct AB { double a02, a03, a12, a13, a23, b00, b01, b10, b11, b20, b21, b31; };
+  __device__ __forceinline__ AB load_ab(int tg, int k, double v) {
+    AB o;
+    if (RK4) {
+      o.a02 = at(tg + 0, k); o.a03 = at(tg + 1, k); o.a12 = at(tg + 2, k); o.a13 = at(tg + 3, k); o.a23 = at(tg + 4, k);
+      o.b00 = at(tg + 5, k); o.b01 = at(tg + 6, k); o.b10 = at(tg + 7, k); o.b11 = at(tg + 8, k); o.b20 = at(tg + 9, k); o.b21 = at(tg + 10, k);
+    } else {
+      const double rL = 1.0 / p.Veh_l, s = at(tg + 0, k), c = at(tg + 1, k), t = at(tg + 2, k);
+      o.a02 = p.T * (-v * s); o.a03 = p.T * c; o.a12 = p.T * (v * c); o.a13 = p.T * s; o.a23 = p.T * (t * rL);
+      o.b00 = 0; o.b01 = 0; o.b10 = 0; o.b11 = 0; o.b20 = p.T * (v * (1.0 + t * t) * rL); o.b21 = 0;
+    }
+    o.b31 = p.T;
+    return o;
+  }
 
   __device__ __forceinline__ double grad_u(int k, int i, double uk, double ukm1, double ukp1) const {
     double v = 2 * p.R[i] * uk;
@@ -141,11 +243,20 @@ struct LaneSolver {
       double xk[NX];
 #pragma unroll
       for (int i = 0; i < NX; i++) xk[i] = p.init_mode == 1 ? x[i] : (zi ? zi[2 * N + NX * k + i] : 0.0);
-      if (p.init_mode == 1 && k < N) {  // Euler roll-out of the guessed controls (PKG/MPC_CBF_optimize_kin.py:207)
-        double s, c, t;
-        d_trig(x[2], uk[0], &s, &c, &t);
-        double f0 = x[3] * c, f1 = x[3] * s, f2 = x[3] * t * (1.0 / p.Veh_l);
-        x[0] = x[0] + p.T * f0; x[1] = x[1] + p.T * f1; x[2] = x[2] + p.T * f2; x[3] = x[3] + p.T * uk[1];
+      if (p.init_mode == 1 && k < N) {  // roll-out of the guessed controls with the step of the defects (PKG/MPC_CBF_optimize_kin.py:207)
+        if (RK4) {
+          Rk4Stages rk;
+          double xn[NX];
+          rk.point(x, uk, p.T, 1.0 / p.Veh_l);
+          rk.step(x, uk, p.T, 1.0 / p.Veh_l, xn);
+#pragma unroll
+          for (int i = 0; i < NX; i++) x[i] = xn[i];
+        } else {
+          double s, c, t;
+          d_trig(x[2], uk[0], &s, &c, &t);
+          double f0 = x[3] * c, f1 = x[3] * s, f2 = x[3] * t * (1.0 / p.Veh_l);
+          x[0] = x[0] + p.T * f0; x[1] = x[1] + p.T * f1; x[2] = x[2] + p.T * f2; x[3] = x[3] + p.T * uk[1];
+        }
       }
 #pragma unroll
       for (int b2 = 0; b2 < NBX; b2++) { int i = bx(b2); xk[i] = push_in(xk[i], p.x_lo[i], p.x_hi[i]); at(L::ZLX + b2, k) = 1.0; at(L::ZUX + b2, k) = 1.0; }
@@ -244,15 +355,28 @@ struct LaneSolver {
         }
       }
       if (k < N) {
-        double s, c, t;
-        d_trig(xk[2], uk[0], &s, &c, &t);
-        at(tg + 0, k) = s; at(tg + 1, k) = c; at(tg + 2, k) = t;
-        double f[NX] = {xk[3] * c, xk[3] * s, xk[3] * t * rL, uk[1]};  // PKG/MPC_CBF_optimize_kin.py:153-156
+        double step[NX];  // Phi(x_k, u_k)
+        if (RK4) {
+          Rk4Stages rk;
+          double J[11];
+          rk.point(xk, uk, p.T, rL);
+          rk.step(xk, uk, p.T, rL, step);
+          rk.jac(p.T, rL, J);
+#pragma unroll
+          for (int i = 0; i < 11; i++) at(tg + i, k) = J[i];
+        } else {
+          double s, c, t;
+          d_trig(xk[2], uk[0], &s, &c, &t);
+          at(tg + 0, k) = s; at(tg + 1, k) = c; at(tg + 2, k) = t;
+          const double f[NX] = {xk[3] * c, xk[3] * s, xk[3] * t * rL, uk[1]};  // PKG/MPC_CBF_optimize_kin.py:153-156
+#pragma unroll
+          for (int i = 0; i < NX; i++) step[i] = xk[i] + p.T * f[i];
+        }
         double xn[NX];
 #pragma unroll
         for (int i = 0; i < NX; i++) {
           xn[i] = at(L::X + i, k + 1) + alpha * at(L::DX + i, k + 1);
-          double d = xn[i] - (xk[i] + p.T * f[i]);
+          double d = xn[i] - step[i];
           th += fabs(d);
           at(cd + i, k + 1) = d;
           double e = xk[i] - xs[i];
@@ -279,7 +403,6 @@ struct LaneSolver {
 
   __device__ void kkt_pieces(Kkt &o) {
     const int cd = cdef(cur), tg = trg(cur);
-    const double rL = 1.0 / p.Veh_l;
     double dual = 0, prim = 0, cmin = INFINITY, cmax = -INFINITY, sl = 0, sz = 0;
 #define MPCB_COMPL(gap, mult) do { double p_ = (gap) * (mult); cmin = fmin(cmin, p_); cmax = fmax(cmax, p_); sz += (mult); } while (0)
     double lam[NX], um[2] = {0, 0}, uc[2] = {at(L::U + 0, 0), at(L::U + 1, 0)};
@@ -290,7 +413,7 @@ struct LaneSolver {
     for (int k = 0; k <= N; k++) {
       pf<L::X, L::OCX - L::X + 4 * MO>(k + 1 + MPCB_LANE_PF_DIST);  // the whole iterate and the obstacle row
       pf<L::CDEF, 8>(k + 1 + MPCB_LANE_PF_DIST);
-      pf<L::TRG, 6>(k + 1 + MPCB_LANE_PF_DIST);
+      pf<L::TRG, 2 * L::NJ>(k + 1 + MPCB_LANE_PF_DIST);
       double xk[NX], l1[NX] = {0, 0, 0, 0}, un[2] = {0, 0};
 #pragma unroll
       for (int i = 0; i < NX; i++) {
@@ -299,11 +422,10 @@ struct LaneSolver {
         sl += fabs(lam[i]);
       }
       double rx[NX] = {lam[0], lam[1], lam[2], lam[3]};
-      double b2 = 0;
+      AB ab = {};
       if (k < N) {
-        const double s = at(tg + 0, k), c = at(tg + 1, k), t = at(tg + 2, k);
-        const double a02 = p.T * (-xk[3] * s), a03 = p.T * c, a12 = p.T * (xk[3] * c), a13 = p.T * s, a23 = p.T * (t * rL);
-        b2 = p.T * (xk[3] * (1.0 + t * t) * rL);
+        ab = load_ab(tg, k, xk[3]);
+        const double a02 = ab.a02, a03 = ab.a03, a12 = ab.a12, a13 = ab.a13, a23 = ab.a23;
 #pragma unroll
         for (int i = 0; i < NX; i++) {
           l1[i] = at(L::LAM + i, k + 1);
@@ -347,7 +469,7 @@ struct LaneSolver {
         for (int i = 0; i < 2; i++) {
           double zl = at(L::ZLU + i, k), zu = at(L::ZUU + i, k);
           double r = sigma * grad_u(k, i, uc[i], um[i], un[i]) - zl + zu;
-          r -= (i == 0) ? b2 * l1[2] : p.T * l1[3];  // - B' lam_{k+1}
+          r -= (i == 0) ? ab.b00 * l1[0] + ab.b10 * l1[1] + ab.b20 * l1[2] : ab.b01 * l1[0] + ab.b11 * l1[1] + ab.b21 * l1[2] + ab.b31 * l1[3];  // - B' lam_{k+1}
           if (NR > 0 && i == 0) {
             if (has_rate(k)) r += lr_c;
             if (has_rate(k + 1)) r -= lr_n;
@@ -400,7 +522,7 @@ struct LaneSolver {
     for (int k = N; k >= 0; k--) {
       pf<L::X, L::OCX - L::X + 4 * MO>(k - 1 - MPCB_LANE_PF_DIST);
       pf<L::CDEF, 8>(k - 1 - MPCB_LANE_PF_DIST);
-      pf<L::TRG, 6>(k - 1 - MPCB_LANE_PF_DIST);
+      pf<L::TRG, 2 * L::NJ>(k - 1 - MPCB_LANE_PF_DIST);
       double xk[NX], h[NX] = {dw, dw, dw, dw}, h01 = 0, h23 = 0, hdv = 0, hdd_f = 0, gx[NX] = {0, 0, 0, 0};
       double a02 = 0, a03 = 0, a12 = 0, a13 = 0, a23 = 0, b2 = 0;
 #pragma unroll
@@ -558,11 +680,195 @@ struct LaneSolver {
     return true;
   }
 
+  // The same pass for the Runge-Kutta defects: B = d Phi/du is full, d2L/(du dx) has four entries, Huu three; the value
+  // function recursion is written with small dense arrays (the compiler unrolls them).
+  __device__ bool backward_rk4() {
+    const int cd = cdef(cur), tg = trg(cur);
+    const double T = p.T, rL = 1.0 / p.Veh_l;
+    double P[4][4], W[4][2], Qw[2][2] = {{0, 0}, {0, 0}}, px[4], pw[2] = {0, 0};
+    double l_next[NX] = {0, 0, 0, 0}, c_next[NX] = {0, 0, 0, 0};
+    double u_k[2] = {0, 0};
+    if (N >= 1) { u_k[0] = at(L::U + 0, N - 1); u_k[1] = at(L::U + 1, N - 1); }
+#pragma unroll 1
+    for (int k = N; k >= 0; k--) {
+      double xk[NX], h[NX] = {dw, dw, dw, dw}, h01 = 0, h23 = 0, gx[NX] = {0, 0, 0, 0};
+      double Hux[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, Hm[10];
+#pragma unroll
+      for (int i = 0; i < 10; i++) Hm[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; i++) xk[i] = at(L::X + i, k);
+      AB ab = {};
+      if (k < N) {
+        ab = load_ab(tg, k, xk[3]);
+        Rk4Stages rk;
+        rk.point(xk, u_k, T, rL);
+        rk.hess(l_next, T, rL, Hm);  // defect = X_{k+1} - Phi: the Lagrangian takes MINUS lam' Phi''
+        h[2] -= Hm[0]; h23 = -Hm[1]; h[3] -= Hm[4];
+        Hux[0][2] = -Hm[2]; Hux[0][3] = -Hm[5]; Hux[1][2] = -Hm[3]; Hux[1][3] = -Hm[6];
+#pragma unroll
+        for (int i = 0; i < NX; i++) { h[i] += sigma * 2 * p.Q[i]; gx[i] = sigma * 2 * p.Q[i] * (xk[i] - xs[i]); }
+      }
+#pragma unroll
+      for (int b_ = 0; b_ < NBX; b_++) {
+        int i = bx(b_);
+        double rl = fast_rcp(xk[i] - p.x_lo[i]), rh = fast_rcp(p.x_hi[i] - xk[i]);
+        h[i] += at(L::ZLX + b_, k) * rl + at(L::ZUX + b_, k) * rh;
+        gx[i] += mu * (rh - rl);
+      }
+      if (has_obs(k)) {
+#pragma unroll
+        for (int j = 0; j < MO; j++) {
+          double dx = xk[0] - at(L::OCX + j, k), dy = xk[1] - at(L::OCY + j, k);
+          double a_ = at(L::ISX + j, k), b_ = at(L::ISY + j, k);
+          double d = dx * dx * a_ + dy * dy * b_ - 1.0;
+          double ox = 2 * dx * a_, oy = 2 * dy * b_;
+          double s = at(L::SO + j, k), rg = fast_rcp(s - p.obs_lo);
+          double D = at(L::VLO + j, k) * rg + dw;
+          double gs = -mu * rg + MPCB_KAPPA_D * mu;
+          double lo = at(L::LO + j, k);
+          double t = D * (d - s) + gs;
+          h[0] += lo * (2 * a_) + D * ox * ox;
+          h01 += D * ox * oy;
+          h[1] += lo * (2 * b_) + D * oy * oy;
+          gx[0] += ox * t;
+          gx[1] += oy * t;
+        }
+      }
+      at(L::HXX + 0, k) = h[0]; at(L::HXX + 1, k) = h01; at(L::HXX + 2, k) = h[1];
+      at(L::HXX + 3, k) = h[2]; at(L::HXX + 4, k) = h23; at(L::HXX + 5, k) = h[3];
+      at(L::HUX + 0, k) = Hux[0][2]; at(L::HUX + 1, k) = Hux[0][3]; at(L::HUX + 2, k) = Hux[1][2]; at(L::HUX + 3, k) = Hux[1][3];
+#pragma unroll
+      for (int i = 0; i < NX; i++) at(L::GX + i, k) = gx[i];
+      double c_k[NX];
+#pragma unroll
+      for (int i = 0; i < NX; i++) c_k[i] = at(cd + i, k);
+      double Hxx[4][4] = {{h[0], h01, 0, 0}, {h01, h[1], 0, 0}, {0, 0, h[2], h23}, {0, 0, h23, h[3]}};
+      if (k == N) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          px[i] = gx[i]; W[i][0] = 0; W[i][1] = 0;
+#pragma unroll
+          for (int j = 0; j < 4; j++) P[i][j] = Hxx[i][j];
+        }
+      } else {
+        double u_m[2] = {0, 0};
+        if (k >= 1) { u_m[0] = at(L::U + 0, k - 1); u_m[1] = at(L::U + 1, k - 1); }
+        double Huu[2][2] = {{0, -Hm[8]}, {-Hm[8], 0}}, gu[2], E[2] = {0, 0}, tk[2] = {0, 0};
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          double uk = u_k[i];
+          double g = sigma * 2 * p.R[i] * uk;
+          double hd = sigma * 2 * p.R[i] + dw - (i == 0 ? Hm[7] : Hm[9]);
+          if (k == 0 && p.du0_cost) { hd += sigma * 2 * p.DR[i]; g += sigma * 2 * p.DR[i] * uk; }
+          double rl = fast_rcp(uk - p.u_lo[i]), rh = fast_rcp(p.u_hi[i] - uk);
+          hd += at(L::ZLU + i, k) * rl + at(L::ZUU + i, k) * rh;
+          g += mu * (rh - rl);
+          Huu[i][i] = hd; gu[i] = g;
+          if (k >= 1) { E[i] = sigma * 2 * p.DR[i]; tk[i] = sigma * 2 * p.DR[i] * (uk - u_m[i]); }
+        }
+        if (has_rate(k)) {
+#pragma unroll
+          for (int r = 0; r < NR; r++) {
+            double s = at(L::SR + r, k);
+            double rl = fast_rcp(s - p.rate_lo[r]), rh = fast_rcp(p.rate_hi[r] - s);
+            double D = at(L::VLR + r, k) * rl + at(L::VUR + r, k) * rh + dw;
+            double gs = mu * (rh - rl);
+            double res = u_k[0] - u_m[0] - s;
+            E[0] += D; tk[0] += D * res + gs;
+          }
+        }
+        const double A[4][4] = {{1, 0, ab.a02, ab.a03}, {0, 1, ab.a12, ab.a13}, {0, 0, 1, ab.a23}, {0, 0, 0, 1}};
+        const double Bm[4][2] = {{ab.b00, ab.b01}, {ab.b10, ab.b11}, {ab.b20, ab.b21}, {0, ab.b31}};
+        double b[4], Pb[4], PA[4][4], PB[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) b[i] = -c_next[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          double a = px[i];
+#pragma unroll
+          for (int j = 0; j < 4; j++) a += P[i][j] * b[j];
+          Pb[i] = a;
+#pragma unroll
+          for (int j = 0; j < 4; j++) { double m = 0; for (int q = 0; q < 4; q++) m += P[i][q] * A[q][j]; PA[i][j] = m; }
+#pragma unroll
+          for (int j = 0; j < 2; j++) { double m = 0; for (int q = 0; q < 4; q++) m += P[i][q] * Bm[q][j]; PB[i][j] = m; }
+        }
+        double Fxx[4][4], Fux[2][4], Fuu[2][2], fx[4], fu[2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) { double m = Hxx[i][j]; for (int q = 0; q < 4; q++) m += A[q][i] * PA[q][j]; Fxx[i][j] = m; }
+          double m = gx[i];
+#pragma unroll
+          for (int q = 0; q < 4; q++) m += A[q][i] * Pb[q];
+          fx[i] = m;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) { double m = Hux[i][j]; for (int q = 0; q < 4; q++) m += Bm[q][i] * PA[q][j] + W[q][i] * A[q][j]; Fux[i][j] = m; }
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            double m = Huu[i][j] + Qw[i][j] + (i == j ? E[i] : 0.0);
+#pragma unroll
+            for (int q = 0; q < 4; q++) m += Bm[q][i] * PB[q][j] + Bm[q][i] * W[q][j] + W[q][i] * Bm[q][j];
+            Fuu[i][j] = m;
+          }
+          double m = gu[i] + tk[i] + pw[i];
+#pragma unroll
+          for (int q = 0; q < 4; q++) m += Bm[q][i] * Pb[q] + W[q][i] * b[q];
+          fu[i] = m;
+        }
+        const double Fda = 0.5 * (Fuu[0][1] + Fuu[1][0]);
+        const double det = Fuu[0][0] * Fuu[1][1] - Fda * Fda;
+        if (!(Fuu[0][0] > 0.0) || !(det > 0.0) || !isfinite(det)) return false;
+        const double id = fast_rcp(det);
+        const double Fi[2][2] = {{Fuu[1][1] * id, -Fda * id}, {-Fda * id, Fuu[0][0] * id}};
+        double Kx[2][4], Kw[2][2], kk[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) Kx[i][j] = -(Fi[i][0] * Fux[0][j] + Fi[i][1] * Fux[1][j]);
+#pragma unroll
+          for (int j = 0; j < 2; j++) Kw[i][j] = Fi[i][j] * E[j];
+          kk[i] = -(Fi[i][0] * fu[0] + Fi[i][1] * fu[1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) { at(L::KX + j, k) = Kx[0][j]; at(L::KX + 4 + j, k) = Kx[1][j]; }
+        at(L::KW + 0, k) = Kw[0][0]; at(L::KW + 1, k) = Kw[0][1]; at(L::KW + 2, k) = Kw[1][0]; at(L::KW + 3, k) = Kw[1][1];
+        at(L::KK + 0, k) = kk[0]; at(L::KK + 1, k) = kk[1];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) P[i][j] = Fxx[i][j] + Fux[0][i] * Kx[0][j] + Fux[1][i] * Kx[1][j];
+#pragma unroll
+          for (int j = 0; j < 2; j++) W[i][j] = Fux[0][i] * Kw[0][j] + Fux[1][i] * Kw[1][j];
+          px[i] = fx[i] + Fux[0][i] * kk[0] + Fux[1][i] * kk[1];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = i + 1; j < 4; j++) { double m = 0.5 * (P[i][j] + P[j][i]); P[i][j] = m; P[j][i] = m; }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+#pragma unroll
+          for (int j = 0; j < 2; j++) Qw[i][j] = (i == j ? E[i] : 0.0) - E[i] * Kw[i][j];
+          pw[i] = -tk[i] - E[i] * kk[i];
+        }
+        { double m = 0.5 * (Qw[0][1] + Qw[1][0]); Qw[0][1] = m; Qw[1][0] = m; }
+        u_k[0] = u_m[0]; u_k[1] = u_m[1];
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) { l_next[i] = at(L::LAM + i, k); c_next[i] = c_k[i]; }
+    }
+    return true;
+  }
+
   // ---------------------------------------------------------------- Newton step, part 2: roll the step out
   // KinSolver::riccati_forward + the stage residual r_k of the adjoint pass + slack_and_steps
   __device__ void forward(double &a_pr, double &a_du, double &gd_out) {
     const int cd = cdef(cur), tg = trg(cur);
-    const double T = p.T, rL = 1.0 / p.Veh_l;
+    const double T = p.T;
     double rp = 0.0, rd = 0.0, g_d = 0.0;
 #define MPCB_LOWER(rgap, dv, z) do { double dz_ = -(z) + (mu - (z) * (dv)) * (rgap); \
     rp = fmax(rp, -(dv) * (rgap)); rd = fmax(rd, -dz_ * fast_rcp(z)); } while (0)
@@ -576,8 +882,8 @@ struct LaneSolver {
     for (int k = 0; k <= N; k++) {
       pf<L::X, L::OCX - L::X + 4 * MO>(k + 1 + MPCB_LANE_PF_DIST);
       pf<L::CDEF, 8>(k + 1 + MPCB_LANE_PF_DIST);
-      pf<L::TRG, 6>(k + 1 + MPCB_LANE_PF_DIST);
-      pf<L::HXX, 11 + 14>(k + 1 + MPCB_LANE_PF_DIST);   // condensed Hessian, gradient and the gains
+      pf<L::TRG, 2 * L::NJ>(k + 1 + MPCB_LANE_PF_DIST);
+      pf<L::HXX, 10 + L::NHUX + 14>(k + 1 + MPCB_LANE_PF_DIST);   // condensed Hessian, gradient and the gains
       double xk[NX], un[2] = {0, 0}, ud = 0, ua = 0, n[NX] = {0, 0, 0, 0};
 #pragma unroll
       for (int i = 0; i < NX; i++) { xk[i] = at(L::X + i, k); at(L::DX + i, k) = d[i]; }
@@ -586,24 +892,30 @@ struct LaneSolver {
              at(L::KW + 0, k) * vd + at(L::KW + 1, k) * va;
         ua = at(L::KK + 1, k) + at(L::KX + 4, k) * d[0] + at(L::KX + 5, k) * d[1] + at(L::KX + 6, k) * d[2] + at(L::KX + 7, k) * d[3] +
              at(L::KW + 2, k) * vd + at(L::KW + 3, k) * va;
-        const double s = at(tg + 0, k), c = at(tg + 1, k), t = at(tg + 2, k);
-        const double a02 = T * (-xk[3] * s), a03 = T * c, a12 = T * (xk[3] * c), a13 = T * s, a23 = T * (t * rL);
-        const double b2 = T * (xk[3] * (1.0 + t * t) * rL);
-        n[0] = d[0] + a02 * d[2] + a03 * d[3] - at(cd + 0, k + 1);
-        n[1] = d[1] + a12 * d[2] + a13 * d[3] - at(cd + 1, k + 1);
-        n[2] = d[2] + a23 * d[3] + b2 * ud - at(cd + 2, k + 1);
+        const AB ab = load_ab(tg, k, xk[3]);
+        n[0] = d[0] + ab.a02 * d[2] + ab.a03 * d[3] - at(cd + 0, k + 1);
+        n[1] = d[1] + ab.a12 * d[2] + ab.a13 * d[3] - at(cd + 1, k + 1);
+        n[2] = d[2] + ab.a23 * d[3] + ab.b20 * ud - at(cd + 2, k + 1);
         n[3] = d[3] + T * ua - at(cd + 3, k + 1);
+        if (RK4) { n[0] += ab.b00 * ud + ab.b01 * ua; n[1] += ab.b10 * ud + ab.b11 * ua; n[2] += ab.b21 * ua; }
         if (k + 1 <= N - 1) { un[0] = at(L::U + 0, k + 1); un[1] = at(L::U + 1, k + 1); }
       }
       at(L::DU + 0, k) = ud; at(L::DU + 1, k) = ua;
       // stage residual of the adjoint recursion: r_k = Hxx_eff dx + Hux' du + gx_eff (written to the LAMP row)
       {
         const double h00 = at(L::HXX + 0, k), h01 = at(L::HXX + 1, k), h11 = at(L::HXX + 2, k), h22 = at(L::HXX + 3, k);
-        const double h23 = at(L::HXX + 4, k), h33 = at(L::HXX + 5, k), hdv = at(L::HUX, k);
+        const double h23 = at(L::HXX + 4, k), h33 = at(L::HXX + 5, k);
+        double r2 = at(L::GX + 2, k) + h22 * d[2] + h23 * d[3], r3 = at(L::GX + 3, k) + h23 * d[2] + h33 * d[3];
+        if (RK4) {  // Hux' du: (delta, phi) (delta, v) (a, phi) (a, v)
+          r2 += at(L::HUX + 0, k) * ud + at(L::HUX + 2, k) * ua;
+          r3 += at(L::HUX + 1, k) * ud + at(L::HUX + 3, k) * ua;
+        } else {
+          r3 += at(L::HUX, k) * ud;
+        }
         at(L::LAMP + 0, k) = at(L::GX + 0, k) + h00 * d[0] + h01 * d[1];
         at(L::LAMP + 1, k) = at(L::GX + 1, k) + h01 * d[0] + h11 * d[1];
-        at(L::LAMP + 2, k) = at(L::GX + 2, k) + h22 * d[2] + h23 * d[3];
-        at(L::LAMP + 3, k) = at(L::GX + 3, k) + h23 * d[2] + h33 * d[3] + hdv * ud;
+        at(L::LAMP + 2, k) = r2;
+        at(L::LAMP + 3, k) = r3;
       }
       // slack steps, new row multipliers, fraction to the boundary, barrier slope
 #pragma unroll
@@ -676,16 +988,15 @@ struct LaneSolver {
   // new dynamics multipliers: lam+_k = A_k' lam+_{k+1} - r_k  (KinSolver::adjoint)
   __device__ void adjoint() {
     const int tg = trg(cur);
-    const double T = p.T, rL = 1.0 / p.Veh_l;
     double l0 = -at(L::LAMP + 0, N), l1 = -at(L::LAMP + 1, N), l2 = -at(L::LAMP + 2, N), l3 = -at(L::LAMP + 3, N);
     at(L::LAMP + 0, N) = l0; at(L::LAMP + 1, N) = l1; at(L::LAMP + 2, N) = l2; at(L::LAMP + 3, N) = l3;
 #pragma unroll 1
     for (int k = N - 1; k >= 0; k--) {
       pf<L::X + 3, 1>(k - 1 - MPCB_LANE_PF_DIST);
-      pf<L::TRG, 6>(k - 1 - MPCB_LANE_PF_DIST);
+      pf<L::TRG, 2 * L::NJ>(k - 1 - MPCB_LANE_PF_DIST);
       pf<L::LAMP, 4>(k - 1 - MPCB_LANE_PF_DIST);
-      const double v = at(L::X + 3, k), s = at(tg + 0, k), c = at(tg + 1, k), t = at(tg + 2, k);
-      const double a02 = T * (-v * s), a03 = T * c, a12 = T * (v * c), a13 = T * s, a23 = T * (t * rL);
+      const AB ab = load_ab(tg, k, RK4 ? 0.0 : at(L::X + 3, k));
+      const double a02 = ab.a02, a03 = ab.a03, a12 = ab.a12, a13 = ab.a13, a23 = ab.a23;
       const double n0 = l0 - at(L::LAMP + 0, k);
       const double n1 = l1 - at(L::LAMP + 1, k);
       const double n2 = l2 + a02 * l0 + a12 * l1 - at(L::LAMP + 2, k);
@@ -842,12 +1153,12 @@ struct LaneSolver {
 #ifndef MPCB_LANE_TRIALS_PER_ROUND
 #define MPCB_LANE_TRIALS_PER_ROUND 1  // trial points a backtracking lane evaluates before the round moves on (4 measured slower: the warp waits)
 #endif
-template <int NR, int MO>
-__global__ void __launch_bounds__(MPCB_LANE_BLOCK, MPCB_LANE_MIN_BLOCKS) kin_lane_kernel(const __grid_constant__ KParams p, double *ws, size_t nslot) {
+template <int NR, int MO, bool RK4 = false>
+__global__ void __launch_bounds__(MPCB_LANE_BLOCK, RK4 ? 2 : MPCB_LANE_MIN_BLOCKS) kin_lane_kernel(const __grid_constant__ KParams p, double *ws, size_t nslot) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  LaneSolver<NR, MO> s(p, ws, nslot, slot);
-  using Kkt = typename LaneSolver<NR, MO>::Kkt;
+  LaneSolver<NR, MO, RK4> s(p, ws, nslot, slot);
+  using Kkt = typename LaneSolver<NR, MO, RK4>::Kkt;
   const double tol = p.tol;
   bool queue_empty = false;
   for (;;) {
@@ -931,7 +1242,7 @@ __global__ void __launch_bounds__(MPCB_LANE_BLOCK, MPCB_LANE_MIN_BLOCKS) kin_lan
     }
     // ---- Newton step with IPOPT's inertia-correction schedule (one factorisation attempt per round)
     if (s.state == LANE_NEWTON) {
-      if (s.backward()) {
+      if (RK4 ? s.backward_rk4() : s.backward()) {
         if (s.dw > 0.0) s.dw_last = s.dw;
         double a_max;
         s.forward(a_max, s.a_dual, s.gd);

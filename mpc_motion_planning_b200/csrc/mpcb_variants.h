@@ -44,6 +44,10 @@ LaneVariant lane_variant_kin_1_1();
 LaneVariant lane_variant_kin_1_2();
 LaneVariant lane_variant_kin_1_3();
 LaneVariant lane_variant_kin_1_4();
+LaneVariant lane_variant_rk4_0_0();  // Runge-Kutta shooting defects
+LaneVariant lane_variant_rk4_1_0();
+LaneVariant lane_variant_rk4_1_1();
+LaneVariant lane_variant_rk4_1_2();
 
 // the candidate that keeps the most warps resident for horizon N (first one wins ties); mpcb_api.cu
 Variant pick_by_occupancy(Variant *cand, int n, int N);

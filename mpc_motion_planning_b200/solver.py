@@ -35,7 +35,8 @@ class BatchSolver:
                  init: str = "rollout", mu_init: float = 30.0, max_iter: int = 100, tol: float = 1e-8,
                  weights=None, bounds: dict | None = None, obs_input: str = "trajectory", cbf_gamma: float | None = None,
                  ref: str = "terminal", cfg_overrides: dict | None = None, dyn_bounds: str = "aligned",
-                 restoration: bool = False, resto_max_calls: int = 1, engine: str = "auto"):
+                 restoration: bool = False, resto_max_calls: int = 1, engine: str = "auto",
+                 integrator: str = "euler"):
         self.lib = _lib.load()
         self.kind = kind
         self.config = config if config is not None else load_config(PACKAGE_PARAMS)
@@ -54,6 +55,8 @@ class BatchSolver:
         # "warp": one scenario per warp (every kind); "lane": one scenario per lane (kinematic kinds, plain rows); "auto"
         # picks per batch size what measures faster
         self.cfg.engine = {"auto": _lib.ENGINE_AUTO, "warp": _lib.ENGINE_WARP, "lane": _lib.ENGINE_LANE}[engine]
+        # "euler": the reference's defects (parity mode); "rk4": classical Runge-Kutta shooting defects (kinematic kinds, lane engine)
+        self.cfg.integrator = {"euler": _lib.INTEGRATOR_EULER, "rk4": _lib.INTEGRATOR_RK4}[integrator]
         for key, val in (cfg_overrides or {}).items():  # any mpcb_cfg field, e.g. {"safe_l": 1.5, "T": 0.08, "Q": [...]}
             cur = getattr(self.cfg, key)
             if hasattr(cur, "__len__"):

@@ -34,7 +34,7 @@ class OrcCfg(C.Structure):
         ("Fymax_f", C.c_double), ("Fymax_r", C.c_double),
         ("tol", C.c_double), ("mu_init", C.c_double), ("bound_relax", C.c_double),
         ("cbf_gamma", C.c_double), ("ref_mode", C.c_int32), ("rows_as_shipped", C.c_int32),
-        ("restoration", C.c_int32), ("resto_max_calls", C.c_int32),
+        ("restoration", C.c_int32), ("resto_max_calls", C.c_int32), ("integrator", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -88,7 +88,7 @@ def lib():
 def make_cfg(kind: str, N: int | None = None, M: int = 1, params: Params | None = None, init_mode: int = 1,
              mu_init: float = 30.0, max_iter: int = 100, tol: float = 1e-8, cbf_gamma: float | None = None,
              ref_trajectory: bool = False, rows_as_shipped: bool = False, restoration: bool = False,
-             resto_max_calls: int = 1) -> OrcCfg:
+             resto_max_calls: int = 1, integrator: str = "euler") -> OrcCfg:
     p = params or Params()
     w = reference_weights(kind)
     c = OrcCfg()
@@ -134,6 +134,8 @@ def make_cfg(kind: str, N: int | None = None, M: int = 1, params: Params | None 
     c.rows_as_shipped = int(rows_as_shipped)  # dyn: bound lists as PKG/MPC_CBF_optimize_dyn.py:112-133 ships them
     c.restoration = int(restoration and kind in ("kin_cbf", "kin_cbf_pre"))
     c.resto_max_calls = int(resto_max_calls)
+    assert integrator in ("euler", "rk4") and (integrator == "euler" or kind != "dyn")
+    c.integrator = int(integrator == "rk4")
     return c
 
 

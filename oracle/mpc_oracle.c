@@ -99,12 +99,74 @@ static double dr2(double v) { double m = fmax(1.0, fabs(v)); return 1.0 / (m * m
 int orc_nx(const orc_cfg *c) { return c->model == ORC_MODEL_DYN ? 6 : 4; }
 
 /* ------------------------------------------------------------------ vehicle models */
+/* kinematic right-hand side g(x,u), its Jacobian wrt z = [x;u] (4x6) and sum_i nu_i g_i'' (6x6)
+ * (PKG/MPC_CBF_optimize_kin.py:153-156) */
+static void kin_g(double L, const double *x, const double *u, double *f) {
+  f[0] = x[3] * cos(x[2]);
+  f[1] = x[3] * sin(x[2]);
+  f[2] = x[3] * tan(u[0]) / L;
+  f[3] = u[1];
+}
+static void kin_gjac(double L, const double *x, const double *u, double G[4][6]) {
+  memset(G, 0, sizeof(double) * 24);
+  double c = cos(x[2]), s = sin(x[2]), t = tan(u[0]);
+  G[0][2] = -x[3] * s; G[0][3] = c;
+  G[1][2] = x[3] * c;  G[1][3] = s;
+  G[2][3] = t / L;     G[2][4] = x[3] * (1.0 + t * t) / L;
+  G[3][5] = 1.0;
+}
+static void kin_ghess(double L, const double *x, const double *u, const double *nu, double M[6][6]) {
+  memset(M, 0, sizeof(double) * 36);
+  double c = cos(x[2]), s = sin(x[2]), t = tan(u[0]), v = x[3], sec2 = 1.0 + t * t;
+  M[2][2] = nu[0] * (-v * c) + nu[1] * (-v * s);
+  M[2][3] = M[3][2] = nu[0] * (-s) + nu[1] * c;
+  M[3][4] = M[4][3] = nu[2] * sec2 / L;
+  M[4][4] = nu[2] * 2.0 * v * sec2 * t / L;
+}
+/* Runge-Kutta increment function (Phi(x,u) - x)/T with its forward-mode Jacobian and second-order adjoint
+ * (oracle/nlp.py Rk4KinModel) */
+static const double RK_A[4] = {0.0, 0.5, 0.5, 1.0}, RK_B[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
+static void rk4_all(double L, double T, const double *x, const double *u, const double *lam, double *f, double J[4][6], double H[6][6]) {
+  double xs[4][4], k[4][4], Z[4][6][6], G[4][4][6], K[4][6];
+  for (int s = 0; s < 4; s++) {
+    for (int i = 0; i < 4; i++) xs[s][i] = x[i] + (s ? RK_A[s] * T * k[s - 1][i] : 0.0);
+    kin_g(L, xs[s], u, k[s]);
+    for (int i = 0; i < 6; i++)
+      for (int j = 0; j < 6; j++) Z[s][i][j] = (i == j ? 1.0 : 0.0) + ((s && i < 4) ? RK_A[s] * T * K[i][j] : 0.0);
+    kin_gjac(L, xs[s], u, G[s]);
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 6; j++) { double a = 0; for (int m = 0; m < 6; m++) a += G[s][i][m] * Z[s][m][j]; K[i][j] = a; }
+    for (int i = 0; i < 4; i++) {
+      if (f) f[i] = (s ? f[i] : 0.0) + RK_B[s] * k[s][i];
+      if (J) for (int j = 0; j < 6; j++) J[i][j] = (s ? J[i][j] : 0.0) + RK_B[s] * K[i][j];
+    }
+  }
+  if (H) {
+    double nu[4], nn[4];
+    memset(H, 0, sizeof(double) * 36);
+    for (int s = 3; s >= 0; s--) {
+      for (int i = 0; i < 4; i++) {
+        double a = RK_B[s] * lam[i];
+        if (s < 3) for (int m = 0; m < 4; m++) a += RK_A[s + 1] * T * G[s + 1][m][i] * nu[m];
+        nn[i] = a;
+      }
+      memcpy(nu, nn, sizeof nu);
+      double M[6][6], MZ[6][6];
+      kin_ghess(L, xs[s], u, nu, M);
+      for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) { double a = 0; for (int m = 0; m < 6; m++) a += M[i][m] * Z[s][m][j]; MZ[i][j] = a; }
+      for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) { double a = 0; for (int m = 0; m < 6; m++) a += Z[s][m][i] * MZ[m][j]; H[i][j] += a; }
+    }
+  }
+}
+#define IS_RK4(w) ((w)->c->integrator == 1 && (w)->c->model == ORC_MODEL_KIN)
+
 static void model_f(const ws_t *w, const double *x, const double *u, double *f) {
-  if (w->c->model == ORC_MODEL_KIN) { /* PKG/MPC_CBF_optimize_kin.py:153-156 */
-    f[0] = x[3] * cos(x[2]);
-    f[1] = x[3] * sin(x[2]);
-    f[2] = x[3] * tan(u[0]) / w->c->Veh_l;
-    f[3] = u[1];
+  if (IS_RK4(w)) {
+    rk4_all(w->c->Veh_l, w->c->T, x, u, 0, f, 0, 0);
+  } else if (w->c->model == ORC_MODEL_KIN) {
+    kin_g(w->c->Veh_l, x, u, f);
   } else {
     dyn_f(x, u, w->pdyn, f);
   }
@@ -113,7 +175,14 @@ static void model_f(const ws_t *w, const double *x, const double *u, double *f) 
 static void model_jac(const ws_t *w, const double *x, const double *u, double Jx[NXM][NXM], double Ju[NXM][2]) {
   memset(Jx, 0, sizeof(double) * NXM * NXM);
   memset(Ju, 0, sizeof(double) * NXM * 2);
-  if (w->c->model == ORC_MODEL_KIN) {
+  if (IS_RK4(w)) {
+    double J[4][6];
+    rk4_all(w->c->Veh_l, w->c->T, x, u, 0, 0, J, 0);
+    for (int i = 0; i < 4; i++) {
+      for (int j = 0; j < 4; j++) Jx[i][j] = J[i][j];
+      Ju[i][0] = J[i][4]; Ju[i][1] = J[i][5];
+    }
+  } else if (w->c->model == ORC_MODEL_KIN) {
     double c = cos(x[2]), s = sin(x[2]), t = tan(u[0]), L = w->c->Veh_l;
     Jx[0][2] = -x[3] * s;
     Jx[0][3] = c;
@@ -136,7 +205,12 @@ static void model_jac(const ws_t *w, const double *x, const double *u, double Jx
 /* H = sum_i lam_i d2 f_i / d[x;u]^2, (nx+2)^2 stored in 8x8 */
 static void model_hess(const ws_t *w, const double *x, const double *u, const double *lam, double H[8][8]) {
   memset(H, 0, sizeof(double) * 64);
-  if (w->c->model == ORC_MODEL_KIN) {
+  if (IS_RK4(w)) {
+    double H6[6][6];
+    rk4_all(w->c->Veh_l, w->c->T, x, u, lam, 0, 0, H6);
+    for (int i = 0; i < 6; i++)
+      for (int j = 0; j < 6; j++) H[i][j] = H6[i][j];
+  } else if (w->c->model == ORC_MODEL_KIN) {
     double c = cos(x[2]), s = sin(x[2]), t = tan(u[0]), L = w->c->Veh_l, v = x[3];
     double sec2 = 1.0 + t * t;
     H[2][2] = lam[0] * (-v * c) + lam[1] * (-v * s);

@@ -67,6 +67,10 @@ typedef struct {
                          ORC_INFEASIBLE (restoration keeps reducing the infeasibility by the required 10 % without ever reaching a
                          point from which the regular phase converges: a locally infeasible start).  IPOPT has no such cap and
                          would use up max_iter; 0 = IPOPT's behaviour. */
+  int32_t integrator;  /* 0: explicit Euler defects X_{k+1} - X_k - T f(X_k,U_k) (the reference, PKG/MPC_CBF_optimize_kin.py:207);
+                         1: classical Runge-Kutta (kinematic model) - the option BASELINE.json's north_star names.  Implemented
+                         as the increment function (Phi_RK4(x,u) - x)/T in place of f, see oracle/nlp.py Rk4KinModel */
+  int32_t reserved;
 } orc_cfg;
 
 typedef struct {

@@ -169,6 +169,73 @@ class KinModel:
         return H
 
 
+class Rk4KinModel(KinModel):
+    """The kinematic bicycle integrated with the classical Runge-Kutta scheme over one step T - the OPTION `north_star`
+    names ("RK4 multiple-shooting rollout"; the reference itself integrates with explicit Euler, PKG/MPC_CBF_optimize_kin.py:207,
+    and the only Runge-Kutta in its tree is the unfinished tutorial Reference/MPC/sim_test.py:35-37).
+
+    Exposed as an INCREMENT function, so that every use of the model in NLP stays as it is:
+        f(x,u) = (Phi(x,u) - x) / T,   Phi = x + T/6 (k1 + 2 k2 + 2 k3 + k4),
+        k1 = g(x,u), k2 = g(x + T/2 k1, u), k3 = g(x + T/2 k2, u), k4 = g(x + T k3, u),   g = the Euler right-hand side.
+    `jac` is the forward-mode Jacobian through the four stages; `hess` the second-order adjoint
+        sum_s Z_s' [nu_s . g''(z_s)] Z_s,   nu_4 = b_4 lam, nu_s = b_s lam + a_{s+1} g_x(z_{s+1})' nu_{s+1},   Z_s = d z_s / d z.
+    A = I + T f_x keeps the sparsity of the Euler step (x, y never enter g); B = T f_u gains five entries."""
+
+    A_COEF = (0.0, 0.5, 0.5, 1.0)
+    B_COEF = (1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0)
+
+    def __init__(self, p: Params, T: float):
+        super().__init__(p)
+        self.T = T
+
+    def _stages(self, x, u):
+        """stage points z_s = (x + a_s T k_{s-1}, u) and slopes k_s"""
+        x = np.asarray(x, float)
+        ks, xs_ = [], []
+        for a in self.A_COEF:
+            xs = x if not ks else x + a * self.T * ks[-1]
+            xs_.append(xs)
+            ks.append(KinModel.f(self, xs, u))
+        return xs_, ks
+
+    def f(self, x, u):
+        _, ks = self._stages(x, u)
+        return sum(b * k for b, k in zip(self.B_COEF, ks))
+
+    def jac(self, x, u):
+        xs_, _ = self._stages(x, u)
+        E = np.eye(6)
+        J = np.zeros((4, 6))
+        K_prev = None
+        for a, b, xs in zip(self.A_COEF, self.B_COEF, xs_):
+            Z = E.copy()
+            if K_prev is not None:
+                Z[:4, :] += a * self.T * K_prev
+            K_prev = KinModel.jac(self, xs, u) @ Z
+            J += b * K_prev
+        return J
+
+    def hess(self, x, u, lam):
+        lam = np.asarray(lam, float)
+        xs_, _ = self._stages(x, u)
+        E = np.eye(6)
+        Zs, Gs, K_prev = [], [], None
+        for a, xs in zip(self.A_COEF, xs_):
+            Z = E.copy()
+            if K_prev is not None:
+                Z[:4, :] += a * self.T * K_prev
+            G = KinModel.jac(self, xs, u)
+            K_prev = G @ Z
+            Zs.append(Z)
+            Gs.append(G)
+        H = np.zeros((6, 6))
+        nu = None
+        for s in (3, 2, 1, 0):
+            nu = self.B_COEF[s] * lam if nu is None else self.B_COEF[s] * lam + self.A_COEF[s + 1] * self.T * (Gs[s + 1][:, :4].T @ nu)
+            H += Zs[s].T @ KinModel.hess(self, xs_[s], u, nu) @ Zs[s]
+        return H
+
+
 class DynModel:
     """x=[x,y,phi,vx,vy,r], u=[df,ax]; PKG/MPC_CBF_optimize_dyn.py:156-170.
 
@@ -253,15 +320,17 @@ class NLP:
     """
 
     def __init__(self, kind: str, x0, xs, obstacles=None, params: Params | None = None, N: int | None = None,
-                 weights: Weights | None = None, cbf_gamma: float | None = None, xref=None):
+                 weights: Weights | None = None, cbf_gamma: float | None = None, xref=None, integrator: str = "euler"):
         assert kind in KINDS
+        assert integrator in ("euler", "rk4") and (integrator == "euler" or kind != "dyn")
         assert cbf_gamma is None or kind in ("kin_cbf", "kin_cbf_pre")
         self.cbf_gamma = cbf_gamma
         self.kind = kind
         self.p = params or Params()
         self.N = N if N is not None else self.p.N_p
         self.T = self.p.T_S
-        self.model = DynModel(self.p) if kind == "dyn" else KinModel(self.p)
+        self.integrator = integrator
+        self.model = DynModel(self.p) if kind == "dyn" else (Rk4KinModel(self.p, self.T) if integrator == "rk4" else KinModel(self.p))
         self.nx, self.nu = self.model.nx, 2
         self.x0 = np.asarray(x0, dtype=float).reshape(self.nx)
         self.xs = np.asarray(xs, dtype=float).reshape(self.nx)

@@ -1101,3 +1101,46 @@ def test_lane_engine_with_restoration_and_order(dev):
     both = (a["status"] <= 1) & (b["status"] <= 1)
     assert np.abs(a["u0"][both] - b["u0"][both]).max() <= U0_ATOL
     assert (b["status"] == 3).sum() < 0.9 * (_gpu(BatchSolver("kin_cbf", engine="lane"), dev, x0, xs, obs)["status"] == 3).sum()
+
+
+# --------------------------------------------------------------------------- Runge-Kutta shooting defects (cfg.integrator)
+@pytest.mark.parametrize("kind,gen,M,B", [("kin_nocbf", "kin_nocbf", 1, 300), ("kin_cbf", "kin_cbf_static", 1, 1000),
+                                           ("kin_cbf_pre", "kin_cbf_moving", 2, 300)])
+def test_rk4_defects_parity_with_the_oracle_in_rk4_mode(dev, kind, gen, M, B):
+    """cfg.integrator = MPCB_INTEGRATOR_RK4: X_{k+1} - Phi_RK4(X_k, U_k) with forward-mode Jacobians through the four
+    stages and the exact second-order adjoint.  Checked against the oracle's own RK4 mode (oracle/nlp.py Rk4KinModel is
+    the specification, its derivatives are checked against finite differences in the CPU suite); parity with the
+    REFERENCE is Euler-only - the two integrators' optima differ by more than the tolerances, which is asserted too."""
+    from mpc_motion_planning_b200 import _lib, scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+    from oracle import c_oracle
+
+    x0, xs, obs = getattr(scenarios, gen)(B)
+    if M == 2:
+        _, _, ob = scenarios.kin_cbf_moving(B, seed=99)
+        ob[:, :, :, 0] += 60.0
+        obs = np.concatenate([obs, ob], axis=1)
+    s = BatchSolver(kind, M=M, integrator="rk4")
+    g = _gpu(s, dev, x0, xs, obs, return_z=True)
+    oobs = obs if obs.shape[1] else None
+    u0, cost, st, it, z = c_oracle.solve_batch(c_oracle.make_cfg(kind, M=M, integrator="rk4"), x0, xs, oobs, want_z=True, nthreads=os.cpu_count())
+    both, same = _check(g, u0, cost, st, 0.6 if M == 2 else 0.8)
+    assert (g["iters"][both] == it[both]).mean() >= 0.9
+    assert np.quantile(np.abs(g["z"][both] - z[both]).max(axis=1), 0.99) <= 1e-5
+    # the returned trajectory satisfies the RK4 defects (fine Euler sub-stepping as an independent integrator)
+    b = int(np.where(both)[0][0])
+    N = 50
+    U, X = g["z"][b, : 2 * N].reshape(N, 2), g["z"][b, 2 * N:].reshape(N + 1, 4)
+    for k in (0, 17, 49):
+        x = X[k].copy()
+        for _ in range(2000):
+            x = x + 5e-5 * np.array([x[3] * np.cos(x[2]), x[3] * np.sin(x[2]), x[3] * np.tan(U[k, 0]) / 2.6, U[k, 1]])
+        assert np.abs(x - X[k + 1]).max() <= 2e-4, (k, np.abs(x - X[k + 1]).max())
+    # Euler and RK4 are different NLPs: their optima are further apart than BASELINE's tolerances
+    e = _gpu(BatchSolver(kind, M=M, engine="lane"), dev, x0, xs, obs)
+    be = both & (e["status"] <= 1)
+    assert (np.abs(e["cost"][be] - g["cost"][be]) / np.abs(g["cost"][be])).max() > COST_RTOL
+    # Runge-Kutta is not offered where it is not implemented
+    for bad in (dict(kind="dyn"), dict(kind="kin_cbf", engine="warp"), dict(kind="kin_cbf", cbf_gamma=0.5), dict(kind="kin_cbf", restoration=True)):
+        with pytest.raises(_lib.MpcbError):
+            BatchSolver(bad.pop("kind"), integrator="rk4", **bad)

@@ -104,3 +104,52 @@ def test_predict_obstacles_is_the_reference_recursion():
         assert tr[k, 0] == x and tr[k, 1] == y
         x = x + 10 * np.cos(np.pi / 4) * 0.1
         y = y + 10 * np.sin(np.pi / 4) * 0.1
+
+
+def test_rk4_increment_model_derivatives_against_finite_differences():
+    """oracle/nlp.py Rk4KinModel: forward-mode Jacobian and second-order adjoint of the Runge-Kutta increment function."""
+    import numpy as np
+
+    from oracle import nlp
+
+    m = nlp.Rk4KinModel(nlp.Params(), 0.1)
+    rng = np.random.default_rng(7)
+    for _ in range(6):
+        x = np.array([rng.uniform(0, 50), rng.uniform(0, 4), rng.uniform(-0.4, 0.4), rng.uniform(2, 30)])
+        u = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-3, 3)])
+        z = np.concatenate([x, u])
+        lam = rng.normal(size=4)
+        J, H = m.jac(x, u), m.hess(x, u, lam)
+        Jn, Hn, h = np.zeros((4, 6)), np.zeros((6, 6)), 1e-6
+        for i in range(6):
+            e = np.zeros(6)
+            e[i] = h
+            Jn[:, i] = (m.f((z + e)[:4], (z + e)[4:]) - m.f((z - e)[:4], (z - e)[4:])) / (2 * h)
+            Hn[:, i] = (lam @ m.jac((z + e)[:4], (z + e)[4:]) - lam @ m.jac((z - e)[:4], (z - e)[4:])) / (2 * h)
+        assert np.abs(J - Jn).max() <= 1e-7 and np.abs(H - Hn).max() <= 1e-6 and np.abs(H - H.T).max() <= 1e-14
+        # A keeps the sparsity of the Euler step, x and y never enter
+        assert np.all(J[:, :2] == 0) and J[2, 2] == 0 and np.all(J[3, :5] == 0) and abs(J[3, 5] - 1.0) <= 1e-15
+        # fourth-order accurate: against a fine explicit-Euler integration of the same right-hand side
+        xe = x.copy()
+        for _ in range(4000):
+            xe = xe + 2.5e-5 * nlp.KinModel.f(m, xe, u)
+        assert np.abs(x + 0.1 * m.f(x, u) - xe).max() <= 2e-4
+
+
+def test_rk4_c_oracle_equals_dense_specification():
+    import numpy as np
+
+    from mpc_motion_planning_b200 import scenarios
+    from oracle import c_oracle, ipm_dense, nlp
+
+    x0, xs, obs = scenarios.kin_cbf_static(8)
+    cfg = c_oracle.make_cfg("kin_cbf", integrator="rk4")
+    n = 0
+    for b in (1, 3):
+        z, lam, info = c_oracle.solve(cfg, x0[b], xs[b], obs[b])
+        P = nlp.NLP("kin_cbf", x0[b], xs[b], obs[b, :, 0, :], integrator="rk4")
+        r = ipm_dense.solve(P, P.rollout_start())
+        assert r.status == info.status == 0 and r.iters == info.iters
+        assert abs(r.f - info.f) <= 1e-10 * abs(r.f) and np.abs(r.z - z).max() <= 1e-8
+        n += 1
+    assert n == 2
