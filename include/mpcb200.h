@@ -246,6 +246,12 @@ int mpcb_set_order(mpcb_handle *h, const int32_t *order, int n);
  * accepted step size of the previous iteration, last inertia regularisation).  rows = 0 disables. */
 int mpcb_set_trace_buffer(mpcb_handle *h, double *trace, int rows);
 
+/* Sanitizer substitute.  The warp-per-scenario kernels reuse shared-memory slots between the phases of an iteration; the
+ * build with -DMPCB_DEBUG_SLOTS (python -m mpc_motion_planning_b200.build --debug-slots -> libmpcb200_debug.so) tags every
+ * store into those slots with the kind of data and checks the tag at every load.  *count = violations seen so far by the
+ * solves on this handle, or -1 when the library is not that build. */
+int mpcb_debug_slot_errors(mpcb_handle *h, int *count);
+
 /* kernel launch statistics of the last solve on this handle */
 typedef struct mpcb_launch_info {
   int32_t grid, block, smem_bytes, regs_per_thread, blocks_per_sm, num_sms;

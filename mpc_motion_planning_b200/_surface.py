@@ -168,6 +168,9 @@ class MPCOptimizeBase:
         # IPOPT answers a failed line search with its restoration phase, as often as it takes (kin-CBF modules)
         self.restoration = True
         self.resto_max_calls = 0
+        # shooting defects: "euler" is what the reference builds (:207) and the only mode with reference parity; "rk4" is the
+        # classical Runge-Kutta option (kinematic modules; served by the lane engine, without the restoration phase)
+        self.integrator = "euler"
         # Two switches the reference keeps as locals of optimize_problem (kin-CBF modules):
         #   aa = 0.0      weight of ref_state in the stage cost target          (:194-197)
         #   gamma = 1.00  with `g.append(h_func)` live and `gamma*h_func + h_dot` commented out (:235-248)
@@ -334,11 +337,13 @@ class MPCOptimizeBase:
         M = 0 if obs_array is None else obs_array.shape[0]
         gamma = float(self.gamma) if self._dcbf() else None
         ref = "trajectory" if self._stage_reference() else "terminal"
-        key = (M, self.max_iter, self.tol, self.mu_init, self.init, gamma, ref, dyn_rows, self.restoration, self.resto_max_calls) + tuple(np.concatenate([np.ravel(v) for v in bounds.values()]).tolist() if bounds else ())
+        rk4 = self.integrator == "rk4"
+        key = (M, self.max_iter, self.tol, self.mu_init, self.init, gamma, ref, dyn_rows, self.restoration, self.resto_max_calls, self.integrator) + tuple(np.concatenate([np.ravel(v) for v in bounds.values()]).tolist() if bounds else ())
         if key not in self._solvers:
             self._solvers[key] = BatchSolver(self.KIND, config=self.config, N=N, M=max(M, 1), init=self.init, mu_init=self.mu_init,
                                              max_iter=self.max_iter, tol=self.tol, bounds=bounds or None, cbf_gamma=gamma, ref=ref,
-                                             dyn_bounds=dyn_rows, restoration=self.restoration, resto_max_calls=self.resto_max_calls)
+                                             dyn_bounds=dyn_rows, restoration=self.restoration and not rk4, resto_max_calls=self.resto_max_calls,
+                                             integrator=self.integrator)
         return self._solvers[key]
 
     def _check_row_bounds(self, lg, ug, bounds, dyn_rows, M):

@@ -27,6 +27,35 @@ def stale() -> bool:
     return any(os.path.exists(s) and os.path.getmtime(s) > t for s in SRCS)
 
 
+SO_DEBUG = os.path.join(HERE, "libmpcb200_debug.so")
+
+
+def build_debug_slots() -> str:
+    """libmpcb200_debug.so: the kinematic warp kernels (rate rows + 1-2 obstacles, plain and discrete-CBF rows, and the
+    row-free family) with -DMPCB_DEBUG_SLOTS - the slot-ownership checker that stands in for compute-sanitizer."""
+    if os.path.exists(SO_DEBUG) and all(os.path.getmtime(s) <= os.path.getmtime(SO_DEBUG) for s in SRCS if os.path.exists(s)):
+        return SO_DEBUG
+    nvcc = os.environ.get("NVCC", "nvcc")
+    flags = NVCC_FLAGS + ["-DMPCB_DEBUG_SLOTS"]
+    os.makedirs(OBJ, exist_ok=True)
+    jobs = [(os.path.join(HERE, "csrc", "mpcb_api.cu"), os.path.join(OBJ, "dbg_api.o"), [])]
+    jobs += [(os.path.join(HERE, "csrc", "mpcb_variants.cu"), os.path.join(OBJ, f"dbg_family{k}.o"), [f"-DMPCB_FAMILY={k}"]) for k in range(N_FAMILIES)]
+    jobs += [(os.path.join(HERE, "csrc", "mpcb_lane.cu"), os.path.join(OBJ, f"dbg_lane{k}.o"), [f"-DMPCB_LANE_FAMILY={k}"]) for k in range(N_LANE_FAMILIES)]
+
+    def compile_one(job):
+        src, obj, defs = job
+        return job, subprocess.run([nvcc] + flags + defs + ["-c", "-o", obj, src], cwd=HERE, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=max(1, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, jobs))
+    for (src, obj, defs), r in results:
+        if r.returncode != 0:
+            sys.stderr.write(f"---- nvcc {' '.join(defs)} {os.path.basename(src)}\n{r.stdout}{r.stderr}")
+            raise subprocess.CalledProcessError(r.returncode, r.args)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_DEBUG] + [obj for _, obj, _ in jobs], cwd=HERE)
+    return SO_DEBUG
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not (force or stale()):
         return SO
@@ -56,3 +85,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--debug-slots" in sys.argv:
+        print(build_debug_slots())

@@ -147,6 +147,7 @@ struct mpcb_handle {
   size_t lane_nslot;
   int lane_grid, lane_min_B;
   mpcb_launch_info lane_info;
+  int *d_debug_errors;  // -DMPCB_DEBUG_SLOTS builds: slot-ownership violations seen by the kernels
 };
 
 extern "C" {
@@ -345,6 +346,12 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
       }
     }
   }
+#ifdef MPCB_DEBUG_SLOTS
+  if (!cuda_ok(cudaMalloc(&h->d_debug_errors, sizeof(int)), "cudaMalloc debug counter")) { mpcb_destroy(h); return MPCB_E_NOMEM; }
+  cudaMemset(h->d_debug_errors, 0, sizeof(int));
+  k.debug_errors = h->d_debug_errors;
+  k.debug_selftest = getenv("MPCB_DEBUG_SLOTS_SELFTEST") ? 1 : 0;
+#endif
   k.resto_max_calls = c.resto_max_calls;
   k.restoration = (c.restoration && var.rs_inline) ? 1 : 0;
   if (c.restoration && !var.rs_inline && var.resto_kernel) {
@@ -393,6 +400,7 @@ void mpcb_destroy(mpcb_handle *h) {
   cudaFree(h->d_resto_count);
   cudaFree(h->d_resto_slab);
   cudaFree(h->d_lane_ws);
+  cudaFree(h->d_debug_errors);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -595,6 +603,16 @@ int mpcb_set_trace_buffer(mpcb_handle *h, double *trace, int rows) {
   if (!h || rows < 0) return MPCB_E_ARG;
   h->kp.trace = rows > 0 ? trace : nullptr;
   h->kp.trace_rows = rows;
+  return MPCB_OK;
+}
+
+int mpcb_debug_slot_errors(mpcb_handle *h, int *count) {
+  if (!h || !count) return MPCB_E_ARG;
+  *count = -1;  // not a debug build
+#ifdef MPCB_DEBUG_SLOTS
+  if (h->has_last) cudaEventSynchronize(h->last_done);
+  if (!cuda_ok(cudaMemcpy(count, h->d_debug_errors, sizeof(int), cudaMemcpyDeviceToHost), "debug counter")) return MPCB_E_CUDA;
+#endif
   return MPCB_OK;
 }
 

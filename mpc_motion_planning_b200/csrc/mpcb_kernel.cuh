@@ -100,6 +100,8 @@ struct KParams {
   int main_warps;        // warps of the main launch (consumer side: when resto_sync[2] reaches it the list is complete)
   int resto_max_calls;
   int restoration;       // RS kernels: enter the restoration phase in place (0: end with status 3 like the kernels without it)
+  int *debug_errors;     // -DMPCB_DEBUG_SLOTS builds: count of shared-memory slots read while another phase's data was in them
+  int debug_selftest;    // ... make one expectation wrong on purpose (the checker must trip)
 };
 
 // ------------------------------------------------------------------------------------
@@ -252,7 +254,12 @@ struct KinLayout {
   static constexpr int NG = NG0 + (RS ? NX + 2 + 8 : 0);
   static constexpr int SG = 132;        // row stride (>= MPCB_NMAX + 1)
   static constexpr int NFA = AS ? ((NF + NG) | 1) : NF;  // record length in shared memory
+#ifdef MPCB_DEBUG_SLOTS
+  // debug build: one owner tag per slot of the aliased regions, kept behind the records of the warp
+  __host__ __device__ static constexpr size_t bytes(int N) { return (sizeof(double) + sizeof(double)) * (size_t)NFA * (size_t)(N + 1); }
+#else
   __host__ __device__ static constexpr size_t bytes(int N) { return sizeof(double) * (size_t)NFA * (size_t)(N + 1); }
+#endif
   __host__ __device__ static constexpr size_t slab_doubles() { return AS ? 0 : (size_t)NG * SG; }
 };
 
@@ -298,6 +305,28 @@ struct KinSolver {
   __device__ KinSolver(const KParams &p_, double *gs_, int woff_, int &tick_, int lane_)
       : p(p_), gs(gs_), woff(woff_), tick(tick_), N(p_.N), lane(lane_) {}
 
+  // ---- sanitizer substitute (compute-sanitizer is closed on this pool): the shared-memory record reuses slots between
+  // phases - LAMP aliases CDEF; the 14-slot region holds [HUU EE GU TK] -> the Riccati gains -> the slack steps and the
+  // trial point's defects.  With -DMPCB_DEBUG_SLOTS every store into those slots records WHICH data it is and every load
+  // states which data it expects; a mismatch is counted in KParams.debug_errors (tests/test_gpu_parity.py runs one
+  // solve per kernel family on this build and asserts zero).  In the regular build both calls compile to nothing.
+  enum { TAG_NONE = 0, TAG_DEFECT = 1, TAG_NEWLAM = 2, TAG_QP = 3, TAG_GAINS = 4, TAG_STEPS = 5, TAG_TRIALDEF = 6 };
+#ifdef MPCB_DEBUG_SLOTS
+  __device__ __forceinline__ double &tag_at(int field, int k) {
+    const int idx = woff + k * L::NFA + (AS && field >= L::G0 ? L::NF + (field - L::G0) : field);
+    return g_smem[idx + (int)(L::bytes(N) / (2 * sizeof(double))) * (int)(blockDim.x >> 5)];
+  }
+  __device__ __forceinline__ void own(int field, int n, int k, int tag) {
+    for (int i = 0; i < n; i++) tag_at(field + i, k) = (double)tag;
+  }
+  __device__ __forceinline__ void expect(int field, int n, int k, int tag) {
+    for (int i = 0; i < n; i++)
+      if (tag_at(field + i, k) != (double)tag && p.debug_errors) atomicAdd(p.debug_errors, 1);
+  }
+#else
+  __device__ __forceinline__ void own(int, int, int, int) {}
+  __device__ __forceinline__ void expect(int, int, int, int) {}
+#endif
   __device__ __forceinline__ bool in_resto() const { return RS && resto; }
   __device__ static __forceinline__ double dr2(double v) { double m = fmax(1.0, fabs(v)); return 1.0 / (m * m); }
   // A row `row(z) - s` condensed into its stage: new row multiplier lam+ = D (J dz) + tt.
@@ -370,6 +399,7 @@ struct KinSolver {
           th += fabs(c0);
           at(cdst + i, 0) = c0;
         }
+        own(cdst, NX, 0, fresh ? TAG_DEFECT : TAG_TRIALDEF);
       }
       if (in_resto()) {
 #pragma unroll
@@ -404,6 +434,7 @@ struct KinSolver {
           double d = xn - (xk[i] + p.T * f[i]);
           th += fabs(d);
           at(cdst + i, k + 1) = d;
+          own(cdst + i, 1, k + 1, fresh ? TAG_DEFECT : TAG_TRIALDEF);
           double e = xk[i] - xref(i, k);
           fo += p.Q[i] * e * e;
         }
@@ -432,6 +463,7 @@ struct KinSolver {
           double um = at(L::U + ci, k - 1) + alpha * at(L::DU + ci, k - 1);
           double ukc = ci == 0 ? uk[0] : uk[1];
           // the slack step lives in the gain region, which holds gains while alpha == 0
+          if (alpha != 0.0) expect(L::DSR + r, 1, k, TAG_STEPS);
           double s = at(L::SR + r, k) + (alpha != 0.0 ? alpha * at(L::DSR + r, k) : 0.0);
           if (RS) thr += fabs(ukc - um - s); else th += fabs(ukc - um - s);
           if (in_resto()) fr += d_psi(ukc - um - s, mu_psi, true).v;
@@ -447,6 +479,7 @@ struct KinSolver {
             double ex = xnext[0] - at(L::OCX + j, k), ey = xnext[1] - at(L::OCY + j, k);
             d = (ex * ex * at(L::ISX + j, k) + ey * ey * at(L::ISY + j, k) - 1.0) - p.cbf_g1 * d;
           }
+          if (alpha != 0.0) expect(L::DSO + j, 1, k, TAG_STEPS);
           double s = at(L::SO + j, k) + (alpha != 0.0 ? alpha * at(L::DSO + j, k) : 0.0);
           if (RS) thr += fabs(d - s); else th += fabs(d - s);
           if (in_resto()) fr += d_psi(d - s, mu_psi, true).v;
@@ -486,6 +519,7 @@ struct KinSolver {
       for (int i = 0; i < NX; i++) {
         xk[i] = at(L::X + i, k);
         lam[i] = at(L::LAM + i, k);
+        expect(L::CDEF + i, 1, k, TAG_DEFECT);
         prim = fmax(prim, fabs(at(L::CDEF + i, k)));
         sl += fabs(lam[i]);
       }
@@ -735,6 +769,8 @@ struct KinSolver {
           g += mu * (rh - rl);
           at(L::HUU + i, k) = hd;
           at(L::GU + i, k) = g;
+          own(L::HUU + i, 1, k, TAG_QP);
+          own(L::GU + i, 1, k, TAG_QP);
           if (k >= 1 && !in_resto()) {
             E[i] = sigma * 2 * p.DR[i];
             t[i] = sigma * 2 * p.DR[i] * (uk - at(L::U + i, k - 1));
@@ -758,6 +794,8 @@ struct KinSolver {
         at(L::EE + 1, k) = E[1];
         at(L::TK + 0, k) = t[0];
         at(L::TK + 1, k) = t[1];
+        own(L::EE, 2, k, TAG_QP);
+        own(L::TK, 2, k, TAG_QP);
       }
     }
     __syncwarp();
@@ -780,6 +818,8 @@ struct KinSolver {
     for (int k = N - 1; k >= 0; k--) {
       const double a02 = at(L::JAC + 0, k), a03 = at(L::JAC + 1, k), a12 = at(L::JAC + 2, k), a13 = at(L::JAC + 3, k);
       const double a23 = at(L::JAC + 4, k), b2 = at(L::JAC + 5, k);
+      expect(L::HUU, 8, k, TAG_QP);
+      expect(L::CDEF, NX, k + 1, TAG_DEFECT);
       const double Ed = at(L::EE + 0, k), Ea = at(L::EE + 1, k), td = at(L::TK + 0, k), ta = at(L::TK + 1, k);
       const double b0 = -at(L::CDEF + 0, k + 1), b1 = -at(L::CDEF + 1, k + 1), b2_ = -at(L::CDEF + 2, k + 1), b3 = -at(L::CDEF + 3, k + 1);
       // M = P A (columns 0,1 are those of P)
@@ -834,6 +874,7 @@ struct KinSolver {
         at(L::KX + 4, k) = ka0; at(L::KX + 5, k) = ka1; at(L::KX + 6, k) = ka2; at(L::KX + 7, k) = ka3;
         at(L::KW + 0, k) = wdd; at(L::KW + 1, k) = wda; at(L::KW + 2, k) = wad; at(L::KW + 3, k) = waa;
         at(L::KK + 0, k) = kkd; at(L::KK + 1, k) = kka;
+        own(L::KX, 14, k, TAG_GAINS);
       }
       // value function of stage k
       p00 = f00 + ud0 * kd0 + ua0 * ka0;
@@ -871,6 +912,8 @@ struct KinSolver {
     if (lane == 0) { at(L::DX + 0, 0) = d0; at(L::DX + 1, 0) = d1; at(L::DX + 2, 0) = d2; at(L::DX + 3, 0) = d3; }
     #pragma unroll 1
     for (int k = 0; k < N; k++) {
+      expect(L::KX, 14, k, TAG_GAINS);
+      expect(L::CDEF, NX, k + 1, TAG_DEFECT);
       const double ud = at(L::KK + 0, k) + at(L::KX + 0, k) * d0 + at(L::KX + 1, k) * d1 + at(L::KX + 2, k) * d2 + at(L::KX + 3, k) * d3 +
                         at(L::KW + 0, k) * vd + at(L::KW + 1, k) * va;
       const double ua = at(L::KK + 1, k) + at(L::KX + 4, k) * d0 + at(L::KX + 5, k) * d1 + at(L::KX + 6, k) * d2 + at(L::KX + 7, k) * d3 +
@@ -910,12 +953,14 @@ struct KinSolver {
         r3 += h03 * d0 + h13 * d1;
       }
       at(L::LAMP + 0, k) = r0; at(L::LAMP + 1, k) = r1; at(L::LAMP + 2, k) = r2; at(L::LAMP + 3, k) = r3;
+      own(L::LAMP, NX, k, TAG_NEWLAM);
     }
     __syncwarp();
     double l0 = -at(L::LAMP + 0, N), l1 = -at(L::LAMP + 1, N), l2 = -at(L::LAMP + 2, N), l3 = -at(L::LAMP + 3, N);
     if (lane == 0) { at(L::LAMP + 0, N) = l0; at(L::LAMP + 1, N) = l1; at(L::LAMP + 2, N) = l2; at(L::LAMP + 3, N) = l3; }
     #pragma unroll 1
     for (int k = N - 1; k >= 0; k--) {
+      expect(L::LAMP, NX, k, TAG_NEWLAM);
       const double n0 = l0 - at(L::LAMP + 0, k);
       const double n1 = l1 - at(L::LAMP + 1, k);
       const double n2 = l2 + at(L::JAC + 0, k) * l0 + at(L::JAC + 2, k) * l1 - at(L::LAMP + 2, k);
@@ -1035,11 +1080,11 @@ struct KinSolver {
       // the gains of this stage are dead (forward sweep done): reuse their slots
       if (has_rate(k)) {
 #pragma unroll
-        for (int r = 0; r < NR; r++) { at(L::DSR + r, k) = dsr[r]; at(L::LRP + r, k) = lrp[r]; }
+        for (int r = 0; r < NR; r++) { at(L::DSR + r, k) = dsr[r]; at(L::LRP + r, k) = lrp[r]; own(L::DSR + r, 1, k, TAG_STEPS); own(L::LRP + r, 1, k, TAG_STEPS); }
       }
       if (has_obs(k)) {
 #pragma unroll
-        for (int j = 0; j < MO; j++) { at(L::DSO + j, k) = dso[j]; at(L::LOP + j, k) = lop[j]; }
+        for (int j = 0; j < MO; j++) { at(L::DSO + j, k) = dso[j]; at(L::LOP + j, k) = lop[j]; own(L::DSO + j, 1, k, TAG_STEPS); own(L::LOP + j, 1, k, TAG_STEPS); }
       }
     }
 #undef MPCB_LOWER
@@ -1057,11 +1102,14 @@ struct KinSolver {
     #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
 #pragma unroll
+      expect(L::LAMP, NX, k, p.debug_selftest ? TAG_GAINS : TAG_NEWLAM);
+      expect(L::CDEFT, NX, k, TAG_TRIALDEF);
       for (int i = 0; i < NX; i++) {
         double l = at(L::LAM + i, k);
         at(L::LAM + i, k) = l + a * (at(L::LAMP + i, k) - l);
         at(L::CDEF + i, k) = at(L::CDEFT + i, k);  // LAMP aliases CDEF: consumed just above
       }
+      own(L::CDEF, NX, k, TAG_DEFECT);
 #pragma unroll
       for (int b = 0; b < NBX; b++) {
         int i = KinModel::bx(b);
@@ -1091,6 +1139,8 @@ struct KinSolver {
       if (has_rate(k)) {
 #pragma unroll
         for (int r = 0; r < NR; r++) {
+          expect(L::DSR + r, 1, k, TAG_STEPS);
+          expect(L::LRP + r, 1, k, TAG_STEPS);
           double s = at(L::SR + r, k), ds = at(L::DSR + r, k);
           double rl = fast_rcp(s - p.rate_lo[r]), rh = fast_rcp(p.rate_hi[r] - s);
           double vl = at(L::VLR + r, k), vu = at(L::VUR + r, k);
@@ -1106,6 +1156,8 @@ struct KinSolver {
       if (has_obs(k)) {
 #pragma unroll
         for (int j = 0; j < MO; j++) {
+          expect(L::DSO + j, 1, k, TAG_STEPS);
+          expect(L::LOP + j, 1, k, TAG_STEPS);
           double s = at(L::SO + j, k), ds = at(L::DSO + j, k);
           double rg = fast_rcp(s - p.obs_lo), vl = at(L::VLO + j, k);
           double dvl = -vl + (mu - vl * ds) * rg;

@@ -271,6 +271,12 @@ class BatchSolver:
             _lib.check(self.lib.mpcb_set_trace_buffer(self._h, C.c_void_p(trace.data_ptr()), int(trace.shape[1])), "mpcb_set_trace_buffer")
             self._trace = trace  # keep it alive
 
+    def debug_slot_errors(self) -> int:
+        """Slot-ownership violations counted by a -DMPCB_DEBUG_SLOTS build (mpcb_debug_slot_errors); -1 otherwise."""
+        n = C.c_int(0)
+        _lib.check(self.lib.mpcb_debug_slot_errors(self._h, C.byref(n)), "mpcb_debug_slot_errors")
+        return int(n.value)
+
     def launch_info(self) -> dict:
         info = _lib.MpcbLaunchInfo()
         _lib.check(self.lib.mpcb_get_launch_info(self._h, C.byref(info)), "mpcb_get_launch_info")

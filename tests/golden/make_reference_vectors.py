@@ -104,6 +104,65 @@ def kkt_at_oracle_solution(rec, kind, x0, xs, obstacles, lbg, ubg, lbx, ubx):
             "g_violation": viol_g, "x_violation": viol_x, "complementarity_scaled": float(r.obj_scale * compl), "iters": r.iters}
 
 
+def _dense_job(args):
+    """one dense interior-point solve of the restated NLP (worker of kkt_batch)"""
+    kind, x0, xs, obstacles = args
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle import ipm_dense
+    from oracle.nlp import NLP
+
+    from threadpoolctl import threadpool_limits
+
+    nlp = NLP(kind, x0, xs, obstacles)
+    with threadpool_limits(1):  # one BLAS thread per worker: the pool already uses every core
+        r = ipm_dense.solve(nlp, nlp.rollout_start(), ipm_dense.IpmOptions())
+    return r.status, r.z, r.f, np.concatenate([r.lam_eq, r.lam_in])[nlp.g_perm()], r.zl, r.zu, r.obj_scale
+
+
+def kkt_batch(rec, kind, x0_draws, xs, obstacles, lbg, ubg, want=64):
+    """`kkt_at_oracle_solution` for many start states: the parameter vector p = [x0; xs] is symbolic in the recorded NLP,
+    so one set of exact derivatives serves every x0.  The first `want` draws whose dense solve converges are kept; for
+    each, the KKT residuals of the oracle's point ON THE REFERENCE'S EXPRESSIONS are recorded next to the point."""
+    from concurrent.futures import ProcessPoolExecutor
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle.nlp import NLP
+
+    xsym = list(rec.prob["x"].a.reshape(-1, order="F"))
+    psym = list(rec.prob["p"].a.reshape(-1, order="F"))
+    pos = {v: i for i, v in enumerate(xsym)}
+    f = rec.prob["f"].a.reshape(-1)[0]
+    g = list(rec.prob["g"].a.reshape(-1, order="F"))
+    entries, exprs = [], [f] + g
+    for row, e in enumerate(exprs):
+        for v in sorted(sp.sympify(e).free_symbols & set(xsym), key=lambda q: pos[q]):
+            entries.append((row, pos[v], sp.diff(e, v)))
+    fun = sp.lambdify([xsym, psym], [e for _, _, e in entries] + exprs, "math", cse=True)
+    nv, ng = len(xsym), len(g)
+    with ProcessPoolExecutor(os.cpu_count()) as ex:
+        sols = list(ex.map(_dense_job, [(kind, x0, xs, obstacles) for x0 in x0_draws]))
+    nlp0 = NLP(kind, x0_draws[0], xs, obstacles)
+    lo, hi = (np.full(ng, float(lbg)), np.full(ng, float(ubg))) if np.isscalar(lbg) else nlp0.lbg_ubg_aligned()
+    keep = {k: [] for k in ("x0", "z", "f_ref", "stationarity_scaled", "g_violation", "complementarity_scaled")}
+    for x0, (status, z, fo, lam_g, zl, zu, osc) in zip(x0_draws, sols):
+        if status != 0 or len(keep["x0"]) >= want:
+            continue
+        pvec = np.concatenate([np.asarray(x0, float), np.asarray(xs, float)])
+        vals = fun(list(z), list(pvec))
+        J = np.zeros((1 + ng, nv))
+        for (row, col, _), v in zip(entries, vals[:len(entries)]):
+            J[row, col] = float(v)
+        fval, gval = float(vals[len(entries)]), np.array([float(v) for v in vals[len(entries) + 1:]])
+        stat = J[0] + J[1:].T @ lam_g - zl + zu
+        act = np.minimum(gval - lo, hi - gval)
+        keep["x0"].append(np.asarray(x0, float)); keep["z"].append(z); keep["f_ref"].append(fval)
+        keep["stationarity_scaled"].append(float(osc * np.max(np.abs(stat))))
+        keep["g_violation"].append(float(max(np.max(lo - gval), np.max(gval - hi), 0.0)))
+        keep["complementarity_scaled"].append(float(osc * np.max(np.abs(lam_g) * np.where(np.isfinite(act), act, 0.0) * (lo != hi))))
+        assert abs(fval - fo) <= 1e-12 * abs(fval)
+    assert len(keep["x0"]) >= want, (kind, len(keep["x0"]))
+    return {k: np.array(v) for k, v in keep.items()}
+
+
 def rollout_points(mod, nx, N, x0, xs, rng):
     """z near an Euler roll-out (keeps the dyn sqrt rows real), p = [x0; xs] perturbed"""
     Z, P = [], []
@@ -146,6 +205,10 @@ if __name__ == "__main__":
     rec1 = mpc.optimize_problem(np.array(x0).reshape(-1, 1), ref, one)
     l1 = mpc.initialize_constraints(one)
     out.update({f"kin_kkt_{k}": v for k, v in kkt_at_oracle_solution(rec1, "kin_cbf", x0, xs, one, *l1).items()})
+    # 64 more start states per NLP (own generator: the draws above stay what they were)
+    rng64 = np.random.default_rng(20261019)
+    kin_draws = [np.array([rng64.uniform(0, 20), rng64.uniform(0, 4.5), rng64.uniform(-0.05, 0.05), rng64.uniform(10, 25)]) for _ in range(160)]
+    out.update({f"kin_kkt64_{k}": v for k, v in kkt_batch(rec1, "kin_cbf", kin_draws, xs, one, l1[0], l1[1]).items()})
     # the quintic lane-change reference (:258-308), unused by the mains
     gr_in, gr_out = [], []
     for a, b in [([0, 3, 0, 15], [400, 3.5, 0, 30]), ([12.5, 0.2, 0.01, 22], [400, 3.5, 0, 25]), ([100, 4.0, 0, 8], [600, 0.0, 0, 12])]:
@@ -173,6 +236,7 @@ if __name__ == "__main__":
     rec1 = mpc.optimize_problem(np.array(x0).reshape(-1, 1), ref, tr1)
     l1 = mpc.initialize_constraints(obs_list[:1])
     out.update({f"pre_kkt_{k}": v for k, v in kkt_at_oracle_solution(rec1, "kin_cbf_pre", x0, xs, tr1, *l1).items()})
+    out.update({f"pre_kkt64_{k}": v for k, v in kkt_batch(rec1, "kin_cbf_pre", kin_draws, xs, tr1, l1[0], l1[1]).items()})
 
     # ---------------- dyn (PKG/main_cbf_dyn_c_sim.py:44-51,77,89): the module reads `Veh_w`, which the
     # shipped YAML spells `Veh_W`: run it from a copy with the key added
@@ -191,6 +255,8 @@ if __name__ == "__main__":
     out.update(dyn_z=Z, dyn_p=P, dyn_f=F, dyn_g=G, dyn_lbg=np.array(lbg, float), dyn_ubg=np.array(ubg, float),
                dyn_lbx=np.array(lbx, float), dyn_ubx=np.array(ubx, float), dyn_obs=obsd, dyn_opts=json.dumps(rec.opts))
     out.update({f"dyn_kkt_{k}": v for k, v in kkt_at_oracle_solution(rec, "dyn", x0d, xsd, obsd, lbg, ubg, lbx, ubx).items()})
+    dyn_draws = [np.array([rng64.uniform(0, 20), rng64.uniform(-0.5, 4.5), rng64.uniform(-0.05, 0.05), rng64.uniform(8, 20), 0.0, 0.0]) for _ in range(110)]
+    out.update({f"dyn_kkt64_{k}": v for k, v in kkt_batch(rec, "dyn", dyn_draws, xsd, obsd, lbg, ubg).items()})
     xq, uq = np.array([1.0, 0.5, 0.02, 12.0, 0.3, 0.05]), np.array([0.03, 1.2])
     out.update(dyn_rhs_in=np.concatenate([xq, uq]), dyn_rhs_out=mpc.f(xq, uq).full().ravel())
     shutil.rmtree(tmp)
@@ -223,6 +289,7 @@ if __name__ == "__main__":
                nocbf_lbx=np.array(lbx, float), nocbf_ubx=np.array(ubx, float), nocbf_opts=json.dumps(rec.opts),
                nocbf_attrs=json.dumps({k: v for k, v in vars(me).items() if isinstance(v, (int, float, str, bool))}))
     out.update({f"nocbf_kkt_{k}": v for k, v in kkt_at_oracle_solution(rec, "kin_nocbf", x0n, xsn, None, lbg, ubg, lbx, ubx).items()})
+    out.update({f"nocbf_kkt64_{k}": v for k, v in kkt_batch(rec, "kin_nocbf", kin_draws[:64], xsn, None, lbg, ubg).items()})
     shutil.rmtree(tmp)
     os.chdir(HERE)
 

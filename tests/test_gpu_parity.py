@@ -1144,3 +1144,77 @@ def test_rk4_defects_parity_with_the_oracle_in_rk4_mode(dev, kind, gen, M, B):
     for bad in (dict(kind="dyn"), dict(kind="kin_cbf", engine="warp"), dict(kind="kin_cbf", cbf_gamma=0.5), dict(kind="kin_cbf", restoration=True)):
         with pytest.raises(_lib.MpcbError):
             BatchSolver(bad.pop("kind"), integrator="rk4", **bad)
+
+
+@pytest.mark.parametrize("tag", ["kin", "pre", "dyn", "nocbf"])
+def test_cuda_reaches_64_kkt_points_per_nlp_verified_on_the_reference_expressions(dev, tag):
+    """tests/golden/reference_nlp.npz `*_kkt64_*`: 64 seeded start states per module whose oracle solutions were checked,
+    at generation time, to be KKT points of the NLP the REFERENCE builds (exact sympy derivatives of its own expressions:
+    stationarity and complementarity <= 2e-8 in IPOPT's scaling, rows feasible to bound_relax_factor).  The CUDA path must
+    land on those points."""
+    from test_reference_vectors import KKT64_XS, KKT_CASES, kkt_case_obs
+
+    from mpc_motion_planning_b200.solver import BatchSolver
+
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_nlp.npz"), allow_pickle=True)
+    kind = KKT_CASES[tag][0]
+    x0 = ref[f"{tag}_kkt64_x0"]
+    B = x0.shape[0]
+    xs = np.tile(np.array(KKT64_XS[tag], float), (B, 1))
+    obs = kkt_case_obs(ref, tag)
+    ob = np.zeros((B, 0, 51, 6)) if obs is None else np.tile(obs[None], (B, 1, 1, 1))
+    g = _gpu(BatchSolver(kind), dev, x0, xs, ob, return_z=True)
+    ok = g["status"] == 0
+    print(f"{tag}: {ok.sum()} of {B} converged; worst |dz| {np.abs(g['z'][ok] - ref[f'{tag}_kkt64_z'][ok]).max():.2e}")
+    assert ok.sum() >= 62
+    assert np.abs(g["z"][ok] - ref[f"{tag}_kkt64_z"][ok]).max() <= 1e-5
+    assert np.abs(g["u0"][ok] - ref[f"{tag}_kkt64_z"][ok][:, :2]).max() <= U0_ATOL
+    fr = ref[f"{tag}_kkt64_f_ref"][ok]
+    assert (np.abs(g["cost"][ok] - fr) / np.abs(fr)).max() <= COST_RTOL
+
+
+# --------------------------------------------------------------------------- sanitizer substitute
+_SLOT_CHECK = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from mpc_motion_planning_b200 import scenarios
+from mpc_motion_planning_b200.solver import BatchSolver
+dev = torch.device("cuda:0")
+t = lambda a: None if a is None or a.shape[1] == 0 else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+total = 0
+for kind, gen, kw, B in (("kin_nocbf", "kin_nocbf", {}, 300), ("kin_cbf", "kin_cbf_static", {}, 3000), ("kin_cbf", "kin_cbf_static", {}, 200),
+                         ("kin_cbf_pre", "kin_cbf_moving", dict(cbf_gamma=0.5), 600), ("kin_cbf_pre", "kin_cbf_moving", dict(N=100), 300),
+                         ("kin_cbf", "kin_cbf_static", dict(restoration=True, resto_max_calls=0), 1500)):
+    x0, xs, obs = getattr(scenarios, gen)(B, **({"N": kw["N"]} if "N" in kw else {}))
+    s = BatchSolver(kind, engine="warp", **kw)
+    out = s.solve(t(x0), t(xs), t(obs))
+    torch.cuda.synchronize()
+    n = s.debug_slot_errors()
+    assert n >= 0, "not a -DMPCB_DEBUG_SLOTS build"
+    print(kind, kw, B, "converged", int((out["status"] <= 1).sum()), "slot errors", n)
+    total += n
+print("TOTAL", total)
+"""
+
+
+def test_debug_build_sees_no_slot_ownership_violation(dev):
+    """compute-sanitizer is closed on this pool; libmpcb200_debug.so (-DMPCB_DEBUG_SLOTS) tags every store into the aliased
+    shared-memory slots (LAMP over CDEF; [HUU EE GU TK] -> gains -> slack steps / trial defects) and checks the tag at every
+    load.  One solve per kernel family (persistent, small-batch all-shared, discrete-CBF, long-horizon layout, restoration
+    sibling) must report zero violations - and the checker must trip when an expectation is made wrong on purpose."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "mpc_motion_planning_b200", "libmpcb200_debug.so")
+    if not os.path.exists(so):
+        pytest.skip("libmpcb200_debug.so not built (python -m mpc_motion_planning_b200.build --debug-slots)")
+    env = dict(os.environ, MPCB200_LIB=so)
+    out = subprocess.run([sys.executable, "-c", _SLOT_CHECK % root], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    print(out.stdout)
+    assert "TOTAL 0" in out.stdout, out.stdout[-2000:]
+    env["MPCB_DEBUG_SLOTS_SELFTEST"] = "1"
+    out = subprocess.run([sys.executable, "-c", _SLOT_CHECK % root], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "TOTAL 0" not in out.stdout and "TOTAL" in out.stdout, out.stdout[-2000:]

@@ -194,6 +194,33 @@ def test_oracle_solutions_are_kkt_points_of_the_reference_nlp(ref, tag):
     assert np.max(np.abs(z - ref[f"{tag}_kkt_z"])) <= 1e-7 and abs(info.f - k("f_ref")) <= 1e-10 * k("f_ref")
 
 
+KKT64_XS = {"kin": [400, 3.5, 0, 30.0], "pre": [400, 3.5, 0, 30.0], "dyn": [600, 3.5, 0, 15, 0, 0.0], "nocbf": [500, 3.5, 0, 30.0]}
+
+
+@pytest.mark.parametrize("tag", ["kin", "pre", "dyn", "nocbf"])
+def test_64_start_states_per_nlp_end_at_kkt_points_of_the_reference_nlp(ref, tag):
+    """64 seeded start states per module (the parameter vector is symbolic in the recorded NLP, so one set of exact sympy
+    derivatives of the REFERENCE'S expressions serves them all): recorded residuals of the oracle's points, and the C
+    oracle reaching the same points."""
+    from oracle import c_oracle
+
+    k = lambda n: ref[f"{tag}_kkt64_{n}"]
+    assert k("x0").shape[0] == 64
+    assert k("stationarity_scaled").max() <= 2e-8 and k("complementarity_scaled").max() <= 2e-8  # IPOPT's tol 1e-8 on its scaled error
+    assert k("g_violation").max() <= 1.01e-8
+    kind = KKT_CASES[tag][0]
+    cfg = c_oracle.make_cfg(kind)
+    obs = kkt_case_obs(ref, tag)
+    B = 64
+    xs = np.tile(np.array(KKT64_XS[tag], float), (B, 1))
+    ob = None if obs is None else np.tile(obs[None], (B, 1, 1, 1))
+    u0, cost, st, it, z = c_oracle.solve_batch(cfg, k("x0"), xs, ob, want_z=True, nthreads=os.cpu_count())
+    ok = st == 0
+    assert ok.sum() >= 62  # the dense specification converged on all 64; the Riccati form may leave the chaotic one or two
+    assert np.abs(z[ok] - k("z")[ok]).max() <= 1e-6
+    assert (np.abs(cost[ok] - k("f_ref")[ok]) / np.abs(k("f_ref")[ok])).max() <= 1e-9
+
+
 def test_dyn_problem_as_shipped_at_oracle_level(ref):
     """The dyn bound lists exactly as shipped define a different problem:
     every rate row becomes an equality (one control pair for the whole horizon) and the x/y defects of
