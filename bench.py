@@ -106,6 +106,14 @@ def make_batch(rank: int, B: int):
     return scenarios.kin_cbf_static(B, N=N_HORIZON, seed=scenarios.BASE_SEED + 2 + 1000 * rank)
 
 
+def bench_config(world: int, B: int) -> dict:
+    """`config` of the JSON line - the same dict for this repo's arm and for the CPU reference arm"""
+    return {"workload": f"kin-CBF static obstacle MPC, N={N_HORIZON}, M=1, B={B}/GPU (BASELINE configs[1])",
+            "start": "zero controls, Euler roll-out states", "mu_init": 30.0, "tol": 1e-8, "max_iter": 100,
+            "inputs": "x0 [B][4], xs [B][4], obstacle rows [B][1][6] as optimize_problem takes them",
+            "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"scenario-sharded x{world} (solve_sharded)", "restoration": "off"}
+
+
 def _stats(status, iters):
     return {"success_frac": float((status <= 1).mean()), "mean_iters": float(iters.mean()), "p99_iters": float(np.percentile(iters, 99)),
             "status_counts": np.bincount(status, minlength=6).tolist()}
@@ -248,8 +256,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"kin-CBF static obstacle MPC, N={N_HORIZON}, M=1, B={B_PER_GPU}/GPU (BASELINE configs[1])",
-                   "sample_per_step": sample, "start": "zero controls, Euler roll-out states"},
+        "config": bench_config(args.gpus, B_PER_GPU),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"first {sample} scenarios of the workload per step, restated CPU IPM (oracle/mpc_oracle.c), not CasADi+IPOPT"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -505,10 +512,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"kin-CBF static obstacle MPC, N={N_HORIZON}, M=1, B={B}/GPU (BASELINE configs[1])",
-                       "start": "zero controls, Euler roll-out states", "mu_init": float(solver.cfg.mu_init), "tol": 1e-8, "max_iter": 100,
-                       "inputs": "x0 [B][4], xs [B][4], obstacle rows [B][1][6] as optimize_problem takes them",
-                       "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"scenario-sharded x{world} (solve_sharded)", "restoration": "off"},
+            "config": bench_config(world, B),
             "solver": {"converged_frac": float((status_all <= 1).mean()), "acceptable_frac": float((status_all == 1).mean()),
                        "mean_iters": float(iters_all.mean()), "p99_iters": float(np.percentile(iters_all, 99)),
                        "status_counts": np.bincount(status_all, minlength=6).tolist(),

@@ -158,11 +158,14 @@ struct LaneSolver {
 #ifndef MPCB_LANE_PF_DIST
 #define MPCB_LANE_PF_DIST 0  // measured: 2 stages ahead costs 9 % at full occupancy and buys 20 % at 4 warps per SM (profiles/experiments)
 #endif
+#ifndef MPCB_LANE_PF_INSTR
+#define MPCB_LANE_PF_INSTR "prefetch.global.L2"
+#endif
   template <int F0, int CNT>
   __device__ __forceinline__ void pf(int k) {
     if (MPCB_LANE_PF_DIST > 0 && k >= 0 && k <= N) {
 #pragma unroll
-      for (int f = 0; f < CNT; f++) asm volatile("prefetch.global.L1 [%0];" ::"l"(&at(F0 + f, k)));
+      for (int f = 0; f < CNT; f++) asm volatile(MPCB_LANE_PF_INSTR " [%0];" ::"l"(&at(F0 + f, k)));
     }
   }
   __device__ __forceinline__ bool has_rate(int k) const { return NR > 0 && k >= 1 && k <= N - 1; }
