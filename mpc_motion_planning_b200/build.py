@@ -28,6 +28,7 @@ def stale() -> bool:
 
 
 SO_DEBUG = os.path.join(HERE, "libmpcb200_debug.so")
+DEBUG_FAMILIES = (0, 2, 5)
 
 
 def build_debug_slots() -> str:
@@ -38,9 +39,13 @@ def build_debug_slots() -> str:
     nvcc = os.environ.get("NVCC", "nvcc")
     flags = NVCC_FLAGS + ["-DMPCB_DEBUG_SLOTS"]
     os.makedirs(OBJ, exist_ok=True)
+    # only the families the checker test exercises are recompiled (row-free, rate row + one obstacle, discrete-CBF rows);
+    # the other families and the lane engine (no aliased slots) are linked from the regular objects - KParams is the same
+    build()
     jobs = [(os.path.join(HERE, "csrc", "mpcb_api.cu"), os.path.join(OBJ, "dbg_api.o"), [])]
-    jobs += [(os.path.join(HERE, "csrc", "mpcb_variants.cu"), os.path.join(OBJ, f"dbg_family{k}.o"), [f"-DMPCB_FAMILY={k}"]) for k in range(N_FAMILIES)]
-    jobs += [(os.path.join(HERE, "csrc", "mpcb_lane.cu"), os.path.join(OBJ, f"dbg_lane{k}.o"), [f"-DMPCB_LANE_FAMILY={k}"]) for k in range(N_LANE_FAMILIES)]
+    jobs += [(os.path.join(HERE, "csrc", "mpcb_variants.cu"), os.path.join(OBJ, f"dbg_family{k}.o"), [f"-DMPCB_FAMILY={k}"]) for k in DEBUG_FAMILIES]
+    regular = [os.path.join(OBJ, f"family{k}.o") for k in range(N_FAMILIES) if k not in DEBUG_FAMILIES]
+    regular += [os.path.join(OBJ, f"lane{k}.o") for k in range(N_LANE_FAMILIES)]
 
     def compile_one(job):
         src, obj, defs = job
@@ -52,7 +57,7 @@ def build_debug_slots() -> str:
         if r.returncode != 0:
             sys.stderr.write(f"---- nvcc {' '.join(defs)} {os.path.basename(src)}\n{r.stdout}{r.stderr}")
             raise subprocess.CalledProcessError(r.returncode, r.args)
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_DEBUG] + [obj for _, obj, _ in jobs], cwd=HERE)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_DEBUG] + [obj for _, obj, _ in jobs] + regular, cwd=HERE)
     return SO_DEBUG
 
 
