@@ -155,6 +155,42 @@ def protocol_legs(dev, x0, xs, obs, K):
     return legs
 
 
+def engine_legs(dev, peak_tflops):
+    """The two engines side by side at 100,000 scenarios (one GPU): the row-free kinematic family (BASELINE configs[0]'s NLP),
+    where the lanes of a warp do not diverge and MPCB_ENGINE_AUTO picks the lane engine, and the kin-CBF moving-obstacle
+    family (configs[2]), where it stays on the warp engine.  Algorithmic flops per iteration from SURVEY.md section 8d."""
+    import torch
+
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+
+    out = {}
+    B = 100000
+    for kind, gen, flop_it in (("kin_nocbf", scenarios.kin_nocbf, 69.8e3), ("kin_cbf_pre", scenarios.kin_cbf_moving, 72.4e3)):
+        x0, xs, obs = gen(B)
+        a, b_ = torch.from_numpy(x0).to(dev), torch.from_numpy(xs).to(dev)
+        c = torch.from_numpy(obs).to(dev) if obs.shape[1] else None
+        for engine in ("warp", "lane"):
+            s = BatchSolver(kind, engine=engine)
+            s.solve(a[:20000], b_[:20000], None if c is None else c[:20000])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            o = s.solve(a, b_, c)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            it = o["iters"].cpu().numpy()
+            tf = float(it.sum()) * flop_it / (ms * 1e-3) / 1e12
+            out[f"{kind}_B100k_{engine}"] = {"value": B / ms * 1e3, "unit": UNIT, "ms": ms, "mean_iters": float(it.mean()),
+                                             "success_frac": float((o["status"].cpu().numpy() <= 1).mean()),
+                                             "fp64_tflops": tf, "roofline_frac": tf / peak_tflops if peak_tflops > 0 else None}
+            s.close()
+        del a, b_, c
+        torch.cuda.empty_cache()
+    return out
+
+
 def configs4_sweep(dev, world, rank, dist):
     """BASELINE.json configs[4]: kin-CBF moving-obstacle MPC, N in {20, 50, 100}, 4M / 4M / 2M scenarios sharded over the
     GPUs (strong scaling: the totals are fixed).  Obstacle states go in as [B][1][6] (prediction on the device); the shard is
@@ -487,6 +523,12 @@ def main():
     legs = None
     if world == 1 and not args.no_legs:
         legs = protocol_legs(dev, dx0, dxs, dobs, max(2, min(K, 3)))
+    engines = None
+    if world == 1 and not args.no_legs:
+        import ctypes as C0
+        pk = C0.c_double(0.0)
+        _lib.check(_lib.load().mpcb_fp64_peak_tflops(C0.byref(pk)), "fp64 peak")
+        engines = engine_legs(dev, float(pk.value))
     # ---- BASELINE configs[4]: horizon sweep, 4M / 4M / 2M scenarios sharded over the GPUs (all ranks take part)
     sweep = None
     if not args.no_sweep:
@@ -525,6 +567,7 @@ def main():
                          "gather_and_bookkeeping_ms": round(total_ms / K - max(rank_solve_ms), 3),
                          "same_shard_on_every_rank_ms": same_ms},
             "protocol": legs,
+            "engines": engines,
             "configs4": sweep,
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
