@@ -146,6 +146,7 @@ struct mpcb_handle {
   double *d_lane_ws;
   size_t lane_nslot;
   int lane_grid, lane_min_B;
+  bool lane_forced;  // cfg.engine = LANE or cfg.integrator = RK4: never fall back to the warp kernels
   mpcb_launch_info lane_info;
   int *d_debug_errors;  // -DMPCB_DEBUG_SLOTS builds: slot-ownership violations seen by the kernels
 };
@@ -332,6 +333,7 @@ int mpcb_create(const mpcb_cfg *cfg, mpcb_handle **out) {
         h->lane = lv;
         h->lane_grid = lb * prop.multiProcessorCount;
         h->lane_nslot = (size_t)h->lane_grid * lv.block;
+        h->lane_forced = engine == MPCB_ENGINE_LANE;
         h->lane_min_B = engine == MPCB_ENGINE_LANE ? 1 : (getenv("MPCB_LANE_MIN_B") ? atoi(getenv("MPCB_LANE_MIN_B")) : MPCB_LANE_MIN_B_DEFAULT);
         size_t bytes = h->lane_nslot * lv.slot_doubles(c.N) * sizeof(double);
         if (!cuda_ok(cudaMalloc(&h->d_lane_ws, bytes), "cudaMalloc lane workspace")) { mpcb_destroy(h); return MPCB_E_NOMEM; }
@@ -442,7 +444,7 @@ int mpcb_solve_batch(mpcb_handle *h, int B, const double *x0, const double *xs, 
   cudaError_t e;
   static const int lat_force = getenv("MPCB_LAT_MAX_B") ? atoi(getenv("MPCB_LAT_MAX_B")) : 0;  // tuning knob
   const bool small_batch = h->lat_grid && (B <= h->lat_grid * h->var.lat_warps || B <= lat_force);
-  const bool lane_engine = h->d_lane_ws && B >= h->lane_min_B && !k.trace;
+  const bool lane_engine = h->d_lane_ws && B >= h->lane_min_B && (!k.trace || h->lane_forced);  // (the lane kernel writes no trace)
   int main_warps = 0;
   if (lane_engine) {
     // one scenario per lane: the lanes of the resident grid pull scenarios from the queue
@@ -601,6 +603,7 @@ int mpcb_set_order(mpcb_handle *h, const int32_t *order, int n) {
 
 int mpcb_set_trace_buffer(mpcb_handle *h, double *trace, int rows) {
   if (!h || rows < 0) return MPCB_E_ARG;
+  if (h->lane_forced && rows > 0) return MPCB_E_ARG;  // the per-iteration log exists in the warp kernels only
   h->kp.trace = rows > 0 ? trace : nullptr;
   h->kp.trace_rows = rows;
   return MPCB_OK;
