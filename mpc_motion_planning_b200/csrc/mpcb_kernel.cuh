@@ -1426,8 +1426,11 @@ struct KinSolver {
 #ifndef MPCB_KIN_RESIDENT_WARPS
 #define MPCB_KIN_RESIDENT_WARPS 12  // register budget: 65536 / (12 * 32) = 170 registers per thread
 #endif
+#ifndef MPCB_RS_INLINE_BOUNDS
+#define MPCB_RS_INLINE_BOUNDS 0  // 1 with -DMPCB_RS_INLINE=1: the restoration-capable kernels ARE the main kernels and keep the register cap
+#endif
 template <int NR, int MO, int OBS_MODE, int W, bool GS, bool AS = false, bool RS = false>
-__global__ void __launch_bounds__(32 * W, AS ? 1 : MPCB_KIN_RESIDENT_WARPS / W) kin_solve_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(32 * W, (AS || (RS && !MPCB_RS_INLINE_BOUNDS)) ? 1 : MPCB_KIN_RESIDENT_WARPS / W) kin_solve_kernel(const __grid_constant__ KParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   using L = KinLayout<NR, MO, OBS_MODE == 3, GS, AS, RS>;
   double *gs = AS ? nullptr : p.slab + ((size_t)blockIdx.x * W + warp) * L::slab_doubles();
