@@ -1218,3 +1218,34 @@ def test_debug_build_sees_no_slot_ownership_violation(dev):
     out = subprocess.run([sys.executable, "-c", _SLOT_CHECK % root], env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-3000:]
     assert "TOTAL 0" not in out.stdout and "TOTAL" in out.stdout, out.stdout[-2000:]
+
+
+# --------------------------------------------------------------------------- the reference's literal first guess
+@pytest.mark.parametrize("kind,gen", [("kin_cbf", "kin_cbf_static"), ("kin_cbf_pre", "kin_cbf_moving"), ("kin_nocbf", "kin_nocbf")])
+@pytest.mark.parametrize("mu_init", [30.0, 0.1])
+def test_parity_from_the_all_zero_guess(dev, kind, gen, mu_init):
+    """The reference's literal protocol: `x0=` all zeros, taken as given (PKG/main_cbf_kin_c_sim.py:47-50,92), with this
+    library's mu_init 30 and with IPOPT's default 0.1.  From that guess most random scenarios do not converge within the
+    reference's max_iter = 100 (`bench.py` carries the rates) - what is asserted is that the CUDA path and
+    the oracle agree: same verdicts up to the chaotic handful, the same answers wherever both converge, the same iteration
+    counts."""
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+    from oracle import c_oracle
+
+    B = 768
+    x0, xs, obs = getattr(scenarios, gen)(B)
+    s = BatchSolver(kind, init="as_given", mu_init=mu_init)
+    g = _gpu(s, dev, x0, xs, obs)  # z_init = None: the all-zero guess
+    cfg = c_oracle.make_cfg(kind, init_mode=0, mu_init=mu_init)
+    u0, cost, st, it, _ = c_oracle.solve_batch(cfg, x0, xs, obs if obs.shape[1] else None, nthreads=os.cpu_count())
+    print(f"{kind} mu_init={mu_init}: gpu {np.bincount(g['status'], minlength=6)} oracle {np.bincount(st, minlength=6)} "
+          f"mean iterations {g['iters'].mean():.1f} / {it.mean():.1f}")
+    # from this guess the solves are long (50-85 iterations) and mostly end in a failed line search: more of them sit on the
+    # chaotic boundary than from the roll-out start (measured 2.3 % verdict differences at mu_init 30 on kin-CBF static)
+    both, same = _check(g, u0, cost, st, 0.0, min_same_verdict=0.95)
+    if both.sum() >= 20:
+        assert (g["iters"][both] == it[both]).mean() >= 0.85
+    # the non-converged iterates (which the reference would consume unchecked) are NOT comparable between two
+    # implementations: reported, not asserted
+    print(f"   first controls within 1e-3 on {100 * (np.abs(g['u0'] - u0).max(axis=1) <= 1e-3).mean():.1f} % of ALL scenarios")
