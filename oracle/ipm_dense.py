@@ -497,6 +497,7 @@ def solve(nlp: NLP, z_init=None, opt: IpmOptions | None = None) -> IpmResult:
 
             alpha = a_max
             armijo = False
+            first = True
             z_new = s_new = None
             while alpha >= a_min:
                 zt, st = z + alpha * dz, s + alpha * ds
@@ -511,6 +512,34 @@ def solve(nlp: NLP, z_init=None, opt: IpmOptions | None = None) -> IpmResult:
                 if ok:
                     accepted, armijo, z_new, s_new = True, arm, zt, st
                     break
+                if first and not resto and np.isfinite(tt) and tt >= th and o.max_soc > 0:
+                    # second-order correction (IPOPT max_soc; off by default in this specification: with max_soc = 4 it is
+                    # never accepted on these NLPs, so the Riccati implementations do not carry it)
+                    c_soc, d_soc = alpha * c + ct, alpha * dd + ddt
+                    th_old = th
+                    for _ in range(o.max_soc):
+                        sol2 = kkt_solve(dw, c_soc, d_soc)
+                        if sol2 is None:
+                            break
+                        dz2, ds2, dlc2, dld2 = sol2
+                        a2 = min(_ftb(z, dz2, zL, zU, tau), _ftb(s, ds2, dL, dU, tau) if ni else 1.0)
+                        zt2, st2 = z + a2 * dz2, s + a2 * ds2
+                        with np.errstate(all="ignore"):
+                            tt2, ct2, ddt2 = theta_of(zt2, st2)
+                            pt2 = barrier(zt2, st2, mu) if np.isfinite(tt2) else INF
+                        ok2, arm2 = acceptable(alpha, tt2, pt2)
+                        if ok2:
+                            accepted, armijo, z_new, s_new = True, arm2, zt2, st2
+                            dlc, dld = dlc2, dld2
+                            n_soc += 1
+                            break
+                        if not np.isfinite(tt2) or tt2 > o.kappa_soc * th_old:
+                            break
+                        th_old = tt2
+                        c_soc, d_soc = a2 * c_soc + ct2, a2 * d_soc + ddt2
+                    if accepted:
+                        break
+                first = False
                 alpha *= 0.5
                 n_bt += 1
         if not accepted:

@@ -198,3 +198,19 @@ def test_psi_penalty_derivatives():
         assert np.allclose((d1p - d1m) / (2 * h), d2, rtol=2e-3)
         p_, n_ = mu / (rho - d1), mu / (rho + d1)  # central path: p z_p = mu with z_p = rho - lambda
         assert np.allclose(p_ - n_, r, atol=1e-9 * np.maximum(1, np.abs(r)))
+
+
+def test_second_order_correction_is_never_accepted_on_these_nlps():
+    """The specification carries IPOPT's second-order correction as an option (max_soc); the Riccati implementations do not.
+    The reason is measured here: with IPOPT's default max_soc = 4 no corrected step is ever accepted, and the iterates are the
+    same as without it - on converging scenarios and on one that ends in a line-search failure."""
+    from mpc_motion_planning_b200 import scenarios
+    from oracle import ipm_dense, nlp
+
+    x0, xs, obs = scenarios.kin_cbf_static(40)
+    for b in (0, 8):  # 8 ends with status 3
+        P = nlp.NLP("kin_cbf", x0[b], xs[b], obs[b, :, 0, :])
+        r0 = ipm_dense.solve(P, P.rollout_start(), ipm_dense.IpmOptions())
+        r4 = ipm_dense.solve(P, P.rollout_start(), ipm_dense.IpmOptions(max_soc=4))
+        assert r4.n_soc == 0 and (r0.status, r0.iters) == (r4.status, r4.iters) and np.array_equal(r0.z, r4.z)
+    assert r0.status == 3
