@@ -232,6 +232,17 @@ int mpcb_shift_batch(mpcb_handle *h, int B, double *x0, double *z, void *stream)
 int mpcb_ref_traj_batch(mpcb_handle *h, int B, double T_horizon, const double *x0, const double *xs, const double *path_x0,
                         int32_t *last_idx, double aa, double *ref, double *stage_targets, void *stream);
 
+/* Batched obs_prediction (PKG/Obs_prediction.py:3-40) and the mains' obstacle update on DEVICE buffers:
+ *   obs_state [n_obstacles][6]      rows [x, y, theta, v, l, w] (a [B][M][6] array has n_obstacles = B*M)
+ *   traj      [n_obstacles][N+1][6] or NULL: the constant-velocity roll-out, x += v cos(theta) dt accumulated step by step
+ *                                   in the reference's operation order (:27-28) - the `obs` argument of mpcb_solve_batch
+ *                                   under MPCB_OBS_TRAJECTORY
+ *   advance != 0                    afterwards moves every obstacle one step, in place (PKG/main_cbf_kin_c_sim_pre.py:106:
+ *                                   `obs = [obs_trajectories_dyn[0][1]]`)
+ * With cfg.obs_input = MPCB_OBS_INITIAL the solve kernels run the same recursion themselves; this entry is for callers
+ * that want the trajectories, and for closed loops that only need the update. */
+int mpcb_obs_prediction_batch(mpcb_handle *h, int n_obstacles, double *obs_state, double *traj, int advance, void *stream);
+
 /* Scheduling hint.  The resident warps pull scenarios from a queue; iteration counts differ by 5x
  * between scenarios, so at small batches (a few scenarios per resident warp) the makespan is set by
  * long scenarios that start late.  `order` (DEVICE, [n] permutation of 0..n-1, read by every later

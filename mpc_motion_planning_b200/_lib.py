@@ -58,7 +58,7 @@ class MpcbLaunchInfo(C.Structure):
 EXPORTS = [
     "mpcb_version", "mpcb_strerror", "mpcb_last_cuda_error", "mpcb_nx", "mpcb_nv", "mpcb_create", "mpcb_destroy",
     "mpcb_workspace_bytes", "mpcb_solve_batch", "mpcb_solve_batch_host", "mpcb_submit_batch_host", "mpcb_wait", "mpcb_shift_batch", "mpcb_ref_traj_batch", "mpcb_get_launch_info", "mpcb_fp64_peak_tflops", "mpcb_set_trace_buffer", "mpcb_set_order",
-    "mpcb_reserve", "mpcb_n_g", "mpcb_set_dual_outputs", "mpcb_debug_slot_errors",
+    "mpcb_reserve", "mpcb_n_g", "mpcb_set_dual_outputs", "mpcb_debug_slot_errors", "mpcb_obs_prediction_batch",
 ]
 
 _lib = None
@@ -104,6 +104,7 @@ def load():
     lib.mpcb_n_g.argtypes = [C.POINTER(MpcbCfg)]
     lib.mpcb_set_dual_outputs.argtypes = [vp, dp, dp, C.c_int]
     lib.mpcb_debug_slot_errors.argtypes = [vp, C.POINTER(C.c_int)]
+    lib.mpcb_obs_prediction_batch.argtypes = [vp, C.c_int, dp, dp, C.c_int, vp]
     _lib = lib
     return lib
 

@@ -92,7 +92,7 @@ def _closed_loop_steps(solver, x0, xs, obs_state, steps, moving, disturbance_ste
     x = x0.clone().to(torch.float64).contiguous()
     z = torch.zeros((B, nv), dtype=torch.float64, device=dev)  # zero first guess (PKG/main_cbf_kin_c_sim.py:47-50)
     xs = xs.to(torch.float64).contiguous()
-    obs = None if obs_state is None else obs_state.clone().to(torch.float64)
+    obs = None if obs_state is None else obs_state.clone().to(torch.float64).contiguous()
     xh = [x.clone()]
     uh, sth, ith = [], [], []
     stage_ref = aa is not None and solver.ref_trajectory
@@ -108,8 +108,8 @@ def _closed_loop_steps(solver, x0, xs, obs_state, steps, moving, disturbance_ste
             traj = None
             if obs is not None and solver.obs_initial:
                 traj = obs if moving else torch.cat([obs[..., :3], torch.zeros_like(obs[..., 3:4]), obs[..., 4:]], dim=-1)  # prediction in-kernel
-            elif obs is not None:
-                traj = predict_obstacles(obs, dt, N) if moving else obs[:, :, None, :].repeat(1, 1, N + 1, 1).contiguous()
+            elif obs is not None:  # one kernel: the reference's obs_prediction for the whole fleet
+                traj = solver.predict_obstacles(obs) if moving else obs[:, :, None, :].repeat(1, 1, N + 1, 1).contiguous()
             out = solver.solve(x, target, traj, z, return_z=True)
             z = out["z"]
             if disturbance_step is not None and step == disturbance_step:
@@ -121,8 +121,7 @@ def _closed_loop_steps(solver, x0, xs, obs_state, steps, moving, disturbance_ste
                 solver.set_order(torch.argsort(out["iters"], descending=True, stable=True).to(torch.int32))
             solver.shift(x, z)  # plant Euler step with U_0 and warm-start shift, in place
             if obs is not None and moving:
-                obs[..., 0] = obs[..., 0] + obs[..., 3] * torch.cos(obs[..., 2]) * dt  # main_cbf_kin_c_sim_pre.py:106
-                obs[..., 1] = obs[..., 1] + obs[..., 3] * torch.sin(obs[..., 2]) * dt
+                solver.predict_obstacles(obs, want_traj=False, advance=True)  # main_cbf_kin_c_sim_pre.py:106, in place
             xh.append(x.clone())
             yield step
     finally:

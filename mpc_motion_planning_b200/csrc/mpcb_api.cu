@@ -696,6 +696,42 @@ extern "C" int mpcb_shift_batch(mpcb_handle *h, int B, double *x0, double *z, vo
 }
 
 // ---------------------------------------------------------------------------------------
+// batched obs_prediction (PKG/Obs_prediction.py:3-40) and the mains' obstacle update
+// (PKG/main_cbf_kin_c_sim_pre.py:106: the obstacle becomes row 1 of its own prediction), one thread per obstacle
+// ---------------------------------------------------------------------------------------
+namespace {
+
+__global__ void obs_predict_kernel(int n, int N, double dt, double *state, double *traj, int advance) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double *o = state + (size_t)i * 6;
+  const double th = o[2], v = o[3], l = o[4], w = o[5];
+  // x + v cos(theta) dt, step by step, in the reference's operation order (:27-28)
+  const double dx = v * cos(th) * dt, dy = v * sin(th) * dt;
+  double x = o[0], y = o[1];
+  if (traj) {
+    double *t = traj + (size_t)i * (N + 1) * 6;
+    for (int k = 0; k <= N; k++) {
+      t[6 * k + 0] = x; t[6 * k + 1] = y; t[6 * k + 2] = th; t[6 * k + 3] = v; t[6 * k + 4] = l; t[6 * k + 5] = w;
+      x = x + dx;
+      y = y + dy;
+    }
+  }
+  if (advance) { o[0] = o[0] + dx; o[1] = o[1] + dy; }
+}
+
+}  // namespace
+
+extern "C" int mpcb_obs_prediction_batch(mpcb_handle *h, int n_obstacles, double *obs_state, double *traj, int advance, void *stream) {
+  if (!h || n_obstacles < 0 || !obs_state || (!traj && !advance)) return MPCB_E_ARG;
+  if (n_obstacles == 0) return MPCB_OK;
+  obs_predict_kernel<<<(n_obstacles + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_obstacles, h->cfg.N, h->cfg.T, obs_state, traj, advance);
+  if (!cuda_ok(cudaGetLastError(), "obs_predict_kernel launch")) return MPCB_E_CUDA;
+  h->info.launches++;
+  return MPCB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // batched RefPathGenerator (PKG/RefPathGenerator.py:9-59): one thread per scenario
 // ---------------------------------------------------------------------------------------
 namespace {

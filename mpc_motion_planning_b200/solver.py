@@ -224,6 +224,22 @@ class BatchSolver:
             rc = self.lib.mpcb_shift_batch(self._h, B, C.c_void_p(x0.data_ptr()), C.c_void_p(z.data_ptr()), stream)
         _lib.check(rc, "mpcb_shift_batch")
 
+    def predict_obstacles(self, obs_state, want_traj: bool = True, advance: bool = False):
+        """Batched `obs_prediction` on the device (mpcb_obs_prediction_batch; PKG/Obs_prediction.py:3-40): obs_state (B,M,6)
+        float64 CUDA tensor -> (B,M,N+1,6); `advance` then moves the obstacles one step in place, the mains' update
+        (PKG/main_cbf_kin_c_sim_pre.py:106)."""
+        import torch
+
+        assert obs_state.is_cuda and obs_state.dtype == torch.float64 and obs_state.is_contiguous() and obs_state.shape[-1] == 6
+        n = obs_state.numel() // 6
+        traj = torch.empty(tuple(obs_state.shape[:-1]) + (self.N + 1, 6), dtype=torch.float64, device=obs_state.device) if want_traj else None
+        stream = C.c_void_p(torch.cuda.current_stream(obs_state.device).cuda_stream)
+        with torch.cuda.device(obs_state.device):
+            rc = self.lib.mpcb_obs_prediction_batch(self._h, n, C.c_void_p(obs_state.data_ptr()),
+                                                    C.c_void_p(traj.data_ptr()) if traj is not None else None, int(advance), stream)
+        _lib.check(rc, "mpcb_obs_prediction_batch")
+        return traj
+
     def ref_traj(self, x0, xs, path_x0, last_idx, T_horizon: float, aa: float | None = None):
         """Batched `RefPathGenerator.find_ref_traj` on the device (PKG/RefPathGenerator.py:27-59) over the
         implicit straight path of `define_ref_path` (:9-24) that starts at x = path_x0[b].

@@ -349,6 +349,13 @@ def test_batched_closed_loop_matches_oracle_loop(dev):
     t = lambda a: torch.from_numpy(a).to(dev)
     assert np.array_equal(predict_obstacles(t(ob0), 0.1, N).cpu().numpy(), obs_prediction_batch(ob0, 0.1, N))
     s = BatchSolver("kin_cbf_pre")
+    # the library's own batched obs_prediction (one kernel) and the mains' obstacle update: the reference's rows, bit for bit
+    # up to the last ulp of device cos/sin against libm's
+    st0 = t(ob0.copy())
+    tr = s.predict_obstacles(st0, advance=True).cpu().numpy()
+    host = obs_prediction_batch(ob0, 0.1, N)
+    assert np.allclose(tr, host, rtol=0, atol=1e-12) and np.array_equal(tr[..., 2:], host[..., 2:])
+    assert np.allclose(st0.cpu().numpy(), host[:, :, 1, :], rtol=0, atol=1e-12)  # advanced by one step = row 1 of the prediction
     out = run_closed_loop(s, t(x0), t(xs), t(ob0), steps)
     torch.cuda.synchronize()
     xg, ug, stg = out["x"].cpu().numpy(), out["u"].cpu().numpy(), out["status"].cpu().numpy()
