@@ -9,6 +9,8 @@ The solve itself goes through the CUDA library (no CasADi, no CPU fallback).
 """
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 
 from . import _lib
@@ -75,11 +77,15 @@ class _Solver:
         z0 = np.zeros(nv) if x0 is None else np.asarray(x0, dtype=np.float64).reshape(-1)
         if z0.size != nv:
             raise ValueError(f"x0 must have {nv} entries, got {z0.size}")
-        if o.KIND == "dyn" and not np.any(z0[2 * N:]):
+        if o.KIND == "dyn" and o.zero_guess == "reintegrate" and not np.any(z0[2 * N:]):
             # The reference's literal first guess (all states zero, PKG/main_cbf_dyn_c_sim.py:47-50) puts vx at its
-            # lower bound 0, where the tire model's slip angles divide by vx: after the bound push the dynamics
-            # Jacobian has entries of 6e3 per stage and the stage-wise recursion overflows.
-            # The controls of the guess are kept; the states are re-integrated from p[:nx] instead.
+            # lower bound 0, where the tire model's slip angles divide by vx: after the bound push the linearised Euler
+            # map has entries of 630 per stage and the value function of the stage-wise recursion grows by 4e5 per stage -
+            # beyond what FP64 can condense, whatever the scaling.  With `zero_guess =
+            # "reintegrate"` (the default, announced by a warning) the controls of the guess are kept and the states are
+            # re-integrated from p[:nx]; `zero_guess = "as_given"` passes the caller's x0= through untouched.
+            warnings.warn("dyn drop-in: the all-zero state guess is replaced by the Euler roll-out of its controls from p[:nx] "
+                          "(set MPC_optimize.zero_guess = 'as_given' to pass x0= through unchanged)", RuntimeWarning, stacklevel=2)
             z0 = z0.copy()
             X = np.zeros((N + 1, nx))
             X[0] = p[:nx]
@@ -165,6 +171,8 @@ class MPCOptimizeBase:
         self.tol = 1e-8
         self.mu_init = 30.0
         self.init = "as_given"  # the CasADi call starts IPOPT at x0= exactly
+        # dyn module only: what the solver call does with an all-zero STATE guess (see _Solver.__call__)
+        self.zero_guess = "reintegrate"
         # IPOPT answers a failed line search with its restoration phase, as often as it takes (kin-CBF modules)
         self.restoration = True
         self.resto_max_calls = 0

@@ -827,6 +827,34 @@ def test_dyn_drop_in_class_solves_what_it_is_given(dev, tmp_path, monkeypatch):
     assert np.allclose(res["aligned"][1][:2], [0.09392595, 3.0], atol=1e-5)
 
 
+def test_dyn_drop_in_zero_guess_switch(dev, tmp_path, monkeypatch):
+    """The dyn class announces that it re-integrates the reference's all-zero state guess (PKG/main_cbf_dyn_c_sim.py:47-50)
+    and `zero_guess = "as_given"` hands the caller's x0= to the solver untouched: vx = 0 puts the tire model's
+    linearisation out of the range the stage-wise recursion can condense, so that call reports failure, loudly."""
+    import warnings
+
+    monkeypatch.chdir(tmp_path)
+    from mpc_motion_planning_b200 import MPC_CBF_optimize_dyn
+
+    mpc = MPC_CBF_optimize_dyn.MPC_optimize()
+    x0 = np.array([0, 0, 0, 10, 0, 0.0]).reshape(-1, 1)
+    xs = np.array([600, 3.5, 0, 15, 0, 0.0]).reshape(-1, 1)
+    N = mpc.N_p
+    z0 = np.zeros((2 * N + 6 * (N + 1), 1))
+    lbg, ubg, lbx, ubx = mpc.initialize_constraints()
+    solver = mpc.optimize_problem(ego_state=x0, ref_state=xs, obstacle=np.array([100, -3.5]))
+    with pytest.warns(RuntimeWarning, match="all-zero state guess"):
+        r = solver(x0=z0, p=np.concatenate((x0, xs)), lbg=lbg, lbx=lbx, ubg=ubg, ubx=ubx)
+    assert solver.stats()["success"] and abs(float(r["f"]) - 1.7116419462e8) <= 1e-6 * 1.7e8
+    mpc.zero_guess = "as_given"
+    solver = mpc.optimize_problem(ego_state=x0, ref_state=xs, obstacle=np.array([100, -3.5]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        solver(x0=z0, p=np.concatenate((x0, xs)), lbg=lbg, lbx=lbx, ubg=ubg, ubx=ubx)
+    st = solver.stats()
+    assert not st["success"] and st["return_status"] in ("Infeasible_Problem_Detected", "Restoration_Failed", "Maximum_Iterations_Exceeded", "Invalid_Number_Detected")
+
+
 def test_plain_c_example_runs(dev, tmp_path):
     """examples/batch_solve.c: a C program against include/mpcb200.h, no Python in the loop."""
     import subprocess
