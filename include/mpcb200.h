@@ -130,7 +130,7 @@ typedef struct mpcb_cfg {
                            (IPOPT: the phases alternate until max_iter).  Library default 1, drop-in classes 0 */
   int32_t engine;       /* MPCB_ENGINE_AUTO (default), _WARP: one scenario per warp (every family), _LANE: one scenario per
                            lane (kinematic model, plain rows, one target per scenario).  AUTO uses the
-                           lane engine where it measures faster: the families without obstacle rows from 32,768 scenarios up */
+                           lane engine where it measures faster: the families without obstacle rows from 20,480 scenarios up */
   int32_t integrator;   /* MPCB_INTEGRATOR_EULER (default) or MPCB_INTEGRATOR_RK4 */
   int32_t reserved;
 } mpcb_cfg;

@@ -151,12 +151,21 @@ struct LaneSolver {
   __device__ LaneSolver(const KParams &p_, double *ws_, size_t nslot_, size_t slot_)
       : p(p_), ws(ws_), nslot(nslot_), slot(slot_), N(p_.N), S(p_.N + 1) {}
 
-  __device__ __forceinline__ double &at(int f, int k) { return ws[((size_t)f * S + k) * nslot + slot]; }
+#ifndef MPCB_LANE_STAGE_MAJOR
+#define MPCB_LANE_STAGE_MAJOR 1
+#endif
+  __device__ __forceinline__ double &at(int f, int k) {
+    if (MPCB_LANE_STAGE_MAJOR == 2) return ws[(size_t)(slot >> 5) * ((size_t)S * L::NFIELD * 32) + (size_t)(((k * L::NFIELD + f) << 5) + (int)(slot & 31))];
+    return MPCB_LANE_STAGE_MAJOR ? ws[((size_t)k * L::NFIELD + f) * nslot + slot] : ws[((size_t)f * S + k) * nslot + slot];
+  }
   // Software prefetch: the stage loops carry their recursions in registers, but nothing lets the hardware see the next
   // stage's loads early; every phase therefore asks for the lines of the stage PF_DIST ahead (one 256-byte line per
   // field and warp) while it works on the current one.  The kernel uses no shared memory, so L1 holds them.
 #ifndef MPCB_LANE_PF_DIST
 #define MPCB_LANE_PF_DIST 0  // measured: 2 stages ahead costs 9 % at full occupancy and buys 20 % at 4 warps per SM (profiles/experiments)
+#endif
+#ifndef MPCB_LANE_KKT_UNROLL
+#define MPCB_LANE_KKT_UNROLL 1
 #endif
 #ifndef MPCB_LANE_PF_INSTR
 #define MPCB_LANE_PF_INSTR "prefetch.global.L2"
@@ -332,9 +341,12 @@ struct LaneSolver {
       pf<L::OCX, 4 * MO>(k + MPCB_LANE_PF_DIST);
       pf<L::DX, 6 + NR + MO>(k + 1 + MPCB_LANE_PF_DIST);
       double gp = 1.0, uk[2] = {0, 0};
+      double xn_[NX] = {0, 0, 0, 0}, dxn_[NX] = {0, 0, 0, 0};  // (every load of the stage before its first store, see LaneSolver)
       if (k < N) {
 #pragma unroll
         for (int i = 0; i < 2; i++) uk[i] = at(L::U + i, k) + alpha * at(L::DU + i, k);
+#pragma unroll
+        for (int i = 0; i < NX; i++) { xn_[i] = at(L::X + i, k + 1); dxn_[i] = at(L::DX + i, k + 1); }
       }
 #pragma unroll
       for (int b2 = 0; b2 < NBX; b2++) { int i = bx(b2); gp *= (xk[i] - p.x_lo[i]) * (p.x_hi[i] - xk[i]); }
@@ -378,7 +390,7 @@ struct LaneSolver {
         double xn[NX];
 #pragma unroll
         for (int i = 0; i < NX; i++) {
-          xn[i] = at(L::X + i, k + 1) + alpha * at(L::DX + i, k + 1);
+          xn[i] = xn_[i] + alpha * dxn_[i];
           double d = xn[i] - step[i];
           th += fabs(d);
           at(cd + i, k + 1) = d;
@@ -412,7 +424,8 @@ struct LaneSolver {
     double lr_c = 0.0;  // multiplier of the rate row of stage k
 #pragma unroll
     for (int i = 0; i < NX; i++) lam[i] = at(L::LAM + i, 0);
-#pragma unroll 1
+    constexpr int KU = MPCB_LANE_KKT_UNROLL;  // the pass stores nothing: unrolled, the loads of KU stages are in flight together
+#pragma unroll KU
     for (int k = 0; k <= N; k++) {
       pf<L::X, L::OCX - L::X + 4 * MO>(k + 1 + MPCB_LANE_PF_DIST);  // the whole iterate and the obstacle row
       pf<L::CDEF, 8>(k + 1 + MPCB_LANE_PF_DIST);
@@ -528,10 +541,35 @@ struct LaneSolver {
       pf<L::TRG, 2 * L::NJ>(k - 1 - MPCB_LANE_PF_DIST);
       double xk[NX], h[NX] = {dw, dw, dw, dw}, h01 = 0, h23 = 0, hdv = 0, hdd_f = 0, gx[NX] = {0, 0, 0, 0};
       double a02 = 0, a03 = 0, a12 = 0, a13 = 0, a23 = 0, b2 = 0;
+      // every load of the stage first (a store whose value waits for a load would hold back the loads behind it)
+      constexpr int NR1 = NR > 0 ? NR : 1, MO1 = MO > 0 ? MO : 1;
+      double tg_[3] = {0, 0, 0}, zlx_[NBX], zux_[NBX], c_k[NX], lam_k[NX], u_m[2] = {0, 0}, zlu_[2] = {0, 0}, zuu_[2] = {0, 0};
+      double sr_[NR1], vlr_[NR1], vur_[NR1], ocx_[MO1], ocy_[MO1], isx_[MO1], isy_[MO1], so_[MO1], vlo_[MO1], lo_[MO1];
+      const bool rate = has_rate(k), obst = has_obs(k);
 #pragma unroll
-      for (int i = 0; i < NX; i++) xk[i] = at(L::X + i, k);
+      for (int i = 0; i < NX; i++) { xk[i] = at(L::X + i, k); c_k[i] = at(cd + i, k); lam_k[i] = at(L::LAM + i, k); }
+#pragma unroll
+      for (int b_ = 0; b_ < NBX; b_++) { zlx_[b_] = at(L::ZLX + b_, k); zux_[b_] = at(L::ZUX + b_, k); }
       if (k < N) {
-        const double s = at(tg + 0, k), c = at(tg + 1, k), t = at(tg + 2, k);
+#pragma unroll
+        for (int i = 0; i < 3; i++) tg_[i] = at(tg + i, k);
+#pragma unroll
+        for (int i = 0; i < 2; i++) { zlu_[i] = at(L::ZLU + i, k); zuu_[i] = at(L::ZUU + i, k); }
+        if (k >= 1) { u_m[0] = at(L::U + 0, k - 1); u_m[1] = at(L::U + 1, k - 1); }
+      }
+      if (rate) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) { sr_[r] = at(L::SR + r, k); vlr_[r] = at(L::VLR + r, k); vur_[r] = at(L::VUR + r, k); }
+      }
+      if (obst) {
+#pragma unroll
+        for (int j = 0; j < MO; j++) {
+          ocx_[j] = at(L::OCX + j, k); ocy_[j] = at(L::OCY + j, k); isx_[j] = at(L::ISX + j, k); isy_[j] = at(L::ISY + j, k);
+          so_[j] = at(L::SO + j, k); vlo_[j] = at(L::VLO + j, k); lo_[j] = at(L::LO + j, k);
+        }
+      }
+      if (k < N) {
+        const double s = tg_[0], c = tg_[1], t = tg_[2];
         a02 = T * (-xk[3] * s); a03 = T * c; a12 = T * (xk[3] * c); a13 = T * s; a23 = T * (t * rL);
         b2 = T * (xk[3] * (1.0 + t * t) * rL);
         const double jd = (T * rL) * (1.0 + t * t);
@@ -546,20 +584,20 @@ struct LaneSolver {
       for (int b_ = 0; b_ < NBX; b_++) {
         int i = bx(b_);
         double rl = fast_rcp(xk[i] - p.x_lo[i]), rh = fast_rcp(p.x_hi[i] - xk[i]);
-        h[i] += at(L::ZLX + b_, k) * rl + at(L::ZUX + b_, k) * rh;
+        h[i] += zlx_[b_] * rl + zux_[b_] * rh;
         gx[i] += mu * (rh - rl);
       }
-      if (has_obs(k)) {
+      if (obst) {
 #pragma unroll
         for (int j = 0; j < MO; j++) {
-          double dx = xk[0] - at(L::OCX + j, k), dy = xk[1] - at(L::OCY + j, k);
-          double a_ = at(L::ISX + j, k), b_ = at(L::ISY + j, k);
+          double dx = xk[0] - ocx_[j], dy = xk[1] - ocy_[j];
+          double a_ = isx_[j], b_ = isy_[j];
           double d = dx * dx * a_ + dy * dy * b_ - 1.0;
           double ox = 2 * dx * a_, oy = 2 * dy * b_;
-          double s = at(L::SO + j, k), rg = fast_rcp(s - p.obs_lo);
-          double D = at(L::VLO + j, k) * rg + dw;
+          double s = so_[j], rg = fast_rcp(s - p.obs_lo);
+          double D = vlo_[j] * rg + dw;
           double gs = -mu * rg + MPCB_KAPPA_D * mu;
-          double lo = at(L::LO + j, k);
+          double lo = lo_[j];
           double t = D * (d - s) + gs;
           h[0] += lo * (2 * a_) + D * ox * ox;
           h01 += D * ox * oy;
@@ -573,16 +611,11 @@ struct LaneSolver {
       at(L::HUX, k) = hdv;
 #pragma unroll
       for (int i = 0; i < NX; i++) at(L::GX + i, k) = gx[i];
-      double c_k[NX];
-#pragma unroll
-      for (int i = 0; i < NX; i++) c_k[i] = at(cd + i, k);
       if (k == N) {
         p00 = h[0]; p01 = h01; p11 = h[1]; p22 = h[2]; p23 = h23; p33 = h[3];
         px0 = gx[0]; px1 = gx[1]; px2 = gx[2]; px3 = gx[3];
       } else {
         // control block of the stage: cost, bounds, coupling with the previous control (rate cost and rate row)
-        double u_m[2] = {0, 0};
-        if (k >= 1) { u_m[0] = at(L::U + 0, k - 1); u_m[1] = at(L::U + 1, k - 1); }
         double Huu[2], gu[2], E[2] = {0, 0}, tk[2] = {0, 0};
 #pragma unroll
         for (int i = 0; i < 2; i++) {
@@ -591,17 +624,17 @@ struct LaneSolver {
           double hd = sigma * 2 * p.R[i] + dw + (i == 0 ? hdd_f : 0.0);
           if (k == 0 && p.du0_cost) { hd += sigma * 2 * p.DR[i]; g += sigma * 2 * p.DR[i] * uk; }
           double rl = fast_rcp(uk - p.u_lo[i]), rh = fast_rcp(p.u_hi[i] - uk);
-          hd += at(L::ZLU + i, k) * rl + at(L::ZUU + i, k) * rh;
+          hd += zlu_[i] * rl + zuu_[i] * rh;
           g += mu * (rh - rl);
           Huu[i] = hd; gu[i] = g;
           if (k >= 1) { E[i] = sigma * 2 * p.DR[i]; tk[i] = sigma * 2 * p.DR[i] * (uk - u_m[i]); }
         }
-        if (has_rate(k)) {
+        if (rate) {
 #pragma unroll
           for (int r = 0; r < NR; r++) {
-            double s = at(L::SR + r, k);
+            double s = sr_[r];
             double rl = fast_rcp(s - p.rate_lo[r]), rh = fast_rcp(p.rate_hi[r] - s);
-            double D = at(L::VLR + r, k) * rl + at(L::VUR + r, k) * rh + dw;
+            double D = vlr_[r] * rl + vur_[r] * rh + dw;
             double gs = mu * (rh - rl);
             double res = u_k[0] - u_m[0] - s;
             E[0] += D; tk[0] += D * res + gs;
@@ -678,7 +711,7 @@ struct LaneSolver {
         u_k[0] = u_m[0]; u_k[1] = u_m[1];
       }
 #pragma unroll
-      for (int i = 0; i < NX; i++) { l_next[i] = at(L::LAM + i, k); c_next[i] = c_k[i]; }
+      for (int i = 0; i < NX; i++) { l_next[i] = lam_k[i]; c_next[i] = c_k[i]; }
     }
     return true;
   }
@@ -887,36 +920,70 @@ struct LaneSolver {
       pf<L::CDEF, 8>(k + 1 + MPCB_LANE_PF_DIST);
       pf<L::TRG, 2 * L::NJ>(k + 1 + MPCB_LANE_PF_DIST);
       pf<L::HXX, 10 + L::NHUX + 14>(k + 1 + MPCB_LANE_PF_DIST);   // condensed Hessian, gradient and the gains
+      constexpr int NR1 = NR > 0 ? NR : 1, MO1 = MO > 0 ? MO : 1, NHUX1 = RK4 ? 4 : 1;
       double xk[NX], un[2] = {0, 0}, ud = 0, ua = 0, n[NX] = {0, 0, 0, 0};
+      // every load of the stage first (a store whose value waits for a load would hold back the loads behind it)
+      double kk_[2] = {0, 0}, kx_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, kw_[4] = {0, 0, 0, 0}, cn_[NX] = {0, 0, 0, 0};
+      double hx_[6], gx_[NX], hux_[NHUX1], zlx_[NBX], zux_[NBX], zlu_[2] = {0, 0}, zuu_[2] = {0, 0};
+      double sr_[NR1], vlr_[NR1], vur_[NR1], ocx_[MO1], ocy_[MO1], isx_[MO1], isy_[MO1], so_[MO1], vlo_[MO1];
+      const bool rate = has_rate(k), obst = has_obs(k);
+      AB ab = {};
 #pragma unroll
-      for (int i = 0; i < NX; i++) { xk[i] = at(L::X + i, k); at(L::DX + i, k) = d[i]; }
+      for (int i = 0; i < NX; i++) { xk[i] = at(L::X + i, k); gx_[i] = at(L::GX + i, k); }
+#pragma unroll
+      for (int i = 0; i < 6; i++) hx_[i] = at(L::HXX + i, k);
+#pragma unroll
+      for (int i = 0; i < NHUX1; i++) hux_[i] = at(L::HUX + i, k);
+#pragma unroll
+      for (int b_ = 0; b_ < NBX; b_++) { zlx_[b_] = at(L::ZLX + b_, k); zux_[b_] = at(L::ZUX + b_, k); }
       if (k < N) {
-        ud = at(L::KK + 0, k) + at(L::KX + 0, k) * d[0] + at(L::KX + 1, k) * d[1] + at(L::KX + 2, k) * d[2] + at(L::KX + 3, k) * d[3] +
-             at(L::KW + 0, k) * vd + at(L::KW + 1, k) * va;
-        ua = at(L::KK + 1, k) + at(L::KX + 4, k) * d[0] + at(L::KX + 5, k) * d[1] + at(L::KX + 6, k) * d[2] + at(L::KX + 7, k) * d[3] +
-             at(L::KW + 2, k) * vd + at(L::KW + 3, k) * va;
-        const AB ab = load_ab(tg, k, xk[3]);
-        n[0] = d[0] + ab.a02 * d[2] + ab.a03 * d[3] - at(cd + 0, k + 1);
-        n[1] = d[1] + ab.a12 * d[2] + ab.a13 * d[3] - at(cd + 1, k + 1);
-        n[2] = d[2] + ab.a23 * d[3] + ab.b20 * ud - at(cd + 2, k + 1);
-        n[3] = d[3] + T * ua - at(cd + 3, k + 1);
-        if (RK4) { n[0] += ab.b00 * ud + ab.b01 * ua; n[1] += ab.b10 * ud + ab.b11 * ua; n[2] += ab.b21 * ua; }
+#pragma unroll
+        for (int i = 0; i < 2; i++) { kk_[i] = at(L::KK + i, k); zlu_[i] = at(L::ZLU + i, k); zuu_[i] = at(L::ZUU + i, k); }
+#pragma unroll
+        for (int i = 0; i < 8; i++) kx_[i] = at(L::KX + i, k);
+#pragma unroll
+        for (int i = 0; i < 4; i++) kw_[i] = at(L::KW + i, k);
+#pragma unroll
+        for (int i = 0; i < NX; i++) cn_[i] = at(cd + i, k + 1);
+        ab = load_ab(tg, k, xk[3]);
         if (k + 1 <= N - 1) { un[0] = at(L::U + 0, k + 1); un[1] = at(L::U + 1, k + 1); }
+      }
+      if (rate) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) { sr_[r] = at(L::SR + r, k); vlr_[r] = at(L::VLR + r, k); vur_[r] = at(L::VUR + r, k); }
+      }
+      if (obst) {
+#pragma unroll
+        for (int j = 0; j < MO; j++) {
+          ocx_[j] = at(L::OCX + j, k); ocy_[j] = at(L::OCY + j, k); isx_[j] = at(L::ISX + j, k); isy_[j] = at(L::ISY + j, k);
+          so_[j] = at(L::SO + j, k); vlo_[j] = at(L::VLO + j, k);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) at(L::DX + i, k) = d[i];
+      if (k < N) {
+        ud = kk_[0] + kx_[0] * d[0] + kx_[1] * d[1] + kx_[2] * d[2] + kx_[3] * d[3] + kw_[0] * vd + kw_[1] * va;
+        ua = kk_[1] + kx_[4] * d[0] + kx_[5] * d[1] + kx_[6] * d[2] + kx_[7] * d[3] + kw_[2] * vd + kw_[3] * va;
+        n[0] = d[0] + ab.a02 * d[2] + ab.a03 * d[3] - cn_[0];
+        n[1] = d[1] + ab.a12 * d[2] + ab.a13 * d[3] - cn_[1];
+        n[2] = d[2] + ab.a23 * d[3] + ab.b20 * ud - cn_[2];
+        n[3] = d[3] + T * ua - cn_[3];
+        if (RK4) { n[0] += ab.b00 * ud + ab.b01 * ua; n[1] += ab.b10 * ud + ab.b11 * ua; n[2] += ab.b21 * ua; }
       }
       at(L::DU + 0, k) = ud; at(L::DU + 1, k) = ua;
       // stage residual of the adjoint recursion: r_k = Hxx_eff dx + Hux' du + gx_eff (written to the LAMP row)
       {
-        const double h00 = at(L::HXX + 0, k), h01 = at(L::HXX + 1, k), h11 = at(L::HXX + 2, k), h22 = at(L::HXX + 3, k);
-        const double h23 = at(L::HXX + 4, k), h33 = at(L::HXX + 5, k);
-        double r2 = at(L::GX + 2, k) + h22 * d[2] + h23 * d[3], r3 = at(L::GX + 3, k) + h23 * d[2] + h33 * d[3];
+        const double h00 = hx_[0], h01 = hx_[1], h11 = hx_[2], h22 = hx_[3];
+        const double h23 = hx_[4], h33 = hx_[5];
+        double r2 = gx_[2] + h22 * d[2] + h23 * d[3], r3 = gx_[3] + h23 * d[2] + h33 * d[3];
         if (RK4) {  // Hux' du: (delta, phi) (delta, v) (a, phi) (a, v)
-          r2 += at(L::HUX + 0, k) * ud + at(L::HUX + 2, k) * ua;
-          r3 += at(L::HUX + 1, k) * ud + at(L::HUX + 3, k) * ua;
+          r2 += hux_[0] * ud + hux_[NHUX1 > 2 ? 2 : 0] * ua;
+          r3 += hux_[NHUX1 > 1 ? 1 : 0] * ud + hux_[NHUX1 > 3 ? 3 : 0] * ua;
         } else {
-          r3 += at(L::HUX, k) * ud;
+          r3 += hux_[0] * ud;
         }
-        at(L::LAMP + 0, k) = at(L::GX + 0, k) + h00 * d[0] + h01 * d[1];
-        at(L::LAMP + 1, k) = at(L::GX + 1, k) + h01 * d[0] + h11 * d[1];
+        at(L::LAMP + 0, k) = gx_[0] + h00 * d[0] + h01 * d[1];
+        at(L::LAMP + 1, k) = gx_[1] + h01 * d[0] + h11 * d[1];
         at(L::LAMP + 2, k) = r2;
         at(L::LAMP + 3, k) = r3;
       }
@@ -930,8 +997,8 @@ struct LaneSolver {
         int i = bx(b_);
         double rl = fast_rcp(xk[i] - p.x_lo[i]), rh = fast_rcp(p.x_hi[i] - xk[i]);
         g_d += mu * (rh - rl) * d[i];
-        MPCB_LOWER(rl, d[i], at(L::ZLX + b_, k));
-        MPCB_UPPER(rh, d[i], at(L::ZUX + b_, k));
+        MPCB_LOWER(rl, d[i], zlx_[b_]);
+        MPCB_UPPER(rh, d[i], zux_[b_]);
       }
       if (k < N) {
         const double du_[2] = {ud, ua};
@@ -939,16 +1006,16 @@ struct LaneSolver {
         for (int i = 0; i < 2; i++) {
           double rl = fast_rcp(uc[i] - p.u_lo[i]), rh = fast_rcp(p.u_hi[i] - uc[i]);
           g_d += (sigma * grad_u(k, i, uc[i], um[i], un[i]) + mu * (rh - rl)) * du_[i];
-          MPCB_LOWER(rl, du_[i], at(L::ZLU + i, k));
-          MPCB_UPPER(rh, du_[i], at(L::ZUU + i, k));
+          MPCB_LOWER(rl, du_[i], zlu_[i]);
+          MPCB_UPPER(rh, du_[i], zuu_[i]);
         }
       }
-      if (has_rate(k)) {
+      if (rate) {
 #pragma unroll
         for (int r = 0; r < NR; r++) {
-          double s = at(L::SR + r, k);
+          double s = sr_[r];
           double rl = fast_rcp(s - p.rate_lo[r]), rh = fast_rcp(p.rate_hi[r] - s);
-          double vl = at(L::VLR + r, k), vu = at(L::VUR + r, k);
+          double vl = vlr_[r], vu = vur_[r];
           double D = vl * rl + vu * rh + dw;
           double gs = mu * (rh - rl);
           double res = uc[0] - um[0] - s;
@@ -960,13 +1027,13 @@ struct LaneSolver {
           MPCB_UPPER(rh, ds, vu);
         }
       }
-      if (has_obs(k)) {
+      if (obst) {
 #pragma unroll
         for (int j = 0; j < MO; j++) {
-          double ex = xk[0] - at(L::OCX + j, k), ey = xk[1] - at(L::OCY + j, k);
-          double a_ = at(L::ISX + j, k), b_ = at(L::ISY + j, k);
+          double ex = xk[0] - ocx_[j], ey = xk[1] - ocy_[j];
+          double a_ = isx_[j], b_ = isy_[j];
           double dd = ex * ex * a_ + ey * ey * b_ - 1.0;
-          double s = at(L::SO + j, k), rg = fast_rcp(s - p.obs_lo), vl = at(L::VLO + j, k);
+          double s = so_[j], rg = fast_rcp(s - p.obs_lo), vl = vlo_[j];
           double D = vl * rg + dw;
           double gs = -mu * rg + MPCB_KAPPA_D * mu;
           double ds = (2 * ex * a_) * d[0] + (2 * ey * b_) * d[1] + (dd - s);
@@ -991,19 +1058,41 @@ struct LaneSolver {
   // new dynamics multipliers: lam+_k = A_k' lam+_{k+1} - r_k  (KinSolver::adjoint)
   __device__ void adjoint() {
     const int tg = trg(cur);
+    constexpr int NT = RK4 ? 5 : 3;
     double l0 = -at(L::LAMP + 0, N), l1 = -at(L::LAMP + 1, N), l2 = -at(L::LAMP + 2, N), l3 = -at(L::LAMP + 3, N);
     at(L::LAMP + 0, N) = l0; at(L::LAMP + 1, N) = l1; at(L::LAMP + 2, N) = l2; at(L::LAMP + 3, N) = l3;
+    // the inputs of stage k-1 are loaded before stage k stores (one stage in flight ahead of the recursion)
+    double v_n = 0, t_n[NT], r_n[NX];
+    if (N >= 1) {
+      v_n = RK4 ? 0.0 : at(L::X + 3, N - 1);
+#pragma unroll
+      for (int i = 0; i < NT; i++) t_n[i] = at(tg + i, N - 1);
+#pragma unroll
+      for (int i = 0; i < NX; i++) r_n[i] = at(L::LAMP + i, N - 1);
+    }
 #pragma unroll 1
     for (int k = N - 1; k >= 0; k--) {
       pf<L::X + 3, 1>(k - 1 - MPCB_LANE_PF_DIST);
       pf<L::TRG, 2 * L::NJ>(k - 1 - MPCB_LANE_PF_DIST);
       pf<L::LAMP, 4>(k - 1 - MPCB_LANE_PF_DIST);
-      const AB ab = load_ab(tg, k, RK4 ? 0.0 : at(L::X + 3, k));
-      const double a02 = ab.a02, a03 = ab.a03, a12 = ab.a12, a13 = ab.a13, a23 = ab.a23;
-      const double n0 = l0 - at(L::LAMP + 0, k);
-      const double n1 = l1 - at(L::LAMP + 1, k);
-      const double n2 = l2 + a02 * l0 + a12 * l1 - at(L::LAMP + 2, k);
-      const double n3 = l3 + a03 * l0 + a13 * l1 + a23 * l2 - at(L::LAMP + 3, k);
+      const double v = v_n, r0 = r_n[0], r1 = r_n[1], r2 = r_n[2], r3 = r_n[3];
+      double a02, a03, a12, a13, a23;
+      if (RK4) { a02 = t_n[0]; a03 = t_n[1]; a12 = t_n[2]; a13 = t_n[NT > 3 ? 3 : 0]; a23 = t_n[NT > 4 ? 4 : 0]; }
+      else {
+        const double rL = 1.0 / p.Veh_l, s_ = t_n[0], c_ = t_n[1], t_ = t_n[2];
+        a02 = p.T * (-v * s_); a03 = p.T * c_; a12 = p.T * (v * c_); a13 = p.T * s_; a23 = p.T * (t_ * rL);
+      }
+      if (k >= 1) {
+        v_n = RK4 ? 0.0 : at(L::X + 3, k - 1);
+#pragma unroll
+        for (int i = 0; i < NT; i++) t_n[i] = at(tg + i, k - 1);
+#pragma unroll
+        for (int i = 0; i < NX; i++) r_n[i] = at(L::LAMP + i, k - 1);
+      }
+      const double n0 = l0 - r0;
+      const double n1 = l1 - r1;
+      const double n2 = l2 + a02 * l0 + a12 * l1 - r2;
+      const double n3 = l3 + a03 * l0 + a13 * l1 + a23 * l2 - r3;
       at(L::LAMP + 0, k) = n0; at(L::LAMP + 1, k) = n1; at(L::LAMP + 2, k) = n2; at(L::LAMP + 3, k) = n3;
       l0 = n0; l1 = n1; l2 = n2; l3 = n3;
     }
@@ -1011,31 +1100,59 @@ struct LaneSolver {
 
   // accept the step: primal a, duals ad (KinSolver::accept_step); the trial point's buffer becomes the current one
   __device__ void accept_step(double a_, double ad) {
+    constexpr int NR1 = NR > 0 ? NR : 1, MO1 = MO > 0 ? MO : 1;
 #pragma unroll 1
     for (int k = 0; k <= N; k++) {
       pf<L::X, L::OCX - L::X>(k + 1 + MPCB_LANE_PF_DIST);
       pf<L::DX, L::CDEF - L::DX>(k + 1 + MPCB_LANE_PF_DIST);
+      // every load of the stage first: a store whose value waits for a load would otherwise hold back the loads behind it
+      double lam[NX], lamp[NX], xv[NX], dxv[NX], zlx[NBX], zux[NBX];
+      double uv[2] = {0, 0}, duv[2] = {0, 0}, zlu[2] = {0, 0}, zuu[2] = {0, 0};
+      double sr[NR1], dsr[NR1], vlr[NR1], vur[NR1], lr[NR1], lrp[NR1];
+      double so[MO1], dso[MO1], vlo[MO1], lo[MO1], lop[MO1];
+      const bool rate = has_rate(k), obst = has_obs(k);
 #pragma unroll
-      for (int i = 0; i < NX; i++) { double l = at(L::LAM + i, k); at(L::LAM + i, k) = l + a_ * (at(L::LAMP + i, k) - l); }
+      for (int i = 0; i < NX; i++) { lam[i] = at(L::LAM + i, k); lamp[i] = at(L::LAMP + i, k); xv[i] = at(L::X + i, k); dxv[i] = at(L::DX + i, k); }
+#pragma unroll
+      for (int b_ = 0; b_ < NBX; b_++) { zlx[b_] = at(L::ZLX + b_, k); zux[b_] = at(L::ZUX + b_, k); }
+      if (k < N) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) { uv[i] = at(L::U + i, k); duv[i] = at(L::DU + i, k); zlu[i] = at(L::ZLU + i, k); zuu[i] = at(L::ZUU + i, k); }
+      }
+      if (rate) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          sr[r] = at(L::SR + r, k); dsr[r] = at(L::DSR + r, k); vlr[r] = at(L::VLR + r, k); vur[r] = at(L::VUR + r, k);
+          lr[r] = at(L::LR + r, k); lrp[r] = at(L::LRP + r, k);
+        }
+      }
+      if (obst) {
+#pragma unroll
+        for (int j = 0; j < MO; j++) {
+          so[j] = at(L::SO + j, k); dso[j] = at(L::DSO + j, k); vlo[j] = at(L::VLO + j, k); lo[j] = at(L::LO + j, k); lop[j] = at(L::LOP + j, k);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) { double l = lam[i]; at(L::LAM + i, k) = l + a_ * (lamp[i] - l); }
 #pragma unroll
       for (int b_ = 0; b_ < NBX; b_++) {
         int i = bx(b_);
-        double x = at(L::X + i, k), dx = at(L::DX + i, k);
+        double x = xv[i], dx = dxv[i];
         double rl = fast_rcp(x - p.x_lo[i]), rh = fast_rcp(p.x_hi[i] - x);
-        double zl = at(L::ZLX + b_, k), zu = at(L::ZUX + b_, k);
+        double zl = zlx[b_], zu = zux[b_];
         double dzl = -zl + (mu - zl * dx) * rl, dzu = -zu + (mu + zu * dx) * rh;
         double xn = x + a_ * dx;
         at(L::ZLX + b_, k) = clampz(zl + ad * dzl, mu, fast_rcp(xn - p.x_lo[i]));
         at(L::ZUX + b_, k) = clampz(zu + ad * dzu, mu, fast_rcp(p.x_hi[i] - xn));
       }
 #pragma unroll
-      for (int i = 0; i < NX; i++) at(L::X + i, k) += a_ * at(L::DX + i, k);
+      for (int i = 0; i < NX; i++) at(L::X + i, k) = xv[i] + a_ * dxv[i];
       if (k < N) {
 #pragma unroll
         for (int i = 0; i < 2; i++) {
-          double u = at(L::U + i, k), du = at(L::DU + i, k);
+          double u = uv[i], du = duv[i];
           double rl = fast_rcp(u - p.u_lo[i]), rh = fast_rcp(p.u_hi[i] - u);
-          double zl = at(L::ZLU + i, k), zu = at(L::ZUU + i, k);
+          double zl = zlu[i], zu = zuu[i];
           double dzl = -zl + (mu - zl * du) * rl, dzu = -zu + (mu + zu * du) * rh;
           double un = u + a_ * du;
           at(L::U + i, k) = un;
@@ -1043,32 +1160,32 @@ struct LaneSolver {
           at(L::ZUU + i, k) = clampz(zu + ad * dzu, mu, fast_rcp(p.u_hi[i] - un));
         }
       }
-      if (has_rate(k)) {
+      if (rate) {
 #pragma unroll
         for (int r = 0; r < NR; r++) {
-          double s = at(L::SR + r, k), ds = at(L::DSR + r, k);
+          double s = sr[r], ds = dsr[r];
           double rl = fast_rcp(s - p.rate_lo[r]), rh = fast_rcp(p.rate_hi[r] - s);
-          double vl = at(L::VLR + r, k), vu = at(L::VUR + r, k);
+          double vl = vlr[r], vu = vur[r];
           double dvl = -vl + (mu - vl * ds) * rl, dvu = -vu + (mu + vu * ds) * rh;
           double sn = s + a_ * ds;
           at(L::SR + r, k) = sn;
           at(L::VLR + r, k) = clampz(vl + ad * dvl, mu, fast_rcp(sn - p.rate_lo[r]));
           at(L::VUR + r, k) = clampz(vu + ad * dvu, mu, fast_rcp(p.rate_hi[r] - sn));
-          double l = at(L::LR + r, k);
-          at(L::LR + r, k) = l + a_ * (at(L::LRP + r, k) - l);
+          double l = lr[r];
+          at(L::LR + r, k) = l + a_ * (lrp[r] - l);
         }
       }
-      if (has_obs(k)) {
+      if (obst) {
 #pragma unroll
         for (int j = 0; j < MO; j++) {
-          double s = at(L::SO + j, k), ds = at(L::DSO + j, k);
-          double rg = fast_rcp(s - p.obs_lo), vl = at(L::VLO + j, k);
+          double s = so[j], ds = dso[j];
+          double rg = fast_rcp(s - p.obs_lo), vl = vlo[j];
           double dvl = -vl + (mu - vl * ds) * rg;
           double sn = s + a_ * ds;
           at(L::SO + j, k) = sn;
           at(L::VLO + j, k) = clampz(vl + ad * dvl, mu, fast_rcp(sn - p.obs_lo));
-          double l = at(L::LO + j, k);
-          at(L::LO + j, k) = l + a_ * (at(L::LOP + j, k) - l);
+          double l = lo[j];
+          at(L::LO + j, k) = l + a_ * (lop[j] - l);
         }
       }
     }
