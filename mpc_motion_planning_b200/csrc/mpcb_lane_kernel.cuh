@@ -525,6 +525,61 @@ struct LaneSolver {
   // ---------------------------------------------------------------- Newton step, part 1: condense + factorise
   // KinSolver::build_qp and riccati_backward in one backward pass; the condensed stage Hessian / gradient is kept for the
   // adjoint pass, the gains for the forward pass.  Returns false when some F_uu is not positive definite.
+  // Condensed stage Hessian and gradient of the Euler families (KinSolver::build_qp): h = diag + (0,1) (2,3) entries,
+  // d2L/(d delta d v), the model part of d2L/d delta^2 and gx.  The factorisation pass and the roll-out both evaluate it
+  // from the iterate (recomputing it costs a few dozen flops; keeping it in the workspace cost 22 doubles of traffic per
+  // scenario-stage in a kernel that is bandwidth-bound).
+  struct StageH { double h[NX], h01, h23, hdv, hdd_f, gx[NX], a02, a03, a12, a13, a23, b2; };
+  __device__ __forceinline__ void stage_h(int k, const double *xk, const double *tg_, const double *l_next, const double *zlx_, const double *zux_,
+                                          bool obst, const double *ocx_, const double *ocy_, const double *isx_, const double *isy_,
+                                          const double *so_, const double *vlo_, const double *lo_, StageH &o) const {
+    const double T = p.T, rL = 1.0 / p.Veh_l;
+    double h[NX] = {dw, dw, dw, dw}, h01 = 0, h23 = 0, hdv = 0, hdd_f = 0, gx[NX] = {0, 0, 0, 0};
+    double a02 = 0, a03 = 0, a12 = 0, a13 = 0, a23 = 0, b2 = 0;
+    if (k < N) {
+      const double s = tg_[0], c = tg_[1], t = tg_[2];
+      a02 = T * (-xk[3] * s); a03 = T * c; a12 = T * (xk[3] * c); a13 = T * s; a23 = T * (t * rL);
+      b2 = T * (xk[3] * (1.0 + t * t) * rL);
+      const double jd = (T * rL) * (1.0 + t * t);
+      h[2] += l_next[0] * a12 - l_next[1] * a02;
+      h23 = l_next[0] * a13 - l_next[1] * a03;
+      hdv = -l_next[2] * jd;
+      hdd_f = -2.0 * l_next[2] * b2 * t;
+#pragma unroll
+      for (int i = 0; i < NX; i++) { h[i] += sigma * 2 * p.Q[i]; gx[i] = sigma * 2 * p.Q[i] * (xk[i] - xs[i]); }
+    }
+#pragma unroll
+    for (int b_ = 0; b_ < NBX; b_++) {
+      int i = bx(b_);
+      double rl = fast_rcp(xk[i] - p.x_lo[i]), rh = fast_rcp(p.x_hi[i] - xk[i]);
+      h[i] += zlx_[b_] * rl + zux_[b_] * rh;
+      gx[i] += mu * (rh - rl);
+    }
+    if (obst) {
+#pragma unroll
+      for (int j = 0; j < MO; j++) {
+        double dx = xk[0] - ocx_[j], dy = xk[1] - ocy_[j];
+        double a_ = isx_[j], b_ = isy_[j];
+        double d = dx * dx * a_ + dy * dy * b_ - 1.0;
+        double ox = 2 * dx * a_, oy = 2 * dy * b_;
+        double s = so_[j], rg = fast_rcp(s - p.obs_lo);
+        double D = vlo_[j] * rg + dw;
+        double gs = -mu * rg + MPCB_KAPPA_D * mu;
+        double lo = lo_[j];
+        double t = D * (d - s) + gs;
+        h[0] += lo * (2 * a_) + D * ox * ox;
+        h01 += D * ox * oy;
+        h[1] += lo * (2 * b_) + D * oy * oy;
+        gx[0] += ox * t;
+        gx[1] += oy * t;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; i++) { o.h[i] = h[i]; o.gx[i] = gx[i]; }
+    o.h01 = h01; o.h23 = h23; o.hdv = hdv; o.hdd_f = hdd_f;
+    o.a02 = a02; o.a03 = a03; o.a12 = a12; o.a13 = a13; o.a23 = a23; o.b2 = b2;
+  }
+
   __device__ bool backward() {
     const int cd = cdef(cur), tg = trg(cur);
     const double T = p.T, rL = 1.0 / p.Veh_l;
@@ -568,49 +623,12 @@ struct LaneSolver {
           so_[j] = at(L::SO + j, k); vlo_[j] = at(L::VLO + j, k); lo_[j] = at(L::LO + j, k);
         }
       }
-      if (k < N) {
-        const double s = tg_[0], c = tg_[1], t = tg_[2];
-        a02 = T * (-xk[3] * s); a03 = T * c; a12 = T * (xk[3] * c); a13 = T * s; a23 = T * (t * rL);
-        b2 = T * (xk[3] * (1.0 + t * t) * rL);
-        const double jd = (T * rL) * (1.0 + t * t);
-        h[2] += l_next[0] * a12 - l_next[1] * a02;
-        h23 = l_next[0] * a13 - l_next[1] * a03;
-        hdv = -l_next[2] * jd;
-        hdd_f = -2.0 * l_next[2] * b2 * t;
+      StageH sh;
+      stage_h(k, xk, tg_, l_next, zlx_, zux_, obst, ocx_, ocy_, isx_, isy_, so_, vlo_, lo_, sh);
 #pragma unroll
-        for (int i = 0; i < NX; i++) { h[i] += sigma * 2 * p.Q[i]; gx[i] = sigma * 2 * p.Q[i] * (xk[i] - xs[i]); }
-      }
-#pragma unroll
-      for (int b_ = 0; b_ < NBX; b_++) {
-        int i = bx(b_);
-        double rl = fast_rcp(xk[i] - p.x_lo[i]), rh = fast_rcp(p.x_hi[i] - xk[i]);
-        h[i] += zlx_[b_] * rl + zux_[b_] * rh;
-        gx[i] += mu * (rh - rl);
-      }
-      if (obst) {
-#pragma unroll
-        for (int j = 0; j < MO; j++) {
-          double dx = xk[0] - ocx_[j], dy = xk[1] - ocy_[j];
-          double a_ = isx_[j], b_ = isy_[j];
-          double d = dx * dx * a_ + dy * dy * b_ - 1.0;
-          double ox = 2 * dx * a_, oy = 2 * dy * b_;
-          double s = so_[j], rg = fast_rcp(s - p.obs_lo);
-          double D = vlo_[j] * rg + dw;
-          double gs = -mu * rg + MPCB_KAPPA_D * mu;
-          double lo = lo_[j];
-          double t = D * (d - s) + gs;
-          h[0] += lo * (2 * a_) + D * ox * ox;
-          h01 += D * ox * oy;
-          h[1] += lo * (2 * b_) + D * oy * oy;
-          gx[0] += ox * t;
-          gx[1] += oy * t;
-        }
-      }
-      at(L::HXX + 0, k) = h[0]; at(L::HXX + 1, k) = h01; at(L::HXX + 2, k) = h[1];
-      at(L::HXX + 3, k) = h[2]; at(L::HXX + 4, k) = h23; at(L::HXX + 5, k) = h[3];
-      at(L::HUX, k) = hdv;
-#pragma unroll
-      for (int i = 0; i < NX; i++) at(L::GX + i, k) = gx[i];
+      for (int i = 0; i < NX; i++) { h[i] = sh.h[i]; gx[i] = sh.gx[i]; }
+      h01 = sh.h01; h23 = sh.h23; hdv = sh.hdv; hdd_f = sh.hdd_f;
+      a02 = sh.a02; a03 = sh.a03; a12 = sh.a12; a13 = sh.a13; a23 = sh.a23; b2 = sh.b2;
       if (k == N) {
         p00 = h[0]; p01 = h01; p11 = h[1]; p22 = h[2]; p23 = h23; p33 = h[3];
         px0 = gx[0]; px1 = gx[1]; px2 = gx[2]; px3 = gx[3];
@@ -925,15 +943,25 @@ struct LaneSolver {
       // every load of the stage first (a store whose value waits for a load would hold back the loads behind it)
       double kk_[2] = {0, 0}, kx_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, kw_[4] = {0, 0, 0, 0}, cn_[NX] = {0, 0, 0, 0};
       double hx_[6], gx_[NX], hux_[NHUX1], zlx_[NBX], zux_[NBX], zlu_[2] = {0, 0}, zuu_[2] = {0, 0};
-      double sr_[NR1], vlr_[NR1], vur_[NR1], ocx_[MO1], ocy_[MO1], isx_[MO1], isy_[MO1], so_[MO1], vlo_[MO1];
+      double sr_[NR1], vlr_[NR1], vur_[NR1], ocx_[MO1], ocy_[MO1], isx_[MO1], isy_[MO1], so_[MO1], vlo_[MO1], lo_[MO1];
+      double tg_[3] = {0, 0, 0}, ln_[NX] = {0, 0, 0, 0};  // Euler families: the stage Hessian is evaluated again (stage_h)
       const bool rate = has_rate(k), obst = has_obs(k);
       AB ab = {};
 #pragma unroll
-      for (int i = 0; i < NX; i++) { xk[i] = at(L::X + i, k); gx_[i] = at(L::GX + i, k); }
+      for (int i = 0; i < NX; i++) xk[i] = at(L::X + i, k);
+      if (RK4) {
 #pragma unroll
-      for (int i = 0; i < 6; i++) hx_[i] = at(L::HXX + i, k);
+        for (int i = 0; i < NX; i++) gx_[i] = at(L::GX + i, k);
 #pragma unroll
-      for (int i = 0; i < NHUX1; i++) hux_[i] = at(L::HUX + i, k);
+        for (int i = 0; i < 6; i++) hx_[i] = at(L::HXX + i, k);
+#pragma unroll
+        for (int i = 0; i < NHUX1; i++) hux_[i] = at(L::HUX + i, k);
+      } else if (k < N) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) tg_[i] = at(tg + i, k);
+#pragma unroll
+        for (int i = 0; i < NX; i++) ln_[i] = at(L::LAM + i, k + 1);
+      }
 #pragma unroll
       for (int b_ = 0; b_ < NBX; b_++) { zlx_[b_] = at(L::ZLX + b_, k); zux_[b_] = at(L::ZUX + b_, k); }
       if (k < N) {
@@ -945,7 +973,7 @@ struct LaneSolver {
         for (int i = 0; i < 4; i++) kw_[i] = at(L::KW + i, k);
 #pragma unroll
         for (int i = 0; i < NX; i++) cn_[i] = at(cd + i, k + 1);
-        ab = load_ab(tg, k, xk[3]);
+        if (RK4) ab = load_ab(tg, k, xk[3]);
         if (k + 1 <= N - 1) { un[0] = at(L::U + 0, k + 1); un[1] = at(L::U + 1, k + 1); }
       }
       if (rate) {
@@ -957,7 +985,17 @@ struct LaneSolver {
         for (int j = 0; j < MO; j++) {
           ocx_[j] = at(L::OCX + j, k); ocy_[j] = at(L::OCY + j, k); isx_[j] = at(L::ISX + j, k); isy_[j] = at(L::ISY + j, k);
           so_[j] = at(L::SO + j, k); vlo_[j] = at(L::VLO + j, k);
+          if (!RK4) lo_[j] = at(L::LO + j, k);
         }
+      }
+      if (!RK4) {
+        StageH sh;
+        stage_h(k, xk, tg_, ln_, zlx_, zux_, obst, ocx_, ocy_, isx_, isy_, so_, vlo_, lo_, sh);
+        hx_[0] = sh.h[0]; hx_[1] = sh.h01; hx_[2] = sh.h[1]; hx_[3] = sh.h[2]; hx_[4] = sh.h23; hx_[5] = sh.h[3];
+        hux_[0] = sh.hdv;
+#pragma unroll
+        for (int i = 0; i < NX; i++) gx_[i] = sh.gx[i];
+        ab.a02 = sh.a02; ab.a03 = sh.a03; ab.a12 = sh.a12; ab.a13 = sh.a13; ab.a23 = sh.a23; ab.b20 = sh.b2; ab.b31 = T;
       }
 #pragma unroll
       for (int i = 0; i < NX; i++) at(L::DX + i, k) = d[i];
