@@ -41,7 +41,9 @@ struct LaneLayout {
   static constexpr int HXX = TRG + 2 * NJ;  // condensed stage Hessian h00 h01 h11 h22 h23 h33, d2L/(du dx), gradient
   static constexpr int NHUX = RK4 ? 4 : 1;  // Euler: (delta, v); RK4: (delta, phi) (delta, v) (a, phi) (a, v)
   static constexpr int HUX = HXX + 6, GX = HUX + NHUX;
-  static constexpr int KX = GX + 4, KW = KX + 8, KK = KW + 4;  // Riccati gains
+  // (the Euler families evaluate the condensed Hessian in both passes, LaneSolver::stage_h, and keep no copy: the ids
+  // above then alias the gains and are never used)
+  static constexpr int KX = RK4 ? GX + 4 : HXX, KW = KX + 8, KK = KW + 4;  // Riccati gains
   static constexpr int FLT = KK + 2;     // filter: 2 rows of theta entries, 2 rows of phi entries
   static constexpr int NFIELD = FLT + 4;
   __host__ __device__ static constexpr size_t slot_doubles(int N) { return (size_t)NFIELD * (size_t)(N + 1); }
@@ -937,7 +939,7 @@ struct LaneSolver {
       pf<L::X, L::OCX - L::X + 4 * MO>(k + 1 + MPCB_LANE_PF_DIST);
       pf<L::CDEF, 8>(k + 1 + MPCB_LANE_PF_DIST);
       pf<L::TRG, 2 * L::NJ>(k + 1 + MPCB_LANE_PF_DIST);
-      pf<L::HXX, 10 + L::NHUX + 14>(k + 1 + MPCB_LANE_PF_DIST);   // condensed Hessian, gradient and the gains
+      pf<L::HXX, (RK4 ? 10 + L::NHUX : 0) + 14>(k + 1 + MPCB_LANE_PF_DIST);   // (condensed Hessian, gradient and) the gains
       constexpr int NR1 = NR > 0 ? NR : 1, MO1 = MO > 0 ? MO : 1, NHUX1 = RK4 ? 4 : 1;
       double xk[NX], un[2] = {0, 0}, ud = 0, ua = 0, n[NX] = {0, 0, 0, 0};
       // every load of the stage first (a store whose value waits for a load would hold back the loads behind it)
