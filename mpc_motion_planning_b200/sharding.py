@@ -22,6 +22,24 @@ def balanced_permutation(B: int, seed: int = 0) -> np.ndarray:
     return np.random.default_rng(seed).permutation(B)
 
 
+_PERM_CACHE: dict = {}
+
+
+def _device_permutation(B: int, seed: int | None, device):
+    """The shuffle as a tensor on `device`, built once per (B, seed, device): it does not depend on the inputs, and
+    generating it on the host and copying it over every step cost more than the result gather itself."""
+    import torch
+
+    key = (B, seed, str(device))
+    perm = _PERM_CACHE.get(key)
+    if perm is None:
+        perm = torch.from_numpy(balanced_permutation(B, seed)).to(device) if seed is not None else torch.arange(B, device=device)
+        if len(_PERM_CACHE) >= 8:
+            _PERM_CACHE.pop(next(iter(_PERM_CACHE)))
+        _PERM_CACHE[key] = perm
+    return perm
+
+
 def solve_sharded(solve_local, x0, xs, obs, z_init=None, group=None, shuffle_seed: int | None = 0):
     """Run `solve_local(x0, xs, obs, z_init) -> dict(u0,cost,status,iters)` (torch tensors) on this
     rank's shard and all-gather the results so every rank returns the full batch in input order.
@@ -32,26 +50,30 @@ def solve_sharded(solve_local, x0, xs, obs, z_init=None, group=None, shuffle_see
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     B = x0.shape[0]
-    perm = torch.from_numpy(balanced_permutation(B, shuffle_seed)).to(x0.device) if shuffle_seed is not None else torch.arange(B, device=x0.device)
+    perm = _device_permutation(B, shuffle_seed, x0.device)
     lo, hi = shard_range(B, world, rank)
     idx = perm[lo:hi]
     take = lambda t: None if t is None else t.index_select(0, idx)
     out = solve_local(take(x0), take(xs), take(obs), take(z_init))
     per = -(-B // world)
-    packed = torch.zeros((per, 5), dtype=torch.float64, device=x0.device)
     n = hi - lo
     if n:
-        packed[:n, 0:2] = out["u0"]
-        packed[:n, 2] = out["cost"]
-        packed[:n, 3] = out["status"].to(torch.float64)
-        packed[:n, 4] = out["iters"].to(torch.float64)
+        packed = torch.cat((out["u0"], out["cost"].unsqueeze(1), out["status"].unsqueeze(1).to(torch.float64),
+                            out["iters"].unsqueeze(1).to(torch.float64)), dim=1)
+        if n < per:  # the padded last shard
+            packed = torch.cat((packed, packed.new_zeros((per - n, 5))))
+    else:
+        packed = torch.zeros((per, 5), dtype=torch.float64, device=x0.device)
     if world > 1:
         full = torch.empty((world * per, 5), dtype=torch.float64, device=x0.device)
         dist.all_gather_into_tensor(full, packed, group=group)
     else:
         full = packed
     # drop the padding of the last shards and undo the shuffle
-    rows = torch.cat([full[r * per: r * per + (shard_range(B, world, r)[1] - shard_range(B, world, r)[0])] for r in range(world)])
+    if world * per == B:
+        rows = full
+    else:
+        rows = torch.cat([full[r * per: r * per + (shard_range(B, world, r)[1] - shard_range(B, world, r)[0])] for r in range(world)])
     res = torch.empty_like(rows)
     res[perm] = rows
     return {"u0": res[:, 0:2].contiguous(), "cost": res[:, 2].contiguous(), "status": res[:, 3].to(torch.int32),
