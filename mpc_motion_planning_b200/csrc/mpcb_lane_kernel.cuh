@@ -751,11 +751,34 @@ struct LaneSolver {
       double Hux[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, Hm[10];
 #pragma unroll
       for (int i = 0; i < 10; i++) Hm[i] = 0.0;
+      // every load of the stage first (see backward)
+      constexpr int NR1 = NR > 0 ? NR : 1, MO1 = MO > 0 ? MO : 1;
+      double zlx_[NBX], zux_[NBX], c_k[NX], lam_k[NX], u_m[2] = {0, 0}, zlu_[2] = {0, 0}, zuu_[2] = {0, 0};
+      double sr_[NR1], vlr_[NR1], vur_[NR1], ocx_[MO1], ocy_[MO1], isx_[MO1], isy_[MO1], so_[MO1], vlo_[MO1], lo_[MO1];
+      const bool rate = has_rate(k), obst = has_obs(k);
 #pragma unroll
-      for (int i = 0; i < NX; i++) xk[i] = at(L::X + i, k);
+      for (int i = 0; i < NX; i++) { xk[i] = at(L::X + i, k); c_k[i] = at(cd + i, k); lam_k[i] = at(L::LAM + i, k); }
+#pragma unroll
+      for (int b_ = 0; b_ < NBX; b_++) { zlx_[b_] = at(L::ZLX + b_, k); zux_[b_] = at(L::ZUX + b_, k); }
       AB ab = {};
       if (k < N) {
         ab = load_ab(tg, k, xk[3]);
+#pragma unroll
+        for (int i = 0; i < 2; i++) { zlu_[i] = at(L::ZLU + i, k); zuu_[i] = at(L::ZUU + i, k); }
+        if (k >= 1) { u_m[0] = at(L::U + 0, k - 1); u_m[1] = at(L::U + 1, k - 1); }
+      }
+      if (rate) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) { sr_[r] = at(L::SR + r, k); vlr_[r] = at(L::VLR + r, k); vur_[r] = at(L::VUR + r, k); }
+      }
+      if (obst) {
+#pragma unroll
+        for (int j = 0; j < MO; j++) {
+          ocx_[j] = at(L::OCX + j, k); ocy_[j] = at(L::OCY + j, k); isx_[j] = at(L::ISX + j, k); isy_[j] = at(L::ISY + j, k);
+          so_[j] = at(L::SO + j, k); vlo_[j] = at(L::VLO + j, k); lo_[j] = at(L::LO + j, k);
+        }
+      }
+      if (k < N) {
         Rk4Stages rk;
         rk.point(xk, u_k, T, rL);
         rk.hess(l_next, T, rL, Hm);  // defect = X_{k+1} - Phi: the Lagrangian takes MINUS lam' Phi''
@@ -768,20 +791,20 @@ struct LaneSolver {
       for (int b_ = 0; b_ < NBX; b_++) {
         int i = bx(b_);
         double rl = fast_rcp(xk[i] - p.x_lo[i]), rh = fast_rcp(p.x_hi[i] - xk[i]);
-        h[i] += at(L::ZLX + b_, k) * rl + at(L::ZUX + b_, k) * rh;
+        h[i] += zlx_[b_] * rl + zux_[b_] * rh;
         gx[i] += mu * (rh - rl);
       }
-      if (has_obs(k)) {
+      if (obst) {
 #pragma unroll
         for (int j = 0; j < MO; j++) {
-          double dx = xk[0] - at(L::OCX + j, k), dy = xk[1] - at(L::OCY + j, k);
-          double a_ = at(L::ISX + j, k), b_ = at(L::ISY + j, k);
+          double dx = xk[0] - ocx_[j], dy = xk[1] - ocy_[j];
+          double a_ = isx_[j], b_ = isy_[j];
           double d = dx * dx * a_ + dy * dy * b_ - 1.0;
           double ox = 2 * dx * a_, oy = 2 * dy * b_;
-          double s = at(L::SO + j, k), rg = fast_rcp(s - p.obs_lo);
-          double D = at(L::VLO + j, k) * rg + dw;
+          double s = so_[j], rg = fast_rcp(s - p.obs_lo);
+          double D = vlo_[j] * rg + dw;
           double gs = -mu * rg + MPCB_KAPPA_D * mu;
-          double lo = at(L::LO + j, k);
+          double lo = lo_[j];
           double t = D * (d - s) + gs;
           h[0] += lo * (2 * a_) + D * ox * ox;
           h01 += D * ox * oy;
@@ -795,9 +818,6 @@ struct LaneSolver {
       at(L::HUX + 0, k) = Hux[0][2]; at(L::HUX + 1, k) = Hux[0][3]; at(L::HUX + 2, k) = Hux[1][2]; at(L::HUX + 3, k) = Hux[1][3];
 #pragma unroll
       for (int i = 0; i < NX; i++) at(L::GX + i, k) = gx[i];
-      double c_k[NX];
-#pragma unroll
-      for (int i = 0; i < NX; i++) c_k[i] = at(cd + i, k);
       double Hxx[4][4] = {{h[0], h01, 0, 0}, {h01, h[1], 0, 0}, {0, 0, h[2], h23}, {0, 0, h23, h[3]}};
       if (k == N) {
 #pragma unroll
@@ -807,8 +827,6 @@ struct LaneSolver {
           for (int j = 0; j < 4; j++) P[i][j] = Hxx[i][j];
         }
       } else {
-        double u_m[2] = {0, 0};
-        if (k >= 1) { u_m[0] = at(L::U + 0, k - 1); u_m[1] = at(L::U + 1, k - 1); }
         double Huu[2][2] = {{0, -Hm[8]}, {-Hm[8], 0}}, gu[2], E[2] = {0, 0}, tk[2] = {0, 0};
 #pragma unroll
         for (int i = 0; i < 2; i++) {
@@ -817,17 +835,17 @@ struct LaneSolver {
           double hd = sigma * 2 * p.R[i] + dw - (i == 0 ? Hm[7] : Hm[9]);
           if (k == 0 && p.du0_cost) { hd += sigma * 2 * p.DR[i]; g += sigma * 2 * p.DR[i] * uk; }
           double rl = fast_rcp(uk - p.u_lo[i]), rh = fast_rcp(p.u_hi[i] - uk);
-          hd += at(L::ZLU + i, k) * rl + at(L::ZUU + i, k) * rh;
+          hd += zlu_[i] * rl + zuu_[i] * rh;
           g += mu * (rh - rl);
           Huu[i][i] = hd; gu[i] = g;
           if (k >= 1) { E[i] = sigma * 2 * p.DR[i]; tk[i] = sigma * 2 * p.DR[i] * (uk - u_m[i]); }
         }
-        if (has_rate(k)) {
+        if (rate) {
 #pragma unroll
           for (int r = 0; r < NR; r++) {
-            double s = at(L::SR + r, k);
+            double s = sr_[r];
             double rl = fast_rcp(s - p.rate_lo[r]), rh = fast_rcp(p.rate_hi[r] - s);
-            double D = at(L::VLR + r, k) * rl + at(L::VUR + r, k) * rh + dw;
+            double D = vlr_[r] * rl + vur_[r] * rh + dw;
             double gs = mu * (rh - rl);
             double res = u_k[0] - u_m[0] - s;
             E[0] += D; tk[0] += D * res + gs;
@@ -915,7 +933,7 @@ struct LaneSolver {
         u_k[0] = u_m[0]; u_k[1] = u_m[1];
       }
 #pragma unroll
-      for (int i = 0; i < NX; i++) { l_next[i] = at(L::LAM + i, k); c_next[i] = c_k[i]; }
+      for (int i = 0; i < NX; i++) { l_next[i] = lam_k[i]; c_next[i] = c_k[i]; }
     }
     return true;
   }
