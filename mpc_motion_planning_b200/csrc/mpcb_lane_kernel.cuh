@@ -4,9 +4,14 @@
 // iteration - backward Riccati, forward roll-out of the step, adjoint recursion - are executed by all 32 lanes on the same
 // values: 73 % of the executed warp instructions, 1 useful lane of 32, and the FP64 pipe is the limiter
 // (profiles/r01_final3_*).  With one scenario per lane every lane does useful FP64 work; the per-stage records then do not
-// fit shared memory, so they live structure-of-arrays across scenarios in global memory ([field][stage][slot], slot
+// fit shared memory, so they live structure-of-arrays across scenarios in global memory ([stage][field][slot], slot
 // fastest): a warp's access to one field of one stage is one 256-byte line, and the sweeps run at the HBM roofline
 // (scripts/micro/lane_sweep.cu: 57.8 M scenario-stages/s/SM against 11 M for the redundant-lane sweeps).
+//
+// Two rules the stage loops follow, both measured: every load of a stage comes before its first
+// store - all fields sit behind one pointer, so the compiler keeps each load behind every earlier store, and a store
+// whose value waits for a load would serialise the stage into several HBM round trips - and the recursions that run
+// backwards load stage k-1 before they store stage k.
 //
 // Same algorithm, same formulas as KinSolver (what replaces IPOPT + MUMPS behind PKG/MPC_CBF_optimize_kin.py:251-254 and
 // the CasADi derivatives of :136-255); only the mapping to the machine differs:
@@ -153,21 +158,15 @@ struct LaneSolver {
   __device__ LaneSolver(const KParams &p_, double *ws_, size_t nslot_, size_t slot_)
       : p(p_), ws(ws_), nslot(nslot_), slot(slot_), N(p_.N), S(p_.N + 1) {}
 
-#ifndef MPCB_LANE_STAGE_MAJOR
-#define MPCB_LANE_STAGE_MAJOR 1
-#endif
-  __device__ __forceinline__ double &at(int f, int k) {
-    if (MPCB_LANE_STAGE_MAJOR == 2) return ws[(size_t)(slot >> 5) * ((size_t)S * L::NFIELD * 32) + (size_t)(((k * L::NFIELD + f) << 5) + (int)(slot & 31))];
-    return MPCB_LANE_STAGE_MAJOR ? ws[((size_t)k * L::NFIELD + f) * nslot + slot] : ws[((size_t)f * S + k) * nslot + slot];
-  }
+  // Workspace layout [stage][field][slot]: one 256-byte line per field, stage and warp, the ~40 fields a stage touches in
+  // consecutive rows.  Measured against [field][stage][slot] (the fields of a stage 23 MB apart: a DRAM page and a TLB
+  // entry each) +18 %, against a warp-private [warp][stage][field][lane] +4 %.
+  __device__ __forceinline__ double &at(int f, int k) { return ws[((size_t)k * L::NFIELD + f) * nslot + slot]; }
   // Software prefetch: the stage loops carry their recursions in registers, but nothing lets the hardware see the next
   // stage's loads early; every phase therefore asks for the lines of the stage PF_DIST ahead (one 256-byte line per
   // field and warp) while it works on the current one.  The kernel uses no shared memory, so L1 holds them.
 #ifndef MPCB_LANE_PF_DIST
 #define MPCB_LANE_PF_DIST 0  // measured: 2 stages ahead costs 9 % at full occupancy and buys 20 % at 4 warps per SM (profiles/experiments)
-#endif
-#ifndef MPCB_LANE_KKT_UNROLL
-#define MPCB_LANE_KKT_UNROLL 1
 #endif
 #ifndef MPCB_LANE_PF_INSTR
 #define MPCB_LANE_PF_INSTR "prefetch.global.L2"
@@ -426,8 +425,7 @@ struct LaneSolver {
     double lr_c = 0.0;  // multiplier of the rate row of stage k
 #pragma unroll
     for (int i = 0; i < NX; i++) lam[i] = at(L::LAM + i, 0);
-    constexpr int KU = MPCB_LANE_KKT_UNROLL;  // the pass stores nothing: unrolled, the loads of KU stages are in flight together
-#pragma unroll KU
+#pragma unroll 1  // (the pass stores nothing, so unrolling would put the loads of several stages in flight: measured -3 % at 2)
     for (int k = 0; k <= N; k++) {
       pf<L::X, L::OCX - L::X + 4 * MO>(k + 1 + MPCB_LANE_PF_DIST);  // the whole iterate and the obstacle row
       pf<L::CDEF, 8>(k + 1 + MPCB_LANE_PF_DIST);
