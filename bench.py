@@ -185,6 +185,28 @@ def engine_legs(dev, peak_tflops):
             out[f"{kind}_B100k_{engine}"] = {"value": B / ms * 1e3, "unit": UNIT, "ms": ms, "mean_iters": float(it.mean()),
                                              "success_frac": float((o["status"].cpu().numpy() <= 1).mean()),
                                              "fp64_tflops": tf, "roofline_frac": tf / peak_tflops if peak_tflops > 0 else None}
+            if engine == "lane" and kind == "kin_nocbf":
+                # one scenario per resident lane (148 SMs x 3 blocks x 128 lanes on a B200): no partially filled last wave
+                info = s.launch_info()
+                Br = min(B, info["num_sms"] * info["blocks_per_sm"] * info["block"])
+                s.solve(a[:Br], b_[:Br], None)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                o = s.solve(a[:Br], b_[:Br], None)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                it = o["iters"].cpu().numpy()
+                tf = float(it.sum()) * flop_it / (ms * 1e-3) / 1e12
+                # this kernel is bound by HBM, not by the FP64 pipe: DRAM bytes per solve from the ncu capture of the same
+                # launch (profiles/r02b_lane_kernel_kin_nocbf_B56832.txt: 62.94 GB read + 24.03 GB written for 56,832 solves)
+                gbs = Br * (62.944738e9 + 24.032219e9) / 56832 / (ms * 1e-3) / 1e9
+                hbm_peak, hbm_src = _peaks()
+                out[f"{kind}_one_wave_{engine}"] = {"scenarios": Br, "value": Br / ms * 1e3, "unit": UNIT, "ms": ms, "mean_iters": float(it.mean()),
+                                                    "fp64_tflops": tf, "roofline_frac": tf / peak_tflops if peak_tflops > 0 else None,
+                                                    "hbm": {"achieved": gbs, "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                                            "traffic_source": "ncu --set full dram__bytes of this launch, profiles/r02b_lane_kernel_kin_nocbf_B56832.txt"}}
             s.close()
         del a, b_, c
         torch.cuda.empty_cache()
