@@ -1118,6 +1118,31 @@ def test_lane_engine_parity(dev, kind, gen, M, B):
         BatchSolver("kin_cbf", cbf_gamma=0.5, engine="lane")
 
 
+def test_lane_engine_beyond_one_wave_and_auto_selection(dev):
+    """More scenarios than resident lanes (the lanes refill from the queue, the grid is sized for equally full waves) and the
+    automatic engine choice: the row-free family goes to the lane engine from 20,480 scenarios up, and every scenario gets the
+    warp engine's answer either way."""
+    from mpc_motion_planning_b200 import scenarios
+    from mpc_motion_planning_b200.solver import BatchSolver
+
+    B = 70000
+    x0, xs, obs = scenarios.kin_nocbf(B)
+    auto = BatchSolver("kin_nocbf")  # engine="auto"
+    g = _gpu(auto, dev, x0, xs, None)
+    info = auto.launch_info()
+    lanes = info["num_sms"] * info["blocks_per_sm"] * info["block"]
+    assert info["smem_bytes"] == 0 and info["block"] == 128  # the lane kernel ran
+    assert B > lanes and info["grid"] * info["block"] < lanes  # two waves, neither of them full
+    assert info["grid"] == -(-(-(-B // 128)) // 2)
+    w = _gpu(BatchSolver("kin_nocbf", engine="warp"), dev, x0, xs, None)
+    assert np.array_equal(g["status"], w["status"]) and (g["status"] == 0).all()
+    assert np.array_equal(g["iters"], w["iters"])
+    assert np.abs(g["u0"] - w["u0"]).max() <= 1e-9 and np.abs(g["cost"] - w["cost"]).max() <= 1e-9 * np.abs(w["cost"]).max()
+    small = _gpu(auto, dev, x0[:4096], xs[:4096], None)  # below the switch: the warp kernel
+    assert auto.launch_info()["smem_bytes"] > 0
+    assert np.array_equal(small["u0"], w["u0"][:4096])
+
+
 def test_lane_engine_with_restoration_and_order(dev):
     """The lane engine hands failed line searches to the same restoration sibling, and honours a processing order."""
     import torch

@@ -250,3 +250,25 @@ def test_only_the_checkers_touch_the_oracle():
                     offenders.append(os.path.join(dirpath, f))
     assert not offenders, offenders
     assert "liboracle" not in open(os.path.join(ROOT, "mpc_motion_planning_b200", "_lib.py")).read()
+
+
+def test_shard_permutation_is_cached_per_batch_size_and_seed():
+    """solve_sharded keeps its shuffle on the device, one per (batch size, seed): two batch sizes in one process must not
+    see each other's permutation, and the result comes back in input order."""
+    import torch
+
+    from mpc_motion_planning_b200 import sharding
+
+    def solve_local(a, b, c, z):
+        n = a.shape[0]
+        return {"u0": torch.stack([a[:, 0], a[:, 0] * 2], 1), "cost": a[:, 0] + 0.5, "status": torch.zeros(n, dtype=torch.int32),
+                "iters": a[:, 0].to(torch.int32)}
+
+    for B in (37, 64, 37):
+        x0 = torch.arange(B, dtype=torch.float64).reshape(B, 1)
+        for seed in (0, 3, None):
+            out = sharding.solve_sharded(solve_local, x0, x0, None, shuffle_seed=seed)
+            assert torch.equal(out["u0"][:, 0], x0[:, 0]) and torch.equal(out["cost"], x0[:, 0] + 0.5)
+            assert torch.equal(out["iters"], torch.arange(B, dtype=torch.int32))
+            perm = sharding._device_permutation(B, seed, x0.device)
+            assert perm.numel() == B and torch.equal(torch.sort(perm).values, torch.arange(B))
