@@ -1141,6 +1141,17 @@ def test_lane_engine_beyond_one_wave_and_auto_selection(dev):
     small = _gpu(auto, dev, x0[:4096], xs[:4096], None)  # below the switch: the warp kernel
     assert auto.launch_info()["smem_bytes"] > 0
     assert np.array_equal(small["u0"], w["u0"][:4096])
+    # warm start (init = as_given with the previous solution, the closed loop's protocol) through both engines
+    n = 24000
+    zw = _gpu(BatchSolver("kin_nocbf", engine="warp"), dev, x0[:n], xs[:n], None, return_z=True)["z"]
+    x1 = x0[:n] + np.array([0.3, 0.02, 0.001, 0.1])
+    res = {}
+    for eng in ("warp", "auto"):
+        sv = BatchSolver("kin_nocbf", engine=eng, init="as_given")
+        res[eng] = _gpu(sv, dev, x1, xs[:n], None, z_init=zw, return_z=True)
+        assert (sv.launch_info()["smem_bytes"] == 0) == (eng == "auto")
+    assert np.array_equal(res["auto"]["status"], res["warp"]["status"]) and (res["warp"]["status"] == 0).all()
+    assert np.abs(res["auto"]["z"] - res["warp"]["z"]).max() <= 1e-7 and res["warp"]["iters"].mean() < 14
 
 
 def test_lane_engine_with_restoration_and_order(dev):
