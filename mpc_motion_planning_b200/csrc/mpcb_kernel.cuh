@@ -1101,9 +1101,9 @@ struct KinSolver {
   __device__ __forceinline__ void accept_step(double a, double ad, double mu) {
     #pragma unroll 1
     for (int k = lane; k <= N; k += 32) {
-#pragma unroll
       expect(L::LAMP, NX, k, p.debug_selftest ? TAG_GAINS : TAG_NEWLAM);
       expect(L::CDEFT, NX, k, TAG_TRIALDEF);
+#pragma unroll
       for (int i = 0; i < NX; i++) {
         double l = at(L::LAM + i, k);
         at(L::LAM + i, k) = l + a * (at(L::LAMP + i, k) - l);
