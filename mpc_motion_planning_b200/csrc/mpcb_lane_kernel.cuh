@@ -582,7 +582,7 @@ struct LaneSolver {
 
   __device__ bool backward() {
     const int cd = cdef(cur), tg = trg(cur);
-    const double T = p.T, rL = 1.0 / p.Veh_l;
+    const double T = p.T;
     double p00, p01, p11, p22, p23, p33, p02 = 0, p03 = 0, p12 = 0, p13 = 0, px0, px1, px2, px3;
     double w0d = 0, w0a = 0, w1d = 0, w1a = 0, w2d = 0, w2a = 0, w3d = 0, w3a = 0;
     double qdd = 0, qda = 0, qaa = 0, pwd = 0, pwa = 0;
